@@ -1,0 +1,327 @@
+"""ctypes bindings for the two CPU checkers (TEST INFRASTRUCTURE):
+
+  RefLib     oracle/_ref/libx264ref.so  -- the unmodified reference C sources + oracle/ref_shim.c
+  OracleLib  oracle/libx264oracle.so    -- our plain-C restatement (oracle/x264_oracle.c)
+
+Both expose the same lookahead driver interface (`Lookahead`) so a test can run the same
+evaluation sequence through either and compare arrays.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "libx264oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libx264ref.so")
+
+SIZES = ["16x16", "16x8", "8x16", "8x8", "8x4", "4x8", "4x4", "4x16"]
+SIZE_WH = [(16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8), (4, 4), (4, 16)]
+KIND = {"sad": 0, "satd": 1, "sa8d": 2}
+
+vp = C.c_void_p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(vp)
+
+
+def build_oracle():
+    src = os.path.join(ROOT, "oracle", "x264_oracle.c")
+    if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    return ORACLE_SO
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+class XoCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "width", "height", "bframes", "subme", "me_method", "me_range", "mv_range", "do_edges",
+        "aq", "weighted_bipred", "bframe_bias", "search_passes")]
+
+
+class _Base:
+    """primitive calls common to both libraries (prefix differs)."""
+
+    def __init__(self, path, prefix):
+        self.lib = C.CDLL(path)
+        self.p = prefix
+        L = self.lib
+        f = getattr(L, prefix + "pixel_cmp_batch")
+        f.argtypes = [C.c_int, C.c_int, vp, C.c_ssize_t, vp, C.c_ssize_t, C.c_int64, vp, vp, vp]
+        f.restype = C.c_int
+        f = getattr(L, prefix + "hadamard_ac_batch")
+        f.argtypes = [C.c_int, vp, C.c_ssize_t, C.c_int64, vp, vp]
+        f = getattr(L, prefix + "sub_dct_batch")
+        f.argtypes = [C.c_int, vp, C.c_ssize_t, vp, C.c_ssize_t, C.c_int64, vp, vp, vp]
+        f = getattr(L, prefix + "quant_batch")
+        f.argtypes = [C.c_int, vp, C.c_int64, vp, vp, vp]
+        f = getattr(L, prefix + "lowres_core")
+        f.argtypes = [vp, C.c_ssize_t, vp, vp, vp, vp, C.c_ssize_t, C.c_int, C.c_int]
+        f.restype = None
+
+    def pixel_cmp(self, kind, size, p1, s1, p2, s2, off1, off2):
+        """p1/p2: flat uint8 arrays; off*: int64 byte offsets of each block's top-left."""
+        off1 = np.ascontiguousarray(off1, dtype=np.int64)
+        off2 = np.ascontiguousarray(off2, dtype=np.int64)
+        out = np.empty(len(off1), dtype=np.int32)
+        r = getattr(self.lib, self.p + "pixel_cmp_batch")(KIND[kind], size, _ptr(p1), s1, _ptr(p2), s2,
+                                                        len(off1), _ptr(off1), _ptr(off2), _ptr(out))
+        assert r == 0
+        return out
+
+    def hadamard_ac(self, size, p, stride, off):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        out = np.empty(len(off), dtype=np.uint64)
+        r = getattr(self.lib, self.p + "hadamard_ac_batch")(size, _ptr(p), stride, len(off), _ptr(off), _ptr(out))
+        assert r == 0
+        return out
+
+    def sub_dct(self, bsize, p1, s1, p2, s2, off1, off2):
+        off1 = np.ascontiguousarray(off1, dtype=np.int64)
+        off2 = np.ascontiguousarray(off2, dtype=np.int64)
+        out = np.empty((len(off1), bsize * bsize), dtype=np.int16)
+        r = getattr(self.lib, self.p + "sub_dct_batch")(bsize, _ptr(p1), s1, _ptr(p2), s2, len(off1),
+                                                      _ptr(off1), _ptr(off2), _ptr(out))
+        assert r == 0
+        return out
+
+    def quant(self, b8x8, coefs, mf, bias):
+        n = 64 if b8x8 else 16
+        coefs = np.ascontiguousarray(coefs, dtype=np.int16).copy()
+        nb = coefs.size // n
+        mf = np.ascontiguousarray(mf, dtype=np.uint16)
+        bias = np.ascontiguousarray(bias, dtype=np.uint16)
+        nz = np.empty(nb, dtype=np.int32)
+        getattr(self.lib, self.p + "quant_batch")(int(b8x8), _ptr(coefs), nb, _ptr(mf), _ptr(bias), _ptr(nz))
+        return coefs, nz
+
+    def lowres_core(self, src, sstride, width, height, dstride):
+        """src: flat uint8 with >= (2*height+1) rows of >= 2*width+1 valid bytes. returns 4 planes."""
+        planes = [np.zeros(dstride * height, dtype=np.uint8) for _ in range(4)]
+        getattr(self.lib, self.p + "lowres_core")(_ptr(src), sstride, *[_ptr(p) for p in planes], dstride, width, height)
+        return [p.reshape(height, dstride)[:, :width].copy() for p in planes]
+
+
+class OracleLib(_Base):
+    def __init__(self):
+        super().__init__(build_oracle(), "xo_")
+        L = self.lib
+        L.xo_open.restype = vp
+        L.xo_open.argtypes = [C.POINTER(XoCfg)]
+        L.xo_close.argtypes = [vp]
+        L.xo_info.argtypes = [vp, vp]
+        L.xo_put_frame.argtypes = [vp, C.c_int, vp, C.c_int, vp]
+        L.xo_get_lowres.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.xo_frame_cost.argtypes = [vp] + [C.c_int] * 6
+        L.xo_get.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.xo_counters.argtypes = [vp, vp]
+        L.xo_mc_luma.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + [C.c_int] * 7
+        L.xo_mc_luma.restype = None
+        L.xo_avg.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, vp, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+        L.xo_avg.restype = None
+        L.xo_intra_cost_8x8.argtypes = [vp, C.c_ssize_t, C.c_int]
+        L.xo_cost_mv_table.argtypes = [vp, C.c_int]
+        L.xo_cost_mv_table.restype = None
+
+    def cost_mv_table(self, n):
+        buf = np.zeros(2 * n + 1, dtype=np.uint16)
+        self.lib.xo_cost_mv_table(C.c_void_p(buf.ctypes.data + 2 * n), n)
+        return buf
+
+    def mc_luma(self, planes, stride, org, mvx, mvy, w, h, weight=None):
+        """planes: 4 flat uint8 arrays; org: offset of the block origin inside each plane."""
+        arr = (vp * 4)(*[p.ctypes.data + org for p in planes])
+        dst = np.zeros((h, w), dtype=np.uint8)
+        sc, dn, of = weight if weight else (0, -1, 0)
+        self.lib.xo_mc_luma(_ptr(dst), w, arr, stride, mvx, mvy, w, h, sc, dn, of)
+        return dst
+
+    def avg(self, a, b, w, h, weight):
+        dst = np.zeros((h, w), dtype=np.uint8)
+        self.lib.xo_avg(_ptr(dst), w, _ptr(a), a.shape[1], _ptr(b), b.shape[1], w, h, weight)
+        return dst
+
+
+class RefLib(_Base):
+    def __init__(self):
+        super().__init__(REF_SO, "ref_")
+        L = self.lib
+        L.ref_la_open.restype = vp
+        L.ref_la_open.argtypes = [C.c_int] * 11
+        L.ref_la_close.argtypes = [vp]
+        L.ref_la_info.argtypes = [vp, vp]
+        L.ref_la_cost_mv.argtypes = [vp, vp, C.c_int]
+        L.ref_la_put_frame.argtypes = [vp, C.c_int, vp, C.c_int, vp]
+        L.ref_la_get_lowres.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.ref_la_lowres_geometry.argtypes = [vp, C.c_int, vp]
+        L.ref_la_frame_cost_serial.argtypes = [vp] + [C.c_int] * 3
+        L.ref_la_frame_cost_jacobi.argtypes = [vp] + [C.c_int] * 4
+        L.ref_la_get.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.ref_la_slicetype_analyse.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+        L.ref_mc_luma.argtypes = [vp, C.c_ssize_t, vp, vp, vp, vp, C.c_ssize_t] + [C.c_int] * 7
+        L.ref_mc_luma.restype = None
+        L.ref_avg.argtypes = [C.c_int, vp, C.c_ssize_t, vp, C.c_ssize_t, vp, C.c_ssize_t, C.c_int]
+        L.ref_avg.restype = None
+        L.ref_cqm_tables.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
+        L.ref_intra_x3_8x8c.argtypes = [C.c_int, vp, vp, vp]
+        L.ref_predict_8x8c.argtypes = [C.c_int, vp]
+        L.ref_predict_8x8_filter.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.ref_predict_8x8.argtypes = [C.c_int, vp, vp]
+        L.ref_pixel_cmp.argtypes = [C.c_int, C.c_int, vp, C.c_ssize_t, vp, C.c_ssize_t]
+        L.ref_sad_x3.argtypes = [C.c_int, vp, vp, vp, vp, C.c_ssize_t, vp]
+        L.ref_sad_x4.argtypes = [C.c_int, vp, vp, vp, vp, vp, C.c_ssize_t, vp]
+        L.ref_now.restype = C.c_double
+
+    def mc_luma(self, planes, stride, org, mvx, mvy, w, h, weight=None):
+        dst = np.zeros((h, w), dtype=np.uint8)
+        sc, dn, of = weight if weight else (0, -1, 0)
+        self.lib.ref_mc_luma(_ptr(dst), w, *[C.c_void_p(p.ctypes.data + org) for p in planes], stride,
+                             mvx, mvy, w, h, sc, dn, of)
+        return dst
+
+    def avg(self, size, a, b, weight):
+        w, h = SIZE_WH[size]
+        dst = np.zeros((h, w), dtype=np.uint8)
+        self.lib.ref_avg(size, _ptr(dst), w, _ptr(a), a.shape[1], _ptr(b), b.shape[1], weight)
+        return dst
+
+    def cqm_tables(self, b8x8, cat, qp):
+        n = 64 if b8x8 else 16
+        mf = np.zeros(n, dtype=np.uint16)
+        bias = np.zeros(n, dtype=np.uint16)
+        assert self.lib.ref_cqm_tables(int(b8x8), cat, qp, _ptr(mf), _ptr(bias)) == 0
+        return mf, bias
+
+    def intra_cost_8x8(self, plane, stride, org, b_satd):
+        """the reference's intra section (slicetype.c:714-746) recomposed from its own predictor
+        and pixel tables, for one block at byte offset `org` of a padded plane."""
+        FDEC = 32
+        L = self.lib
+        buf = np.zeros(9 * FDEC + 64, dtype=np.uint8)
+        pixo = 8 + FDEC          # pix = &pix1[8+FDEC_STRIDE]
+        fenc = np.zeros(16 * 8, dtype=np.uint8)
+        for y in range(8):
+            fenc[y * 16:y * 16 + 8] = plane[org + y * stride: org + y * stride + 8]
+        buf[pixo - FDEC: pixo - FDEC + 16] = plane[org - stride: org - stride + 16]
+        for i in range(-1, 8):
+            buf[pixo + i * FDEC - 4: pixo + i * FDEC] = plane[org + i * stride - 4: org + i * stride]
+        pix = C.c_void_p(buf.ctypes.data + pixo)
+        res = (C.c_int * 3)()
+        L.ref_intra_x3_8x8c(int(b_satd), _ptr(fenc), pix, res)
+        best = min(res)
+        if b_satd:
+            kind = 1
+            L.ref_predict_8x8c(3, pix)   # I_PRED_CHROMA_P
+            best = min(best, L.ref_pixel_cmp(kind, 3, _ptr(fenc), 16, pix, FDEC))
+            edge = np.zeros(40, dtype=np.uint8)
+            L.ref_predict_8x8_filter(pix, _ptr(edge), 0xF, 0xF)   # ALL_NEIGHBORS
+            for m in range(3, 9):
+                L.ref_predict_8x8(m, pix, _ptr(edge))
+                best = min(best, L.ref_pixel_cmp(kind, 3, _ptr(fenc), 16, pix, FDEC))
+        return best + 5 + 4
+
+
+GET_LOWRES_COSTS, GET_MVS, GET_MV_COSTS, GET_ROW_SATDS, GET_STATS, GET_INTRA, GET_INVQ = range(7)
+
+
+class Lookahead:
+    """uniform driver over RefLib ('ref': Jacobi schedule on the unmodified slicetype_mb_cost;
+    'ref_serial': the reference's own raster-serial slicetype_frame_cost) and OracleLib ('oracle')."""
+
+    def __init__(self, lib, kind, width, height, bframes=3, subme=7, mbtree=1, aq=1, passes=2,
+                 b_adapt=2, rc_lookahead=40, la_threads=1, mv_range=None):
+        self.lib, self.kind = lib, kind
+        self.W, self.H, self.passes = width, height, passes
+        if kind.startswith("ref"):
+            self.ctx = lib.lib.ref_la_open(width, height, bframes, subme, mbtree, aq, 0, b_adapt, la_threads, rc_lookahead, 0)
+            assert self.ctx
+            info = (C.c_int * 10)()
+            lib.lib.ref_la_info(self.ctx, info)
+            self.info = list(info)
+            self.mbw, self.mbh, self.mv_range = info[0], info[1], info[2]
+        else:
+            cfg = XoCfg(width, height, bframes, subme, 1, 16, mv_range, mbtree, aq, 1, 0, passes)
+            self.ctx = lib.lib.xo_open(C.byref(cfg))
+            assert self.ctx
+            info = (C.c_int * 4)()
+            lib.lib.xo_info(self.ctx, info)
+            self.mbw, self.mbh = info[0], info[1]
+            self.mv_range = mv_range
+        self.nmb = self.mbw * self.mbh
+
+    def close(self):
+        if self.ctx:
+            (self.lib.lib.ref_la_close if self.kind.startswith("ref") else self.lib.lib.xo_close)(self.ctx)
+            self.ctx = None
+
+    def put_frame(self, idx, luma, inv_qscale=None):
+        luma = np.ascontiguousarray(luma, dtype=np.uint8)
+        assert luma.shape == (self.H, self.W)
+        q = None if inv_qscale is None else _ptr(np.ascontiguousarray(inv_qscale, dtype=np.uint16))
+        f = self.lib.lib.ref_la_put_frame if self.kind.startswith("ref") else self.lib.lib.xo_put_frame
+        assert f(self.ctx, idx, _ptr(luma), self.W, q) == 0
+
+    def lowres(self, idx, plane):
+        w, h = self.mbw * 8 + 64, self.mbh * 8 + 64
+        out = np.zeros((h, w), dtype=np.uint8)
+        f = self.lib.lib.ref_la_get_lowres if self.kind.startswith("ref") else self.lib.lib.xo_get_lowres
+        assert f(self.ctx, idx, plane, _ptr(out)) == 0
+        return out
+
+    def frame_cost(self, p0, p1, b):
+        if self.kind == "ref":
+            return self.lib.lib.ref_la_frame_cost_jacobi(self.ctx, p0, p1, b, self.passes)
+        if self.kind == "ref_serial":
+            return self.lib.lib.ref_la_frame_cost_serial(self.ctx, p0, p1, b)
+        return self.lib.lib.xo_frame_cost(self.ctx, p0, p1, b, 0, -1, 0)
+
+    def get(self, idx, what, i=0, j=0):
+        shape, dt = {
+            GET_LOWRES_COSTS: ((self.nmb,), np.uint16), GET_MVS: ((self.nmb, 2), np.int16),
+            GET_MV_COSTS: ((self.nmb,), np.int32), GET_ROW_SATDS: ((self.mbh,), np.int32),
+            GET_STATS: ((3,), np.int32), GET_INTRA: ((self.nmb,), np.uint16), GET_INVQ: ((self.nmb,), np.uint16)}[what]
+        out = np.zeros(shape, dtype=dt)
+        f = self.lib.lib.ref_la_get if self.kind.startswith("ref") else self.lib.lib.xo_get
+        assert f(self.ctx, idx, what, i, j, _ptr(out)) == 0, (what, i, j)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic content: panning texture + moving square + noise
+# ------------------------------------------------------------------------------------------------
+def synth_frames(width, height, n, seed=7, pan=(3, 1), noise=3, scene_cut_at=None, fade_at=None):
+    rng = np.random.default_rng(seed)
+    margin = 64 + max(abs(pan[0]), abs(pan[1])) * n
+    tw, th = width + 2 * margin, height + 2 * margin
+
+    def texture(r):
+        t = r.integers(0, 256, (th // 8 + 2, tw // 8 + 2)).astype(np.float32)
+        t = np.kron(t, np.ones((8, 8), dtype=np.float32))[:th, :tw]
+        # cheap separable blur so that sub-pel interpolation matters
+        for ax in (0, 1):
+            t = (np.roll(t, 1, ax) + 2 * t + np.roll(t, -1, ax)) / 4
+            t = (np.roll(t, 2, ax) + 2 * t + np.roll(t, -2, ax)) / 4
+        fine = r.integers(-24, 25, (th, tw)).astype(np.float32)
+        return np.clip(t * 0.8 + 25 + fine, 0, 255)
+
+    tex = texture(rng)
+    tex2 = None
+    frames = []
+    for i in range(n):
+        if scene_cut_at is not None and i == scene_cut_at:
+            tex2 = texture(np.random.default_rng(seed + 1000))
+        src = tex2 if (tex2 is not None and i >= scene_cut_at) else tex
+        ox, oy = margin + pan[0] * i, margin + pan[1] * i
+        f = src[oy:oy + height, ox:ox + width].copy()
+        sq = min(160, width // 4, height // 4)
+        sx, sy = (40 + 11 * i) % max(1, width - sq), (30 + 5 * i) % max(1, height - sq)
+        f[sy:sy + sq, sx:sx + sq] = 255 - f[sy:sy + sq, sx:sx + sq]
+        if fade_at is not None and fade_at <= i < fade_at + 12:
+            f = f * (1.0 - (i - fade_at + 1) / 16.0) + 8
+        f = f + rng.integers(-noise, noise + 1, f.shape)
+        frames.append(np.clip(f, 0, 255).astype(np.uint8))
+    return frames
