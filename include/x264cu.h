@@ -1,0 +1,172 @@
+/* x264cu.h -- C ABI of libx264cuda.so: the B200 (sm_100a) lookahead cost engine.
+ *
+ * This library sits where the reference's OpenCL lookahead backend sits
+ * (common/opencl.c + encoder/slicetype-cl.c behind encoder/slicetype.c:878-899,1530,1740 and
+ * encoder/encoder.c:1744-1754,1797-1800).  Plain pointers and sizes only; no x264 or torch types.
+ * INTEGRATION.md shows the ~200-line glue that implements the reference's x264_opencl_* entry
+ * points (encoder/slicetype-cl.h:29-42, common/opencl.h:796-807) on top of these calls.
+ *
+ * Conventions: every int-returning call returns 0 on success and -1 on failure (the reference's
+ * OCLCHECK convention, slicetype-cl.c:44-56); x264cu_last_error() describes the failure.
+ * There is no CPU fallback: without a CUDA device x264cu_open fails.
+ * A context is single-threaded, like the reference's one in-order queue (opencl.c:525); several
+ * contexts (encode streams) may share a device, each with its own CUDA stream.
+ */
+#ifndef X264CU_H
+#define X264CU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X264CU_BFRAME_MAX 16        /* X264_BFRAME_MAX, common/base.h:136 */
+
+typedef struct x264cu_ctx   x264cu_ctx;     /* replaces x264_opencl_t        (common/opencl.h:720-778) */
+typedef struct x264cu_frame x264cu_frame;   /* replaces x264_frame_opencl_t  (common/opencl.h:780-792) */
+
+/* block sizes, in the order of the reference's PIXEL_* enum (common/pixel.h:41-52) */
+enum { X264CU_16x16, X264CU_16x8, X264CU_8x16, X264CU_8x8, X264CU_8x4, X264CU_4x8, X264CU_4x4, X264CU_4x16 };
+/* metrics of x264_pixel_function_t (common/pixel.h:82-103) */
+enum { X264CU_SAD, X264CU_SATD, X264CU_SA8D };
+
+/* The x264_param_t fields that steer the path (common/base.c:378-460). */
+typedef struct
+{
+    int width, height;        /* i_width / i_height: luma size before mod-16 padding                      */
+    int bframes;              /* i_bframe (0..16)                                                         */
+    int subme;                /* analyse.i_subpel_refine: >1 selects SATD + HEX + subme 4 (slicetype.c:50) */
+    int me_method;            /* analyse.i_me_method: 0 dia, >=1 hex (min(HEX,param), slicetype.c:52)      */
+    int me_range;             /* analyse.i_me_range (16)                                                  */
+    int mv_range;             /* analyse.i_mv_range after x264's level-based validation (e.g. 512 @1080p) */
+    int do_edges;             /* rc.b_mb_tree || rc.i_vbv_buffer_size (slicetype.c:823)                   */
+    int aq;                   /* rc.i_aq_mode != 0 (slicetype.c:749,779)                                  */
+    int weighted_bipred;      /* analyse.b_weighted_bipred (slicetype.c:529)                              */
+    int bframe_bias;          /* i_bframe_bias (slicetype.c:985)                                          */
+    int search_passes;        /* K of the dependency-free schedule; >= 1, default 2           */
+    int max_frames;           /* frame handles that may be alive at once (rc.i_lookahead + bframes + 3)   */
+    const uint16_t *cost_mv;  /* optional: host pointer to the CENTRE of h->cost_mv[X264_LOOKAHEAD_QP]
+                               * (analyse.c:143-157), valid for +-8*mv_range; NULL: rebuilt with the same
+                               * formula                                                                  */
+} x264cu_cfg;
+
+/* explicit weighted prediction of list 0 of a P evaluation: x264_weight_t (common/mc.h:235-245) */
+typedef struct { int enabled, scale, denom, offset; } x264cu_weight;
+
+/* Host destinations of one evaluation: the x264_frame_t lookahead fields (common/frame.h:103-127).
+ * NULL members are not copied.  Filled when x264cu_flush returns. */
+typedef struct
+{
+    uint16_t *lowres_costs;   /* lowres_costs[b-p0][p1-b]      u16 x mb_count: min(cost,0x3FFF)+(list<<14) */
+    int16_t  *mvs[2];         /* lowres_mvs[l][dist-1]         i16 x 2 x mb_count (qpel)                   */
+    int32_t  *mv_costs[2];    /* lowres_mv_costs[l][dist-1]    i32 x mb_count                              */
+    int32_t  *row_satds;      /* i_row_satds[b-p0][p1-b]       i32 x mb_height                             */
+    int32_t  *stats;          /* [0] i_cost_est[b-p0][p1-b] (B: already x100/(120+bias)), [1] i_cost_est_aq,
+                               * [2] i_intra_mbs[b-p0], [3] raw (unscaled) cost                            */
+    uint16_t *intra_costs;    /* i_intra_cost                  u16 x mb_count                              */
+    int32_t  *intra_row_satds;/* i_row_satds[0][0]             i32 x mb_height                             */
+    int32_t  *intra_stats;    /* [0] i_cost_est[0][0], [1] i_cost_est_aq[0][0]                             */
+} x264cu_out;
+
+/* One frame-cost evaluation of a batch: slicetype_frame_cost(h,a,frames,p0,p1,b) (slicetype.c:836). */
+typedef struct
+{
+    x264cu_frame *fenc, *fref0, *fref1;   /* frames[b], frames[p0], frames[p1] */
+    int d0, d1;                           /* b-p0 and p1-b                     */
+    x264cu_weight weight;                 /* used only when d1 == 0            */
+    x264cu_out out;
+} x264cu_job;
+
+/* ---- library / context: x264_opencl_load_library, x264_opencl_lookahead_init/_delete (opencl.h:796-804) ---- */
+int          x264cu_device_count( void );
+const char  *x264cu_last_error( void );
+x264cu_ctx  *x264cu_open( int device, const x264cu_cfg *cfg );
+void         x264cu_close( x264cu_ctx *ctx );
+/* [0] mb_width [1] mb_height [2] lowres width [3] lowres height [4] device plane stride [5] SM count */
+int          x264cu_info( x264cu_ctx *ctx, int *out6 );
+
+/* ---- frames: lazily created device objects of x264_opencl_lowres_init (slicetype-cl.c:101-160),
+ *      released by x264_opencl_frame_delete (opencl.c:620) ---- */
+x264cu_frame *x264cu_frame_new( x264cu_ctx *ctx );
+void          x264cu_frame_free( x264cu_ctx *ctx, x264cu_frame *f );
+
+/* x264_frame_init_lowres (mc.c:458-482) + x264_opencl_lowres_init (slicetype-cl.c:82-282):
+ * upload the luma plane (width x height, `stride` bytes per row) and inv_qscale_factor
+ * (u16 x mb_count, NULL: 256 everywhere), build the four lowres phase planes with their 32-pixel
+ * border, the intra costs and their row/frame sums, and reset the frame's cost/MV caches.
+ * `luma`/`inv_qscale` are HOST pointers; the _device variant takes DEVICE pointers (no PCIe copy). */
+int x264cu_frame_upload( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *luma, int stride, const uint16_t *inv_qscale );
+int x264cu_frame_upload_device( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint16_t *d_inv_qscale );
+
+/* slicetype_frame_cost through the GPU hook (slicetype.c:878-897): enqueue, asynchronously, the
+ * searches this evaluation still needs (x264_opencl_motionsearch), the mode decision and sums
+ * (x264_opencl_finalize_cost) and the copies into `out`.  Evaluations are cached per frame exactly
+ * like i_cost_est / the 0x7FFF MV sentinel (slicetype.c:848-867). */
+int x264cu_frame_cost( x264cu_ctx *ctx, const x264cu_job *job );
+/* x264_opencl_slicetype_prep (slicetype-cl.c:653-712): many evaluations, semantically in array
+ * order, executed as a few wide launches (all searches of a pass together, all decisions together). */
+int x264cu_frame_cost_batch( x264cu_ctx *ctx, const x264cu_job *jobs, int n_jobs );
+/* x264_opencl_flush (slicetype-cl.c:58-70): wait for the stream, then complete the queued copies. */
+int x264cu_flush( x264cu_ctx *ctx );
+/* number of kernels launched by this context so far */
+int64_t x264cu_launch_count( x264cu_ctx *ctx );
+/* device-side time of the kernels between the last two flushes, in milliseconds, per kernel class:
+ * [0] lowres [1] intra [2] search [3] finalize; also returns their launch counts in n4 (may be NULL) */
+int x264cu_kernel_times( x264cu_ctx *ctx, float *ms4, int *n4 );
+/* per-class CUDA-event timing of the kernels (off by default: two event records per launch) */
+int x264cu_set_profiling( x264cu_ctx *ctx, int on );
+/* copy a device lowres plane (incl. border; pitch = lowres width + 64) back to the host: test hook */
+int x264cu_frame_get_lowres( x264cu_ctx *ctx, x264cu_frame *f, int plane, uint8_t *out );
+
+/* ---- batched pixel primitives (config "checkasm-style"): x264_pixel_function_t sad/satd/sa8d/
+ *      hadamard_ac (pixel.h:82-103), x264_dct_function_t sub4x4/8x8/16x16_dct (dct.h:28-33),
+ *      x264_quant_function_t quant_4x4/8x8 (quant.h:30-33), frame_init_lowres_core (mc.h:303).
+ *      Pointers are DEVICE pointers when on_device != 0, else HOST pointers (copied through). ---- */
+
+/* n independent block pairs at byte offsets off1[i] / off2[i] of two planes (checkasm.c:393-397) */
+int x264cu_pixel_cmp( x264cu_ctx *ctx, int metric, int size, const uint8_t *pix1, int64_t len1, int stride1,
+                      const uint8_t *pix2, int64_t len2, int stride2, int64_t n, const int64_t *off1,
+                      const int64_t *off2, int32_t *out, int on_device );
+/* every non-overlapping block of pix1 (width x height) against pix2 displaced by (dx,dy) >= 0;
+ * pix2 must cover (width+dx) x (height+dy).  out: (height/bh) x (width/bw) scores, raster order. */
+int x264cu_pixel_cmp_grid( x264cu_ctx *ctx, int metric, int size, const uint8_t *pix1, int stride1,
+                           const uint8_t *pix2, int stride2, int width, int height, int dx, int dy,
+                           int32_t *out, int on_device );
+/* sad_x3 / sad_x4 (pixel.c:441-464): fenc has stride 16, the refs share `stride` */
+int x264cu_sad_x( x264cu_ctx *ctx, int size, int nref, const uint8_t *fenc, const uint8_t *refs, int64_t reflen,
+                  int stride, const int64_t *ref_off, int32_t *scores );
+int x264cu_hadamard_ac( x264cu_ctx *ctx, int size, const uint8_t *pix, int64_t len, int stride, int64_t n,
+                        const int64_t *off, uint64_t *out, int on_device );
+int x264cu_hadamard_ac_grid( x264cu_ctx *ctx, int size, const uint8_t *pix, int stride, int width, int height,
+                             uint64_t *out, int on_device );
+/* bsize 4, 8 or 16; out: n x bsize*bsize coefficients in the reference's order (dct.c:157-205) */
+int x264cu_sub_dct( x264cu_ctx *ctx, int bsize, const uint8_t *pix1, int64_t len1, int stride1,
+                    const uint8_t *pix2, int64_t len2, int stride2, int64_t n, const int64_t *off1,
+                    const int64_t *off2, int16_t *out, int on_device );
+int x264cu_sub_dct_grid( x264cu_ctx *ctx, int bsize, const uint8_t *pix1, int stride1, const uint8_t *pix2,
+                         int stride2, int width, int height, int16_t *out, int on_device );
+/* in-place quant of nblocks blocks of 16 (b8x8 = 0) or 64 coefficients; nz[i] = !!nonzero (quant.c:59-73) */
+int x264cu_quant( x264cu_ctx *ctx, int b8x8, int16_t *coefs, int64_t nblocks, const uint16_t *mf,
+                  const uint16_t *bias, int32_t *nz, int on_device );
+/* frame_init_lowres_core (mc.c:484-507): src must have 2*height+1 rows of 2*width+1 valid bytes */
+int x264cu_lowres_core( x264cu_ctx *ctx, const uint8_t *src, int src_stride, uint8_t *dst0, uint8_t *dsth,
+                        uint8_t *dstv, uint8_t *dstc, int dst_stride, int width, int height, int on_device );
+
+/* device memory helpers for callers that keep data resident (bench, tests) */
+void *x264cu_malloc( x264cu_ctx *ctx, size_t bytes );
+void  x264cu_free( x264cu_ctx *ctx, void *p );
+/* page-locked host memory (the reference's CL_MEM_ALLOC_HOST_PTR buffer, opencl.c:380-392): uploads
+ * from it and results into it skip the internal staging copy */
+void *x264cu_host_alloc( x264cu_ctx *ctx, size_t bytes );
+void  x264cu_host_free( x264cu_ctx *ctx, void *p );
+int   x264cu_memcpy_h2d( x264cu_ctx *ctx, void *dst, const void *src, size_t bytes );
+int   x264cu_memcpy_d2h( x264cu_ctx *ctx, void *dst, const void *src, size_t bytes );
+/* bracket device work with CUDA events on the context's stream: returns elapsed ms of [begin,end) */
+int   x264cu_timer_begin( x264cu_ctx *ctx );
+float x264cu_timer_end( x264cu_ctx *ctx );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

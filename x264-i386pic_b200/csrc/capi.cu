@@ -1,0 +1,877 @@
+// capi.cu -- host side of libx264cuda.so: the C ABI of include/x264cu.h.
+//
+// Owns what common/opencl.c + encoder/slicetype-cl.c own in the reference: the device context and
+// its single in-order stream (opencl.c:525), the page-locked staging buffer and the deferred
+// copy list drained by flush (opencl.h:712-718, slicetype-cl.c:58-70), per-frame device objects
+// created on first use (slicetype-cl.c:101-160), and the evaluation caches that mirror
+// i_cost_est / the 0x7FFF MV sentinel (slicetype.c:848-867).  No CPU fallback anywhere.
+#include "../../include/x264cu.h"
+#include "lookahead.cuh"
+#include "primitives.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+#define FAIL( ... ) do { snprintf( g_err, sizeof(g_err), __VA_ARGS__ ); return -1; } while( 0 )
+#define CU( call ) do { cudaError_t e_ = (call); if( e_ != cudaSuccess ) { \
+    snprintf( g_err, sizeof(g_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString( e_ ) ); return -1; } } while( 0 )
+#define CUP( call ) do { cudaError_t e_ = (call); if( e_ != cudaSuccess ) { \
+    snprintf( g_err, sizeof(g_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString( e_ ) ); return NULL; } } while( 0 )
+
+enum { K_LOWRES, K_INTRA, K_SEARCH, K_FINAL, K_NCLASS };
+
+struct PendingCopy { void *dst; const void *src; size_t bytes; };   // bytes == 0: stats fix-up (finish_stats)
+struct TimedSpan { cudaEvent_t a, b; int cls; };
+
+struct x264cu_frame
+{
+    uint8_t  *planes;        // padded origin of plane F; H,V,C follow at plane_size
+    uint16_t *inv_qscale;
+    uint16_t *costs;         // [(B+2)*(B+2)][nmb]; [0] is i_intra_cost (alias of lowres_costs[0][0], frame.c:287)
+    int16_t  *mvs;           // [2*(B+1)][nmb][2]
+    int32_t  *mvcosts;       // [2*(B+1)][nmb]
+    int32_t  *stats;         // [(B+2)*(B+2)][stat_pitch]: row_satds[mbh], cost_est, cost_est_aq, intra_mbs
+    uint8_t   searched[2][X264CU_BFRAME_MAX+1];
+    uint8_t   evaluated[X264CU_BFRAME_MAX+2][X264CU_BFRAME_MAX+2];
+    bool      uploaded;
+};
+
+struct x264cu_ctx
+{
+    int device;
+    x264cu_cfg cfg;
+    LaParams P;
+    int sm_count;
+    cudaStream_t st;
+    uint16_t *d_cost_mv;
+    int stat_pitch;
+    size_t plane_alloc;      // bytes of the 4 planes + slack
+    // full-resolution luma staging on the device (double buffered)
+    uint8_t *d_luma[2]; int luma_pitch; int luma_sel;
+    cudaEvent_t luma_free[2];
+    // pinned staging (H2D inputs, D2H results) and the deferred copy list
+    uint8_t *pin; size_t pin_size, pin_used;
+    std::vector<PendingCopy> copies;
+    // job tables: pinned host ring mirrored to a device ring
+    uint8_t *h_jobs, *d_jobs; size_t jobs_size, jobs_used;
+    // device workspace arena for per-batch temporaries (MV ping-pong fields, weighted planes)
+    uint8_t *arena; size_t arena_size, arena_used;
+    int64_t launches;
+    // timing
+    bool profiling;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    float class_ms[K_NCLASS]; int class_n[K_NCLASS];
+    cudaEvent_t tm_a, tm_b;
+    std::vector<x264cu_frame *> frames;
+};
+
+extern "C" const char *x264cu_last_error( void ) { return g_err; }
+
+extern "C" int x264cu_device_count( void )
+{
+    int n = 0;
+    if( cudaGetDeviceCount( &n ) != cudaSuccess ) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int ctx_sync( x264cu_ctx *c );
+
+static inline size_t align_up( size_t v, size_t a ) { return ( v + a - 1 ) / a * a; }
+
+extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
+{
+    if( !cfg || cfg->width < 16 || cfg->height < 16 || cfg->bframes < 0 || cfg->bframes > X264CU_BFRAME_MAX || cfg->mv_range < 32 )
+    { snprintf( g_err, sizeof(g_err), "x264cu_open: bad configuration" ); return NULL; }
+    int ndev = x264cu_device_count();
+    if( ndev <= 0 ) { snprintf( g_err, sizeof(g_err), "x264cu_open: no CUDA device (there is no CPU fallback)" ); return NULL; }
+    if( device < 0 || device >= ndev ) { snprintf( g_err, sizeof(g_err), "x264cu_open: device %d of %d", device, ndev ); return NULL; }
+    CUP( cudaSetDevice( device ) );
+    x264cu_ctx *c = new x264cu_ctx();
+    c->device = device;
+    c->cfg = *cfg;
+    if( c->cfg.search_passes < 1 ) c->cfg.search_passes = 2;
+    if( c->cfg.me_range < 4 ) c->cfg.me_range = 16;
+    if( c->cfg.max_frames < 4 ) c->cfg.max_frames = 64;
+    cudaDeviceProp prop;
+    CUP( cudaGetDeviceProperties( &prop, device ) );
+    c->sm_count = prop.multiProcessorCount;
+    LaParams &P = c->P;
+    P.mbw = ( cfg->width + 15 ) / 16; P.mbh = ( cfg->height + 15 ) / 16; P.nmb = P.mbw * P.mbh;
+    P.lw = P.mbw * 8; P.lh = P.mbh * 8;
+    P.stride = (int)align_up( P.lw + 2*X264CU_PAD, 128 );
+    P.plane_size = (int64_t)P.stride * ( P.lh + 2*X264CU_PAD );
+    P.mv_range2 = 2 * cfg->mv_range;
+    P.me_range = c->cfg.me_range;
+    P.b_satd = cfg->subme > 1;
+    P.me_method = P.b_satd ? ( cfg->me_method >= 1 ? 1 : 0 ) : 0;      // slicetype.c:50-59
+    P.do_edges = cfg->do_edges != 0;
+    P.aq = cfg->aq != 0;
+    P.weighted_bipred = cfg->weighted_bipred != 0;
+    P.cost_mv_n = 8 * cfg->mv_range;
+    c->plane_alloc = 4 * (size_t)P.plane_size + 256;
+    c->stat_pitch = (int)align_up( P.mbh + 4, 4 );
+    CUP( cudaStreamCreateWithFlags( &c->st, cudaStreamNonBlocking ) );
+    // mv cost table: lambda * (log2(|d|+1)*2 + 1.718) rounded, lambda = 1 at X264_LOOKAHEAD_QP (analyse.c:153-157,186-188)
+    {
+        std::vector<uint16_t> tab( P.cost_mv_n + 1 );
+        for( int i = 0; i <= P.cost_mv_n; i++ )
+        {
+            if( cfg->cost_mv ) tab[i] = cfg->cost_mv[i];
+            else
+            {
+                float l = i ? log2f( (float)( i+1 ) ) * 2.0f + 1.718f : 0.718f;
+                int v = (int)( 1 * l + .5f );
+                tab[i] = (uint16_t)( v < 65535 ? v : 65535 );
+            }
+        }
+        CUP( cudaMalloc( &c->d_cost_mv, tab.size() * sizeof(uint16_t) ) );
+        CUP( cudaMemcpy( c->d_cost_mv, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice ) );
+        P.cost_mv = c->d_cost_mv;
+    }
+    c->luma_pitch = (int)align_up( cfg->width, 256 );
+    for( int i = 0; i < 2; i++ )
+    {
+        CUP( cudaMalloc( &c->d_luma[i], (size_t)c->luma_pitch * cfg->height + 256 ) );
+        CUP( cudaEventCreateWithFlags( &c->luma_free[i], cudaEventDisableTiming ) );
+    }
+    c->pin_size = (size_t)64 << 20;            // cf. PAGE_LOCKED_BUF_SIZE 32 MiB (opencl.h:715)
+    while( c->pin_size < 4 * (size_t)c->luma_pitch * cfg->height ) c->pin_size <<= 1;
+    CUP( cudaHostAlloc( &c->pin, c->pin_size, cudaHostAllocDefault ) );
+    c->jobs_size = (size_t)1 << 20;
+    CUP( cudaHostAlloc( &c->h_jobs, c->jobs_size, cudaHostAllocDefault ) );
+    CUP( cudaMalloc( &c->d_jobs, c->jobs_size ) );
+    c->arena_size = (size_t)P.nmb * 4 * 2 * 128 + 8 * (size_t)P.plane_size;
+    CUP( cudaMalloc( &c->arena, c->arena_size ) );
+    CUP( cudaEventCreate( &c->tm_a ) );
+    CUP( cudaEventCreate( &c->tm_b ) );
+    g_err[0] = 0;
+    return c;
+}
+
+extern "C" int x264cu_info( x264cu_ctx *c, int *out )
+{
+    if( !c ) FAIL( "null context" );
+    out[0] = c->P.mbw; out[1] = c->P.mbh; out[2] = c->P.lw; out[3] = c->P.lh; out[4] = c->P.stride; out[5] = c->sm_count;
+    return 0;
+}
+
+extern "C" void x264cu_frame_free( x264cu_ctx *c, x264cu_frame *f )
+{
+    if( !c || !f ) return;
+    cudaSetDevice( c->device );
+    ctx_sync( c );
+    cudaFree( f->planes ); cudaFree( f->inv_qscale ); cudaFree( f->costs );
+    cudaFree( f->mvs ); cudaFree( f->mvcosts ); cudaFree( f->stats );
+    for( size_t i = 0; i < c->frames.size(); i++ )
+        if( c->frames[i] == f ) { c->frames.erase( c->frames.begin() + i ); break; }
+    delete f;
+}
+
+extern "C" void x264cu_close( x264cu_ctx *c )
+{
+    if( !c ) return;
+    cudaSetDevice( c->device );
+    ctx_sync( c );
+    while( !c->frames.empty() ) x264cu_frame_free( c, c->frames.back() );
+    for( cudaEvent_t e : c->ev_pool ) cudaEventDestroy( e );
+    for( int i = 0; i < 2; i++ ) { cudaFree( c->d_luma[i] ); cudaEventDestroy( c->luma_free[i] ); }
+    cudaFree( c->d_cost_mv ); cudaFree( c->d_jobs ); cudaFree( c->arena );
+    cudaFreeHost( c->pin ); cudaFreeHost( c->h_jobs );
+    cudaEventDestroy( c->tm_a ); cudaEventDestroy( c->tm_b );
+    cudaStreamDestroy( c->st );
+    delete c;
+}
+
+extern "C" x264cu_frame *x264cu_frame_new( x264cu_ctx *c )
+{
+    if( !c ) { snprintf( g_err, sizeof(g_err), "null context" ); return NULL; }
+    CUP( cudaSetDevice( c->device ) );
+    const LaParams &P = c->P;
+    const int B = c->cfg.bframes;
+    x264cu_frame *f = new x264cu_frame();
+    memset( f, 0, sizeof(*f) );
+    size_t ntri = (size_t)( B+2 ) * ( B+2 ), nfield = 2 * (size_t)( B+1 );
+    if( cudaMalloc( &f->planes, c->plane_alloc ) != cudaSuccess ||
+        cudaMalloc( &f->inv_qscale, (size_t)P.nmb * 2 ) != cudaSuccess ||
+        cudaMalloc( &f->costs, ntri * P.nmb * 2 ) != cudaSuccess ||
+        cudaMalloc( &f->mvs, nfield * P.nmb * 4 ) != cudaSuccess ||
+        cudaMalloc( &f->mvcosts, nfield * P.nmb * 4 ) != cudaSuccess ||
+        cudaMalloc( &f->stats, ntri * c->stat_pitch * 4 ) != cudaSuccess )
+    {
+        snprintf( g_err, sizeof(g_err), "x264cu_frame_new: out of device memory" );
+        cudaGetLastError();
+        cudaFree( f->planes ); cudaFree( f->inv_qscale ); cudaFree( f->costs ); cudaFree( f->mvs ); cudaFree( f->mvcosts ); cudaFree( f->stats );
+        delete f;
+        return NULL;
+    }
+    c->frames.push_back( f );
+    return f;
+}
+
+// ---- timing spans ----
+static cudaEvent_t get_event( x264cu_ctx *c )
+{
+    if( !c->ev_pool.empty() ) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate( &e ); return e;
+}
+struct Span
+{
+    x264cu_ctx *c; TimedSpan s; bool on;
+    Span( x264cu_ctx *c_, int cls, int nlaunch ) : c( c_ ), on( c_->profiling )
+    {
+        c->launches += nlaunch; c->class_n[cls] += nlaunch;
+        if( on ) { s.cls = cls; s.a = get_event( c ); s.b = get_event( c ); cudaEventRecord( s.a, c->st ); }
+    }
+    ~Span() { if( on ) { cudaEventRecord( s.b, c->st ); c->spans.push_back( s ); } }
+};
+
+// i_cost_est semantics completed on the host when the deferred copies are drained (slicetype.c:946-989).
+// p: [0..2] raw sums of the evaluation, [4..5] intra sums of the frame, [6] kind (0 I, 1 P, 2 B), [7] bframe_bias
+static void finish_stats( int32_t *dst, const uint8_t *p )
+{
+    const int32_t *raw = (const int32_t *)p, *intra = (const int32_t *)( p + 16 ), *meta = (const int32_t *)( p + 24 );
+    if( meta[0] == 0 )
+    {   // I evaluation: the sums are the intra sums (slicetype.c:949-953,965-966)
+        dst[0] = intra[0]; dst[1] = intra[1]; dst[2] = raw[2]; dst[3] = intra[0];
+    }
+    else
+    {
+        dst[3] = raw[0];
+        dst[0] = meta[0] == 2 ? (int32_t)( (uint64_t)raw[0] * 100 / ( 120 + meta[1] ) ) : raw[0];     // :984-985
+        dst[1] = raw[1]; dst[2] = raw[2];
+    }
+}
+
+static int ctx_sync( x264cu_ctx *c )
+{
+    CU( cudaStreamSynchronize( c->st ) );
+    for( const PendingCopy &p : c->copies )
+    {
+        if( p.bytes ) memcpy( p.dst, p.src, p.bytes );
+        else finish_stats( (int32_t *)p.dst, (const uint8_t *)p.src );
+    }
+    c->copies.clear();
+    c->pin_used = 0; c->jobs_used = 0; c->arena_used = 0;
+    for( TimedSpan &s : c->spans )
+    {
+        float ms = 0;
+        cudaEventElapsedTime( &ms, s.a, s.b );
+        c->class_ms[s.cls] += ms;
+        c->ev_pool.push_back( s.a ); c->ev_pool.push_back( s.b );
+    }
+    c->spans.clear();
+    return 0;
+}
+
+extern "C" int x264cu_flush( x264cu_ctx *c )
+{
+    if( !c ) FAIL( "null context" );
+    CU( cudaSetDevice( c->device ) );
+    if( ctx_sync( c ) ) return -1;
+    CU( cudaGetLastError() );
+    return 0;
+}
+
+extern "C" int64_t x264cu_launch_count( x264cu_ctx *c ) { return c ? c->launches : 0; }
+
+extern "C" int x264cu_kernel_times( x264cu_ctx *c, float *ms4, int *n4 )
+{
+    if( !c ) FAIL( "null context" );
+    for( int i = 0; i < K_NCLASS; i++ )
+    {
+        if( ms4 ) ms4[i] = c->class_ms[i];
+        if( n4 ) n4[i] = c->class_n[i];
+        c->class_ms[i] = 0; c->class_n[i] = 0;
+    }
+    return 0;
+}
+
+extern "C" int x264cu_set_profiling( x264cu_ctx *c, int on )
+{
+    if( !c ) FAIL( "null context" );
+    c->profiling = on != 0;
+    return 0;
+}
+
+// pinned staging: returns NULL when full (caller syncs and retries)
+static uint8_t *pin_alloc( x264cu_ctx *c, size_t bytes )
+{
+    size_t a = align_up( c->pin_used, 256 );
+    if( a + bytes > c->pin_size ) return NULL;
+    c->pin_used = a + bytes;
+    return c->pin + a;
+}
+static uint8_t *pin_alloc_sync( x264cu_ctx *c, size_t bytes )
+{
+    uint8_t *p = pin_alloc( c, bytes );
+    if( !p ) { if( ctx_sync( c ) ) return NULL; p = pin_alloc( c, bytes ); }
+    if( !p ) snprintf( g_err, sizeof(g_err), "staging buffer too small for %zu bytes", bytes );
+    return p;
+}
+static bool is_pinned( const void *p )
+{
+    cudaPointerAttributes at;
+    if( cudaPointerGetAttributes( &at, p ) != cudaSuccess ) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// queue a device->host result copy: straight into pinned user memory, else via staging + deferred memcpy
+static int queue_d2h( x264cu_ctx *c, void *dst, const void *dsrc, size_t bytes )
+{
+    if( !dst ) return 0;
+    if( is_pinned( dst ) ) { CU( cudaMemcpyAsync( dst, dsrc, bytes, cudaMemcpyDeviceToHost, c->st ) ); return 0; }
+    uint8_t *p = pin_alloc_sync( c, bytes );
+    if( !p ) return -1;
+    CU( cudaMemcpyAsync( p, dsrc, bytes, cudaMemcpyDeviceToHost, c->st ) );
+    c->copies.push_back( { dst, p, bytes } );
+    return 0;
+}
+
+static void reset_caches( x264cu_frame *f )
+{   // mc.c:473-481: i_cost_est = -1, MV sentinels = 0x7FFF
+    memset( f->searched, 0, sizeof(f->searched) );
+    memset( f->evaluated, 0, sizeof(f->evaluated) );
+}
+
+static int upload_common( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int pitch )
+{
+    const LaParams &P = c->P;
+    const int B = c->cfg.bframes;
+    reset_caches( f );
+    size_t ntri = (size_t)( B+2 ) * ( B+2 );
+    CU( cudaMemsetAsync( f->stats, 0, ntri * c->stat_pitch * 4, c->st ) );
+    {
+        Span s( c, K_LOWRES, 1 );
+        launch_lowres( d_luma, pitch, c->cfg.width, c->cfg.height, f->planes, P, c->st );
+    }
+    {
+        Span s( c, K_INTRA, 1 );
+        const uint8_t *F = f->planes + (size_t)X264CU_PAD * P.stride + X264CU_PAD;
+        launch_intra( F, f->inv_qscale, f->costs, f->stats, f->stats + P.mbh, P, c->st );
+    }
+    CU( cudaGetLastError() );
+    f->uploaded = true;
+    return 0;
+}
+
+extern "C" int x264cu_frame_upload( x264cu_ctx *c, x264cu_frame *f, const uint8_t *luma, int stride, const uint16_t *inv_qscale )
+{
+    if( !c || !f || !luma ) FAIL( "x264cu_frame_upload: null argument" );
+    CU( cudaSetDevice( c->device ) );
+    const LaParams &P = c->P;
+    const int W = c->cfg.width, H = c->cfg.height;
+    int sel = c->luma_sel; c->luma_sel ^= 1;
+    const uint8_t *src = luma; int spitch = stride;
+    if( !is_pinned( luma ) )
+    {   // pageable caller memory: stage through the page-locked buffer (slicetype-cl.c:166-168)
+        uint8_t *p = pin_alloc_sync( c, (size_t)W * H );
+        if( !p ) return -1;
+        for( int y = 0; y < H; y++ ) memcpy( p + (size_t)y*W, luma + (size_t)y*stride, W );
+        src = p; spitch = W;
+    }
+    CU( cudaStreamWaitEvent( c->st, c->luma_free[sel], 0 ) );
+    CU( cudaMemcpy2DAsync( c->d_luma[sel], c->luma_pitch, src, spitch, W, H, cudaMemcpyHostToDevice, c->st ) );
+    if( inv_qscale )
+    {
+        const uint16_t *q = inv_qscale;
+        if( !is_pinned( q ) )
+        {
+            uint8_t *p = pin_alloc_sync( c, (size_t)P.nmb * 2 );
+            if( !p ) return -1;
+            memcpy( p, inv_qscale, (size_t)P.nmb * 2 );
+            q = (const uint16_t *)p;
+        }
+        CU( cudaMemcpyAsync( f->inv_qscale, q, (size_t)P.nmb * 2, cudaMemcpyHostToDevice, c->st ) );
+    }
+    else
+        launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );         // memset_int16 (downscale.cl:132)
+    if( upload_common( c, f, c->d_luma[sel], c->luma_pitch ) ) return -1;
+    CU( cudaEventRecord( c->luma_free[sel], c->st ) );
+    return 0;
+}
+
+extern "C" int x264cu_frame_upload_device( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint16_t *d_inv_qscale )
+{
+    if( !c || !f || !d_luma ) FAIL( "x264cu_frame_upload_device: null argument" );
+    CU( cudaSetDevice( c->device ) );
+    if( d_inv_qscale )
+        CU( cudaMemcpyAsync( f->inv_qscale, d_inv_qscale, (size_t)c->P.nmb * 2, cudaMemcpyDeviceToDevice, c->st ) );
+    else
+        launch_fill_u16( f->inv_qscale, 256, c->P.nmb, c->st );
+    return upload_common( c, f, d_luma, stride );
+}
+
+extern "C" int x264cu_frame_get_lowres( x264cu_ctx *c, x264cu_frame *f, int plane, uint8_t *out )
+{
+    if( !c || !f || plane < 0 || plane > 3 ) FAIL( "x264cu_frame_get_lowres: bad argument" );
+    CU( cudaSetDevice( c->device ) );
+    const LaParams &P = c->P;
+    if( ctx_sync( c ) ) return -1;
+    CU( cudaMemcpy2D( out, P.lw + 2*X264CU_PAD, f->planes + plane*P.plane_size, P.stride, P.lw + 2*X264CU_PAD,
+                      P.lh + 2*X264CU_PAD, cudaMemcpyDeviceToHost ) );
+    return 0;
+}
+
+// ---- job tables and workspace ----
+template<typename T> static int push_jobs( x264cu_ctx *c, const std::vector<T> &v, const T **d_out )
+{
+    size_t bytes = v.size() * sizeof(T);
+    size_t a = align_up( c->jobs_used, 16 );
+    if( a + bytes > c->jobs_size )
+    {
+        if( bytes > c->jobs_size ) FAIL( "job table too large" );
+        if( ctx_sync( c ) ) return -1;
+        a = 0;
+    }
+    memcpy( c->h_jobs + a, v.data(), bytes );
+    CU( cudaMemcpyAsync( c->d_jobs + a, c->h_jobs + a, bytes, cudaMemcpyHostToDevice, c->st ) );
+    c->jobs_used = a + bytes;
+    *d_out = (const T *)( c->d_jobs + a );
+    return 0;
+}
+
+static uint8_t *arena_alloc( x264cu_ctx *c, size_t bytes )
+{
+    size_t a = align_up( c->arena_used, 256 );
+    if( a + bytes > c->arena_size ) return NULL;
+    c->arena_used = a + bytes;
+    return c->arena + a;
+}
+
+struct SearchTask { x264cu_frame *fenc, *fref; int list, dist; x264cu_weight w; };
+
+static inline uint8_t *planeF( x264cu_ctx *c, x264cu_frame *f ) { return f->planes + (size_t)X264CU_PAD * c->P.stride + X264CU_PAD; }
+static inline int tri_index( x264cu_ctx *c, int d0, int d1 ) { return d0 * ( c->cfg.bframes + 2 ) + d1; }
+static inline int field_index( x264cu_ctx *c, int list, int dist ) { return list * ( c->cfg.bframes + 1 ) + dist - 1; }
+
+static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
+{
+    const LaParams &P = c->P;
+    const int B = c->cfg.bframes, K = c->cfg.search_passes;
+    std::vector<SearchTask> tasks;
+    std::vector<FinalJob> finals;
+    // pass 1 over the jobs in semantic order: cache bookkeeping exactly as slicetype_frame_cost does it
+    for( int i = 0; i < n; i++ )
+    {
+        const x264cu_job &j = jobs[i];
+        if( !j.fenc || !j.fref0 || !j.fref1 || j.d0 < 0 || j.d1 < 0 || j.d0 + j.d1 > B + 1 )
+            FAIL( "x264cu_frame_cost: bad job %d (d0=%d d1=%d bframes=%d)", i, j.d0, j.d1, B );
+        if( !j.fenc->uploaded || !j.fref0->uploaded || !j.fref1->uploaded ) FAIL( "x264cu_frame_cost: frame not uploaded" );
+        if( j.fenc->evaluated[j.d0][j.d1] ) continue;                  // i_cost_est >= 0 (slicetype.c:848)
+        j.fenc->evaluated[j.d0][j.d1] = 1;
+        FinalJob F;
+        memset( &F, 0, sizeof(F) );
+        F.fenc = planeF( c, j.fenc ); F.ref0 = planeF( c, j.fref0 ); F.ref1 = planeF( c, j.fref1 );
+        F.b_bidir = j.d1 > 0; F.b_intra_only = j.d0 == 0 && j.d1 == 0;
+        for( int l = 0; l < 2; l++ )
+        {
+            int dist = l ? j.d1 : j.d0;
+            if( dist == 0 ) continue;
+            int fi = field_index( c, l, dist );
+            if( !j.fenc->searched[l][dist-1] )
+            {   // do_search[l] (slicetype.c:855-867)
+                j.fenc->searched[l][dist-1] = 1;
+                SearchTask t = { j.fenc, l ? j.fref1 : j.fref0, l, dist, { 0, 0, 0, 0 } };
+                if( l == 0 && j.d1 == 0 && j.weight.enabled ) t.w = j.weight;      // w only when b == p1 (:859-864)
+                tasks.push_back( t );
+            }
+            F.mv[l] = j.fenc->mvs + (size_t)fi * P.nmb * 2;
+            F.mvcost[l] = j.fenc->mvcosts + (size_t)fi * P.nmb;
+        }
+        if( F.b_bidir && j.fref1->searched[0][j.d0 + j.d1 - 1] )      // slicetype.c:629
+            F.dmv_src = j.fref1->mvs + (size_t)field_index( c, 0, j.d0 + j.d1 ) * P.nmb * 2;
+        F.intra = j.fenc->costs;
+        F.inv_qscale = j.fenc->inv_qscale;
+        int ti = tri_index( c, j.d0, j.d1 );
+        F.lowres_costs = j.fenc->costs + (size_t)ti * P.nmb;
+        F.row_satds = j.fenc->stats + (size_t)ti * c->stat_pitch;
+        F.stats = F.row_satds + P.mbh;
+        if( F.b_intra_only ) { F.row_satds = NULL; }                   // intra sums were produced at upload
+        F.dist_scale_factor = ( j.d0 + j.d1 ) ? ( ( j.d0 << 8 ) + ( ( j.d0 + j.d1 ) >> 1 ) ) / ( j.d0 + j.d1 ) : 128;   // :869-870
+        F.bipred_weight = P.weighted_bipred ? 64 - ( F.dist_scale_factor >> 2 ) : 32;                                    // :529
+        finals.push_back( F );
+    }
+    // searches: K passes, each one launch over all fields
+    if( !tasks.empty() )
+    {
+        size_t field_bytes = (size_t)P.nmb * 4;
+        size_t need = tasks.size() * 2 * align_up( field_bytes, 256 );
+        for( const SearchTask &t : tasks ) if( t.w.enabled ) need += align_up( (size_t)P.plane_size, 256 );
+        if( c->arena_used + need + 4096 > c->arena_size )
+        {
+            if( ctx_sync( c ) ) return -1;
+            if( need + 4096 > c->arena_size )
+            {
+                cudaFree( c->arena );
+                c->arena_size = need * 2;
+                CU( cudaMalloc( &c->arena, c->arena_size ) );
+            }
+        }
+        std::vector<uint8_t *> tmp0( tasks.size() ), tmp1( tasks.size() ), wpl( tasks.size(), NULL );
+        for( size_t t = 0; t < tasks.size(); t++ )
+        {
+            tmp0[t] = arena_alloc( c, field_bytes ); tmp1[t] = arena_alloc( c, field_bytes );
+            if( tasks[t].w.enabled )
+            {
+                wpl[t] = arena_alloc( c, (size_t)P.plane_size );
+                c->launches++;
+                launch_weight_plane( tasks[t].fref->planes, wpl[t], P.plane_size, tasks[t].w.scale, tasks[t].w.denom, tasks[t].w.offset, c->st );
+            }
+        }
+        for( int pass = 0; pass < K; pass++ )
+        {
+            std::vector<SearchJob> sj( tasks.size() );
+            for( size_t t = 0; t < tasks.size(); t++ )
+            {
+                const SearchTask &T = tasks[t];
+                int fi = field_index( c, T.list, T.dist );
+                SearchJob &S = sj[t];
+                S.fenc = planeF( c, T.fenc ); S.ref = planeF( c, T.fref );
+                S.ref_w = wpl[t] ? wpl[t] + (size_t)X264CU_PAD * P.stride + X264CU_PAD : S.ref;
+                S.mv_in = pass == 0 ? NULL : (const int16_t *)( ( pass & 1 ) ? tmp0[t] : tmp1[t] );
+                S.mv_out = pass == K-1 ? T.fenc->mvs + (size_t)fi * P.nmb * 2 : (int16_t *)( ( pass & 1 ) ? tmp1[t] : tmp0[t] );
+                S.cost_out = T.fenc->mvcosts + (size_t)fi * P.nmb;
+                S.wscale = T.w.scale; S.wdenom = T.w.enabled ? T.w.denom : -1; S.woffset = T.w.offset;
+            }
+            const SearchJob *d;
+            if( push_jobs( c, sj, &d ) ) return -1;
+            Span s( c, K_SEARCH, 1 );
+            launch_search( d, (int)sj.size(), P, c->st );
+        }
+    }
+    if( !finals.empty() )
+    {
+        const FinalJob *d;
+        if( push_jobs( c, finals, &d ) ) return -1;
+        Span s( c, K_FINAL, 1 );
+        launch_final( d, (int)finals.size(), P, c->st );
+    }
+    CU( cudaGetLastError() );
+    // result copies (slicetype-cl.c:254-280,513-535,613-649)
+    for( int i = 0; i < n; i++ )
+    {
+        const x264cu_job &j = jobs[i];
+        const x264cu_out &o = j.out;
+        int ti = tri_index( c, j.d0, j.d1 );
+        const int32_t *st = j.fenc->stats + (size_t)ti * c->stat_pitch;
+        if( queue_d2h( c, o.lowres_costs, j.fenc->costs + (size_t)ti * P.nmb, (size_t)P.nmb * 2 ) ) return -1;
+        for( int l = 0; l < 2; l++ )
+        {
+            int dist = l ? j.d1 : j.d0;
+            if( dist == 0 ) continue;
+            int fi = field_index( c, l, dist );
+            if( queue_d2h( c, o.mvs[l], j.fenc->mvs + (size_t)fi * P.nmb * 2, (size_t)P.nmb * 4 ) ) return -1;
+            if( queue_d2h( c, o.mv_costs[l], j.fenc->mvcosts + (size_t)fi * P.nmb, (size_t)P.nmb * 4 ) ) return -1;
+        }
+        if( queue_d2h( c, o.row_satds, j.d0 + j.d1 ? st : j.fenc->stats, (size_t)P.mbh * 4 ) ) return -1;
+        if( queue_d2h( c, o.intra_costs, j.fenc->costs, (size_t)P.nmb * 2 ) ) return -1;
+        if( queue_d2h( c, o.intra_row_satds, j.fenc->stats, (size_t)P.mbh * 4 ) ) return -1;
+        if( queue_d2h( c, o.intra_stats, j.fenc->stats + P.mbh, 8 ) ) return -1;
+        if( o.stats )
+        {   // raw device sums -> i_cost_est semantics are completed on the host at flush (slicetype.c:983-989)
+            uint8_t *p = pin_alloc_sync( c, 32 );
+            if( !p ) return -1;
+            CU( cudaMemcpyAsync( p, st + P.mbh, 12, cudaMemcpyDeviceToHost, c->st ) );
+            CU( cudaMemcpyAsync( p + 16, j.fenc->stats + P.mbh, 8, cudaMemcpyDeviceToHost, c->st ) );
+            c->copies.push_back( { o.stats, p, 0 } );     // bytes == 0: marks a stats fix-up, see below
+            // encode what the fix-up needs right behind the raw data
+            int32_t *meta = (int32_t *)( p + 24 );
+            meta[0] = ( j.d0 + j.d1 == 0 ) ? 0 : ( j.d1 > 0 ? 2 : 1 );
+            meta[1] = c->cfg.bframe_bias;
+        }
+    }
+    return 0;
+}
+
+extern "C" int x264cu_frame_cost_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
+{
+    if( !c || ( !jobs && n ) ) FAIL( "x264cu_frame_cost_batch: null argument" );
+    CU( cudaSetDevice( c->device ) );
+    return run_batch( c, jobs, n );
+}
+
+extern "C" int x264cu_frame_cost( x264cu_ctx *c, const x264cu_job *job ) { return x264cu_frame_cost_batch( c, job, 1 ); }
+
+// ---- small helpers exported for callers that keep data resident ----
+extern "C" void *x264cu_malloc( x264cu_ctx *c, size_t bytes )
+{
+    if( !c ) return NULL;
+    void *p = NULL;
+    cudaSetDevice( c->device );
+    if( cudaMalloc( &p, bytes ) != cudaSuccess ) { snprintf( g_err, sizeof(g_err), "x264cu_malloc(%zu) failed", bytes ); cudaGetLastError(); return NULL; }
+    return p;
+}
+extern "C" void x264cu_free( x264cu_ctx *c, void *p ) { if( c && p ) { cudaSetDevice( c->device ); ctx_sync( c ); cudaFree( p ); } }
+extern "C" void *x264cu_host_alloc( x264cu_ctx *c, size_t bytes )
+{
+    if( !c ) return NULL;
+    void *p = NULL;
+    cudaSetDevice( c->device );
+    if( cudaHostAlloc( &p, bytes, cudaHostAllocDefault ) != cudaSuccess ) { snprintf( g_err, sizeof(g_err), "x264cu_host_alloc(%zu) failed", bytes ); cudaGetLastError(); return NULL; }
+    return p;
+}
+extern "C" void x264cu_host_free( x264cu_ctx *c, void *p ) { if( c && p ) { cudaSetDevice( c->device ); cudaFreeHost( p ); } }
+extern "C" int x264cu_memcpy_h2d( x264cu_ctx *c, void *dst, const void *src, size_t bytes )
+{
+    if( !c ) FAIL( "null context" );
+    CU( cudaSetDevice( c->device ) );
+    CU( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyHostToDevice, c->st ) );
+    CU( cudaStreamSynchronize( c->st ) );
+    return 0;
+}
+extern "C" int x264cu_memcpy_d2h( x264cu_ctx *c, void *dst, const void *src, size_t bytes )
+{
+    if( !c ) FAIL( "null context" );
+    CU( cudaSetDevice( c->device ) );
+    CU( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyDeviceToHost, c->st ) );
+    CU( cudaStreamSynchronize( c->st ) );
+    return 0;
+}
+extern "C" int x264cu_timer_begin( x264cu_ctx *c )
+{
+    if( !c ) FAIL( "null context" );
+    CU( cudaSetDevice( c->device ) );
+    CU( cudaEventRecord( c->tm_a, c->st ) );
+    return 0;
+}
+extern "C" float x264cu_timer_end( x264cu_ctx *c )
+{
+    if( !c ) return -1.f;
+    cudaSetDevice( c->device );
+    float ms = -1.f;
+    if( cudaEventRecord( c->tm_b, c->st ) != cudaSuccess ) return -1.f;
+    if( cudaEventSynchronize( c->tm_b ) != cudaSuccess ) return -1.f;
+    cudaEventElapsedTime( &ms, c->tm_a, c->tm_b );
+    return ms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched primitives
+// ------------------------------------------------------------------------------------------------
+static const int g_bw[8] = { 16, 16, 8, 8, 8, 4, 4, 4 };
+static const int g_bh[8] = { 16, 8, 16, 8, 4, 8, 4, 16 };
+
+// RAII device temporaries for the host-pointer convenience path
+struct DevTmp
+{
+    x264cu_ctx *c; std::vector<void *> ptrs; bool ok;
+    DevTmp( x264cu_ctx *c_ ) : c( c_ ), ok( true ) {}
+    void *up( const void *host, size_t bytes, size_t slack = 64 )
+    {
+        void *d = NULL;
+        if( cudaMalloc( &d, bytes + slack ) != cudaSuccess ) { ok = false; return NULL; }
+        ptrs.push_back( d );
+        if( host && cudaMemcpyAsync( d, host, bytes, cudaMemcpyHostToDevice, c->st ) != cudaSuccess ) ok = false;
+        return d;
+    }
+    int down( void *host, const void *dev, size_t bytes )
+    {
+        if( cudaMemcpyAsync( host, dev, bytes, cudaMemcpyDeviceToHost, c->st ) != cudaSuccess ) return -1;
+        return cudaStreamSynchronize( c->st ) == cudaSuccess ? 0 : -1;
+    }
+    ~DevTmp() { cudaStreamSynchronize( c->st ); for( void *p : ptrs ) cudaFree( p ); }
+};
+#define PRIM_ENTER( c ) if( !(c) ) FAIL( "null context" ); CU( cudaSetDevice( (c)->device ) )
+#define PRIM_CHECK( r, name ) do { if( (r) == -2 ) FAIL( name ": misaligned pointer or stride" ); if( (r) ) FAIL( name ": unsupported metric/size" ); \
+                                   c->launches++; CU( cudaGetLastError() ); } while( 0 )
+
+extern "C" int x264cu_pixel_cmp( x264cu_ctx *c, int metric, int size, const uint8_t *pix1, int64_t len1, int stride1,
+                                 const uint8_t *pix2, int64_t len2, int stride2, int64_t n, const int64_t *off1,
+                                 const int64_t *off2, int32_t *out, int on_device )
+{
+    PRIM_ENTER( c );
+    if( on_device )
+    {
+        int r = launch_pixel_cmp( metric, size, pix1, stride1, pix2, stride2, n, off1, off2, out, c->st );
+        PRIM_CHECK( r, "x264cu_pixel_cmp" );
+        return 0;
+    }
+    DevTmp t( c );
+    uint8_t *d1 = (uint8_t *)t.up( pix1, len1 ), *d2 = (uint8_t *)t.up( pix2, len2 );
+    int64_t *o1 = (int64_t *)t.up( off1, n*8 ), *o2 = (int64_t *)t.up( off2, n*8 );
+    int32_t *dout = (int32_t *)t.up( NULL, n*4 );
+    if( !t.ok ) FAIL( "x264cu_pixel_cmp: device allocation/copy failed" );
+    int r = launch_pixel_cmp( metric, size, d1, stride1, d2, stride2, n, o1, o2, dout, c->st );
+    PRIM_CHECK( r, "x264cu_pixel_cmp" );
+    if( t.down( out, dout, n*4 ) ) FAIL( "x264cu_pixel_cmp: copy back failed: %s", cudaGetErrorString( cudaGetLastError() ) );
+    return 0;
+}
+
+extern "C" int x264cu_pixel_cmp_grid( x264cu_ctx *c, int metric, int size, const uint8_t *pix1, int stride1,
+                                      const uint8_t *pix2, int stride2, int width, int height, int dx, int dy,
+                                      int32_t *out, int on_device )
+{
+    PRIM_ENTER( c );
+    if( size < 0 || size > 7 || dx < 0 || dy < 0 ) FAIL( "x264cu_pixel_cmp_grid: bad argument" );
+    int64_t nout = (int64_t)( width / g_bw[size] ) * ( height / g_bh[size] );
+    if( on_device )
+    {
+        int r = launch_pixel_cmp_grid( metric, size, pix1, stride1, pix2 + (size_t)dy*stride2 + dx, stride2, width, height, out, c->st );
+        PRIM_CHECK( r, "x264cu_pixel_cmp_grid" );
+        return 0;
+    }
+    DevTmp t( c );
+    // host planes are re-pitched to 256-byte aligned device rows
+    int p1 = (int)align_up( width, 256 ), p2 = (int)align_up( width + dx, 256 );
+    uint8_t *d1 = (uint8_t *)t.up( NULL, (size_t)p1 * height ), *d2 = (uint8_t *)t.up( NULL, (size_t)p2 * ( height + dy ) );
+    int32_t *dout = (int32_t *)t.up( NULL, nout*4 );
+    if( !t.ok ) FAIL( "x264cu_pixel_cmp_grid: device allocation failed" );
+    CU( cudaMemcpy2DAsync( d1, p1, pix1, stride1, width, height, cudaMemcpyHostToDevice, c->st ) );
+    CU( cudaMemcpy2DAsync( d2, p2, pix2, stride2, width + dx, height + dy, cudaMemcpyHostToDevice, c->st ) );
+    int r = launch_pixel_cmp_grid( metric, size, d1, p1, d2 + (size_t)dy*p2 + dx, p2, width, height, dout, c->st );
+    PRIM_CHECK( r, "x264cu_pixel_cmp_grid" );
+    if( t.down( out, dout, nout*4 ) ) FAIL( "x264cu_pixel_cmp_grid: copy back failed" );
+    return 0;
+}
+
+extern "C" int x264cu_sad_x( x264cu_ctx *c, int size, int nref, const uint8_t *fenc, const uint8_t *refs, int64_t reflen,
+                             int stride, const int64_t *ref_off, int32_t *scores )
+{
+    PRIM_ENTER( c );
+    if( nref < 1 || nref > 4 || size < 0 || size > 6 ) FAIL( "x264cu_sad_x: bad argument" );
+    int64_t zero[4] = { 0, 0, 0, 0 };
+    // fenc has FENC_STRIDE 16 (pixel.c:441-456)
+    return x264cu_pixel_cmp( c, X264CU_SAD, size, fenc, 16*g_bh[size], 16, refs, reflen, stride, nref, zero, ref_off, scores, 0 );
+}
+
+extern "C" int x264cu_hadamard_ac( x264cu_ctx *c, int size, const uint8_t *pix, int64_t len, int stride, int64_t n,
+                                   const int64_t *off, uint64_t *out, int on_device )
+{
+    PRIM_ENTER( c );
+    if( on_device )
+    {
+        int r = launch_hadamard_ac( size, pix, stride, n, off, out, c->st );
+        PRIM_CHECK( r, "x264cu_hadamard_ac" );
+        return 0;
+    }
+    DevTmp t( c );
+    uint8_t *d = (uint8_t *)t.up( pix, len );
+    int64_t *o = (int64_t *)t.up( off, n*8 );
+    uint64_t *dout = (uint64_t *)t.up( NULL, n*8 );
+    if( !t.ok ) FAIL( "x264cu_hadamard_ac: device allocation/copy failed" );
+    int r = launch_hadamard_ac( size, d, stride, n, o, dout, c->st );
+    PRIM_CHECK( r, "x264cu_hadamard_ac" );
+    if( t.down( out, dout, n*8 ) ) FAIL( "x264cu_hadamard_ac: copy back failed" );
+    return 0;
+}
+
+extern "C" int x264cu_hadamard_ac_grid( x264cu_ctx *c, int size, const uint8_t *pix, int stride, int width, int height,
+                                        uint64_t *out, int on_device )
+{
+    PRIM_ENTER( c );
+    if( size < 0 || size > 3 ) FAIL( "x264cu_hadamard_ac_grid: bad size" );
+    int64_t nout = (int64_t)( width / g_bw[size] ) * ( height / g_bh[size] );
+    if( on_device )
+    {
+        int r = launch_hadamard_ac_grid( size, pix, stride, width, height, out, c->st );
+        PRIM_CHECK( r, "x264cu_hadamard_ac_grid" );
+        return 0;
+    }
+    DevTmp t( c );
+    int p = (int)align_up( width, 256 );
+    uint8_t *d = (uint8_t *)t.up( NULL, (size_t)p * height );
+    uint64_t *dout = (uint64_t *)t.up( NULL, nout*8 );
+    if( !t.ok ) FAIL( "x264cu_hadamard_ac_grid: device allocation failed" );
+    CU( cudaMemcpy2DAsync( d, p, pix, stride, width, height, cudaMemcpyHostToDevice, c->st ) );
+    int r = launch_hadamard_ac_grid( size, d, p, width, height, dout, c->st );
+    PRIM_CHECK( r, "x264cu_hadamard_ac_grid" );
+    if( t.down( out, dout, nout*8 ) ) FAIL( "x264cu_hadamard_ac_grid: copy back failed" );
+    return 0;
+}
+
+extern "C" int x264cu_sub_dct( x264cu_ctx *c, int bsize, const uint8_t *pix1, int64_t len1, int stride1,
+                               const uint8_t *pix2, int64_t len2, int stride2, int64_t n, const int64_t *off1,
+                               const int64_t *off2, int16_t *out, int on_device )
+{
+    PRIM_ENTER( c );
+    if( on_device )
+    {
+        int r = launch_sub_dct( bsize, pix1, stride1, pix2, stride2, n, off1, off2, out, c->st );
+        PRIM_CHECK( r, "x264cu_sub_dct" );
+        return 0;
+    }
+    DevTmp t( c );
+    uint8_t *d1 = (uint8_t *)t.up( pix1, len1 ), *d2 = (uint8_t *)t.up( pix2, len2 );
+    int64_t *o1 = (int64_t *)t.up( off1, n*8 ), *o2 = (int64_t *)t.up( off2, n*8 );
+    size_t ob = (size_t)n * bsize * bsize * 2;
+    int16_t *dout = (int16_t *)t.up( NULL, ob );
+    if( !t.ok ) FAIL( "x264cu_sub_dct: device allocation/copy failed" );
+    int r = launch_sub_dct( bsize, d1, stride1, d2, stride2, n, o1, o2, dout, c->st );
+    PRIM_CHECK( r, "x264cu_sub_dct" );
+    if( t.down( out, dout, ob ) ) FAIL( "x264cu_sub_dct: copy back failed" );
+    return 0;
+}
+
+extern "C" int x264cu_sub_dct_grid( x264cu_ctx *c, int bsize, const uint8_t *pix1, int stride1, const uint8_t *pix2,
+                                    int stride2, int width, int height, int16_t *out, int on_device )
+{
+    PRIM_ENTER( c );
+    if( bsize != 4 && bsize != 8 && bsize != 16 ) FAIL( "x264cu_sub_dct_grid: bad block size" );
+    size_t ob = (size_t)( width / bsize ) * ( height / bsize ) * bsize * bsize * 2;
+    if( on_device )
+    {
+        int r = launch_sub_dct_grid( bsize, pix1, stride1, pix2, stride2, width, height, out, c->st );
+        PRIM_CHECK( r, "x264cu_sub_dct_grid" );
+        return 0;
+    }
+    DevTmp t( c );
+    int p = (int)align_up( width, 256 );
+    uint8_t *d1 = (uint8_t *)t.up( NULL, (size_t)p * height ), *d2 = (uint8_t *)t.up( NULL, (size_t)p * height );
+    int16_t *dout = (int16_t *)t.up( NULL, ob );
+    if( !t.ok ) FAIL( "x264cu_sub_dct_grid: device allocation failed" );
+    CU( cudaMemcpy2DAsync( d1, p, pix1, stride1, width, height, cudaMemcpyHostToDevice, c->st ) );
+    CU( cudaMemcpy2DAsync( d2, p, pix2, stride2, width, height, cudaMemcpyHostToDevice, c->st ) );
+    int r = launch_sub_dct_grid( bsize, d1, p, d2, p, width, height, dout, c->st );
+    PRIM_CHECK( r, "x264cu_sub_dct_grid" );
+    if( t.down( out, dout, ob ) ) FAIL( "x264cu_sub_dct_grid: copy back failed" );
+    return 0;
+}
+
+extern "C" int x264cu_quant( x264cu_ctx *c, int b8x8, int16_t *coefs, int64_t nblocks, const uint16_t *mf,
+                             const uint16_t *bias, int32_t *nz, int on_device )
+{
+    PRIM_ENTER( c );
+    int n = b8x8 ? 64 : 16;
+    if( on_device )
+    {
+        int r = launch_quant( b8x8, coefs, nblocks, mf, bias, nz, c->st );
+        PRIM_CHECK( r, "x264cu_quant" );
+        return 0;
+    }
+    DevTmp t( c );
+    int16_t *d = (int16_t *)t.up( coefs, (size_t)nblocks * n * 2 );
+    uint16_t *dm = (uint16_t *)t.up( mf, n*2 ), *db = (uint16_t *)t.up( bias, n*2 );
+    int32_t *dz = (int32_t *)t.up( NULL, nblocks*4 );
+    if( !t.ok ) FAIL( "x264cu_quant: device allocation/copy failed" );
+    int r = launch_quant( b8x8, d, nblocks, dm, db, dz, c->st );
+    PRIM_CHECK( r, "x264cu_quant" );
+    if( t.down( coefs, d, (size_t)nblocks * n * 2 ) || t.down( nz, dz, nblocks*4 ) ) FAIL( "x264cu_quant: copy back failed" );
+    return 0;
+}
+
+extern "C" int x264cu_lowres_core( x264cu_ctx *c, const uint8_t *src, int src_stride, uint8_t *dst0, uint8_t *dsth,
+                                   uint8_t *dstv, uint8_t *dstc, int dst_stride, int width, int height, int on_device )
+{
+    PRIM_ENTER( c );
+    if( on_device )
+    {
+        int r = launch_lowres_core( src, src_stride, dst0, dsth, dstv, dstc, dst_stride, width, height, c->st );
+        PRIM_CHECK( r, "x264cu_lowres_core" );
+        return 0;
+    }
+    DevTmp t( c );
+    size_t sb = (size_t)src_stride * ( 2*height + 1 ), db = (size_t)dst_stride * height;
+    uint8_t *ds = (uint8_t *)t.up( src, sb );
+    uint8_t *d[4]; for( int i = 0; i < 4; i++ ) d[i] = (uint8_t *)t.up( NULL, db );
+    if( !t.ok ) FAIL( "x264cu_lowres_core: device allocation/copy failed" );
+    for( int i = 0; i < 4; i++ ) CU( cudaMemsetAsync( d[i], 0, db, c->st ) );
+    int r = launch_lowres_core( ds, src_stride, d[0], d[1], d[2], d[3], dst_stride, width, height, c->st );
+    PRIM_CHECK( r, "x264cu_lowres_core" );
+    uint8_t *h[4] = { dst0, dsth, dstv, dstc };
+    for( int i = 0; i < 4; i++ ) if( t.down( h[i], d[i], db ) ) FAIL( "x264cu_lowres_core: copy back failed" );
+    return 0;
+}

@@ -1,0 +1,729 @@
+// lookahead.cu -- sm_100a kernels of the lowres lookahead cost engine.
+//
+//   lowres_kernel     frame_init_lowres_core + border (mc.c:458-507, frame.c:535-555,627-631)
+//   weight_kernel     x264_weight_scale_plane of the reference F plane (frame.c:825-840, mc.c:117-137)
+//   intra_kernel      intra section of slicetype_mb_cost (slicetype.c:714-757)
+//   search_kernel     x264_me_search_ref for PIXEL_8x8 (me.c:182-420,774-797,865-992) under the
+//                     MV-predictor rule of slicetype.c:658-697, one pass of the dependency-free schedule
+//   final_kernel      bidir candidates, intra/inter decision, AQ, packing, sums (slicetype.c:616-652,
+//                     703-712,758-790,946-989)
+//
+// Thread mapping of the three block kernels: one 8-lane group per 8x8 block, lane r owning pixel
+// row r (two 32-bit words).  SAD = VABSDIFF4.U8.ACC on the words, reduced with 3 xor-shuffles
+// (two candidates per shuffle, packed 16:16); SATD = packed-lane Hadamard, horizontal stage in
+// registers, vertical stage as a warp-shuffle butterfly over the rows of each 8x4 half.
+// A CTA of 256 threads covers 32 consecutive blocks in raster order, so the 4 blocks of a warp are
+// horizontal neighbours and their row loads fall in the same 128-byte lines.
+#include "lookahead.cuh"
+
+#define GROUPS_PER_CTA 32
+#define CTA_THREADS (GROUPS_PER_CTA*8)
+
+__constant__ uint8_t c_hpel_ref0[16] = {0,1,1,1,0,1,1,1,2,3,3,3,0,1,1,1};   // tables.c:183
+__constant__ uint8_t c_hpel_ref1[16] = {0,0,1,0,2,2,3,2,2,2,3,2,2,2,3,2};   // tables.c:184
+
+// ------------------------------------------------------------------------------------------------
+// lowres
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lum( const uint8_t *luma, int ls, int W, int H, int x, int y )
+{   // mod-16 padding (frame.c:640-668) and the +1 row/column dup (mc.c:465-468) are pure replication
+    return luma[(size_t)min( y, H-1 ) * ls + min( x, W-1 )];
+}
+#define FILT(a,b,c,d) ((((((a)+(b)+1)>>1)+(((c)+(d)+1)>>1)+1)>>1))
+
+__global__ void __launch_bounds__(128) lowres_kernel( const uint8_t *__restrict__ luma, int ls, int W, int H,
+                                                      uint8_t *__restrict__ planes, LaParams P )
+{
+    const int pw4 = ( P.lw + 2*X264CU_PAD ) >> 2;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = blockIdx.y;
+    if( g >= pw4 ) return;
+    const int y = min( max( py - X264CU_PAD, 0 ), P.lh - 1 );
+    const int x0 = g*4 - X264CU_PAD;
+    u32 o[4];
+    const uint8_t *r0 = luma + (size_t)min( 2*y,   H-1 ) * ls;
+    const uint8_t *r1 = luma + (size_t)min( 2*y+1, H-1 ) * ls;
+    const uint8_t *r2 = luma + (size_t)min( 2*y+2, H-1 ) * ls;
+    const bool fast = x0 >= 0 && x0 + 4 <= P.lw && 2*x0 + 8 <= W-1 && ( ( (uintptr_t)luma | (uintptr_t)ls ) & 7 ) == 0;
+    if( fast )
+    {   // 9 input pixels per row: two aligned words + one byte
+        const int c = 2*x0;
+        uint2 a = *(const uint2 *)( r0 + c ), b = *(const uint2 *)( r1 + c ), d = *(const uint2 *)( r2 + c );
+        u32 a8 = r0[c+8], b8 = r1[c+8], d8 = r2[c+8];
+        u32 v0 = avg4( a.x, b.x ), v1 = avg4( a.y, b.y ), v8 = ( a8 + b8 + 1 ) >> 1;   // rows 2y,2y+1
+        u32 w0 = avg4( b.x, d.x ), w1 = avg4( b.y, d.y ), w8 = ( b8 + d8 + 1 ) >> 1;   // rows 2y+1,2y+2
+        u32 ve = __byte_perm( v0, v1, 0x6420 ), vo = __byte_perm( v0, v1, 0x7531 ), ve2 = ( ve >> 8 ) | ( v8 << 24 );
+        u32 we = __byte_perm( w0, w1, 0x6420 ), wo = __byte_perm( w0, w1, 0x7531 ), we2 = ( we >> 8 ) | ( w8 << 24 );
+        o[0] = avg4( ve, vo ); o[1] = avg4( vo, ve2 ); o[2] = avg4( we, wo ); o[3] = avg4( wo, we2 );
+    }
+    else
+    {
+        o[0] = o[1] = o[2] = o[3] = 0;
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            int x = min( max( x0 + k, 0 ), P.lw - 1 );
+            int p00 = lum( luma, ls, W, H, 2*x, 2*y ),   p10 = lum( luma, ls, W, H, 2*x+1, 2*y ),   p20 = lum( luma, ls, W, H, 2*x+2, 2*y );
+            int p01 = lum( luma, ls, W, H, 2*x, 2*y+1 ), p11 = lum( luma, ls, W, H, 2*x+1, 2*y+1 ), p21 = lum( luma, ls, W, H, 2*x+2, 2*y+1 );
+            int p02 = lum( luma, ls, W, H, 2*x, 2*y+2 ), p12 = lum( luma, ls, W, H, 2*x+1, 2*y+2 ), p22 = lum( luma, ls, W, H, 2*x+2, 2*y+2 );
+            o[0] |= (u32)FILT( p00, p01, p10, p11 ) << ( 8*k );
+            o[1] |= (u32)FILT( p10, p11, p20, p21 ) << ( 8*k );
+            o[2] |= (u32)FILT( p01, p02, p11, p12 ) << ( 8*k );
+            o[3] |= (u32)FILT( p11, p12, p21, p22 ) << ( 8*k );
+        }
+    }
+    size_t off = (size_t)py * P.stride + (size_t)g*4;      // planes[] points at the padded origin
+#pragma unroll
+    for( int k = 0; k < 4; k++ )
+        *(u32 *)( planes + k*P.plane_size + off ) = o[k];
+}
+
+void launch_lowres( const uint8_t *luma, int stride, int width, int height, uint8_t *planes, const LaParams &P, cudaStream_t st )
+{
+    int pw4 = ( P.lw + 2*X264CU_PAD ) >> 2;
+    dim3 grid( ( pw4 + 127 ) / 128, P.lh + 2*X264CU_PAD );
+    lowres_kernel<<<grid, 128, 0, st>>>( luma, stride, width, height, planes, P );
+}
+
+__device__ __forceinline__ int weight_px( int v, int scale, int denom, int offset )
+{   // mc.c:117-118
+    int r = denom >= 1 ? ( ( v*scale + ( 1 << ( denom-1 ) ) ) >> denom ) + offset : v*scale + offset;
+    return min( max( r, 0 ), 255 );
+}
+__device__ __forceinline__ u32 weight4( u32 w, int scale, int denom, int offset )
+{
+    return (u32)weight_px( w & 0xff, scale, denom, offset ) | ( (u32)weight_px( ( w >> 8 ) & 0xff, scale, denom, offset ) << 8 )
+         | ( (u32)weight_px( ( w >> 16 ) & 0xff, scale, denom, offset ) << 16 ) | ( (u32)weight_px( w >> 24, scale, denom, offset ) << 24 );
+}
+
+__global__ void weight_kernel( const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t nwords, int scale, int denom, int offset )
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < nwords ) dst[i] = weight4( src[i], scale, denom, offset );
+}
+
+void launch_weight_plane( const uint8_t *src, uint8_t *dst, int64_t bytes, int scale, int denom, int offset, cudaStream_t st )
+{
+    int64_t nwords = bytes >> 2;
+    weight_kernel<<<(unsigned)( ( nwords + 255 ) / 256 ), 256, 0, st>>>( (const u32 *)src, (u32 *)dst, nwords, scale, denom, offset );
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-lane metrics
+// ------------------------------------------------------------------------------------------------
+struct Grp
+{
+    unsigned mask;    // the 8 lanes of this block
+    int r;            // row owned by this lane
+};
+
+__device__ __forceinline__ int red8( int v, const Grp &g )
+{
+    v += __shfl_xor_sync( g.mask, v, 1 );
+    v += __shfl_xor_sync( g.mask, v, 2 );
+    v += __shfl_xor_sync( g.mask, v, 4 );
+    return v;
+}
+// two partial sums (each < 2^16 after reduction) per shuffle
+__device__ __forceinline__ void red8x2( int &a, int &b, const Grp &g )
+{
+    u32 v = (u32)a | ( (u32)b << 16 );
+    v += __shfl_xor_sync( g.mask, v, 1 );
+    v += __shfl_xor_sync( g.mask, v, 2 );
+    v += __shfl_xor_sync( g.mask, v, 4 );
+    a = v & 0xffff; b = v >> 16;
+}
+
+// x264_pixel_satd_8x8 = satd_8x4(top) + satd_8x4(bottom) (pixel.c:290-330), rows across lanes
+__device__ __forceinline__ int satd_rows( uint2 a, uint2 b, const Grp &g )
+{
+    u32 d[4], h0, h1, h2, h3;
+    diff_row8( a, b, d );
+    HADAMARD4( h0, h1, h2, h3, d[0], d[1], d[2], d[3] );
+#define VSTAGE( v, bit ) { u32 o_ = __shfl_xor_sync( g.mask, v, bit ); v = ( g.r & bit ) ? o_ - v : v + o_; }
+    VSTAGE( h0, 1 ) VSTAGE( h1, 1 ) VSTAGE( h2, 1 ) VSTAGE( h3, 1 )
+    VSTAGE( h0, 2 ) VSTAGE( h1, 2 ) VSTAGE( h2, 2 ) VSTAGE( h3, 2 )
+#undef VSTAGE
+    u32 s = abs2( h0 ) + abs2( h1 ) + abs2( h2 ) + abs2( h3 );
+    s += __shfl_xor_sync( g.mask, s, 1 );
+    s += __shfl_xor_sync( g.mask, s, 2 );
+    int v = (int)( ( ( s & 0xffff ) + ( s >> 16 ) ) >> 1 );
+    v += __shfl_xor_sync( g.mask, v, 4 );
+    return v;
+}
+
+__device__ __forceinline__ int cmp_rows( uint2 a, uint2 b, const Grp &g, int b_satd )
+{
+    return b_satd ? satd_rows( a, b, g ) : red8( (int)sad8( a, b ), g );
+}
+
+// get_ref (mc.c:221-249) for this lane's row: `ref` points at this lane's row of the F plane at mv 0
+__device__ __forceinline__ uint2 qpel_row( const uint8_t *ref, const LaParams &P, int mvx, int mvy, int wscale, int wdenom, int woffset )
+{
+    int qidx = ( ( mvy & 3 ) << 2 ) + ( mvx & 3 );
+    int64_t off = (int64_t)( mvy >> 2 ) * P.stride + ( mvx >> 2 );
+    const uint8_t *s1 = ref + c_hpel_ref0[qidx] * P.plane_size + off + ( ( mvy & 3 ) == 3 ? P.stride : 0 );
+    uint2 v = load8u( s1 );
+    if( qidx & 5 )
+    {
+        const uint8_t *s2 = ref + c_hpel_ref1[qidx] * P.plane_size + off + ( ( mvx & 3 ) == 3 );
+        uint2 w = load8u( s2 );
+        v.x = avg4( v.x, w.x ); v.y = avg4( v.y, w.y );
+    }
+    if( wdenom >= 0 )
+    {
+        v.x = weight4( v.x, wscale, wdenom, woffset );
+        v.y = weight4( v.y, wscale, wdenom, woffset );
+    }
+    return v;
+}
+
+// pixel_avg_8x8 with weight (mc.c:63-99)
+__device__ __forceinline__ u32 biavg4( u32 a, u32 b, int w )
+{
+    if( w == 32 ) return avg4( a, b );
+    u32 r = 0;
+#pragma unroll
+    for( int k = 0; k < 4; k++ )
+    {
+        int v = ( (int)byte_of( a, k ) * w + (int)byte_of( b, k ) * ( 64 - w ) + 32 ) >> 6;
+        r |= (u32)min( max( v, 0 ), 255 ) << ( 8*k );
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// intra
+// ------------------------------------------------------------------------------------------------
+#define F1(a,b)   (((a)+(b)+1)>>1)
+#define F2(a,b,c) (((a)+2*(b)+(c)+2)>>2)
+
+__global__ void __launch_bounds__(CTA_THREADS) intra_kernel( const uint8_t *__restrict__ planeF, const uint16_t *__restrict__ inv_qscale,
+                                                             uint16_t *__restrict__ intra, int32_t *row_satds, int32_t *stats, LaParams P )
+{
+    // per group: raw[0]=tl, raw[1..16]=t0..t15, raw[17..24]=l0..l7 ; v[0..7]=l7..l0 filtered, v[8]=lt, v[9..24]=t0..t15 filtered
+    __shared__ uint8_t s_raw[GROUPS_PER_CTA][28];
+    __shared__ uint8_t s_v[GROUPS_PER_CTA][28];
+    const int gi = threadIdx.x >> 3;
+    Grp g; g.r = threadIdx.x & 7; g.mask = 0xffu << ( threadIdx.x & 24 );
+    const int blk = blockIdx.x * GROUPS_PER_CTA + gi;
+    if( blk >= P.nmb ) return;
+    const int bx = blk % P.mbw, by = blk / P.mbw;
+    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
+    const bool tiny = P.mbw <= 2 || P.mbh <= 2;
+    if( border && !P.do_edges && !tiny )
+    {   // never evaluated by slicetype_slice_cost (slicetype.c:823-828): keeps frame_new's 0xFFFF
+        if( g.r == 0 ) intra[blk] = 0xFFFF;
+        return;
+    }
+    const uint8_t *src = planeF + (size_t)( by*8 ) * P.stride + bx*8;
+    uint8_t *raw = s_raw[gi], *v = s_v[gi];
+    const int r = g.r;
+    // neighbours (slicetype.c:724-727): 16 above (+ top-left), 8 to the left
+    raw[1+r] = src[r - P.stride];
+    raw[9+r] = src[r + 8 - P.stride];
+    raw[17+r] = src[-1 + r*P.stride];
+    if( r == 0 ) raw[0] = src[-1 - P.stride];
+    __syncwarp( g.mask );
+#define T(i) ((int)raw[1+(i)])
+#define L(i) ((int)raw[17+(i)])
+#define TL   ((int)raw[0])
+    // predict_8x8_filter_c with all neighbours (predict.c:632-676)
+    {
+        int fl = r == 0 ? ( TL + 2*L(0) + L(1) + 2 ) >> 2 : r == 7 ? ( L(6) + 3*L(7) + 2 ) >> 2 : F2( L(r-1), L(r), L(r+1) );
+        v[7-r] = fl;
+        int ft = r == 0 ? ( TL + 2*T(0) + T(1) + 2 ) >> 2 : F2( T(r-1), T(r), T(r+1) );
+        v[9+r] = ft;
+        int ft2 = r == 7 ? ( T(14) + 3*T(15) + 2 ) >> 2 : F2( T(r+7), T(r+8), T(r+9) );
+        v[17+r] = ft2;
+        if( r == 0 ) v[8] = ( T(0) + 2*TL + L(0) + 2 ) >> 2;
+    }
+    __syncwarp( g.mask );
+    uint2 fenc = *(const uint2 *)( src + (size_t)r * P.stride );
+    int best;
+    uint2 p;
+#define PACK8( expr ) { u32 lo_ = 0, hi_ = 0; _Pragma("unroll") for( int x = 0; x < 4; x++ ) { lo_ |= (u32)(expr) << (8*x); } \
+                        _Pragma("unroll") for( int x = 4; x < 8; x++ ) { hi_ |= (u32)(expr) << (8*(x-4)); } p = make_uint2( lo_, hi_ ); }
+#define TRY() { int c_ = cmp_rows( fenc, p, g, P.b_satd ); best = min( best, c_ ); }
+    {   // 8x8c DC (predict.c:221-257)
+        int s0 = T(0)+T(1)+T(2)+T(3), s1 = T(4)+T(5)+T(6)+T(7), s2 = L(0)+L(1)+L(2)+L(3), s3 = L(4)+L(5)+L(6)+L(7);
+        int dl = r < 4 ? ( s0 + s2 + 4 ) >> 3 : ( s3 + 2 ) >> 2;
+        int dr = r < 4 ? ( s1 + 2 ) >> 2 : ( s1 + s3 + 4 ) >> 3;
+        p = make_uint2( dl * 0x01010101u, dr * 0x01010101u );
+        best = cmp_rows( fenc, p, g, P.b_satd );
+    }
+    p = make_uint2( L(r) * 0x01010101u, L(r) * 0x01010101u ); TRY()                       // 8x8c H
+    PACK8( T(x) ) TRY()                                                                     // 8x8c V
+    if( P.b_satd )
+    {
+        {   // 8x8c plane (predict.c:282-304)
+            int H = 0, V = 0;
+#pragma unroll
+            for( int i = 0; i < 4; i++ )
+            {
+                H += ( i+1 ) * ( T(4+i) - ( i == 3 ? TL : T(2-i) ) );
+                V += ( i+1 ) * ( L(4+i) - ( i == 3 ? TL : L(2-i) ) );
+            }
+            int a = 16 * ( L(7) + T(7) ), b = ( 17*H + 16 ) >> 5, c = ( 17*V + 16 ) >> 5;
+            int i00 = a - 3*b - 3*c + 16 + r*c;
+            PACK8( min( max( ( i00 + x*b ) >> 5, 0 ), 255 ) ) TRY()
+        }
+#define V_(i) ((int)v[(i)])
+#define FT(i) ((int)v[9+(i)])
+#define FL(i) ((int)v[7-(i)])
+        const int y = r;
+        // DDL (predict.c:741-760)
+        PACK8( ( x+y < 14 ? F2( FT(x+y), FT(x+y+1), FT(x+y+2) ) : F2( FT(14), FT(15), FT(15) ) ) ) TRY()
+        // DDR (:761-781): centre tap v[8+x-y]
+        PACK8( F2( V_(7+x-y), V_(8+x-y), V_(9+x-y) ) ) TRY()
+        // VR (:783-811)
+        PACK8( ( 2*x-y >= 0 ? ( ( (2*x-y) & 1 ) ? F2( V_(7+x-(y>>1)), V_(8+x-(y>>1)), V_(9+x-(y>>1)) ) : F1( V_(8+x-(y>>1)), V_(9+x-(y>>1)) ) )
+                 : 2*x-y == -1 ? F2( V_(7), V_(8), V_(9) )
+                 : F2( V_(8-(y-2*x-1)-1), V_(8-(y-2*x-1)), V_(8-(y-2*x-1)+1) ) ) ) TRY()
+        // HD (:812-837)
+        PACK8( ( 2*y-x >= 0 ? ( ( (2*y-x) & 1 ) ? F2( V_(7-(y-(x>>1))), V_(8-(y-(x>>1))), V_(9-(y-(x>>1))) ) : F1( V_(7-(y-(x>>1))), V_(8-(y-(x>>1))) ) )
+                 : 2*y-x == -1 ? F2( V_(7), V_(8), V_(9) )
+                 : F2( V_(8+(x-2*y-1)-1), V_(8+(x-2*y-1)), V_(8+(x-2*y-1)+1) ) ) ) TRY()
+        // VL (:838-864)
+        PACK8( ( ( y & 1 ) ? F2( FT(x+(y>>1)), FT(x+(y>>1)+1), FT(x+(y>>1)+2) ) : F1( FT(x+(y>>1)), FT(x+(y>>1)+1) ) ) ) TRY()
+        // HU (:865-887)
+        PACK8( ( x+2*y > 13 ? FL(7) : x+2*y == 13 ? F2( FL(6), FL(7), FL(7) )
+                 : ( (x+2*y) & 1 ) ? F2( FL((x+2*y)>>1), FL(((x+2*y)>>1)+1), FL(((x+2*y)>>1)+2) ) : F1( FL((x+2*y)>>1), FL(((x+2*y)>>1)+1) ) ) ) TRY()
+    }
+    if( g.r == 0 )
+    {
+        int icost = best + 5 + 4;                 // + 5*lambda + lowres_penalty (slicetype.c:720,746)
+        intra[blk] = (uint16_t)icost;
+        int icost_aq = P.aq ? ( icost * inv_qscale[blk] + 128 ) >> 8 : icost;
+        atomicAdd( &row_satds[by], icost_aq );
+        if( !border || tiny )
+        {
+            atomicAdd( &stats[0], icost );
+            atomicAdd( &stats[1], icost_aq );
+        }
+    }
+}
+
+void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *intra, int32_t *row_satds, int32_t *stats,
+                   const LaParams &P, cudaStream_t st )
+{
+    intra_kernel<<<( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, CTA_THREADS, 0, st>>>( planeF, inv_qscale, intra, row_satds, stats, P );
+}
+
+// ------------------------------------------------------------------------------------------------
+// motion search
+// ------------------------------------------------------------------------------------------------
+struct Me
+{
+    uint2 fenc;
+    const uint8_t *ref;      // this lane's row of the reference F plane at mv 0
+    const uint8_t *ref_w;    // same in the fullpel (possibly weighted) plane
+    int wscale, wdenom, woffset;
+    int mvpx, mvpy;
+    int fminx, fminy, fmaxx, fmaxy;     // mv_limit_fpel
+    int sminx, sminy, smaxx, smaxy;     // mv_min_spel / mv_max_spel
+};
+
+__device__ __forceinline__ int mvcost( const uint16_t *tab, const Me &m, int mx, int my )
+{   // p_cost_mvx[mx] + p_cost_mvy[my] (me.c:211-212); the table is symmetric (analyse.c:153-157)
+    return tab[abs( mx - m.mvpx )] + tab[abs( my - m.mvpy )];
+}
+__device__ __forceinline__ int fpel_part( const Me &m, const LaParams &P, int mx, int my )
+{
+    return (int)sad8( m.fenc, load8u( m.ref_w + (int64_t)my * P.stride + mx ) );
+}
+__device__ __forceinline__ int qpel_sad_part( const Me &m, const LaParams &P, int mx, int my )
+{
+    return (int)sad8( m.fenc, qpel_row( m.ref, P, mx, my, m.wscale, m.wdenom, m.woffset ) );
+}
+__device__ __forceinline__ bool in_range( const Me &m, int mx, int my )
+{   // CHECK_MVRANGE (me.c:209)
+    return mx >= m.fminx && mx <= m.fmaxx && my >= m.fminy && my <= m.fmaxy;
+}
+
+__constant__ int8_t c_hex2[8][2] = {{-1,-2}, {-2,0}, {-1,2}, {1,2}, {2,0}, {1,-2}, {-1,-2}, {-2,0}};   // me.c:55
+__constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1}, {-1,1}, {1,-1}, {1,1}}; // me.c:56
+
+#define FPEL(v) (((v)+2)>>2)
+
+// refine_subpel (me.c:865-992), p_halfpel_thresh == NULL, b_refine_qpel == 0, no chroma
+__device__ __forceinline__ void refine_subpel( const Me &m, const LaParams &P, const uint16_t *tab, const Grp &g,
+                                               int &bmx, int &bmy, int &bcost, int hpel_iters, int qpel_iters )
+{
+    if( hpel_iters )
+    {
+        if( !P.b_satd )
+        {   // la subme 2 (< 3): try the subpel component of the predictor (me.c:889-895)
+            int mx = iclip3( m.mvpx, m.sminx + 2, m.smaxx - 2 );
+            int my = iclip3( m.mvpy, m.sminy + 2, m.smaxy - 2 );
+            if( ( mx - bmx ) | ( my - bmy ) )
+            {
+                int cost = red8( qpel_sad_part( m, P, mx, my ), g ) + mvcost( tab, m, mx, my );
+                if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
+            }
+        }
+        for( int i = hpel_iters; i > 0; i-- )
+        {   // me.c:898-921, tie order: up, down, left, right
+            int omx = bmx, omy = bmy;
+            int c0 = qpel_sad_part( m, P, omx, omy-2 ), c1 = qpel_sad_part( m, P, omx, omy+2 );
+            int c2 = qpel_sad_part( m, P, omx-2, omy ), c3 = qpel_sad_part( m, P, omx+2, omy );
+            red8x2( c0, c1, g ); red8x2( c2, c3, g );
+            c0 += mvcost( tab, m, omx, omy-2 ); c1 += mvcost( tab, m, omx, omy+2 );
+            c2 += mvcost( tab, m, omx-2, omy ); c3 += mvcost( tab, m, omx+2, omy );
+            int best = -1;
+            if( c0 < bcost ) { bcost = c0; best = 0; }
+            if( c1 < bcost ) { bcost = c1; best = 1; }
+            if( c2 < bcost ) { bcost = c2; best = 2; }
+            if( c3 < bcost ) { bcost = c3; best = 3; }
+            if( best < 0 ) break;
+            bmx = omx + ( best == 2 ? -2 : best == 3 ? 2 : 0 );
+            bmy = omy + ( best == 0 ? -2 : best == 1 ? 2 : 0 );
+        }
+    }
+    if( P.b_satd )   // mbcmp != fpelcmp: re-measure the winner with SATD (me.c:925-929)
+        bcost = satd_rows( m.fenc, qpel_row( m.ref, P, bmx, bmy, m.wscale, m.wdenom, m.woffset ), g ) + mvcost( tab, m, bmx, bmy );
+    int bdir = -1;
+    for( int i = qpel_iters; i > 0; i-- )
+    {   // me.c:947-963
+        if( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx ) break;
+        int odir = bdir, omx = bmx, omy = bmy;
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+            if( ( k ^ 1 ) != odir )
+            {
+                int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
+                int cost = satd_rows( m.fenc, qpel_row( m.ref, P, mx, my, m.wscale, m.wdenom, m.woffset ), g ) + mvcost( tab, m, mx, my );
+                if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; bdir = k; }
+            }
+        if( bmx == omx && bmy == omy ) break;
+    }
+}
+
+// x264_me_search_ref (me.c:182-420,774-797) for one block; result mv (qpel) and cost
+__device__ __forceinline__ void me_search( const Me &m, const LaParams &P, const uint16_t *tab, const Grp &g,
+                                           const int (*mvc)[2], int i_mvc, int &out_mx, int &out_my, int &out_cost )
+{
+    int bmx, bmy, bcost = X264CU_COST_MAX, bpred_cost = X264CU_COST_MAX, bpred_mx = 0, bpred_my = 0, pmvx, pmvy;
+#define COST_MV( mx_, my_ ) { int c_ = red8( fpel_part( m, P, mx_, my_ ), g ) + mvcost( tab, m, (mx_)*4, (my_)*4 ); \
+                              if( c_ < bcost ) { bcost = c_; bmx = mx_; bmy = my_; } }
+    if( P.b_satd )
+    {   // la subme 4 (>= 3): subpel predictors (me.c:216-275)
+        bpred_mx = iclip3( m.mvpx, 4*m.fminx, 4*m.fmaxx );
+        bpred_my = iclip3( m.mvpy, 4*m.fminy, 4*m.fmaxy );
+        pmvx = bpred_mx; pmvy = bpred_my;
+        bpred_cost = red8( qpel_sad_part( m, P, bpred_mx, bpred_my ), g ) + mvcost( tab, m, bpred_mx, bpred_my );
+        int pmv_cost = bpred_cost;
+        for( int i = 0; i < i_mvc; i++ )
+        {   // x264_predictor_clip (common.h:790-805): drop zero and == pmv, clip the rest
+            int mx = mvc[i][0], my = mvc[i][1];
+            if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
+            mx = iclip3( mx, 4*m.fminx, 4*m.fmaxx );
+            my = iclip3( my, 4*m.fminy, 4*m.fmaxy );
+            int cost = red8( qpel_sad_part( m, P, mx, my ), g ) + mvcost( tab, m, mx, my );
+            if( cost < bpred_cost ) { bpred_cost = cost; bpred_mx = mx; bpred_my = my; }
+        }
+        bmx = FPEL( bpred_mx ); bmy = FPEL( bpred_my );
+        if( ( bpred_mx & 3 ) | ( bpred_my & 3 ) ) COST_MV( bmx, bmy )
+        else bcost = bpred_cost;
+        if( pmvx | pmvy ) { if( bmx | bmy ) COST_MV( 0, 0 ) }
+        else if( pmv_cost < bcost ) { bcost = pmv_cost; bmx = 0; bmy = 0; }
+    }
+    else
+    {   // la subme 2: fullpel predictors (me.c:278-317)
+        bmx = iclip3( FPEL( m.mvpx ), m.fminx, m.fmaxx );
+        bmy = iclip3( FPEL( m.mvpy ), m.fminy, m.fmaxy );
+        pmvx = bmx; pmvy = bmy;
+        bcost = red8( fpel_part( m, P, bmx, bmy ), g );
+        int sx = bmx, sy = bmy;
+        for( int i = 0; i < i_mvc; i++ )
+        {   // x264_predictor_roundclip (common.h:774-788)
+            int mx = ( mvc[i][0] + 2 ) >> 2, my = ( mvc[i][1] + 2 ) >> 2;
+            if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
+            mx = iclip3( mx, m.fminx, m.fmaxx );
+            my = iclip3( my, m.fminy, m.fmaxy );
+            int cost = red8( fpel_part( m, P, mx, my ), g ) + mvcost( tab, m, mx*4, my*4 );
+            if( cost < bcost ) { bcost = cost; sx = mx; sy = my; }
+        }
+        bmx = sx; bmy = sy;
+        if( pmvx | pmvy ) COST_MV( 0, 0 )
+    }
+
+    if( P.me_method == 0 )
+    {   // DIA (me.c:322-342): tie order up, down, left, right
+        int i = P.me_range;
+        do
+        {
+            int ox = bmx, oy = bmy;
+            int c0 = fpel_part( m, P, ox, oy-1 ), c1 = fpel_part( m, P, ox, oy+1 );
+            int c2 = fpel_part( m, P, ox-1, oy ), c3 = fpel_part( m, P, ox+1, oy );
+            red8x2( c0, c1, g ); red8x2( c2, c3, g );
+            c0 += mvcost( tab, m, ox*4, (oy-1)*4 ); c1 += mvcost( tab, m, ox*4, (oy+1)*4 );
+            c2 += mvcost( tab, m, (ox-1)*4, oy*4 ); c3 += mvcost( tab, m, (ox+1)*4, oy*4 );
+            int best = -1;
+            if( c0 < bcost ) { bcost = c0; best = 0; }
+            if( c1 < bcost ) { bcost = c1; best = 1; }
+            if( c2 < bcost ) { bcost = c2; best = 2; }
+            if( c3 < bcost ) { bcost = c3; best = 3; }
+            if( best < 0 ) break;
+            bmx = ox + ( best == 2 ? -1 : best == 3 ? 1 : 0 );
+            bmy = oy + ( best == 0 ? -1 : best == 1 ? 1 : 0 );
+        } while( --i && in_range( m, bmx, bmy ) );
+    }
+    else
+    {   // HEX (me.c:344-420)
+        int c[6];
+#pragma unroll
+        for( int k = 0; k < 6; k++ ) c[k] = fpel_part( m, P, bmx + c_hex2[k+1][0], bmy + c_hex2[k+1][1] );
+        red8x2( c[0], c[1], g ); red8x2( c[2], c[3], g ); red8x2( c[4], c[5], g );
+        int best = -1;
+#pragma unroll
+        for( int k = 0; k < 6; k++ )
+        {
+            int cost = c[k] + mvcost( tab, m, ( bmx + c_hex2[k+1][0] )*4, ( bmy + c_hex2[k+1][1] )*4 );
+            if( cost < bcost ) { bcost = cost; best = k; }
+        }
+        if( best >= 0 )
+        {
+            int dir = best;
+            bmx += c_hex2[dir+1][0]; bmy += c_hex2[dir+1][1];
+            for( int i = ( P.me_range >> 1 ) - 1; i > 0 && in_range( m, bmx, bmy ); i-- )
+            {   // half hexagon not overlapping the previous one
+                int h0 = fpel_part( m, P, bmx + c_hex2[dir][0],   bmy + c_hex2[dir][1] );
+                int h1 = fpel_part( m, P, bmx + c_hex2[dir+1][0], bmy + c_hex2[dir+1][1] );
+                int h2 = fpel_part( m, P, bmx + c_hex2[dir+2][0], bmy + c_hex2[dir+2][1] );
+                red8x2( h0, h1, g ); h2 = red8( h2, g );
+                h0 += mvcost( tab, m, ( bmx + c_hex2[dir][0] )*4,   ( bmy + c_hex2[dir][1] )*4 );
+                h1 += mvcost( tab, m, ( bmx + c_hex2[dir+1][0] )*4, ( bmy + c_hex2[dir+1][1] )*4 );
+                h2 += mvcost( tab, m, ( bmx + c_hex2[dir+2][0] )*4, ( bmy + c_hex2[dir+2][1] )*4 );
+                int b2 = -1;
+                if( h0 < bcost ) { bcost = h0; b2 = 0; }
+                if( h1 < bcost ) { bcost = h1; b2 = 1; }
+                if( h2 < bcost ) { bcost = h2; b2 = 2; }
+                if( b2 < 0 ) break;
+                dir += b2 - 1;
+                dir = dir < 0 ? dir + 6 : dir >= 6 ? dir - 6 : dir;      // mod6m1 (me.c:53)
+                bmx += c_hex2[dir+1][0]; bmy += c_hex2[dir+1][1];
+            }
+        }
+        // square refine (me.c:404-418)
+        int s[8];
+#pragma unroll
+        for( int k = 0; k < 8; k++ ) s[k] = fpel_part( m, P, bmx + c_sq1[k+1][0], bmy + c_sq1[k+1][1] );
+        red8x2( s[0], s[1], g ); red8x2( s[2], s[3], g ); red8x2( s[4], s[5], g ); red8x2( s[6], s[7], g );
+        int bs = 0;
+#pragma unroll
+        for( int k = 0; k < 8; k++ )
+        {
+            int cost = s[k] + mvcost( tab, m, ( bmx + c_sq1[k+1][0] )*4, ( bmy + c_sq1[k+1][1] )*4 );
+            if( cost < bcost ) { bcost = cost; bs = k+1; }
+        }
+        bmx += c_sq1[bs][0]; bmy += c_sq1[bs][1];
+    }
+#undef COST_MV
+
+    // -> qpel mv (me.c:774-797)
+    int mx, my, cost;
+    if( !P.b_satd )
+    {
+        cost = bcost;
+        if( bmx == pmvx && bmy == pmvy ) cost += mvcost( tab, m, bmx*4, bmy*4 );
+        mx = bmx*4; my = bmy*4;
+        refine_subpel( m, P, tab, g, mx, my, cost, 1, 0 );      // subpel_iterations[2] = {0,1,1,0}
+    }
+    else
+    {
+        if( bpred_cost < bcost ) { mx = bpred_mx; my = bpred_my; }
+        else                     { mx = bmx*4;    my = bmy*4; }
+        cost = min( bpred_cost, bcost );
+        refine_subpel( m, P, tab, g, mx, my, cost, 1, 1 );      // subpel_iterations[4] = {0,2,1,1}
+    }
+    out_mx = mx; out_my = my; out_cost = cost;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) search_kernel( const SearchJob *__restrict__ jobs, LaParams P )
+{
+    extern __shared__ uint16_t s_tab[];
+    for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
+    __syncthreads();
+
+    const SearchJob J = jobs[blockIdx.y];
+    Grp g; g.r = threadIdx.x & 7; g.mask = 0xffu << ( threadIdx.x & 24 );
+    const int blk = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );
+    if( blk >= P.nmb ) return;
+    const int bx = blk % P.mbw, by = blk / P.mbw;
+    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
+    if( border && !P.do_edges && P.mbw > 2 && P.mbh > 2 )
+    {   // not evaluated (slicetype.c:823-828): the field keeps frame_new's zeros (frame.c:283-285)
+        if( g.r == 0 ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; }
+        return;
+    }
+    Me m;
+    const int64_t pel = (int64_t)( by*8 + g.r ) * P.stride + bx*8;
+    m.fenc = *(const uint2 *)( J.fenc + pel );
+    m.ref = J.ref + pel; m.ref_w = J.ref_w + pel;
+    m.wscale = J.wscale; m.wdenom = J.wdenom; m.woffset = J.woffset;
+    // slicetype.c:550-562
+    m.sminx = max( 4*( -8*bx - 12 ), -P.mv_range2 );
+    m.smaxx = min( 4*( 8*( P.mbw - bx - 1 ) + 12 ), P.mv_range2 - 1 );
+    m.sminy = max( 4*( -8*by - 12 ), -P.mv_range2 );
+    m.smaxy = min( 4*( 8*( P.mbh - by - 1 ) + 12 ), P.mv_range2 - 1 );
+    m.fminx = m.sminx >> 2; m.fmaxx = m.smaxx >> 2; m.fminy = m.sminy >> 2; m.fmaxy = m.smaxy >> 2;
+
+    // MV predictor from the previous pass's field (slicetype.c:658-680): right, below, below-left, below-right
+    int mvc[4][2] = {{0,0},{0,0},{0,0},{0,0}}, i_mvc = 0;
+    if( J.mv_in )
+    {
+        const int *f = (const int *)J.mv_in + blk;
+#define MVC( o ) { int v_ = __ldg( f + (o) ); mvc[i_mvc][0] = (int16_t)( v_ & 0xffff ); mvc[i_mvc][1] = v_ >> 16; i_mvc++; }
+        if( bx < P.mbw-1 ) MVC( 1 )
+        if( by < P.mbh-1 )
+        {
+            MVC( P.mbw )
+            if( bx > 0 ) MVC( P.mbw-1 )
+            if( bx < P.mbw-1 ) MVC( P.mbw+1 )
+        }
+#undef MVC
+    }
+    if( i_mvc <= 1 ) { m.mvpx = mvc[0][0]; m.mvpy = mvc[0][1]; }
+    else
+    {
+        m.mvpx = imedian( mvc[0][0], mvc[1][0], mvc[2][0] );
+        m.mvpy = imedian( mvc[0][1], mvc[1][1], mvc[2][1] );
+    }
+    int mx = 0, my = 0, cost;
+    bool skip = false;
+    if( !( m.mvpx | m.mvpy ) )
+    {   // zero-predictor shortcut (slicetype.c:684-692): unweighted F plane at mv 0
+        cost = cmp_rows( m.fenc, load8u( m.ref ), g, P.b_satd );
+        skip = cost < 64;
+    }
+    if( !skip )
+    {
+        me_search( m, P, s_tab, g, mvc, i_mvc, mx, my, cost );
+        cost -= s_tab[0];                              // slicetype.c:695
+        if( mx | my ) cost += 5;                       // 5 * lambda (:696-697)
+    }
+    if( g.r == 0 )
+    {
+        ( (int *)J.mv_out )[blk] = ( mx & 0xffff ) | ( my << 16 );
+        J.cost_out[blk] = cost;
+    }
+}
+
+void launch_search( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
+{
+    dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
+    size_t smem = ( P.cost_mv_n + 1 ) * sizeof(uint16_t);
+    search_kernel<<<grid, CTA_THREADS, smem, st>>>( d_jobs, P );
+}
+
+// ------------------------------------------------------------------------------------------------
+// mode decision + sums
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bidir_cost( uint2 fenc, const uint8_t *r0, const uint8_t *r1, const LaParams &P, const Grp &g,
+                                           int mv0x, int mv0y, int mv1x, int mv1y, int w )
+{   // TRY_BIDIR without the penalty (slicetype.c:579-603)
+    uint2 a, b;
+    if( !P.b_satd )
+    {   // subme <= 1: hpel planes addressed directly (slicetype.c:582-589)
+        int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
+        a = load8u( r0 + i0*P.plane_size + ( mv0x >> 2 ) + (int64_t)( mv0y >> 2 ) * P.stride );
+        b = load8u( r1 + i1*P.plane_size + ( mv1x >> 2 ) + (int64_t)( mv1y >> 2 ) * P.stride );
+    }
+    else
+    {
+        a = qpel_row( r0, P, mv0x, mv0y, 0, -1, 0 );
+        b = qpel_row( r1, P, mv1x, mv1y, 0, -1, 0 );
+    }
+    uint2 p = make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) );
+    return cmp_rows( fenc, p, g, P.b_satd );
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) final_kernel( const FinalJob *__restrict__ jobs, LaParams P )
+{
+    const FinalJob J = jobs[blockIdx.y];
+    Grp g; g.r = threadIdx.x & 7; g.mask = 0xffu << ( threadIdx.x & 24 );
+    const int blk = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );
+    if( blk >= P.nmb ) return;
+    const int bx = blk % P.mbw, by = blk / P.mbw;
+    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
+    const bool tiny = P.mbw <= 2 || P.mbh <= 2;
+    if( border && !P.do_edges && !tiny )
+    {
+        if( g.r == 0 && !J.b_intra_only ) J.lowres_costs[blk] = 0;
+        return;
+    }
+    int bcost = X264CU_COST_MAX, list_used = 0;
+    if( !J.b_intra_only )
+    {
+        const int64_t pel = (int64_t)( by*8 + g.r ) * P.stride + bx*8;
+        const uint2 fenc = *(const uint2 *)( J.fenc + pel );
+        int mv[2][2] = {{0,0},{0,0}}, mc[2] = { X264CU_COST_MAX, X264CU_COST_MAX };
+        for( int l = 0; l < 1 + J.b_bidir; l++ )
+        {
+            int v = __ldg( (const int *)J.mv[l] + blk );
+            mv[l][0] = (int16_t)( v & 0xffff ); mv[l][1] = v >> 16;
+            mc[l] = __ldg( J.mvcost[l] + blk );
+        }
+        if( J.b_bidir )
+        {   // slicetype.c:616-652
+            const int sminx = max( 4*( -8*bx - 12 ), -P.mv_range2 ), smaxx = min( 4*( 8*( P.mbw - bx - 1 ) + 12 ), P.mv_range2 - 1 );
+            const int sminy = max( 4*( -8*by - 12 ), -P.mv_range2 ), smaxy = min( 4*( 8*( P.mbh - by - 1 ) + 12 ), P.mv_range2 - 1 );
+            int d0x = 0, d0y = 0, d1x = 0, d1y = 0;
+            if( J.dmv_src )
+            {
+                int v = __ldg( (const int *)J.dmv_src + blk );
+                int mrx = (int16_t)( v & 0xffff ), mry = v >> 16;
+                d0x = ( mrx * J.dist_scale_factor + 128 ) >> 8;
+                d0y = ( mry * J.dist_scale_factor + 128 ) >> 8;
+                d1x = d0x - mrx; d1y = d0y - mry;
+                d0x = iclip3( d0x, sminx, smaxx ); d0y = iclip3( d0y, sminy, smaxy );
+                d1x = iclip3( d1x, sminx, smaxx ); d1y = iclip3( d1y, sminy, smaxy );
+                if( !P.b_satd ) { d0x &= ~1; d0y &= ~1; d1x &= ~1; d1y &= ~1; }
+            }
+            int cost = bidir_cost( fenc, J.ref0 + pel, J.ref1 + pel, P, g, d0x, d0y, d1x, d1y, J.bipred_weight );
+            if( cost < bcost ) { bcost = cost; list_used = 3; }
+            if( d0x | d0y | d1x | d1y )
+            {
+                uint2 a = load8u( J.ref0 + pel ), b = load8u( J.ref1 + pel );
+                uint2 p = make_uint2( biavg4( a.x, b.x, J.bipred_weight ), biavg4( a.y, b.y, J.bipred_weight ) );
+                cost = cmp_rows( fenc, p, g, P.b_satd );
+                if( cost < bcost ) { bcost = cost; list_used = 3; }
+            }
+        }
+        for( int l = 0; l < 1 + J.b_bidir; l++ )
+            if( mc[l] < bcost ) { bcost = mc[l]; list_used = l+1; }
+        if( J.b_bidir && ( mv[0][0] | mv[0][1] | mv[1][0] | mv[1][1] ) )
+        {   // slicetype.c:711-712
+            int cost = 5 + bidir_cost( fenc, J.ref0 + pel, J.ref1 + pel, P, g, mv[0][0], mv[0][1], mv[1][0], mv[1][1], J.bipred_weight );
+            if( cost < bcost ) { bcost = cost; list_used = 3; }
+        }
+    }
+    if( g.r != 0 ) return;
+    bcost += 4;                                         // lowres_penalty (slicetype.c:758)
+    const bool score = !border || tiny;
+    if( !J.b_bidir )
+    {   // slicetype.c:762-773
+        int icost = J.intra[blk];
+        int b_intra = icost < bcost;
+        if( b_intra ) { bcost = icost; list_used = 0; }
+        if( score && b_intra ) atomicAdd( &J.stats[2], 1 );
+    }
+    if( !J.b_intra_only )
+    {   // slicetype.c:776-788
+        int bcost_aq = P.aq ? ( bcost * J.inv_qscale[blk] + 128 ) >> 8 : bcost;
+        atomicAdd( &J.row_satds[by], bcost_aq );
+        if( score )
+        {
+            atomicAdd( &J.stats[0], bcost );
+            atomicAdd( &J.stats[1], bcost_aq );
+        }
+    }
+    J.lowres_costs[blk] = (uint16_t)( min( bcost, 0x3FFF ) + ( list_used << 14 ) );     // slicetype.c:790
+}
+
+void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
+{
+    dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
+    final_kernel<<<grid, CTA_THREADS, 0, st>>>( d_jobs, P );
+}

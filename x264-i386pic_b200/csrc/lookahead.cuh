@@ -1,0 +1,57 @@
+// lookahead.cuh -- device-side descriptors shared between the lookahead kernels and the C ABI.
+#pragma once
+#include "common.cuh"
+
+// Geometry and policy of one context; passed by value to every kernel.
+struct LaParams
+{
+    int mbw, mbh, nmb;          // 8x8 lowres blocks (== 16x16 macroblocks of the full frame)
+    int lw, lh;                 // lowres plane size
+    int stride;                 // device plane pitch (bytes); planes carry a 32-px border
+    int64_t plane_size;         // bytes between the four phase planes F,H,V,C of one frame
+    int mv_range2;              // 2 * analyse.i_mv_range (slicetype.c:550)
+    int me_range;
+    int me_method;              // 0 dia, 1 hex (after lowres_context_init, slicetype.c:50-59)
+    int b_satd;                 // param subme > 1: mbcmp == SATD, la subme 4; else SAD, la subme 2
+    int do_edges;
+    int aq;
+    int weighted_bipred;
+    int cost_mv_n;              // table covers |d| <= cost_mv_n
+    const uint16_t *cost_mv;    // device table indexed by |mvd| in qpel
+};
+
+// One motion-search pass over one (fenc, ref, list) field: x264_me_search for every block.
+struct SearchJob
+{
+    const uint8_t *fenc;        // F plane of the frame being predicted, pixel (0,0)
+    const uint8_t *ref;         // F plane of the reference, pixel (0,0); H,V,C follow at plane_size
+    const uint8_t *ref_w;       // fullpel plane: `ref`, or its weighted copy (slicetype.c:612-614)
+    const int16_t *mv_in;       // MV field of the previous pass (NULL: the zero field)
+    int16_t *mv_out;            // MV field written by this pass (x,y int16 per block, qpel)
+    int32_t *cost_out;          // lowres_mv_costs written by this pass
+    int wscale, wdenom, woffset;// wdenom < 0: unweighted
+};
+
+// Mode decision + sums of one (b,p0,p1) evaluation: the tail of slicetype_mb_cost.
+struct FinalJob
+{
+    const uint8_t *fenc, *ref0, *ref1;      // F planes, pixel (0,0)
+    const int16_t *mv[2];                   // searched fields (NULL when the list is unused)
+    const int32_t *mvcost[2];
+    const int16_t *dmv_src;                 // fref1->lowres_mvs[0][p1-p0-1] if already searched, else NULL
+    const uint16_t *intra;                  // fenc intra costs
+    const uint16_t *inv_qscale;
+    uint16_t *lowres_costs;                 // out, per block
+    int32_t *row_satds;                     // out, mbh sums (pre-zeroed)
+    int32_t *stats;                         // out: cost_est, cost_est_aq, intra_mbs (pre-zeroed)
+    int b_bidir, b_intra_only;              // b < p1 ; p0 == p1
+    int dist_scale_factor, bipred_weight;
+};
+
+void launch_lowres( const uint8_t *luma, int stride, int width, int height, uint8_t *planes,
+                    const LaParams &P, cudaStream_t st );
+void launch_weight_plane( const uint8_t *src, uint8_t *dst, int64_t bytes, int scale, int denom, int offset, cudaStream_t st );
+void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *intra, int32_t *row_satds,
+                   int32_t *stats, const LaParams &P, cudaStream_t st );
+void launch_search( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );
+void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );

@@ -1,0 +1,522 @@
+// primitives.cu -- batched pixel / dct / quant primitives (the x264_pixel_function_t,
+// x264_dct_function_t and x264_quant_function_t entries named by the north star), sm_100a.
+//
+// Two shapes per primitive:
+//   *_offsets : n independent block pairs at arbitrary byte offsets (checkasm's pbuf2+j pattern,
+//               tools/checkasm.c:393-397); one thread per block pair, alignment-agnostic loads.
+//   *_grid    : every non-overlapping block of a (tall) image pair; one thread per 8-pixel-wide
+//               column of a block row, so a warp reads 256 contiguous bytes per image row.
+// The arithmetic is the reference's packed 16:16 form (pixel.c:242-259), word for word.
+#include "primitives.cuh"
+#include <type_traits>
+
+__constant__ int c_bw[8] = { 16, 16, 8, 8, 8, 4, 4, 4 };
+__constant__ int c_bh[8] = { 16, 8, 16, 8, 4, 8, 4, 16 };
+static const int h_bw[8] = { 16, 16, 8, 8, 8, 4, 4, 4 };
+static const int h_bh[8] = { 16, 8, 16, 8, 4, 8, 4, 16 };
+
+__global__ void fill_u16_kernel( uint16_t *dst, int value, int n )
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < n ) dst[i] = (uint16_t)value;
+}
+void launch_fill_u16( uint16_t *dst, int value, int n, cudaStream_t st )
+{
+    fill_u16_kernel<<<( n + 255 ) / 256, 256, 0, st>>>( dst, value, n );
+}
+
+// ---- per-thread kernels on rows held as words -------------------------------------------------
+struct Ld8  { __device__ __forceinline__ uint2 operator()( const uint8_t *p ) const { return load8u( p ); } };
+struct Ld8A { __device__ __forceinline__ uint2 operator()( const uint8_t *p ) const { return __ldg( (const uint2 *)p ); } };
+
+// packed sum of |coef| of one 8x4 (pixel.c:290-307); satd_8x4 = (lo+hi)>>1
+template<class LD1, class LD2>
+__device__ __forceinline__ u32 satd_8x4_sum( const uint8_t *p1, int s1, const uint8_t *p2, int s2, LD1 ld1, LD2 ld2 )
+{
+    u32 t[4][4];
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        u32 d[4];
+        diff_row8( ld1( p1 + (size_t)i*s1 ), ld2( p2 + (size_t)i*s2 ), d );
+        HADAMARD4( t[i][0], t[i][1], t[i][2], t[i][3], d[0], d[1], d[2], d[3] );
+    }
+    u32 sum = 0;
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        u32 a0, a1, a2, a3;
+        HADAMARD4( a0, a1, a2, a3, t[0][i], t[1][i], t[2][i], t[3][i] );
+        sum += abs2( a0 ) + abs2( a1 ) + abs2( a2 ) + abs2( a3 );
+    }
+    return sum;
+}
+__device__ __forceinline__ int fold16( u32 s ) { return (int)( ( s & 0xffff ) + ( s >> 16 ) ); }
+
+// pixel.c:265-288
+__device__ __forceinline__ int satd_4x4( u32 a[4], u32 b[4] )   // one word (4 px) per row
+{
+    u32 t0[4], t1[4];
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        u32 a0 = byte_of( a[i], 0 ) - byte_of( b[i], 0 ), a1 = byte_of( a[i], 1 ) - byte_of( b[i], 1 );
+        u32 a2 = byte_of( a[i], 2 ) - byte_of( b[i], 2 ), a3 = byte_of( a[i], 3 ) - byte_of( b[i], 3 );
+        u32 b0 = ( a0 + a1 ) + ( ( a0 - a1 ) << 16 ), b1 = ( a2 + a3 ) + ( ( a2 - a3 ) << 16 );
+        t0[i] = b0 + b1; t1[i] = b0 - b1;
+    }
+    u32 a0, a1, a2, a3, sum = 0;
+    HADAMARD4( a0, a1, a2, a3, t0[0], t0[1], t0[2], t0[3] );
+    a0 = abs2( a0 ) + abs2( a1 ) + abs2( a2 ) + abs2( a3 ); sum += ( a0 & 0xffff ) + ( a0 >> 16 );
+    HADAMARD4( a0, a1, a2, a3, t1[0], t1[1], t1[2], t1[3] );
+    a0 = abs2( a0 ) + abs2( a1 ) + abs2( a2 ) + abs2( a3 ); sum += ( a0 & 0xffff ) + ( a0 >> 16 );
+    return (int)( sum >> 1 );
+}
+
+// pixel.c:334-366
+template<class LD1, class LD2>
+__device__ __forceinline__ int sa8d_8x8_raw( const uint8_t *p1, int s1, const uint8_t *p2, int s2, LD1 ld1, LD2 ld2 )
+{
+    u32 t[8][4];
+#pragma unroll
+    for( int i = 0; i < 8; i++ )
+    {
+        uint2 a = ld1( p1 + (size_t)i*s1 ), b = ld2( p2 + (size_t)i*s2 );
+        u32 d[8];
+#pragma unroll
+        for( int k = 0; k < 4; k++ ) { d[k] = byte_of( a.x, k ) - byte_of( b.x, k ); d[4+k] = byte_of( a.y, k ) - byte_of( b.y, k ); }
+        u32 b0 = ( d[0] + d[1] ) + ( ( d[0] - d[1] ) << 16 ), b1 = ( d[2] + d[3] ) + ( ( d[2] - d[3] ) << 16 );
+        u32 b2 = ( d[4] + d[5] ) + ( ( d[4] - d[5] ) << 16 ), b3 = ( d[6] + d[7] ) + ( ( d[6] - d[7] ) << 16 );
+        HADAMARD4( t[i][0], t[i][1], t[i][2], t[i][3], b0, b1, b2, b3 );
+    }
+    u32 sum = 0;
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        u32 a0, a1, a2, a3, a4, a5, a6, a7;
+        HADAMARD4( a0, a1, a2, a3, t[0][i], t[1][i], t[2][i], t[3][i] );
+        HADAMARD4( a4, a5, a6, a7, t[4][i], t[5][i], t[6][i], t[7][i] );
+        u32 b0 = abs2( a0 + a4 ) + abs2( a0 - a4 );
+        b0 += abs2( a1 + a5 ) + abs2( a1 - a5 );
+        b0 += abs2( a2 + a6 ) + abs2( a2 - a6 );
+        b0 += abs2( a3 + a7 ) + abs2( a3 - a7 );
+        sum += ( b0 & 0xffff ) + ( b0 >> 16 );
+    }
+    return (int)sum;
+}
+
+// pixel.c:383-418: returns (sum8<<32)+sum4 of one 8x8
+template<class LD>
+__device__ __forceinline__ uint64_t hadamard_ac_8x8( const uint8_t *p, int st, LD ld )
+{
+    u32 tmp[32];
+#pragma unroll
+    for( int i = 0; i < 8; i++ )
+    {
+        uint2 r = ld( p + (size_t)i*st );
+        u32 px[8];
+#pragma unroll
+        for( int k = 0; k < 4; k++ ) { px[k] = byte_of( r.x, k ); px[4+k] = byte_of( r.y, k ); }
+        const int o = ( i & 3 ) + ( i & 4 ) * 4;
+        u32 a0 = ( px[0] + px[1] ) + ( ( px[0] - px[1] ) << 16 ), a1 = ( px[2] + px[3] ) + ( ( px[2] - px[3] ) << 16 );
+        tmp[o] = a0 + a1; tmp[o+4] = a0 - a1;
+        u32 a2 = ( px[4] + px[5] ) + ( ( px[4] - px[5] ) << 16 ), a3 = ( px[6] + px[7] ) + ( ( px[6] - px[7] ) << 16 );
+        tmp[o+8] = a2 + a3; tmp[o+12] = a2 - a3;
+    }
+    u32 sum4 = 0, sum8 = 0;
+#pragma unroll
+    for( int i = 0; i < 8; i++ )
+    {
+        u32 a0, a1, a2, a3;
+        HADAMARD4( a0, a1, a2, a3, tmp[i*4+0], tmp[i*4+1], tmp[i*4+2], tmp[i*4+3] );
+        tmp[i*4+0] = a0; tmp[i*4+1] = a1; tmp[i*4+2] = a2; tmp[i*4+3] = a3;
+        sum4 += abs2( a0 ) + abs2( a1 ) + abs2( a2 ) + abs2( a3 );
+    }
+#pragma unroll
+    for( int i = 0; i < 8; i++ )
+    {
+        u32 a0, a1, a2, a3;
+        HADAMARD4( a0, a1, a2, a3, tmp[i], tmp[8+i], tmp[16+i], tmp[24+i] );
+        sum8 += abs2( a0 ) + abs2( a1 ) + abs2( a2 ) + abs2( a3 );
+    }
+    u32 dc = ( tmp[0] + tmp[8] + tmp[16] + tmp[24] ) & 0xffff;
+    sum4 = ( sum4 & 0xffff ) + ( sum4 >> 16 ) - dc;
+    sum8 = ( sum8 & 0xffff ) + ( sum8 >> 16 ) - dc;
+    return ( (uint64_t)sum8 << 32 ) + sum4;
+}
+
+// dct.c:157-189: one 4x4, rows as words; writes 16 coefficients
+__device__ __forceinline__ void sub4x4_dct( int16_t *dct, const u32 a[4], const u32 b[4] )
+{
+    int tmp[16];
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        int d0 = (int)byte_of( a[i], 0 ) - (int)byte_of( b[i], 0 ), d1 = (int)byte_of( a[i], 1 ) - (int)byte_of( b[i], 1 );
+        int d2 = (int)byte_of( a[i], 2 ) - (int)byte_of( b[i], 2 ), d3 = (int)byte_of( a[i], 3 ) - (int)byte_of( b[i], 3 );
+        int s03 = d0 + d3, s12 = d1 + d2, d03 = d0 - d3, d12 = d1 - d2;
+        tmp[0*4+i] = s03 + s12; tmp[1*4+i] = 2*d03 + d12; tmp[2*4+i] = s03 - s12; tmp[3*4+i] = d03 - 2*d12;
+    }
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        int s03 = tmp[i*4+0] + tmp[i*4+3], s12 = tmp[i*4+1] + tmp[i*4+2];
+        int d03 = tmp[i*4+0] - tmp[i*4+3], d12 = tmp[i*4+1] - tmp[i*4+2];
+        dct[i*4+0] = (int16_t)( s03 + s12 ); dct[i*4+1] = (int16_t)( 2*d03 + d12 );
+        dct[i*4+2] = (int16_t)( s03 - s12 ); dct[i*4+3] = (int16_t)( d03 - 2*d12 );
+    }
+}
+
+// ---- metric of a whole block, one thread -------------------------------------------------------
+template<class LD1, class LD2>
+__device__ __forceinline__ int block_metric( int metric, int bw, int bh, const uint8_t *p1, int s1, const uint8_t *p2, int s2, LD1 ld1, LD2 ld2 )
+{
+    int sum = 0;
+    if( metric == 0 )
+    {   // pixel.c:55-80
+        for( int y = 0; y < bh; y++ )
+        {
+            if( bw == 4 ) sum += __vsadu4( load4u( p1 + (size_t)y*s1 ), load4u( p2 + (size_t)y*s2 ) );
+            else
+                for( int x = 0; x < bw; x += 8 )
+                    sum += sad8( ld1( p1 + (size_t)y*s1 + x ), ld2( p2 + (size_t)y*s2 + x ) );
+        }
+    }
+    else if( metric == 1 )
+    {   // pixel.c:311-332
+        for( int y = 0; y < bh; y += 4 )
+        {
+            if( bw == 4 )
+            {
+                u32 a[4], b[4];
+#pragma unroll
+                for( int i = 0; i < 4; i++ ) { a[i] = load4u( p1 + (size_t)( y+i )*s1 ); b[i] = load4u( p2 + (size_t)( y+i )*s2 ); }
+                sum += satd_4x4( a, b );
+            }
+            else
+                for( int x = 0; x < bw; x += 8 )
+                    sum += fold16( satd_8x4_sum( p1 + (size_t)y*s1 + x, s1, p2 + (size_t)y*s2 + x, s2, ld1, ld2 ) ) >> 1;
+        }
+    }
+    else
+    {   // pixel.c:368-381
+        for( int y = 0; y < bh; y += 8 )
+            for( int x = 0; x < bw; x += 8 )
+                sum += sa8d_8x8_raw( p1 + (size_t)y*s1 + x, s1, p2 + (size_t)y*s2 + x, s2, ld1, ld2 );
+        sum = ( sum + 2 ) >> 2;
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(128) pixel_cmp_offsets_kernel( int metric, int size, const uint8_t *__restrict__ p1, int s1,
+        const uint8_t *__restrict__ p2, int s2, int64_t n, const int64_t *__restrict__ off1, const int64_t *__restrict__ off2, int32_t *__restrict__ out )
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= n ) return;
+    out[i] = block_metric( metric, c_bw[size], c_bh[size], p1 + off1[i], s1, p2 + off2[i], s2, Ld8(), Ld8() );
+}
+
+int launch_pixel_cmp( int metric, int size, const uint8_t *p1, int s1, const uint8_t *p2, int s2, int64_t n,
+                      const int64_t *off1, const int64_t *off2, int32_t *out, cudaStream_t st )
+{
+    if( metric < 0 || metric > 2 || size < 0 || size > 7 ) return -1;
+    if( metric == 2 && size != 0 && size != 3 ) return -1;            // sa8d: 16x16 and 8x8 only (pixel.c:855-856)
+    if( n <= 0 ) return 0;
+    pixel_cmp_offsets_kernel<<<(unsigned)( ( n + 127 ) / 128 ), 128, 0, st>>>( metric, size, p1, s1, p2, s2, n, off1, off2, out );
+    return 0;
+}
+
+// ---- grid shape ---------------------------------------------------------------------------------
+// One thread per 8-pixel column of one block row.  BW in {4,8,16}: a thread covers two 4-wide
+// blocks, one 8-wide block, or half of a 16-wide block (halves are combined with one shuffle).
+template<int METRIC, int BW, int BH, bool ALIGNED2>
+__global__ void __launch_bounds__(128) pixel_cmp_grid_kernel( const uint8_t *__restrict__ p1, int s1, const uint8_t *__restrict__ p2, int s2,
+                                                              int cols8, int nbx, int32_t *__restrict__ out )
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;      // 8-px column index
+    const int by = blockIdx.y;
+    const bool live = c < cols8;
+    const uint8_t *a = p1 + (size_t)by * BH * s1 + (size_t)min( c, cols8-1 ) * 8;
+    const uint8_t *b = p2 + (size_t)by * BH * s2 + (size_t)min( c, cols8-1 ) * 8;
+    typedef typename std::conditional<ALIGNED2, Ld8A, Ld8>::type LD2;
+    int v0 = 0, v1 = 0;
+    if( METRIC == 0 )
+    {
+#pragma unroll 4
+        for( int y = 0; y < BH; y++ )
+        {
+            uint2 ra = Ld8A()( a + (size_t)y*s1 ), rb = LD2()( b + (size_t)y*s2 );
+            v0 += __vsadu4( ra.x, rb.x ); v1 += __vsadu4( ra.y, rb.y );
+        }
+        if( BW != 4 ) v0 += v1;
+    }
+    else if( METRIC == 1 )
+    {
+        if( BW == 4 )
+        {
+            for( int y = 0; y < BH; y += 4 )
+            {
+                u32 al[4], ah[4], bl[4], bh_[4];
+#pragma unroll
+                for( int i = 0; i < 4; i++ )
+                {
+                    uint2 ra = Ld8A()( a + (size_t)( y+i )*s1 ), rb = LD2()( b + (size_t)( y+i )*s2 );
+                    al[i] = ra.x; ah[i] = ra.y; bl[i] = rb.x; bh_[i] = rb.y;
+                }
+                v0 += satd_4x4( al, bl ); v1 += satd_4x4( ah, bh_ );
+            }
+        }
+        else
+            for( int y = 0; y < BH; y += 4 )
+                v0 += fold16( satd_8x4_sum( a + (size_t)y*s1, s1, b + (size_t)y*s2, s2, Ld8A(), LD2() ) ) >> 1;
+    }
+    else
+    {
+        for( int y = 0; y < BH; y += 8 )
+            v0 += sa8d_8x8_raw( a + (size_t)y*s1, s1, b + (size_t)y*s2, s2, Ld8A(), LD2() );
+    }
+    if( BW == 16 )
+    {
+        v0 += __shfl_xor_sync( 0xffffffffu, v0, 1 );
+        if( METRIC == 2 ) v0 = ( v0 + 2 ) >> 2;
+        if( live && !( c & 1 ) ) out[(size_t)by * nbx + ( c >> 1 )] = v0;
+    }
+    else if( BW == 8 )
+    {
+        if( METRIC == 2 ) v0 = ( v0 + 2 ) >> 2;
+        if( live ) out[(size_t)by * nbx + c] = v0;
+    }
+    else if( live )
+    {
+        int2 *o = (int2 *)( out + (size_t)by * nbx + 2*c );      // nbx even for BW 4 when width % 8 == 0
+        *o = make_int2( v0, v1 );
+    }
+}
+
+template<int METRIC, int BW, int BH>
+static int cmp_grid_launch( const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height, int32_t *out, cudaStream_t st )
+{
+    int cols8 = width / 8, nbx = width / BW, nby = height / BH;
+    if( cols8 <= 0 || nby <= 0 ) return 0;
+    dim3 grid( ( cols8 + 127 ) / 128, nby );
+    bool al2 = ( ( (uintptr_t)p2 | (uintptr_t)s2 ) & 7 ) == 0;
+    if( al2 ) pixel_cmp_grid_kernel<METRIC, BW, BH, true><<<grid, 128, 0, st>>>( p1, s1, p2, s2, cols8, nbx, out );
+    else      pixel_cmp_grid_kernel<METRIC, BW, BH, false><<<grid, 128, 0, st>>>( p1, s1, p2, s2, cols8, nbx, out );
+    return 0;
+}
+
+int launch_pixel_cmp_grid( int metric, int size, const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height,
+                           int32_t *out, cudaStream_t st )
+{
+    if( ( ( (uintptr_t)p1 | (uintptr_t)s1 ) & 7 ) || ( width & 7 ) ) return -2;      // pix1 rows must be 8-byte aligned
+#define CASE( M, S, W, H ) if( metric == M && size == S ) return cmp_grid_launch<M, W, H>( p1, s1, p2, s2, width, height, out, st );
+    CASE( 0, 0, 16, 16 ) CASE( 0, 1, 16, 8 ) CASE( 0, 2, 8, 16 ) CASE( 0, 3, 8, 8 ) CASE( 0, 4, 8, 4 ) CASE( 0, 5, 4, 8 ) CASE( 0, 6, 4, 4 ) CASE( 0, 7, 4, 16 )
+    CASE( 1, 0, 16, 16 ) CASE( 1, 1, 16, 8 ) CASE( 1, 2, 8, 16 ) CASE( 1, 3, 8, 8 ) CASE( 1, 4, 8, 4 ) CASE( 1, 5, 4, 8 ) CASE( 1, 6, 4, 4 ) CASE( 1, 7, 4, 16 )
+    CASE( 2, 0, 16, 16 ) CASE( 2, 3, 8, 8 )
+#undef CASE
+    return -1;
+}
+
+// ---- hadamard_ac ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t hadamard_ac_finish( uint64_t sum )
+{   // pixel.c:430
+    return ( ( sum >> 34 ) << 32 ) + ( (uint32_t)sum >> 1 );
+}
+
+__global__ void __launch_bounds__(128) hadamard_ac_offsets_kernel( int size, const uint8_t *__restrict__ p, int st, int64_t n,
+                                                                   const int64_t *__restrict__ off, uint64_t *__restrict__ out )
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= n ) return;
+    const uint8_t *q = p + off[i];
+    uint64_t sum = 0;
+    for( int y = 0; y < c_bh[size]; y += 8 )
+        for( int x = 0; x < c_bw[size]; x += 8 )
+            sum += hadamard_ac_8x8( q + (size_t)y*st + x, st, Ld8() );
+    out[i] = hadamard_ac_finish( sum );
+}
+
+int launch_hadamard_ac( int size, const uint8_t *p, int stride, int64_t n, const int64_t *off, uint64_t *out, cudaStream_t st )
+{
+    if( size < 0 || size > 3 ) return -1;
+    if( n <= 0 ) return 0;
+    hadamard_ac_offsets_kernel<<<(unsigned)( ( n + 127 ) / 128 ), 128, 0, st>>>( size, p, stride, n, off, out );
+    return 0;
+}
+
+template<int BW, int BH>
+__global__ void __launch_bounds__(128) hadamard_ac_grid_kernel( const uint8_t *__restrict__ p, int s, int cols8, int nbx, uint64_t *__restrict__ out )
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y;
+    const bool live = c < cols8;
+    const uint8_t *a = p + (size_t)by * BH * s + (size_t)min( c, cols8-1 ) * 8;
+    uint64_t sum = 0;
+    for( int y = 0; y < BH; y += 8 ) sum += hadamard_ac_8x8( a + (size_t)y*s, s, Ld8A() );
+    if( BW == 16 )
+    {
+        sum += __shfl_xor_sync( 0xffffffffu, sum, 1 );
+        if( live && !( c & 1 ) ) out[(size_t)by * nbx + ( c >> 1 )] = hadamard_ac_finish( sum );
+    }
+    else if( live ) out[(size_t)by * nbx + c] = hadamard_ac_finish( sum );
+}
+
+int launch_hadamard_ac_grid( int size, const uint8_t *p, int stride, int width, int height, uint64_t *out, cudaStream_t st )
+{
+    if( size < 0 || size > 3 ) return -1;
+    if( ( ( (uintptr_t)p | (uintptr_t)stride ) & 7 ) || ( width & 7 ) ) return -2;
+    int cols8 = width / 8, nbx = width / h_bw[size], nby = height / h_bh[size];
+    if( cols8 <= 0 || nby <= 0 ) return 0;
+    dim3 grid( ( cols8 + 127 ) / 128, nby );
+    switch( size )
+    {
+        case 0: hadamard_ac_grid_kernel<16,16><<<grid, 128, 0, st>>>( p, stride, cols8, nbx, out ); break;
+        case 1: hadamard_ac_grid_kernel<16,8><<<grid, 128, 0, st>>>( p, stride, cols8, nbx, out ); break;
+        case 2: hadamard_ac_grid_kernel<8,16><<<grid, 128, 0, st>>>( p, stride, cols8, nbx, out ); break;
+        case 3: hadamard_ac_grid_kernel<8,8><<<grid, 128, 0, st>>>( p, stride, cols8, nbx, out ); break;
+    }
+    return 0;
+}
+
+// ---- sub_dct --------------------------------------------------------------------------------------
+// one thread per 4x4; 4x4 blocks of a bsize block are emitted in the reference's nested Z order (dct.c:191-205)
+__device__ __forceinline__ void z_order( int bsize, int k, int &ox, int &oy )
+{   // k-th 4x4 of a block: bits (b0: x of 4x4 in 8x8, b1: y), (b2: x of 8x8 in 16x16, b3: y)
+    ox = ( ( k & 1 ) + ( ( k >> 2 ) & 1 ) * 2 ) * 4;
+    oy = ( ( ( k >> 1 ) & 1 ) + ( ( k >> 3 ) & 1 ) * 2 ) * 4;
+    (void)bsize;
+}
+
+__global__ void __launch_bounds__(128) sub_dct_offsets_kernel( int bsize, const uint8_t *__restrict__ p1, int s1, const uint8_t *__restrict__ p2, int s2,
+        int64_t n, const int64_t *__restrict__ off1, const int64_t *__restrict__ off2, int16_t *__restrict__ out )
+{
+    const int per = ( bsize / 4 ) * ( bsize / 4 );
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if( t >= n * per ) return;
+    int64_t i = t / per; int k = (int)( t % per ), ox, oy;
+    z_order( bsize, k, ox, oy );
+    const uint8_t *a = p1 + off1[i] + (size_t)oy*s1 + ox, *b = p2 + off2[i] + (size_t)oy*s2 + ox;
+    u32 ra[4], rb[4];
+#pragma unroll
+    for( int y = 0; y < 4; y++ ) { ra[y] = load4u( a + (size_t)y*s1 ); rb[y] = load4u( b + (size_t)y*s2 ); }
+    __align__(16) int16_t d[16];
+    sub4x4_dct( d, ra, rb );
+    uint4 *o = (uint4 *)( out + t*16 );
+    o[0] = ( (uint4 *)d )[0]; o[1] = ( (uint4 *)d )[1];
+}
+
+int launch_sub_dct( int bsize, const uint8_t *p1, int s1, const uint8_t *p2, int s2, int64_t n, const int64_t *off1,
+                    const int64_t *off2, int16_t *out, cudaStream_t st )
+{
+    if( bsize != 4 && bsize != 8 && bsize != 16 ) return -1;
+    if( n <= 0 ) return 0;
+    int64_t nt = n * ( bsize/4 ) * ( bsize/4 );
+    sub_dct_offsets_kernel<<<(unsigned)( ( nt + 127 ) / 128 ), 128, 0, st>>>( bsize, p1, s1, p2, s2, n, off1, off2, out );
+    return 0;
+}
+
+// grid: thread per 4x4 ordered so that consecutive threads write consecutive 32-byte outputs
+__global__ void __launch_bounds__(128) sub_dct_grid_kernel( int bsize, const uint8_t *__restrict__ p1, int s1, const uint8_t *__restrict__ p2, int s2,
+                                                            int nbx, int64_t nt, int16_t *__restrict__ out )
+{
+    const int per = ( bsize / 4 ) * ( bsize / 4 );
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if( t >= nt ) return;
+    int64_t blk = t / per; int k = (int)( t % per ), ox, oy;
+    z_order( bsize, k, ox, oy );
+    int64_t by = blk / nbx; int bx = (int)( blk % nbx );
+    const uint8_t *a = p1 + ( by*bsize + oy ) * s1 + bx*bsize + ox, *b = p2 + ( by*bsize + oy ) * s2 + bx*bsize + ox;
+    u32 ra[4], rb[4];
+#pragma unroll
+    for( int y = 0; y < 4; y++ ) { ra[y] = __ldg( (const u32 *)( a + (size_t)y*s1 ) ); rb[y] = __ldg( (const u32 *)( b + (size_t)y*s2 ) ); }
+    __align__(16) int16_t d[16];
+    sub4x4_dct( d, ra, rb );
+    uint4 *o = (uint4 *)( out + t*16 );
+    o[0] = ( (uint4 *)d )[0]; o[1] = ( (uint4 *)d )[1];
+}
+
+int launch_sub_dct_grid( int bsize, const uint8_t *p1, int s1, const uint8_t *p2, int s2, int width, int height, int16_t *out, cudaStream_t st )
+{
+    if( bsize != 4 && bsize != 8 && bsize != 16 ) return -1;
+    if( ( ( (uintptr_t)p1 | (uintptr_t)s1 | (uintptr_t)p2 | (uintptr_t)s2 ) & 3 ) ) return -2;
+    int nbx = width / bsize, nby = height / bsize;
+    int64_t nt = (int64_t)nbx * nby * ( bsize/4 ) * ( bsize/4 );
+    if( nt <= 0 ) return 0;
+    sub_dct_grid_kernel<<<(unsigned)( ( nt + 127 ) / 128 ), 128, 0, st>>>( bsize, p1, s1, p2, s2, nbx, nt, out );
+    return 0;
+}
+
+// ---- quant ---------------------------------------------------------------------------------------
+// quant.c:50-73; 8 coefficients (one 128-bit word) per thread, nz reduced over the block's threads
+template<int N>
+__global__ void __launch_bounds__(256) quant_kernel( int16_t *__restrict__ coefs, int64_t nblocks, const uint16_t *__restrict__ mf,
+                                                     const uint16_t *__restrict__ bias, int32_t *__restrict__ nz )
+{
+    __shared__ uint16_t s_mf[N], s_bias[N];
+    if( threadIdx.x < N ) { s_mf[threadIdx.x] = mf[threadIdx.x]; s_bias[threadIdx.x] = bias[threadIdx.x]; }
+    __syncthreads();
+    constexpr int TPB = N / 8;                      // threads per block of coefficients
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < nblocks * TPB;
+    int k0 = (int)( t % TPB ) * 8, any = 0;
+    if( live )
+    {
+        uint4 v = ( (uint4 *)coefs )[t];
+        u32 w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for( int j = 0; j < 4; j++ )
+        {
+            u32 r = 0;
+#pragma unroll
+            for( int h = 0; h < 2; h++ )
+            {
+                int c = (int16_t)( w[j] >> ( 16*h ) );
+                int k = k0 + 2*j + h;
+                int q = c > 0 ? (int)( ( (u32)s_bias[k] + (u32)c ) * s_mf[k] >> 16 )
+                              : -(int)( ( (u32)s_bias[k] + (u32)( -c ) ) * s_mf[k] >> 16 );
+                any |= q;
+                r |= ( (u32)q & 0xffffu ) << ( 16*h );
+            }
+            w[j] = r;
+        }
+        ( (uint4 *)coefs )[t] = make_uint4( w[0], w[1], w[2], w[3] );
+    }
+    any = ( any & 0xffff ) != 0;                    // nz |= (coef) on int16 values
+#pragma unroll
+    for( int m = 1; m < TPB; m <<= 1 ) any |= __shfl_xor_sync( 0xffffffffu, any, m );
+    if( live && k0 == 0 ) nz[t / TPB] = any;
+}
+
+int launch_quant( int b8x8, int16_t *coefs, int64_t nblocks, const uint16_t *mf, const uint16_t *bias, int32_t *nz, cudaStream_t st )
+{
+    if( nblocks <= 0 ) return 0;
+    if( (uintptr_t)coefs & 15 ) return -2;
+    if( b8x8 ) quant_kernel<64><<<(unsigned)( ( nblocks*8 + 255 ) / 256 ), 256, 0, st>>>( coefs, nblocks, mf, bias, nz );
+    else       quant_kernel<16><<<(unsigned)( ( nblocks*2 + 255 ) / 256 ), 256, 0, st>>>( coefs, nblocks, mf, bias, nz );
+    return 0;
+}
+
+// ---- frame_init_lowres_core with the reference's own signature (mc.c:484-507) ------------------------
+__global__ void __launch_bounds__(128) lowres_core_kernel( const uint8_t *__restrict__ src, int ss, uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc,
+                                                           int ds, int width, int height )
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if( x >= width ) return;
+    const uint8_t *r0 = src + (size_t)2*y*ss + 2*x, *r1 = r0 + ss, *r2 = r1 + ss;
+#define FILT(a,b,c,d) ((((((a)+(b)+1)>>1)+(((c)+(d)+1)>>1)+1)>>1))
+    int a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b1 = r1[1], b2 = r1[2], c0 = r2[0], c1 = r2[1], c2 = r2[2];
+    d0[(size_t)y*ds + x] = FILT( a0, b0, a1, b1 );
+    dh[(size_t)y*ds + x] = FILT( a1, b1, a2, b2 );
+    dv[(size_t)y*ds + x] = FILT( b0, c0, b1, c1 );
+    dc[(size_t)y*ds + x] = FILT( b1, c1, b2, c2 );
+#undef FILT
+}
+
+int launch_lowres_core( const uint8_t *src, int sstride, uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, int dstride,
+                        int width, int height, cudaStream_t st )
+{
+    if( width <= 0 || height <= 0 ) return 0;
+    dim3 grid( ( width + 127 ) / 128, height );
+    lowres_core_kernel<<<grid, 128, 0, st>>>( src, sstride, d0, dh, dv, dc, dstride, width, height );
+    return 0;
+}
