@@ -37,6 +37,7 @@ struct x264cu_frame
     uint8_t   searched[2][X264CU_BFRAME_MAX+1];
     uint8_t   evaluated[X264CU_BFRAME_MAX+2][X264CU_BFRAME_MAX+2];
     bool      uploaded;
+    bool      any_eval;      // some evaluation already produced i_cost_est[0][0] (slicetype.c:848,949-953)
 };
 
 struct x264cu_ctx
@@ -335,6 +336,7 @@ static void reset_caches( x264cu_frame *f )
 {   // mc.c:473-481: i_cost_est = -1, MV sentinels = 0x7FFF
     memset( f->searched, 0, sizeof(f->searched) );
     memset( f->evaluated, 0, sizeof(f->evaluated) );
+    f->any_eval = false;
 }
 
 static int upload_common( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int pitch )
@@ -461,6 +463,10 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
         if( !j.fenc || !j.fref0 || !j.fref1 || j.d0 < 0 || j.d1 < 0 || j.d0 + j.d1 > B + 1 )
             FAIL( "x264cu_frame_cost: bad job %d (d0=%d d1=%d bframes=%d)", i, j.d0, j.d1, B );
         if( !j.fenc->uploaded || !j.fref0->uploaded || !j.fref1->uploaded ) FAIL( "x264cu_frame_cost: frame not uploaded" );
+        // An I evaluation after any other evaluation of the frame is a cache hit in the reference
+        // (i_cost_est[0][0] was filled by the intra section of that evaluation, slicetype.c:848,949-953)
+        if( j.d0 == 0 && j.d1 == 0 && j.fenc->any_eval ) j.fenc->evaluated[0][0] = 1;
+        j.fenc->any_eval = true;
         if( j.fenc->evaluated[j.d0][j.d1] ) continue;                  // i_cost_est >= 0 (slicetype.c:848)
         j.fenc->evaluated[j.d0][j.d1] = 1;
         FinalJob F;
