@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- lookahead frames/s at 1080p on N B200 (BASELINE.json metric), plus the SATD primitive
+against the HBM roofline, next to the reference's CPU path timed on the host cores.
+
+Workload (BASELINE.json configs[2], "lowres lookahead frame-cost matrix, 1080p, bframes=16, b-adapt 2"):
+a step = one new 1920x1080 frame entering one encoder's lookahead window: luma upload, lowres
+downscale (4 phase planes + border), intra costs, and the whole increment of the B-frame cost
+matrix that b-adapt 2 can query for that frame -- slicetype_frame_cost(p0, n, b) for
+n-17 <= p0 < b <= n plus the I cost: 154 evaluations, 33 new motion-search fields (K=2 passes).
+Each rank runs S independent encode streams round-robin (configs[4] style, weak scaling); their
+windows together exceed L2.  Windows are filled (17 frames per stream) before warm-up, so every
+warm-up/timed step is a steady-state step.
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA arm (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's own C path on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "x264-i386pic_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H = 1920, 1080
+BFRAMES = 16
+RAMP = BFRAMES + 1            # frames that fill a window
+METRIC = "lookahead frames/s at 1080p (bframes=16 cost-matrix increment per frame)"
+
+
+def make_stream_frames(seed, count):
+    """deterministic synthetic 1080p luma: panning texture + moving inverted square + noise
+    (SURVEY.md section 8d config 1), cheap enough to generate hundreds of frames."""
+    rng = np.random.default_rng(seed)
+    margin = 64
+    tw, th = W + 2 * margin + 4 * count, H + 2 * margin + 2 * count
+    t = rng.integers(0, 256, (th // 8 + 2, tw // 8 + 2)).astype(np.float32)
+    t = np.kron(t, np.ones((8, 8), dtype=np.float32))[:th, :tw]
+    for ax in (0, 1):
+        t = (np.roll(t, 1, ax) + 2 * t + np.roll(t, -1, ax)) / 4
+        t = (np.roll(t, 2, ax) + 2 * t + np.roll(t, -2, ax)) / 4
+    t = np.clip(t * 0.8 + 25 + rng.integers(-24, 25, t.shape), 3, 252).astype(np.uint8)
+    frames = []
+    for i in range(count):
+        ox, oy = margin + 3 * i, margin + i
+        f = t[oy:oy + H, ox:ox + W].copy()
+        sx, sy = (40 + 11 * i) % (W - 160), (30 + 5 * i) % (H - 160)
+        f[sy:sy + 160, sx:sx + 160] = 255 - f[sy:sy + 160, sx:sx + 160]
+        f = (f.astype(np.int16) + rng.integers(-3, 4, f.shape, dtype=np.int16)).astype(np.uint8)
+        frames.append(f)
+    return frames
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in out.strip().split(",")]
+                if len(p) >= 6:
+                    self.samples.append(p)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi samples"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def dist_setup(n_gpus):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def barrier_sync(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize(local)
+
+
+def run_cuda_pass(x264cu, ctx, frames, streams_n, warmup, steps, e2e, pinned=None, dev=None, profile=False, dist=None, local=0):
+    """ramp (untimed) -> warmup -> timed steps; returns (ms, evals per step, launches, kernel times, bytes)."""
+    L = ctx.L
+    wins = [L.x264cu_stream_open(ctx.ctx, BFRAMES, 1 if e2e else 0) for _ in range(streams_n)]
+    assert all(wins), x264cu.last_error()
+    pos = [0] * streams_n
+
+    def push(s):
+        i = pos[s]
+        pos[s] += 1
+        if e2e:
+            r = L.x264cu_stream_push(wins[s], pinned[s][i], W, None, 0)
+        else:
+            r = L.x264cu_stream_push(wins[s], dev[s][i], W, None, 1)
+        if r < 0:
+            raise RuntimeError("x264cu_stream_push: " + x264cu.last_error())
+        return r
+
+    for s in range(streams_n):                       # fill the windows
+        for _ in range(RAMP):
+            push(s)
+        x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")
+    for k in range(warmup):
+        push(k % streams_n)
+        x264cu.check(L.x264cu_stream_sync(wins[k % streams_n]), "sync")
+    ctx.kernel_times()
+    ctx.set_profiling(profile)
+    l0 = ctx.launches()
+    barrier_sync(dist, local)
+    ctx.timer_begin()
+    t0 = time.perf_counter()
+    evals = 0
+    for k in range(steps):
+        s = (warmup + k) % streams_n
+        evals += push(s)
+        x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")      # results of this step are on the host here
+    ms = ctx.timer_end()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier_sync(dist, local)
+    ctx.set_profiling(False)
+    kt = ctx.kernel_times()
+    launches = ctx.launches() - l0
+    res_bytes = int(L.x264cu_stream_result_bytes(wins[0])) if e2e else 0
+    # a result the caller would read: the P cost of the newest frame against its predecessor
+    st = (x264cu.C.c_int32 * 4)()
+    L.x264cu_stream_cost(wins[(warmup + steps - 1) % streams_n], 1, 0, st)
+    assert st[0] > 0, list(st)
+    for w in wins:
+        L.x264cu_stream_close(w)
+    return ms, wall_ms, evals / max(steps, 1), launches, kt, res_bytes, int(st[0])
+
+
+def bench_satd(x264cu, ctx, peak_gbs):
+    """SATD 8x8 (and SAD 16x16) over every non-overlapping block of two tall image stacks of 1080p
+    frames that together exceed L2 (2 x 128 frames = 531 MB); CUDA events; algorithmic bytes = 2 B/pixel."""
+    L = ctx.L
+    nfr = 128
+    hh = 1080 * nfr
+    nbytes = W * hh
+    d1, d2 = ctx.malloc(nbytes + 256), ctx.malloc(nbytes + 256)
+    rng = np.random.default_rng(5)
+    chunk = rng.integers(0, 256, W * 1080 * 8, dtype=np.uint8)
+    for k in range(nfr // 8):
+        x264cu.check(L.x264cu_memcpy_h2d(ctx.ctx, d1 + k * chunk.nbytes, chunk.ctypes.data, chunk.nbytes))
+        x264cu.check(L.x264cu_memcpy_h2d(ctx.ctx, d2 + k * chunk.nbytes, chunk[::-1].copy().ctypes.data, chunk.nbytes))
+    out = {}
+    for name, metric, size, bw, bh in (("satd_8x8", 1, 3, 8, 8), ("sad_16x16", 0, 0, 16, 16), ("satd_16x16", 1, 0, 16, 16), ("sa8d_8x8", 2, 3, 8, 8)):
+        dout = ctx.malloc((W // bw) * (hh // bh) * 4)
+        for _ in range(3):
+            x264cu.check(L.x264cu_pixel_cmp_grid(ctx.ctx, metric, size, d1, W, d2, W, W, hh, 0, 0, dout, 1), name)
+        reps = 10
+        ctx.timer_begin()
+        for _ in range(reps):
+            L.x264cu_pixel_cmp_grid(ctx.ctx, metric, size, d1, W, d2, W, W, hh, 0, 0, dout, 1)
+        ms = ctx.timer_end() / reps
+        gpix = W * hh / ms / 1e6
+        gbs = (2 * W * hh + (W // bw) * (hh // bh) * 4) / ms / 1e6
+        out[name] = {"gpix_s": round(gpix, 1), "gb_s": round(gbs, 1), "hbm_frac": round(gbs / peak_gbs, 4), "ms": round(ms, 4)}
+        ctx.free(dout)
+    ctx.free(d1)
+    ctx.free(d2)
+    return out
+
+
+def cpu_reference_run(frames, warmup, steps, threads, ramp=RAMP):
+    """the reference's own slicetype_frame_cost (raster-serial C path with lookahead slices,
+    slicetype.c:836-995) on the same frames, same evaluations in the same order as a CUDA step."""
+    from checkers import Lookahead, OracleLib, RefLib, have_ref
+    if have_ref():
+        la = Lookahead(RefLib(), "ref_serial", W, H, bframes=BFRAMES, subme=7, mbtree=1, aq=1, la_threads=threads)
+        kind = "reference"
+    else:
+        la = Lookahead(OracleLib(), "oracle", W, H, bframes=BFRAMES, subme=7, mbtree=1, aq=1, passes=2, mv_range=512)
+        kind, threads = "port", 1
+    # the checkers address frames by absolute index (the shim holds up to 512); frames that left the window are released
+    def step_abs(n):
+        la.put_frame(n, frames[n])
+        if kind == "reference" and n - (BFRAMES + 2) >= 0:
+            la.lib.lib.ref_la_release(la.ctx, n - (BFRAMES + 2))
+        cnt = 0
+        la.frame_cost(n, n, n); cnt += 1
+        for p0 in range(n - 1, max(n - (BFRAMES + 1), 0) - 1, -1):
+            la.frame_cost(p0, n, n); cnt += 1
+            for b in range(p0 + 1, n):
+                la.frame_cost(p0, n, b); cnt += 1
+        return cnt
+
+    for n in range(ramp):
+        step_abs(n)
+    for k in range(warmup):
+        step_abs(ramp + k)
+    t0 = time.perf_counter()
+    evals = 0
+    for k in range(steps):
+        evals += step_abs(ramp + warmup + k)
+    dt = time.perf_counter() - t0
+    la.close()
+    return dt, evals, kind, threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--streams", type=int, default=4, help="independent encode streams per GPU (round-robin)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-primitives", action="store_true", help="skip the SATD/SAD primitive roofline section")
+    ap.add_argument("--value-only", action="store_true", help="profiling aid: skip the end-to-end pass")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3)
+    nproc = os.cpu_count() or 1
+    config = {"workload": "lowres lookahead frame-cost matrix, 1080p, bframes=16, b-adapt 2 (BASELINE.json configs[2])",
+              "width": W, "height": H, "bframes": BFRAMES, "search_passes": 2, "subme": 7, "mbtree_edges": 1, "aq": 1,
+              "evals_per_step": 154, "new_search_fields_per_step": 33, "streams_per_gpu": args.streams,
+              "sharding": "independent encode streams per GPU, no collective",
+              "l2": "inputs larger than L2: %d windows x 18 frames x ~10 MB of planes+cost arrays per GPU" % args.streams}
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", 0))
+        if rank != 0:
+            return 0
+        threads = min(16, nproc)             # X264_LOOKAHEAD_THREAD_MAX (common/base.h)
+        steps = args.steps
+        frames = make_stream_frames(100, RAMP + warmup + steps)
+        dt, evals, kind, threads = cpu_reference_run(frames, warmup, steps, threads)
+        v = steps / dt
+        sample = ("%d steady-state steps of stream 0 after an untimed %d-frame window fill; reference C sources built "
+                  "without asm (no nasm in the image), %d lookahead slice threads" % (steps, RAMP, threads))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "frames/s", "n_gpus": args.gpus,
+                          "steps": steps, "warmup": warmup, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": round(v, 4), "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
+                          "e2e": {"value": round(v, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import x264cu
+    rank, world, local, dist = dist_setup(args.gpus)
+    S = args.streams
+    per_stream = RAMP + (warmup + args.steps + S - 1) // S + 1
+    ctx = x264cu.Context(W, H, bframes=BFRAMES, subme=7, do_edges=1, aq=1, passes=2, device=local)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    frames = [make_stream_frames(1000 * rank + 7 * s + 1, per_stream) for s in range(S)]
+    fbytes = W * H
+    pinned, dev = [], []
+    for s in range(S):
+        hp = ctx.host_alloc(fbytes * per_stream)
+        dp = ctx.malloc(fbytes * per_stream + 256)
+        for i, f in enumerate(frames[s]):
+            x264cu.C.memmove(hp + i * fbytes, f.ctypes.data, fbytes)
+        x264cu.check(ctx.L.x264cu_memcpy_h2d(ctx.ctx, dp, hp, fbytes * per_stream))
+        pinned.append([hp + i * fbytes for i in range(per_stream)])
+        dev.append([dp + i * fbytes for i in range(per_stream)])
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # device-resident pass ("value"): inputs already in HBM, only the cost scalars come back
+    ms_v, wall_v, evals, launches, kt, _, chk_v = run_cuda_pass(x264cu, ctx, frames, S, warmup, args.steps, False, dev=dev, profile=True, dist=dist, local=local)
+    # end-to-end pass: pinned host luma in, every result array of the hook protocol out, per step
+    if args.value_only:
+        ms_e, wall_e, res_bytes, chk_e = ms_v, wall_v, 0, chk_v
+    else:
+        ms_e, wall_e, _, _, _, res_bytes, chk_e = run_cuda_pass(x264cu, ctx, frames, S, warmup, args.steps, True, pinned=pinned, dist=dist, local=local)
+    clocks = sampler.summary()
+    assert chk_v > 0 and chk_e > 0
+
+    t_v, t_e = ms_v, ms_e
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_v, ms_e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_v, t_e = float(t[0]), float(t[1])
+    value = world * args.steps / (t_v / 1e3)
+    e2e = world * args.steps / (t_e / 1e3)
+
+    out = {"metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+           "ms_per_step": round(t_v / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8", "data": "synthetic", "config": config, "clocks": clocks,
+           "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": fbytes, "d2h_bytes_per_step": res_bytes + 154 * 32,
+                   "ms_per_step": round(t_e / args.steps, 4)},
+           "gpu_launches": int(launches)}
+    # roofline of the dominant kernel: the motion-search pass (2 launches per step, 33 fields each)
+    nmb = ctx.nmb
+    s_ms, s_n = kt["search"]
+    if s_n:
+        # algorithmic bytes of one block-field search pass: fenc 64 B + 4 reference phase planes 256 B
+        # + MV/cost out 8 B + previous-pass MV in 4 B; one launch = 33 fields x 8160 blocks in steady state
+        per_block = 64 + 256 + 8 + 4
+        fields = 33
+        alg = per_block * nmb * fields
+        avg_ms = s_ms / s_n
+        ach = alg / avg_ms / 1e6
+        out["roofline"] = {"kernel": "search_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
+                           "frac": round(ach / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
+                           "avg_launch_ms": round(avg_ms, 4), "launches_timed": s_n, "algorithmic_bytes_per_launch": alg,
+                           "note": "compulsory bytes are tiny; the kernel is integer-pipe/latency bound (see profiles/)"}
+        out["kernel_ms_per_step"] = {k: round(v[0] / args.steps, 4) for k, v in kt.items()}
+    if rank == 0:
+        if not args.no_primitives:
+            out["primitives"] = bench_satd(x264cu, ctx, peak_gbs)
+        if world == 1 and not args.no_cpu_baseline:
+            dt, ev, kind, thr = cpu_reference_run(frames[0], 0, 2, min(16, nproc))
+            out["cpu_baseline"] = {"value": round(2 / dt, 4), "unit": "frames/s", "cores": thr, "kind": kind,
+                                   "sample": "2 steady-state steps of stream 0 after an untimed 17-frame window fill; C-only build of the reference (no nasm)"}
+        print(json.dumps(out))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

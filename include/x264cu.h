@@ -119,6 +119,22 @@ int x264cu_set_profiling( x264cu_ctx *ctx, int on );
 /* copy a device lowres plane (incl. border; pitch = lowres width + 64) back to the host: test hook */
 int x264cu_frame_get_lowres( x264cu_ctx *ctx, x264cu_frame *f, int plane, uint8_t *out );
 
+/* ---- lookahead window (host C++, x264-i386pic_b200/host/stream.cpp): what one encoder's lookahead
+ *      holds (encoder/lookahead.c:68-129).  Each push uploads frame n and evaluates the whole
+ *      increment of the B-frame cost matrix, slicetype_frame_cost(p0, n, b) for
+ *      n-(bframes+1) <= p0 < b <= n plus the I cost, in the order slicetype_path_cost issues them
+ *      (slicetype.c:1288-1331): per p0 the P evaluation, then the B evaluations. ---- */
+typedef struct x264cu_stream x264cu_stream;
+x264cu_stream *x264cu_stream_open( x264cu_ctx *ctx, int bframes, int want_arrays );
+void     x264cu_stream_close( x264cu_stream *s );
+/* returns the number of evaluations enqueued (asynchronously) or -1; on_device: device pointers */
+int      x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int stride, const uint16_t *inv_qscale, int on_device );
+int      x264cu_stream_sync( x264cu_stream *s );
+/* after sync: stats of slicetype_frame_cost(p0, n, b) of the newest frame n, d0 = b-p0, d1 = n-b */
+int      x264cu_stream_cost( x264cu_stream *s, int d0, int d1, int32_t *out4 );
+int64_t  x264cu_stream_frames( x264cu_stream *s );
+int64_t  x264cu_stream_result_bytes( x264cu_stream *s );
+
 /* ---- batched pixel primitives (config "checkasm-style"): x264_pixel_function_t sad/satd/sa8d/
  *      hadamard_ac (pixel.h:82-103), x264_dct_function_t sub4x4/8x8/16x16_dct (dct.h:28-33),
  *      x264_quant_function_t quant_4x4/8x8 (quant.h:30-33), frame_init_lowres_core (mc.h:303).

@@ -352,6 +352,15 @@ EXPORT int ref_la_put_frame( void *ctx, int idx, const uint8_t *luma, int stride
     return 0;
 }
 
+EXPORT int ref_la_release( void *ctx, int idx )
+{
+    ref_la_t *c = ctx;
+    if( idx < 0 || idx >= LA_MAX_FRAMES || !c->frames[idx] ) return -1;
+    x264_frame_push_unused( c->h, c->frames[idx] );
+    c->frames[idx] = NULL;
+    return 0;
+}
+
 EXPORT int ref_la_lowres_geometry( void *ctx, int idx, int *out )
 {
     ref_la_t *c = ctx;

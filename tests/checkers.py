@@ -156,6 +156,7 @@ class RefLib(_Base):
         L.ref_la_info.argtypes = [vp, vp]
         L.ref_la_cost_mv.argtypes = [vp, vp, C.c_int]
         L.ref_la_put_frame.argtypes = [vp, C.c_int, vp, C.c_int, vp]
+        L.ref_la_release.argtypes = [vp, C.c_int]
         L.ref_la_get_lowres.argtypes = [vp, C.c_int, C.c_int, vp]
         L.ref_la_lowres_geometry.argtypes = [vp, C.c_int, vp]
         L.ref_la_frame_cost_serial.argtypes = [vp] + [C.c_int] * 3

@@ -23,7 +23,7 @@ static thread_local char g_err[512] = "";
 
 enum { K_LOWRES, K_INTRA, K_SEARCH, K_FINAL, K_NCLASS };
 
-struct PendingCopy { void *dst; const void *src; size_t bytes; };   // bytes == 0: stats fix-up (finish_stats)
+struct PendingCopy { void *dst; const void *src; size_t bytes; int kind, bias; };   // kind < 0: raw copy; 0/1/2: I/P/B stats fix-up
 struct TimedSpan { cudaEvent_t a, b; int cls; };
 
 struct x264cu_frame
@@ -231,18 +231,18 @@ struct Span
 };
 
 // i_cost_est semantics completed on the host when the deferred copies are drained (slicetype.c:946-989).
-// p: [0..2] raw sums of the evaluation, [4..5] intra sums of the frame, [6] kind (0 I, 1 P, 2 B), [7] bframe_bias
-static void finish_stats( int32_t *dst, const uint8_t *p )
+// p: [0..2] raw sums of the evaluation (cost_est, cost_est_aq, intra_mbs), [4..5] intra sums of the frame
+static void finish_stats( int32_t *dst, const uint8_t *p, int kind, int bias )
 {
-    const int32_t *raw = (const int32_t *)p, *intra = (const int32_t *)( p + 16 ), *meta = (const int32_t *)( p + 24 );
-    if( meta[0] == 0 )
+    const int32_t *raw = (const int32_t *)p, *intra = (const int32_t *)( p + 16 );
+    if( kind == 0 )
     {   // I evaluation: the sums are the intra sums (slicetype.c:949-953,965-966)
         dst[0] = intra[0]; dst[1] = intra[1]; dst[2] = raw[2]; dst[3] = intra[0];
     }
     else
     {
         dst[3] = raw[0];
-        dst[0] = meta[0] == 2 ? (int32_t)( (uint64_t)raw[0] * 100 / ( 120 + meta[1] ) ) : raw[0];     // :984-985
+        dst[0] = kind == 2 ? (int32_t)( (uint64_t)raw[0] * 100 / ( 120 + bias ) ) : raw[0];     // :984-985
         dst[1] = raw[1]; dst[2] = raw[2];
     }
 }
@@ -252,8 +252,8 @@ static int ctx_sync( x264cu_ctx *c )
     CU( cudaStreamSynchronize( c->st ) );
     for( const PendingCopy &p : c->copies )
     {
-        if( p.bytes ) memcpy( p.dst, p.src, p.bytes );
-        else finish_stats( (int32_t *)p.dst, (const uint8_t *)p.src );
+        if( p.kind < 0 ) memcpy( p.dst, p.src, p.bytes );
+        else finish_stats( (int32_t *)p.dst, (const uint8_t *)p.src, p.kind, p.bias );
     }
     c->copies.clear();
     c->pin_used = 0; c->jobs_used = 0; c->arena_used = 0;
@@ -328,7 +328,7 @@ static int queue_d2h( x264cu_ctx *c, void *dst, const void *dsrc, size_t bytes )
     uint8_t *p = pin_alloc_sync( c, bytes );
     if( !p ) return -1;
     CU( cudaMemcpyAsync( p, dsrc, bytes, cudaMemcpyDeviceToHost, c->st ) );
-    c->copies.push_back( { dst, p, bytes } );
+    c->copies.push_back( { dst, p, bytes, -1, 0 } );
     return 0;
 }
 
@@ -557,38 +557,119 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
         launch_final( d, (int)finals.size(), P, c->st );
     }
     CU( cudaGetLastError() );
-    // result copies (slicetype-cl.c:254-280,513-535,613-649)
+    // result copies (slicetype-cl.c:254-280,513-535,613-649): every requested array is gathered on the
+    // device into one staging block (one launch), which then crosses PCIe as ONE transfer -- straight
+    // into the caller's memory when that is page-locked and laid out like the block, else through the
+    // page-locked buffer with the per-array memcpy deferred to flush, as the reference does.
+    struct HostOut { void *dst; size_t off, bytes; int kind; };
+    std::vector<GatherSeg> segs;
+    std::vector<HostOut> arrs, sts;
+    size_t offA = 0, offS = 0;
+    auto addA = [&]( void *dst, const void *dsrc, size_t bytes )
+    {
+        if( !dst ) return;
+        segs.push_back( { (const uint8_t *)dsrc, (unsigned long long)offA, (unsigned)bytes } );
+        arrs.push_back( { dst, offA, bytes, -1 } );
+        offA += align_up( bytes, 64 );
+    };
     for( int i = 0; i < n; i++ )
     {
         const x264cu_job &j = jobs[i];
         const x264cu_out &o = j.out;
         int ti = tri_index( c, j.d0, j.d1 );
         const int32_t *st = j.fenc->stats + (size_t)ti * c->stat_pitch;
-        if( queue_d2h( c, o.lowres_costs, j.fenc->costs + (size_t)ti * P.nmb, (size_t)P.nmb * 2 ) ) return -1;
+        // order: intra_costs, lowres_costs, row_satds, mvs[0], mv_costs[0], mvs[1], mv_costs[1], intra_row_satds, intra_stats
+        addA( o.intra_costs, j.fenc->costs, (size_t)P.nmb * 2 );
+        addA( o.lowres_costs, j.fenc->costs + (size_t)ti * P.nmb, (size_t)P.nmb * 2 );
+        addA( o.row_satds, j.d0 + j.d1 ? st : j.fenc->stats, (size_t)P.mbh * 4 );
         for( int l = 0; l < 2; l++ )
         {
             int dist = l ? j.d1 : j.d0;
             if( dist == 0 ) continue;
             int fi = field_index( c, l, dist );
-            if( queue_d2h( c, o.mvs[l], j.fenc->mvs + (size_t)fi * P.nmb * 2, (size_t)P.nmb * 4 ) ) return -1;
-            if( queue_d2h( c, o.mv_costs[l], j.fenc->mvcosts + (size_t)fi * P.nmb, (size_t)P.nmb * 4 ) ) return -1;
+            addA( o.mvs[l], j.fenc->mvs + (size_t)fi * P.nmb * 2, (size_t)P.nmb * 4 );
+            addA( o.mv_costs[l], j.fenc->mvcosts + (size_t)fi * P.nmb, (size_t)P.nmb * 4 );
         }
-        if( queue_d2h( c, o.row_satds, j.d0 + j.d1 ? st : j.fenc->stats, (size_t)P.mbh * 4 ) ) return -1;
-        if( queue_d2h( c, o.intra_costs, j.fenc->costs, (size_t)P.nmb * 2 ) ) return -1;
-        if( queue_d2h( c, o.intra_row_satds, j.fenc->stats, (size_t)P.mbh * 4 ) ) return -1;
-        if( queue_d2h( c, o.intra_stats, j.fenc->stats + P.mbh, 8 ) ) return -1;
-        if( o.stats )
-        {   // raw device sums -> i_cost_est semantics are completed on the host at flush (slicetype.c:983-989)
-            uint8_t *p = pin_alloc_sync( c, 32 );
-            if( !p ) return -1;
-            CU( cudaMemcpyAsync( p, st + P.mbh, 12, cudaMemcpyDeviceToHost, c->st ) );
-            CU( cudaMemcpyAsync( p + 16, j.fenc->stats + P.mbh, 8, cudaMemcpyDeviceToHost, c->st ) );
-            c->copies.push_back( { o.stats, p, 0 } );     // bytes == 0: marks a stats fix-up, see below
-            // encode what the fix-up needs right behind the raw data
-            int32_t *meta = (int32_t *)( p + 24 );
-            meta[0] = ( j.d0 + j.d1 == 0 ) ? 0 : ( j.d1 > 0 ? 2 : 1 );
-            meta[1] = c->cfg.bframe_bias;
+        addA( o.intra_row_satds, j.fenc->stats, (size_t)P.mbh * 4 );
+        addA( o.intra_stats, j.fenc->stats + P.mbh, 8 );
+    }
+    for( int i = 0; i < n; i++ )
+    {
+        const x264cu_job &j = jobs[i];
+        if( !j.out.stats ) continue;
+        int ti = tri_index( c, j.d0, j.d1 );
+        const int32_t *st = j.fenc->stats + (size_t)ti * c->stat_pitch;
+        sts.push_back( { j.out.stats, offS, 32, ( j.d0 + j.d1 == 0 ) ? 0 : ( j.d1 > 0 ? 2 : 1 ) } );
+        offS += 32;
+    }
+    if( segs.empty() && sts.empty() ) return 0;
+    const size_t baseS = align_up( offA, 256 ), total = baseS + offS;
+    if( c->arena_used + total + 4096 > c->arena_size )
+    {
+        if( ctx_sync( c ) ) return -1;
+        if( total + 4096 > c->arena_size )
+        {
+            cudaFree( c->arena );
+            c->arena_size = total * 2;
+            CU( cudaMalloc( &c->arena, c->arena_size ) );
         }
+    }
+    uint8_t *dstage = arena_alloc( c, total );
+    for( const HostOut &h : sts )
+    {
+        // recover the job: raw sums live right behind its row sums, intra sums behind the frame's intra rows
+        (void)h;
+    }
+    {
+        size_t k = 0;
+        for( int i = 0; i < n; i++ )
+        {
+            const x264cu_job &j = jobs[i];
+            if( !j.out.stats ) continue;
+            int ti = tri_index( c, j.d0, j.d1 );
+            const int32_t *st = j.fenc->stats + (size_t)ti * c->stat_pitch;
+            segs.push_back( { (const uint8_t *)( st + P.mbh ), (unsigned long long)( baseS + sts[k].off ), 12u } );
+            segs.push_back( { (const uint8_t *)( j.fenc->stats + P.mbh ), (unsigned long long)( baseS + sts[k].off + 16 ), 8u } );
+            k++;
+        }
+    }
+    const GatherSeg *dsegs;
+    if( push_jobs( c, segs, &dsegs ) ) return -1;
+    c->launches++;
+    launch_gather( dsegs, (int)segs.size(), dstage, c->st );
+    CU( cudaGetLastError() );
+    if( offA )
+    {
+        bool direct = is_pinned( arrs[0].dst );
+        uint8_t *base = (uint8_t *)arrs[0].dst - arrs[0].off;
+        for( const HostOut &h : arrs ) direct = direct && (uint8_t *)h.dst == base + h.off;
+        if( direct )
+            CU( cudaMemcpyAsync( base, dstage, offA, cudaMemcpyDeviceToHost, c->st ) );
+        else
+        {
+            uint8_t *p = pin_alloc( c, offA );
+            if( !p )
+            {   // staging full: drain what is queued; the kernels above are then complete as well
+                if( ctx_sync( c ) ) return -1;
+                p = pin_alloc( c, offA );
+                if( !p ) FAIL( "staging buffer too small for %zu result bytes", offA );
+                // the arena was recycled by the sync but its contents are intact until the next batch
+            }
+            CU( cudaMemcpyAsync( p, dstage, offA, cudaMemcpyDeviceToHost, c->st ) );
+            for( const HostOut &h : arrs ) c->copies.push_back( { h.dst, p + h.off, h.bytes, -1, 0 } );
+        }
+    }
+    if( offS )
+    {
+        uint8_t *p = pin_alloc( c, offS );
+        if( !p )
+        {
+            if( ctx_sync( c ) ) return -1;
+            p = pin_alloc( c, offS );
+            if( !p ) FAIL( "staging buffer too small" );
+        }
+        CU( cudaMemcpyAsync( p, dstage + baseS, offS, cudaMemcpyDeviceToHost, c->st ) );
+        for( const HostOut &h : sts ) c->copies.push_back( { h.dst, p + h.off, 32, h.kind, c->cfg.bframe_bias } );
     }
     return 0;
 }

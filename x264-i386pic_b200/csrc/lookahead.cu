@@ -727,3 +727,32 @@ void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStr
     dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
     final_kernel<<<grid, CTA_THREADS, 0, st>>>( d_jobs, P );
 }
+
+// ------------------------------------------------------------------------------------------------
+// result gather: one CTA per requested array, 128-bit copies when both ends allow it
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_kernel( const GatherSeg *__restrict__ segs, uint8_t *__restrict__ dst_base )
+{
+    const GatherSeg s = segs[blockIdx.x];
+    const uint8_t *src = s.src;
+    uint8_t *dst = dst_base + s.dst_off;
+    if( ( ( (uintptr_t)src | (uintptr_t)dst ) & 15 ) == 0 )
+    {
+        const unsigned n16 = s.bytes >> 4;
+        for( unsigned i = threadIdx.x; i < n16; i += blockDim.x ) ( (uint4 *)dst )[i] = __ldg( (const uint4 *)src + i );
+        for( unsigned i = ( n16 << 4 ) + threadIdx.x; i < s.bytes; i += blockDim.x ) dst[i] = src[i];
+    }
+    else if( ( ( (uintptr_t)src | (uintptr_t)dst ) & 3 ) == 0 )
+    {
+        const unsigned n4 = s.bytes >> 2;
+        for( unsigned i = threadIdx.x; i < n4; i += blockDim.x ) ( (u32 *)dst )[i] = __ldg( (const u32 *)src + i );
+        for( unsigned i = ( n4 << 2 ) + threadIdx.x; i < s.bytes; i += blockDim.x ) dst[i] = src[i];
+    }
+    else
+        for( unsigned i = threadIdx.x; i < s.bytes; i += blockDim.x ) dst[i] = src[i];
+}
+
+void launch_gather( const GatherSeg *d_segs, int nsegs, uint8_t *dst_base, cudaStream_t st )
+{
+    if( nsegs > 0 ) gather_kernel<<<nsegs, 256, 0, st>>>( d_segs, dst_base );
+}

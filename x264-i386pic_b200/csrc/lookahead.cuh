@@ -48,6 +48,10 @@ struct FinalJob
     int dist_scale_factor, bipred_weight;
 };
 
+// One contiguous copy of the result gather (device -> device staging block).
+struct GatherSeg { const uint8_t *src; unsigned long long dst_off; unsigned bytes; };
+void launch_gather( const GatherSeg *d_segs, int nsegs, uint8_t *dst_base, cudaStream_t st );
+
 void launch_lowres( const uint8_t *luma, int stride, int width, int height, uint8_t *planes,
                     const LaParams &P, cudaStream_t st );
 void launch_weight_plane( const uint8_t *src, uint8_t *dst, int64_t bytes, int scale, int denom, int offset, cudaStream_t st );

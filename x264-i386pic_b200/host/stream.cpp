@@ -1,0 +1,137 @@
+// stream.cpp -- host-side lookahead window over the C ABI (plain C++, no CUDA here).
+//
+// One x264cu_stream is what one encoder's lookahead thread holds (encoder/lookahead.c:68-129): a
+// sliding window of frames.  Pushing a frame does what x264_frame_init_lowres +
+// x264_opencl_slicetype_prep (slicetype-cl.c:653-712) do for the newest frame n, generalised to
+// the whole B-frame cost matrix: every slicetype_frame_cost(p0, p1 = n, b) with
+// n - (bframes+1) <= p0 < b <= n that slicetype_path (slicetype.c:1333-1390) or scenecut (:1430)
+// can ask for, plus the I cost -- 33 new searches and 153 + 1 evaluations per frame at bframes = 16.
+// The decision logic then reads costs from the matrix instead of calling into the device.
+#include "../../include/x264cu.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+struct x264cu_stream
+{
+    x264cu_ctx *ctx;
+    int bframes, depth;                 // depth = bframes + 2 frames alive
+    int mbw, mbh, nmb;
+    int want_arrays;                    // also bring lowres_costs / row_satds / MVs back (the full hook protocol)
+    std::vector<x264cu_frame *> ring;   // frame n lives in ring[n % depth]
+    int64_t n_pushed;
+    // host results of the most recent push: stats[d0][d1][4] for p1 = newest
+    std::vector<int32_t> stats;         // (B+2)*(B+2)*4, indexed [d0*(B+2)+d1]
+    std::vector<int32_t> intra_stats;   // 2
+    // optional array destinations (pinned when possible)
+    uint8_t *arr; size_t arr_bytes; bool arr_pinned;
+    std::vector<x264cu_job> jobs;
+};
+
+extern "C" void *x264cu_host_alloc( x264cu_ctx *ctx, size_t bytes );
+extern "C" void  x264cu_host_free( x264cu_ctx *ctx, void *p );
+
+extern "C" x264cu_stream *x264cu_stream_open( x264cu_ctx *ctx, int bframes, int want_arrays )
+{
+    int info[6];
+    if( !ctx || bframes < 0 || bframes > X264CU_BFRAME_MAX || x264cu_info( ctx, info ) ) return NULL;
+    x264cu_stream *s = new x264cu_stream();
+    s->ctx = ctx; s->bframes = bframes; s->depth = bframes + 2;
+    s->mbw = info[0]; s->mbh = info[1]; s->nmb = info[0] * info[1];
+    s->want_arrays = want_arrays;
+    s->n_pushed = 0;
+    s->stats.assign( (size_t)( bframes+2 ) * ( bframes+2 ) * 4, -1 );
+    s->intra_stats.assign( 2, -1 );
+    s->arr = NULL; s->arr_bytes = 0; s->arr_pinned = false;
+    for( int i = 0; i < s->depth; i++ )
+    {
+        x264cu_frame *f = x264cu_frame_new( ctx );
+        if( !f ) { for( x264cu_frame *g : s->ring ) x264cu_frame_free( ctx, g ); delete s; return NULL; }
+        s->ring.push_back( f );
+    }
+    if( want_arrays )
+    {   // per evaluation: lowres_costs (u16 x nmb) + row_satds (i32 x mbh); per new search: mvs (i16x2 x nmb)
+        size_t ntri = (size_t)( bframes+1 ) * ( bframes+2 ) / 2 + 1, nsearch = 2 * (size_t)bframes + 1;
+        s->arr_bytes = ntri * ( (size_t)s->nmb * 2 + (size_t)s->mbh * 4 + 64 ) + nsearch * ( (size_t)s->nmb * 4 + 64 );
+        s->arr = (uint8_t *)x264cu_host_alloc( ctx, s->arr_bytes );
+        s->arr_pinned = s->arr != NULL;
+        if( !s->arr ) s->arr = (uint8_t *)malloc( s->arr_bytes );
+    }
+    return s;
+}
+
+extern "C" void x264cu_stream_close( x264cu_stream *s )
+{
+    if( !s ) return;
+    x264cu_flush( s->ctx );
+    for( x264cu_frame *f : s->ring ) x264cu_frame_free( s->ctx, f );
+    if( s->arr ) { if( s->arr_pinned ) x264cu_host_free( s->ctx, s->arr ); else free( s->arr ); }
+    delete s;
+}
+
+// Enqueue frame n = number of frames pushed so far.  on_device: `luma`/`inv_qscale` are device pointers.
+// Returns the number of evaluations enqueued, or -1.
+extern "C" int x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int stride, const uint16_t *inv_qscale, int on_device )
+{
+    if( !s || !luma ) return -1;
+    const int B = s->bframes, D = s->depth;
+    const int64_t n = s->n_pushed;
+    x264cu_frame *fn = s->ring[n % D];
+    int r = on_device ? x264cu_frame_upload_device( s->ctx, fn, luma, stride, inv_qscale )
+                      : x264cu_frame_upload( s->ctx, fn, luma, stride, inv_qscale );
+    if( r ) return -1;
+    s->jobs.clear();
+    std::fill( s->stats.begin(), s->stats.end(), -1 );
+    uint8_t *ap = s->arr;
+    auto take = [&]( size_t bytes ) { uint8_t *p = ap; ap += ( bytes + 63 ) & ~(size_t)63; return p; };
+    // the I cost of the new frame (scenecut needs icost, slicetype.c:1401)
+    {
+        x264cu_job j;
+        memset( &j, 0, sizeof(j) );
+        j.fenc = j.fref0 = j.fref1 = fn; j.d0 = j.d1 = 0;
+        j.out.stats = &s->stats[0];
+        j.out.intra_stats = s->intra_stats.data();
+        if( s->want_arrays ) j.out.intra_costs = (uint16_t *)take( (size_t)s->nmb * 2 );
+        s->jobs.push_back( j );
+    }
+    // P evaluations first (they provide fref1->lowres_mvs[0] for the temporal-direct candidate of the
+    // B evaluations between p0 and n, slicetype.c:629), then the B evaluations, as slicetype_path_cost orders them
+    const int64_t lo = n - ( B + 1 ) < 0 ? 0 : n - ( B + 1 );
+    for( int64_t p0 = n - 1; p0 >= lo; p0-- )
+        for( int k = 0; k < (int)( n - p0 ); k++ )
+        {   // k == 0: the P evaluation b = n; then the B evaluations b = p0+1 .. n-1
+            const int64_t b = k == 0 ? n : p0 + k;
+            x264cu_job j;
+            memset( &j, 0, sizeof(j) );
+            j.fenc = s->ring[b % D]; j.fref0 = s->ring[p0 % D]; j.fref1 = fn;
+            j.d0 = (int)( b - p0 ); j.d1 = (int)( n - b );
+            j.out.stats = &s->stats[( (size_t)j.d0 * ( B+2 ) + j.d1 ) * 4];
+            if( s->want_arrays )
+            {
+                j.out.lowres_costs = (uint16_t *)take( (size_t)s->nmb * 2 );
+                j.out.row_satds = (int32_t *)take( (size_t)s->mbh * 4 );
+                // MV fields of the searches that are new with frame n: L0 of frame n, L1 of older frames towards n
+                if( b == n ) j.out.mvs[0] = (int16_t *)take( (size_t)s->nmb * 4 );
+                else if( p0 == b - 1 ) j.out.mvs[1] = (int16_t *)take( (size_t)s->nmb * 4 );
+            }
+            s->jobs.push_back( j );
+        }
+    if( x264cu_frame_cost_batch( s->ctx, s->jobs.data(), (int)s->jobs.size() ) ) return -1;
+    s->n_pushed++;
+    return (int)s->jobs.size();
+}
+
+extern "C" int x264cu_stream_sync( x264cu_stream *s ) { return s ? x264cu_flush( s->ctx ) : -1; }
+
+// stats of slicetype_frame_cost( p0 = n-d0-d1.., ) for the newest frame n as p1: d0 = b-p0, d1 = n-b.
+// out4: cost_est (B: scaled), cost_est_aq, intra_mbs, raw cost; -1 when not evaluated.
+extern "C" int x264cu_stream_cost( x264cu_stream *s, int d0, int d1, int32_t *out4 )
+{
+    if( !s || d0 < 0 || d1 < 0 || d0 + d1 > s->bframes + 1 ) return -1;
+    memcpy( out4, &s->stats[( (size_t)d0 * ( s->bframes+2 ) + d1 ) * 4], 16 );
+    return 0;
+}
+
+extern "C" int64_t x264cu_stream_frames( x264cu_stream *s ) { return s ? s->n_pushed : -1; }
+extern "C" int64_t x264cu_stream_result_bytes( x264cu_stream *s ) { return s ? (int64_t)s->arr_bytes : -1; }

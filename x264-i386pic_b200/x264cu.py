@@ -81,6 +81,16 @@ def load():
     L.x264cu_sub_dct_grid.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.x264cu_quant.argtypes = [vp, C.c_int, vp, C.c_int64, vp, vp, vp, C.c_int]
     L.x264cu_lowres_core.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.x264cu_stream_open.restype = vp
+    L.x264cu_stream_open.argtypes = [vp, C.c_int, C.c_int]
+    L.x264cu_stream_close.argtypes = [vp]
+    L.x264cu_stream_push.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.x264cu_stream_sync.argtypes = [vp]
+    L.x264cu_stream_cost.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.x264cu_stream_frames.argtypes = [vp]
+    L.x264cu_stream_frames.restype = C.c_int64
+    L.x264cu_stream_result_bytes.argtypes = [vp]
+    L.x264cu_stream_result_bytes.restype = C.c_int64
     L.x264cu_malloc.restype = vp
     L.x264cu_malloc.argtypes = [vp, C.c_size_t]
     L.x264cu_free.argtypes = [vp, vp]
