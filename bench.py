@@ -278,7 +278,9 @@ def main():
         pass
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
 
-    frames = [make_stream_frames(1000 * rank + 7 * s + 1, per_stream) for s in range(S)]
+    import shard
+    my_streams = shard.assign_streams(S * world, world, rank)        # global stream ids of this rank
+    frames = [make_stream_frames(shard.stream_seed(g), per_stream) for g in my_streams]
     fbytes = W * H
     pinned, dev = [], []
     for s in range(S):

@@ -104,6 +104,11 @@ int x264cu_frame_upload_device( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t 
  * (x264_opencl_finalize_cost) and the copies into `out`.  Evaluations are cached per frame exactly
  * like i_cost_est / the 0x7FFF MV sentinel (slicetype.c:848-867). */
 int x264cu_frame_cost( x264cu_ctx *ctx, const x264cu_job *job );
+/* x264_opencl_motionsearch (slicetype-cl.c:349): enqueue only the search of one field
+ * (frame `fenc` against `fref`, list 0/1, dist = |b - ref|), unless it is cached.  `w` applies to
+ * list 0 only; mvs / mv_costs are optional host destinations (i16x2 / i32 per block). */
+int x264cu_motionsearch( x264cu_ctx *ctx, x264cu_frame *fenc, x264cu_frame *fref, int list, int dist,
+                         const x264cu_weight *w, int16_t *mvs, int32_t *mv_costs );
 /* x264_opencl_slicetype_prep (slicetype-cl.c:653-712): many evaluations, semantically in array
  * order, executed as a few wide launches (all searches of a pass together, all decisions together). */
 int x264cu_frame_cost_batch( x264cu_ctx *ctx, const x264cu_job *jobs, int n_jobs );

@@ -450,58 +450,12 @@ static inline uint8_t *planeF( x264cu_ctx *c, x264cu_frame *f ) { return f->plan
 static inline int tri_index( x264cu_ctx *c, int d0, int d1 ) { return d0 * ( c->cfg.bframes + 2 ) + d1; }
 static inline int field_index( x264cu_ctx *c, int list, int dist ) { return list * ( c->cfg.bframes + 1 ) + dist - 1; }
 
-static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
+// K passes of the dependency-free schedule over a set of (fenc, ref, list, dist) fields, each pass
+// ONE launch over all fields (x264_opencl_motionsearch batched as in x264_opencl_slicetype_prep).
+static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
 {
     const LaParams &P = c->P;
-    const int B = c->cfg.bframes, K = c->cfg.search_passes;
-    std::vector<SearchTask> tasks;
-    std::vector<FinalJob> finals;
-    // pass 1 over the jobs in semantic order: cache bookkeeping exactly as slicetype_frame_cost does it
-    for( int i = 0; i < n; i++ )
-    {
-        const x264cu_job &j = jobs[i];
-        if( !j.fenc || !j.fref0 || !j.fref1 || j.d0 < 0 || j.d1 < 0 || j.d0 + j.d1 > B + 1 )
-            FAIL( "x264cu_frame_cost: bad job %d (d0=%d d1=%d bframes=%d)", i, j.d0, j.d1, B );
-        if( !j.fenc->uploaded || !j.fref0->uploaded || !j.fref1->uploaded ) FAIL( "x264cu_frame_cost: frame not uploaded" );
-        // An I evaluation after any other evaluation of the frame is a cache hit in the reference
-        // (i_cost_est[0][0] was filled by the intra section of that evaluation, slicetype.c:848,949-953)
-        if( j.d0 == 0 && j.d1 == 0 && j.fenc->any_eval ) j.fenc->evaluated[0][0] = 1;
-        j.fenc->any_eval = true;
-        if( j.fenc->evaluated[j.d0][j.d1] ) continue;                  // i_cost_est >= 0 (slicetype.c:848)
-        j.fenc->evaluated[j.d0][j.d1] = 1;
-        FinalJob F;
-        memset( &F, 0, sizeof(F) );
-        F.fenc = planeF( c, j.fenc ); F.ref0 = planeF( c, j.fref0 ); F.ref1 = planeF( c, j.fref1 );
-        F.b_bidir = j.d1 > 0; F.b_intra_only = j.d0 == 0 && j.d1 == 0;
-        for( int l = 0; l < 2; l++ )
-        {
-            int dist = l ? j.d1 : j.d0;
-            if( dist == 0 ) continue;
-            int fi = field_index( c, l, dist );
-            if( !j.fenc->searched[l][dist-1] )
-            {   // do_search[l] (slicetype.c:855-867)
-                j.fenc->searched[l][dist-1] = 1;
-                SearchTask t = { j.fenc, l ? j.fref1 : j.fref0, l, dist, { 0, 0, 0, 0 } };
-                if( l == 0 && j.d1 == 0 && j.weight.enabled ) t.w = j.weight;      // w only when b == p1 (:859-864)
-                tasks.push_back( t );
-            }
-            F.mv[l] = j.fenc->mvs + (size_t)fi * P.nmb * 2;
-            F.mvcost[l] = j.fenc->mvcosts + (size_t)fi * P.nmb;
-        }
-        if( F.b_bidir && j.fref1->searched[0][j.d0 + j.d1 - 1] )      // slicetype.c:629
-            F.dmv_src = j.fref1->mvs + (size_t)field_index( c, 0, j.d0 + j.d1 ) * P.nmb * 2;
-        F.intra = j.fenc->costs;
-        F.inv_qscale = j.fenc->inv_qscale;
-        int ti = tri_index( c, j.d0, j.d1 );
-        F.lowres_costs = j.fenc->costs + (size_t)ti * P.nmb;
-        F.row_satds = j.fenc->stats + (size_t)ti * c->stat_pitch;
-        F.stats = F.row_satds + P.mbh;
-        if( F.b_intra_only ) { F.row_satds = NULL; }                   // intra sums were produced at upload
-        F.dist_scale_factor = ( j.d0 + j.d1 ) ? ( ( j.d0 << 8 ) + ( ( j.d0 + j.d1 ) >> 1 ) ) / ( j.d0 + j.d1 ) : 128;   // :869-870
-        F.bipred_weight = P.weighted_bipred ? 64 - ( F.dist_scale_factor >> 2 ) : 32;                                    // :529
-        finals.push_back( F );
-    }
-    // searches: K passes, each one launch over all fields
+    const int K = c->cfg.search_passes;
     if( !tasks.empty() )
     {
         size_t field_bytes = (size_t)P.nmb * 4;
@@ -549,6 +503,61 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
             launch_search( d, (int)sj.size(), P, c->st );
         }
     }
+    return 0;
+}
+
+static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
+{
+    const LaParams &P = c->P;
+    const int B = c->cfg.bframes;
+    std::vector<SearchTask> tasks;
+    std::vector<FinalJob> finals;
+    // pass 1 over the jobs in semantic order: cache bookkeeping exactly as slicetype_frame_cost does it
+    for( int i = 0; i < n; i++ )
+    {
+        const x264cu_job &j = jobs[i];
+        if( !j.fenc || !j.fref0 || !j.fref1 || j.d0 < 0 || j.d1 < 0 || j.d0 + j.d1 > B + 1 )
+            FAIL( "x264cu_frame_cost: bad job %d (d0=%d d1=%d bframes=%d)", i, j.d0, j.d1, B );
+        if( !j.fenc->uploaded || !j.fref0->uploaded || !j.fref1->uploaded ) FAIL( "x264cu_frame_cost: frame not uploaded" );
+        // An I evaluation after any other evaluation of the frame is a cache hit in the reference
+        // (i_cost_est[0][0] was filled by the intra section of that evaluation, slicetype.c:848,949-953)
+        if( j.d0 == 0 && j.d1 == 0 && j.fenc->any_eval ) j.fenc->evaluated[0][0] = 1;
+        j.fenc->any_eval = true;
+        if( j.fenc->evaluated[j.d0][j.d1] ) continue;                  // i_cost_est >= 0 (slicetype.c:848)
+        j.fenc->evaluated[j.d0][j.d1] = 1;
+        FinalJob F;
+        memset( &F, 0, sizeof(F) );
+        F.fenc = planeF( c, j.fenc ); F.ref0 = planeF( c, j.fref0 ); F.ref1 = planeF( c, j.fref1 );
+        F.b_bidir = j.d1 > 0; F.b_intra_only = j.d0 == 0 && j.d1 == 0;
+        for( int l = 0; l < 2; l++ )
+        {
+            int dist = l ? j.d1 : j.d0;
+            if( dist == 0 ) continue;
+            int fi = field_index( c, l, dist );
+            if( !j.fenc->searched[l][dist-1] )
+            {   // do_search[l] (slicetype.c:855-867)
+                j.fenc->searched[l][dist-1] = 1;
+                SearchTask t = { j.fenc, l ? j.fref1 : j.fref0, l, dist, { 0, 0, 0, 0 } };
+                if( l == 0 && j.d1 == 0 && j.weight.enabled ) t.w = j.weight;      // w only when b == p1 (:859-864)
+                tasks.push_back( t );
+            }
+            F.mv[l] = j.fenc->mvs + (size_t)fi * P.nmb * 2;
+            F.mvcost[l] = j.fenc->mvcosts + (size_t)fi * P.nmb;
+        }
+        if( F.b_bidir && j.fref1->searched[0][j.d0 + j.d1 - 1] )      // slicetype.c:629
+            F.dmv_src = j.fref1->mvs + (size_t)field_index( c, 0, j.d0 + j.d1 ) * P.nmb * 2;
+        F.intra = j.fenc->costs;
+        F.inv_qscale = j.fenc->inv_qscale;
+        int ti = tri_index( c, j.d0, j.d1 );
+        F.lowres_costs = j.fenc->costs + (size_t)ti * P.nmb;
+        F.row_satds = j.fenc->stats + (size_t)ti * c->stat_pitch;
+        F.stats = F.row_satds + P.mbh;
+        if( F.b_intra_only ) { F.row_satds = NULL; }                   // intra sums were produced at upload
+        F.dist_scale_factor = ( j.d0 + j.d1 ) ? ( ( j.d0 << 8 ) + ( ( j.d0 + j.d1 ) >> 1 ) ) / ( j.d0 + j.d1 ) : 128;   // :869-870
+        F.bipred_weight = P.weighted_bipred ? 64 - ( F.dist_scale_factor >> 2 ) : 32;                                    // :529
+        finals.push_back( F );
+    }
+    if( run_searches( c, tasks ) ) return -1;
     if( !finals.empty() )
     {
         const FinalJob *d;
@@ -679,6 +688,27 @@ extern "C" int x264cu_frame_cost_batch( x264cu_ctx *c, const x264cu_job *jobs, i
     if( !c || ( !jobs && n ) ) FAIL( "x264cu_frame_cost_batch: null argument" );
     CU( cudaSetDevice( c->device ) );
     return run_batch( c, jobs, n );
+}
+
+extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_frame *fref, int list, int dist,
+                                    const x264cu_weight *w, int16_t *mvs, int32_t *mv_costs )
+{
+    if( !c || !fenc || !fref || list < 0 || list > 1 || dist < 1 || dist > c->cfg.bframes + 1 ) FAIL( "x264cu_motionsearch: bad argument" );
+    if( !fenc->uploaded || !fref->uploaded ) FAIL( "x264cu_motionsearch: frame not uploaded" );
+    CU( cudaSetDevice( c->device ) );
+    if( !fenc->searched[list][dist-1] )
+    {
+        fenc->searched[list][dist-1] = 1;
+        std::vector<SearchTask> tasks( 1 );
+        tasks[0] = { fenc, fref, list, dist, { 0, 0, 0, 0 } };
+        if( list == 0 && w && w->enabled ) tasks[0].w = *w;
+        if( run_searches( c, tasks ) ) return -1;
+        CU( cudaGetLastError() );
+    }
+    int fi = field_index( c, list, dist );
+    if( queue_d2h( c, mvs, fenc->mvs + (size_t)fi * c->P.nmb * 2, (size_t)c->P.nmb * 4 ) ) return -1;
+    if( queue_d2h( c, mv_costs, fenc->mvcosts + (size_t)fi * c->P.nmb, (size_t)c->P.nmb * 4 ) ) return -1;
+    return 0;
 }
 
 extern "C" int x264cu_frame_cost( x264cu_ctx *c, const x264cu_job *job ) { return x264cu_frame_cost_batch( c, job, 1 ); }

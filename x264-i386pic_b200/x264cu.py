@@ -63,6 +63,7 @@ def load():
     L.x264cu_frame_upload_device.argtypes = [vp, vp, vp, C.c_int, vp]
     L.x264cu_frame_cost.argtypes = [vp, C.POINTER(Job)]
     L.x264cu_frame_cost_batch.argtypes = [vp, C.POINTER(Job), C.c_int]
+    L.x264cu_motionsearch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
     L.x264cu_flush.argtypes = [vp]
     L.x264cu_launch_count.argtypes = [vp]
     L.x264cu_launch_count.restype = C.c_int64
