@@ -84,6 +84,33 @@ def test_frame_costs_match_oracle(W, H, subme, mbtree, aq, passes):
         gpu.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 8])
+@pytest.mark.parametrize("W,H,subme,mbtree,aq", [(352, 288, 7, 1, 1), (360, 270, 1, 0, 1), (200, 120, 7, 0, 0), (32, 32, 7, 1, 1)])
+def test_both_lane_mappings(monkeypatch, lanes, W, H, subme, mbtree, aq):
+    """the thread-per-block kernels (wide launches) and the 8-lanes-per-block kernels (single
+    evaluations) are two mappings of the same search: both must match the oracle bit for bit."""
+    monkeypatch.setenv("X264CU_LANES", str(lanes))
+    x264cu = _cu()
+    frames = synth_frames(W, H, 6, seed=17, pan=(4, -1))
+    rng = np.random.default_rng(6)
+    mvr = x264cu.default_mv_range(W, H)
+    cpu = Lookahead(OracleLib(), "oracle", W, H, bframes=3, subme=subme, mbtree=mbtree, aq=aq, mv_range=mvr)
+    gpu = x264cu.CudaLookahead(W, H, bframes=3, subme=subme, mbtree=mbtree, aq=aq, mv_range=mvr)
+    try:
+        for i, f in enumerate(frames):
+            q = rng.integers(128, 512, cpu.nmb).astype(np.uint16) if aq else None
+            cpu.put_frame(i, f, q)
+            gpu.put_frame(i, f, q)
+        triples = [(0, 0, 0), (0, 1, 1), (0, 4, 4), (0, 4, 2), (0, 4, 1), (0, 4, 3), (2, 5, 3), (2, 5, 5), (3, 4, 4)]
+        sg = gpu.frame_cost_many(triples)
+        for (p0, p1, b), s in zip(triples, sg):
+            assert cpu.frame_cost(p0, p1, b) == s
+            compare_eval(gpu, cpu, p0, p1, b, f"lanes={lanes} ({p0},{p1},{b})")
+    finally:
+        cpu.close()
+        gpu.close()
+
+
 def test_batch_equals_sequential():
     """x264cu_frame_cost_batch == the same evaluations issued one by one (array order semantics)."""
     x264cu = _cu()

@@ -113,6 +113,10 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
     P.aq = cfg->aq != 0;
     P.weighted_bipred = cfg->weighted_bipred != 0;
     P.cost_mv_n = 8 * cfg->mv_range;
+    {   // tuning/test knob: force one of the two lane mappings (default: chosen per launch)
+        const char *e = getenv( "X264CU_LANES" );
+        P.lanes_per_block = e ? atoi( e ) : 0;
+    }
     c->plane_alloc = 4 * (size_t)P.plane_size + 256;
     c->stat_pitch = (int)align_up( P.mbh + 4, 4 );
     CUP( cudaStreamCreateWithFlags( &c->st, cudaStreamNonBlocking ) );

@@ -311,35 +311,234 @@ void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *
 }
 
 // ------------------------------------------------------------------------------------------------
-// motion search
+// motion search and mode decision
+//
+// The control flow (x264_me_search_ref, refine_subpel, the tail of slicetype_mb_cost) is written ONCE,
+// templated on a cost "backend" that says how a block's pixels are spread over lanes:
+//   GroupBE  -- 8 lanes per block (lane = pixel row): lowest latency, used when a launch has few
+//               blocks (single evaluations through the per-call hook);
+//   ThreadBE -- 1 thread per block, 32 horizontally adjacent blocks per warp: a warp-wide row load
+//               touches 2-3 cache lines instead of 8 and nothing is recomputed per lane; used for
+//               the wide launches of the batched path (ncu r01: the 8-lane form was L1TEX-wavefront
+//               bound at 91 %).
+// Both produce identical results (tests run each mapping against the oracle).
 // ------------------------------------------------------------------------------------------------
-struct Me
+struct MeGeo
 {
-    uint2 fenc;
-    const uint8_t *ref;      // this lane's row of the reference F plane at mv 0
-    const uint8_t *ref_w;    // same in the fullpel (possibly weighted) plane
     int wscale, wdenom, woffset;
     int mvpx, mvpy;
     int fminx, fminy, fmaxx, fmaxy;     // mv_limit_fpel
     int sminx, sminy, smaxx, smaxy;     // mv_min_spel / mv_max_spel
 };
 
-__device__ __forceinline__ int mvcost( const uint16_t *tab, const Me &m, int mx, int my )
+__device__ __forceinline__ void me_limits( MeGeo &m, const LaParams &P, int bx, int by )
+{   // slicetype.c:550-562 (the y limits are refreshed at every row start, so they depend on by only)
+    m.sminx = max( 4*( -8*bx - 12 ), -P.mv_range2 );
+    m.smaxx = min( 4*( 8*( P.mbw - bx - 1 ) + 12 ), P.mv_range2 - 1 );
+    m.sminy = max( 4*( -8*by - 12 ), -P.mv_range2 );
+    m.smaxy = min( 4*( 8*( P.mbh - by - 1 ) + 12 ), P.mv_range2 - 1 );
+    m.fminx = m.sminx >> 2; m.fmaxx = m.smaxx >> 2; m.fminy = m.sminy >> 2; m.fmaxy = m.smaxy >> 2;
+}
+
+__device__ __forceinline__ int mvcost( const uint16_t *tab, const MeGeo &m, int mx, int my )
 {   // p_cost_mvx[mx] + p_cost_mvy[my] (me.c:211-212); the table is symmetric (analyse.c:153-157)
     return tab[abs( mx - m.mvpx )] + tab[abs( my - m.mvpy )];
 }
-__device__ __forceinline__ int fpel_part( const Me &m, const LaParams &P, int mx, int my )
-{
-    return (int)sad8( m.fenc, load8u( m.ref_w + (int64_t)my * P.stride + mx ) );
-}
-__device__ __forceinline__ int qpel_sad_part( const Me &m, const LaParams &P, int mx, int my )
-{
-    return (int)sad8( m.fenc, qpel_row( m.ref, P, mx, my, m.wscale, m.wdenom, m.woffset ) );
-}
-__device__ __forceinline__ bool in_range( const Me &m, int mx, int my )
+__device__ __forceinline__ bool in_range( const MeGeo &m, int mx, int my )
 {   // CHECK_MVRANGE (me.c:209)
     return mx >= m.fminx && mx <= m.fmaxx && my >= m.fminy && my <= m.fmaxy;
 }
+
+// 8 pixels at word pointer q (aligned) shifted by sh bits: the row loader of ThreadBE
+__device__ __forceinline__ uint2 ld8w( const u32 *q, u32 sh )
+{
+    u32 w0 = __ldg( q ), w1 = __ldg( q + 1 ), w2 = __ldg( q + 2 );
+    return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+}
+
+// ---- 8 lanes per block -------------------------------------------------------------------------------
+struct GroupBE
+{
+    Grp g;
+    uint2 fenc;              // this lane's row of the block
+    const uint8_t *ref0;     // this lane's row of reference 0's F plane at mv 0
+    const uint8_t *ref1;     // same for reference 1 (decision kernel only)
+    const uint8_t *ref_w;    // this lane's row of the fullpel (possibly weighted) plane of reference 0
+    const LaParams *P;
+
+    __device__ __forceinline__ bool leader() const { return g.r == 0; }
+    __device__ __forceinline__ int zero_cmp( int b_satd ) const { return cmp_rows( fenc, load8u( ref0 ), g, b_satd ); }
+    template<int N> __device__ __forceinline__ void fpel( const int ( &mx )[N], const int ( &my )[N], int ( &c )[N] ) const
+    {
+#pragma unroll
+        for( int k = 0; k < N; k++ ) c[k] = (int)sad8( fenc, load8u( ref_w + (int64_t)my[k] * P->stride + mx[k] ) );
+#pragma unroll
+        for( int k = 0; k + 1 < N; k += 2 ) red8x2( c[k], c[k+1], g );
+        if( N & 1 ) c[N-1] = red8( c[N-1], g );
+    }
+    template<int N> __device__ __forceinline__ void qsad( const MeGeo &m, const int ( &mx )[N], const int ( &my )[N], int ( &c )[N] ) const
+    {
+#pragma unroll
+        for( int k = 0; k < N; k++ ) c[k] = (int)sad8( fenc, qpel_row( ref0, *P, mx[k], my[k], m.wscale, m.wdenom, m.woffset ) );
+#pragma unroll
+        for( int k = 0; k + 1 < N; k += 2 ) red8x2( c[k], c[k+1], g );
+        if( N & 1 ) c[N-1] = red8( c[N-1], g );
+    }
+    __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
+    {
+        return satd_rows( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ), g );
+    }
+    // TRY_BIDIR without the penalty (slicetype.c:579-603)
+    __device__ __forceinline__ int bidir( int mv0x, int mv0y, int mv1x, int mv1y, int w ) const
+    {
+        uint2 a, b;
+        if( !P->b_satd )
+        {   // subme <= 1: hpel planes addressed directly (slicetype.c:582-589)
+            int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
+            a = load8u( ref0 + i0*P->plane_size + ( mv0x >> 2 ) + (int64_t)( mv0y >> 2 ) * P->stride );
+            b = load8u( ref1 + i1*P->plane_size + ( mv1x >> 2 ) + (int64_t)( mv1y >> 2 ) * P->stride );
+        }
+        else
+        {
+            a = qpel_row( ref0, *P, mv0x, mv0y, 0, -1, 0 );
+            b = qpel_row( ref1, *P, mv1x, mv1y, 0, -1, 0 );
+        }
+        return cmp_rows( fenc, make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ), g, P->b_satd );
+    }
+    __device__ __forceinline__ int bidir_zero( int w ) const
+    {   // slicetype.c:648-649
+        uint2 a = load8u( ref0 ), b = load8u( ref1 );
+        return cmp_rows( fenc, make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ), g, P->b_satd );
+    }
+};
+
+// ---- 1 thread per block ---------------------------------------------------------------------------
+template<class RowFn>
+__device__ __forceinline__ int sad8x8_t( const uint2 ( &fenc )[8], RowFn pred )
+{
+    u32 s0 = 0, s1 = 0;
+#pragma unroll
+    for( int r = 0; r < 8; r++ ) { uint2 p = pred( r ); s0 += __vsadu4( fenc[r].x, p.x ); s1 += __vsadu4( fenc[r].y, p.y ); }
+    return (int)( s0 + s1 );
+}
+// x264_pixel_satd_8x8 = two satd_8x4 (pixel.c:290-330), all in registers
+template<class RowFn>
+__device__ __forceinline__ int satd8x8_t( const uint2 ( &fenc )[8], RowFn pred )
+{
+    int total = 0;
+#pragma unroll
+    for( int h = 0; h < 2; h++ )
+    {
+        u32 t[4][4];
+#pragma unroll
+        for( int i = 0; i < 4; i++ )
+        {
+            u32 d[4];
+            diff_row8( fenc[4*h+i], pred( 4*h+i ), d );
+            HADAMARD4( t[i][0], t[i][1], t[i][2], t[i][3], d[0], d[1], d[2], d[3] );
+        }
+        u32 sum = 0;
+#pragma unroll
+        for( int i = 0; i < 4; i++ )
+        {
+            u32 a0, a1, a2, a3;
+            HADAMARD4( a0, a1, a2, a3, t[0][i], t[1][i], t[2][i], t[3][i] );
+            sum += abs2( a0 ) + abs2( a1 ) + abs2( a2 ) + abs2( a3 );
+        }
+        total += (int)( ( ( sum & 0xffff ) + ( sum >> 16 ) ) >> 1 );
+    }
+    return total;
+}
+
+// get_ref (mc.c:221-249) as a row generator: plane/offset selection hoisted out of the row loop
+struct QpelRows
+{
+    const u32 *q1, *q2;      // word pointers of the two source planes at row 0
+    u32 sh1, sh2;            // bit shifts
+    int stride4;             // plane pitch in words
+    bool avg;
+    int wscale, wdenom, woffset;
+    __device__ __forceinline__ QpelRows( const uint8_t *ref, const LaParams &P, int mvx, int mvy, int ws, int wd, int wo )
+    {   // ref: 8-byte aligned block origin in the F plane; plane_size and stride are multiples of 4
+        int qidx = ( ( mvy & 3 ) << 2 ) + ( mvx & 3 );
+        int off = ( mvy >> 2 ) * P.stride + ( mvx >> 2 );
+        int o1 = off + ( ( mvy & 3 ) == 3 ? P.stride : 0 );
+        int o2 = off + ( ( mvx & 3 ) == 3 );
+        q1 = (const u32 *)( ref + c_hpel_ref0[qidx] * P.plane_size ) + ( o1 >> 2 ); sh1 = ( o1 & 3 ) * 8;
+        q2 = (const u32 *)( ref + c_hpel_ref1[qidx] * P.plane_size ) + ( o2 >> 2 ); sh2 = ( o2 & 3 ) * 8;
+        stride4 = P.stride >> 2;
+        avg = ( qidx & 5 ) != 0;
+        wscale = ws; wdenom = wd; woffset = wo;
+    }
+    __device__ __forceinline__ uint2 operator()( int r ) const
+    {
+        uint2 v = ld8w( q1 + r*stride4, sh1 );
+        if( avg )
+        {
+            uint2 w = ld8w( q2 + r*stride4, sh2 );
+            v.x = avg4( v.x, w.x ); v.y = avg4( v.y, w.y );
+        }
+        if( wdenom >= 0 ) { v.x = weight4( v.x, wscale, wdenom, woffset ); v.y = weight4( v.y, wscale, wdenom, woffset ); }
+        return v;
+    }
+};
+
+struct ThreadBE
+{
+    uint2 fenc[8];
+    const uint8_t *ref0, *ref1, *ref_w;      // block origins (8-byte aligned)
+    const LaParams *P;
+
+    __device__ __forceinline__ bool leader() const { return true; }
+    __device__ __forceinline__ int zero_cmp( int b_satd ) const
+    {
+        const u32 *q = (const u32 *)ref0; const int s4 = P->stride >> 2;
+        auto rows = [&]( int r ) { return __ldg( (const uint2 *)( q + r*s4 ) ); };
+        return b_satd ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
+    }
+    template<int N> __device__ __forceinline__ void fpel( const int ( &mx )[N], const int ( &my )[N], int ( &c )[N] ) const
+    {
+        const int s4 = P->stride >> 2;
+#pragma unroll
+        for( int k = 0; k < N; k++ )
+        {
+            int off = my[k] * P->stride + mx[k];
+            const u32 *q = (const u32 *)ref_w + ( off >> 2 ); const u32 sh = ( off & 3 ) * 8;
+            c[k] = sad8x8_t( fenc, [&]( int r ) { return ld8w( q + r*s4, sh ); } );
+        }
+    }
+    template<int N> __device__ __forceinline__ void qsad( const MeGeo &m, const int ( &mx )[N], const int ( &my )[N], int ( &c )[N] ) const
+    {
+#pragma unroll
+        for( int k = 0; k < N; k++ ) c[k] = sad8x8_t( fenc, QpelRows( ref0, *P, mx[k], my[k], m.wscale, m.wdenom, m.woffset ) );
+    }
+    __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
+    {
+        return satd8x8_t( fenc, QpelRows( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) );
+    }
+    __device__ __forceinline__ int bidir( int mv0x, int mv0y, int mv1x, int mv1y, int w ) const
+    {
+        if( !P->b_satd )
+        {
+            const int s4 = P->stride >> 2;
+            int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
+            int o0 = ( mv0x >> 2 ) + ( mv0y >> 2 ) * P->stride, o1 = ( mv1x >> 2 ) + ( mv1y >> 2 ) * P->stride;
+            const u32 *q0 = (const u32 *)( ref0 + i0*P->plane_size ) + ( o0 >> 2 ), *q1 = (const u32 *)( ref1 + i1*P->plane_size ) + ( o1 >> 2 );
+            const u32 h0 = ( o0 & 3 ) * 8, h1 = ( o1 & 3 ) * 8;
+            return sad8x8_t( fenc, [&]( int r ) { uint2 a = ld8w( q0 + r*s4, h0 ), b = ld8w( q1 + r*s4, h1 );
+                                                  return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+        }
+        QpelRows r0( ref0, *P, mv0x, mv0y, 0, -1, 0 ), r1( ref1, *P, mv1x, mv1y, 0, -1, 0 );
+        return satd8x8_t( fenc, [&]( int r ) { uint2 a = r0( r ), b = r1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+    }
+    __device__ __forceinline__ int bidir_zero( int w ) const
+    {
+        const u32 *q0 = (const u32 *)ref0, *q1 = (const u32 *)ref1; const int s4 = P->stride >> 2;
+        auto rows = [&]( int r ) { uint2 a = __ldg( (const uint2 *)( q0 + r*s4 ) ), b = __ldg( (const uint2 *)( q1 + r*s4 ) );
+                                   return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); };
+        return P->b_satd ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
+    }
+};
 
 __constant__ int8_t c_hex2[8][2] = {{-1,-2}, {-2,0}, {-1,2}, {1,2}, {2,0}, {1,-2}, {-1,-2}, {-2,0}};   // me.c:55
 __constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1}, {-1,1}, {1,-1}, {1,1}}; // me.c:56
@@ -347,52 +546,54 @@ __constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1},
 #define FPEL(v) (((v)+2)>>2)
 
 // refine_subpel (me.c:865-992), p_halfpel_thresh == NULL, b_refine_qpel == 0, no chroma
-__device__ __forceinline__ void refine_subpel( const Me &m, const LaParams &P, const uint16_t *tab, const Grp &g,
+template<class BE>
+__device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, const LaParams &P, const uint16_t *tab,
                                                int &bmx, int &bmy, int &bcost, int hpel_iters, int qpel_iters )
 {
     if( hpel_iters )
     {
         if( !P.b_satd )
         {   // la subme 2 (< 3): try the subpel component of the predictor (me.c:889-895)
-            int mx = iclip3( m.mvpx, m.sminx + 2, m.smaxx - 2 );
-            int my = iclip3( m.mvpy, m.sminy + 2, m.smaxy - 2 );
-            if( ( mx - bmx ) | ( my - bmy ) )
+            int mx[1] = { iclip3( m.mvpx, m.sminx + 2, m.smaxx - 2 ) };
+            int my[1] = { iclip3( m.mvpy, m.sminy + 2, m.smaxy - 2 ) };
+            if( ( mx[0] - bmx ) | ( my[0] - bmy ) )
             {
-                int cost = red8( qpel_sad_part( m, P, mx, my ), g ) + mvcost( tab, m, mx, my );
-                if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
+                int c[1];
+                be.qsad( m, mx, my, c );
+                int cost = c[0] + mvcost( tab, m, mx[0], my[0] );
+                if( cost < bcost ) { bcost = cost; bmx = mx[0]; bmy = my[0]; }
             }
         }
         for( int i = hpel_iters; i > 0; i-- )
         {   // me.c:898-921, tie order: up, down, left, right
-            int omx = bmx, omy = bmy;
-            int c0 = qpel_sad_part( m, P, omx, omy-2 ), c1 = qpel_sad_part( m, P, omx, omy+2 );
-            int c2 = qpel_sad_part( m, P, omx-2, omy ), c3 = qpel_sad_part( m, P, omx+2, omy );
-            red8x2( c0, c1, g ); red8x2( c2, c3, g );
-            c0 += mvcost( tab, m, omx, omy-2 ); c1 += mvcost( tab, m, omx, omy+2 );
-            c2 += mvcost( tab, m, omx-2, omy ); c3 += mvcost( tab, m, omx+2, omy );
+            const int omx = bmx, omy = bmy;
+            int mx[4] = { omx, omx, omx-2, omx+2 }, my[4] = { omy-2, omy+2, omy, omy }, c[4];
+            be.qsad( m, mx, my, c );
             int best = -1;
-            if( c0 < bcost ) { bcost = c0; best = 0; }
-            if( c1 < bcost ) { bcost = c1; best = 1; }
-            if( c2 < bcost ) { bcost = c2; best = 2; }
-            if( c3 < bcost ) { bcost = c3; best = 3; }
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+            {
+                int cost = c[k] + mvcost( tab, m, mx[k], my[k] );
+                if( cost < bcost ) { bcost = cost; best = k; }
+            }
             if( best < 0 ) break;
             bmx = omx + ( best == 2 ? -2 : best == 3 ? 2 : 0 );
             bmy = omy + ( best == 0 ? -2 : best == 1 ? 2 : 0 );
         }
     }
     if( P.b_satd )   // mbcmp != fpelcmp: re-measure the winner with SATD (me.c:925-929)
-        bcost = satd_rows( m.fenc, qpel_row( m.ref, P, bmx, bmy, m.wscale, m.wdenom, m.woffset ), g ) + mvcost( tab, m, bmx, bmy );
+        bcost = be.qsatd( m, bmx, bmy ) + mvcost( tab, m, bmx, bmy );
     int bdir = -1;
     for( int i = qpel_iters; i > 0; i-- )
     {   // me.c:947-963
         if( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx ) break;
-        int odir = bdir, omx = bmx, omy = bmy;
+        const int odir = bdir, omx = bmx, omy = bmy;
 #pragma unroll
         for( int k = 0; k < 4; k++ )
             if( ( k ^ 1 ) != odir )
             {
                 int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
-                int cost = satd_rows( m.fenc, qpel_row( m.ref, P, mx, my, m.wscale, m.wdenom, m.woffset ), g ) + mvcost( tab, m, mx, my );
+                int cost = be.qsatd( m, mx, my ) + mvcost( tab, m, mx, my );
                 if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; bdir = k; }
             }
         if( bmx == omx && bmy == omy ) break;
@@ -400,27 +601,33 @@ __device__ __forceinline__ void refine_subpel( const Me &m, const LaParams &P, c
 }
 
 // x264_me_search_ref (me.c:182-420,774-797) for one block; result mv (qpel) and cost
-__device__ __forceinline__ void me_search( const Me &m, const LaParams &P, const uint16_t *tab, const Grp &g,
+template<class BE>
+__device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const LaParams &P, const uint16_t *tab,
                                            const int (*mvc)[2], int i_mvc, int &out_mx, int &out_my, int &out_cost )
 {
     int bmx, bmy, bcost = X264CU_COST_MAX, bpred_cost = X264CU_COST_MAX, bpred_mx = 0, bpred_my = 0, pmvx, pmvy;
-#define COST_MV( mx_, my_ ) { int c_ = red8( fpel_part( m, P, mx_, my_ ), g ) + mvcost( tab, m, (mx_)*4, (my_)*4 ); \
-                              if( c_ < bcost ) { bcost = c_; bmx = mx_; bmy = my_; } }
+#define COST_MV( mx_, my_ ) { int x_[1] = { mx_ }, y_[1] = { my_ }, c_[1]; be.fpel( x_, y_, c_ ); \
+                              c_[0] += mvcost( tab, m, (mx_)*4, (my_)*4 ); \
+                              if( c_[0] < bcost ) { bcost = c_[0]; bmx = mx_; bmy = my_; } }
     if( P.b_satd )
     {   // la subme 4 (>= 3): subpel predictors (me.c:216-275)
         bpred_mx = iclip3( m.mvpx, 4*m.fminx, 4*m.fmaxx );
         bpred_my = iclip3( m.mvpy, 4*m.fminy, 4*m.fmaxy );
         pmvx = bpred_mx; pmvy = bpred_my;
-        bpred_cost = red8( qpel_sad_part( m, P, bpred_mx, bpred_my ), g ) + mvcost( tab, m, bpred_mx, bpred_my );
-        int pmv_cost = bpred_cost;
+        {
+            int x_[1] = { bpred_mx }, y_[1] = { bpred_my }, c_[1];
+            be.qsad( m, x_, y_, c_ );
+            bpred_cost = c_[0] + mvcost( tab, m, bpred_mx, bpred_my );
+        }
+        const int pmv_cost = bpred_cost;
         for( int i = 0; i < i_mvc; i++ )
         {   // x264_predictor_clip (common.h:790-805): drop zero and == pmv, clip the rest
             int mx = mvc[i][0], my = mvc[i][1];
             if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
-            mx = iclip3( mx, 4*m.fminx, 4*m.fmaxx );
-            my = iclip3( my, 4*m.fminy, 4*m.fmaxy );
-            int cost = red8( qpel_sad_part( m, P, mx, my ), g ) + mvcost( tab, m, mx, my );
-            if( cost < bpred_cost ) { bpred_cost = cost; bpred_mx = mx; bpred_my = my; }
+            int x_[1] = { iclip3( mx, 4*m.fminx, 4*m.fmaxx ) }, y_[1] = { iclip3( my, 4*m.fminy, 4*m.fmaxy ) }, c_[1];
+            be.qsad( m, x_, y_, c_ );
+            int cost = c_[0] + mvcost( tab, m, x_[0], y_[0] );
+            if( cost < bpred_cost ) { bpred_cost = cost; bpred_mx = x_[0]; bpred_my = y_[0]; }
         }
         bmx = FPEL( bpred_mx ); bmy = FPEL( bpred_my );
         if( ( bpred_mx & 3 ) | ( bpred_my & 3 ) ) COST_MV( bmx, bmy )
@@ -433,16 +640,20 @@ __device__ __forceinline__ void me_search( const Me &m, const LaParams &P, const
         bmx = iclip3( FPEL( m.mvpx ), m.fminx, m.fmaxx );
         bmy = iclip3( FPEL( m.mvpy ), m.fminy, m.fmaxy );
         pmvx = bmx; pmvy = bmy;
-        bcost = red8( fpel_part( m, P, bmx, bmy ), g );
+        {
+            int x_[1] = { bmx }, y_[1] = { bmy }, c_[1];
+            be.fpel( x_, y_, c_ );
+            bcost = c_[0];
+        }
         int sx = bmx, sy = bmy;
         for( int i = 0; i < i_mvc; i++ )
         {   // x264_predictor_roundclip (common.h:774-788)
             int mx = ( mvc[i][0] + 2 ) >> 2, my = ( mvc[i][1] + 2 ) >> 2;
             if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
-            mx = iclip3( mx, m.fminx, m.fmaxx );
-            my = iclip3( my, m.fminy, m.fmaxy );
-            int cost = red8( fpel_part( m, P, mx, my ), g ) + mvcost( tab, m, mx*4, my*4 );
-            if( cost < bcost ) { bcost = cost; sx = mx; sy = my; }
+            int x_[1] = { iclip3( mx, m.fminx, m.fmaxx ) }, y_[1] = { iclip3( my, m.fminy, m.fmaxy ) }, c_[1];
+            be.fpel( x_, y_, c_ );
+            int cost = c_[0] + mvcost( tab, m, x_[0]*4, y_[0]*4 );
+            if( cost < bcost ) { bcost = cost; sx = x_[0]; sy = y_[0]; }
         }
         bmx = sx; bmy = sy;
         if( pmvx | pmvy ) COST_MV( 0, 0 )
@@ -453,17 +664,16 @@ __device__ __forceinline__ void me_search( const Me &m, const LaParams &P, const
         int i = P.me_range;
         do
         {
-            int ox = bmx, oy = bmy;
-            int c0 = fpel_part( m, P, ox, oy-1 ), c1 = fpel_part( m, P, ox, oy+1 );
-            int c2 = fpel_part( m, P, ox-1, oy ), c3 = fpel_part( m, P, ox+1, oy );
-            red8x2( c0, c1, g ); red8x2( c2, c3, g );
-            c0 += mvcost( tab, m, ox*4, (oy-1)*4 ); c1 += mvcost( tab, m, ox*4, (oy+1)*4 );
-            c2 += mvcost( tab, m, (ox-1)*4, oy*4 ); c3 += mvcost( tab, m, (ox+1)*4, oy*4 );
+            const int ox = bmx, oy = bmy;
+            int mx[4] = { ox, ox, ox-1, ox+1 }, my[4] = { oy-1, oy+1, oy, oy }, c[4];
+            be.fpel( mx, my, c );
             int best = -1;
-            if( c0 < bcost ) { bcost = c0; best = 0; }
-            if( c1 < bcost ) { bcost = c1; best = 1; }
-            if( c2 < bcost ) { bcost = c2; best = 2; }
-            if( c3 < bcost ) { bcost = c3; best = 3; }
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+            {
+                int cost = c[k] + mvcost( tab, m, mx[k]*4, my[k]*4 );
+                if( cost < bcost ) { bcost = cost; best = k; }
+            }
             if( best < 0 ) break;
             bmx = ox + ( best == 2 ? -1 : best == 3 ? 1 : 0 );
             bmy = oy + ( best == 0 ? -1 : best == 1 ? 1 : 0 );
@@ -471,15 +681,15 @@ __device__ __forceinline__ void me_search( const Me &m, const LaParams &P, const
     }
     else
     {   // HEX (me.c:344-420)
-        int c[6];
+        int mx[6], my[6], c[6];
 #pragma unroll
-        for( int k = 0; k < 6; k++ ) c[k] = fpel_part( m, P, bmx + c_hex2[k+1][0], bmy + c_hex2[k+1][1] );
-        red8x2( c[0], c[1], g ); red8x2( c[2], c[3], g ); red8x2( c[4], c[5], g );
+        for( int k = 0; k < 6; k++ ) { mx[k] = bmx + c_hex2[k+1][0]; my[k] = bmy + c_hex2[k+1][1]; }
+        be.fpel( mx, my, c );
         int best = -1;
 #pragma unroll
         for( int k = 0; k < 6; k++ )
         {
-            int cost = c[k] + mvcost( tab, m, ( bmx + c_hex2[k+1][0] )*4, ( bmy + c_hex2[k+1][1] )*4 );
+            int cost = c[k] + mvcost( tab, m, mx[k]*4, my[k]*4 );
             if( cost < bcost ) { bcost = cost; best = k; }
         }
         if( best >= 0 )
@@ -488,17 +698,17 @@ __device__ __forceinline__ void me_search( const Me &m, const LaParams &P, const
             bmx += c_hex2[dir+1][0]; bmy += c_hex2[dir+1][1];
             for( int i = ( P.me_range >> 1 ) - 1; i > 0 && in_range( m, bmx, bmy ); i-- )
             {   // half hexagon not overlapping the previous one
-                int h0 = fpel_part( m, P, bmx + c_hex2[dir][0],   bmy + c_hex2[dir][1] );
-                int h1 = fpel_part( m, P, bmx + c_hex2[dir+1][0], bmy + c_hex2[dir+1][1] );
-                int h2 = fpel_part( m, P, bmx + c_hex2[dir+2][0], bmy + c_hex2[dir+2][1] );
-                red8x2( h0, h1, g ); h2 = red8( h2, g );
-                h0 += mvcost( tab, m, ( bmx + c_hex2[dir][0] )*4,   ( bmy + c_hex2[dir][1] )*4 );
-                h1 += mvcost( tab, m, ( bmx + c_hex2[dir+1][0] )*4, ( bmy + c_hex2[dir+1][1] )*4 );
-                h2 += mvcost( tab, m, ( bmx + c_hex2[dir+2][0] )*4, ( bmy + c_hex2[dir+2][1] )*4 );
+                int hx[3], hy[3], hc[3];
+#pragma unroll
+                for( int k = 0; k < 3; k++ ) { hx[k] = bmx + c_hex2[dir+k][0]; hy[k] = bmy + c_hex2[dir+k][1]; }
+                be.fpel( hx, hy, hc );
                 int b2 = -1;
-                if( h0 < bcost ) { bcost = h0; b2 = 0; }
-                if( h1 < bcost ) { bcost = h1; b2 = 1; }
-                if( h2 < bcost ) { bcost = h2; b2 = 2; }
+#pragma unroll
+                for( int k = 0; k < 3; k++ )
+                {
+                    int cost = hc[k] + mvcost( tab, m, hx[k]*4, hy[k]*4 );
+                    if( cost < bcost ) { bcost = cost; b2 = k; }
+                }
                 if( b2 < 0 ) break;
                 dir += b2 - 1;
                 dir = dir < 0 ? dir + 6 : dir >= 6 ? dir - 6 : dir;      // mod6m1 (me.c:53)
@@ -506,15 +716,15 @@ __device__ __forceinline__ void me_search( const Me &m, const LaParams &P, const
             }
         }
         // square refine (me.c:404-418)
-        int s[8];
+        int sx[8], sy[8], sc[8];
 #pragma unroll
-        for( int k = 0; k < 8; k++ ) s[k] = fpel_part( m, P, bmx + c_sq1[k+1][0], bmy + c_sq1[k+1][1] );
-        red8x2( s[0], s[1], g ); red8x2( s[2], s[3], g ); red8x2( s[4], s[5], g ); red8x2( s[6], s[7], g );
+        for( int k = 0; k < 8; k++ ) { sx[k] = bmx + c_sq1[k+1][0]; sy[k] = bmy + c_sq1[k+1][1]; }
+        be.fpel( sx, sy, sc );
         int bs = 0;
 #pragma unroll
         for( int k = 0; k < 8; k++ )
         {
-            int cost = s[k] + mvcost( tab, m, ( bmx + c_sq1[k+1][0] )*4, ( bmy + c_sq1[k+1][1] )*4 );
+            int cost = sc[k] + mvcost( tab, m, sx[k]*4, sy[k]*4 );
             if( cost < bcost ) { bcost = cost; bs = k+1; }
         }
         bmx += c_sq1[bs][0]; bmy += c_sq1[bs][1];
@@ -528,47 +738,26 @@ __device__ __forceinline__ void me_search( const Me &m, const LaParams &P, const
         cost = bcost;
         if( bmx == pmvx && bmy == pmvy ) cost += mvcost( tab, m, bmx*4, bmy*4 );
         mx = bmx*4; my = bmy*4;
-        refine_subpel( m, P, tab, g, mx, my, cost, 1, 0 );      // subpel_iterations[2] = {0,1,1,0}
+        refine_subpel( be, m, P, tab, mx, my, cost, 1, 0 );      // subpel_iterations[2] = {0,1,1,0}
     }
     else
     {
         if( bpred_cost < bcost ) { mx = bpred_mx; my = bpred_my; }
         else                     { mx = bmx*4;    my = bmy*4; }
         cost = min( bpred_cost, bcost );
-        refine_subpel( m, P, tab, g, mx, my, cost, 1, 1 );      // subpel_iterations[4] = {0,2,1,1}
+        refine_subpel( be, m, P, tab, mx, my, cost, 1, 1 );      // subpel_iterations[4] = {0,2,1,1}
     }
     out_mx = mx; out_my = my; out_cost = cost;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) search_kernel( const SearchJob *__restrict__ jobs, LaParams P )
+// one block of one search pass (slicetype.c:654-702)
+template<class BE>
+__device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, const LaParams &P, const uint16_t *tab,
+                                              int bx, int by, int blk )
 {
-    extern __shared__ uint16_t s_tab[];
-    for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
-    __syncthreads();
-
-    const SearchJob J = jobs[blockIdx.y];
-    Grp g; g.r = threadIdx.x & 7; g.mask = 0xffu << ( threadIdx.x & 24 );
-    const int blk = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );
-    if( blk >= P.nmb ) return;
-    const int bx = blk % P.mbw, by = blk / P.mbw;
-    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
-    if( border && !P.do_edges && P.mbw > 2 && P.mbh > 2 )
-    {   // not evaluated (slicetype.c:823-828): the field keeps frame_new's zeros (frame.c:283-285)
-        if( g.r == 0 ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; }
-        return;
-    }
-    Me m;
-    const int64_t pel = (int64_t)( by*8 + g.r ) * P.stride + bx*8;
-    m.fenc = *(const uint2 *)( J.fenc + pel );
-    m.ref = J.ref + pel; m.ref_w = J.ref_w + pel;
+    MeGeo m;
     m.wscale = J.wscale; m.wdenom = J.wdenom; m.woffset = J.woffset;
-    // slicetype.c:550-562
-    m.sminx = max( 4*( -8*bx - 12 ), -P.mv_range2 );
-    m.smaxx = min( 4*( 8*( P.mbw - bx - 1 ) + 12 ), P.mv_range2 - 1 );
-    m.sminy = max( 4*( -8*by - 12 ), -P.mv_range2 );
-    m.smaxy = min( 4*( 8*( P.mbh - by - 1 ) + 12 ), P.mv_range2 - 1 );
-    m.fminx = m.sminx >> 2; m.fmaxx = m.smaxx >> 2; m.fminy = m.sminy >> 2; m.fmaxy = m.smaxy >> 2;
-
+    me_limits( m, P, bx, by );
     // MV predictor from the previous pass's field (slicetype.c:658-680): right, below, below-left, below-right
     int mvc[4][2] = {{0,0},{0,0},{0,0},{0,0}}, i_mvc = 0;
     if( J.mv_in )
@@ -590,116 +779,150 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel( const SearchJob *_
         m.mvpx = imedian( mvc[0][0], mvc[1][0], mvc[2][0] );
         m.mvpy = imedian( mvc[0][1], mvc[1][1], mvc[2][1] );
     }
-    int mx = 0, my = 0, cost;
+    int mx = 0, my = 0, cost = 0;
     bool skip = false;
     if( !( m.mvpx | m.mvpy ) )
     {   // zero-predictor shortcut (slicetype.c:684-692): unweighted F plane at mv 0
-        cost = cmp_rows( m.fenc, load8u( m.ref ), g, P.b_satd );
+        cost = be.zero_cmp( P.b_satd );
         skip = cost < 64;
     }
     if( !skip )
     {
-        me_search( m, P, s_tab, g, mvc, i_mvc, mx, my, cost );
-        cost -= s_tab[0];                              // slicetype.c:695
+        me_search( be, m, P, tab, mvc, i_mvc, mx, my, cost );
+        cost -= tab[0];                                // slicetype.c:695
         if( mx | my ) cost += 5;                       // 5 * lambda (:696-697)
     }
-    if( g.r == 0 )
+    if( be.leader() )
     {
         ( (int *)J.mv_out )[blk] = ( mx & 0xffff ) | ( my << 16 );
         J.cost_out[blk] = cost;
     }
 }
 
-void launch_search( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
-{
-    dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
-    size_t smem = ( P.cost_mv_n + 1 ) * sizeof(uint16_t);
-    search_kernel<<<grid, CTA_THREADS, smem, st>>>( d_jobs, P );
+__device__ __forceinline__ bool skipped_border( const LaParams &P, int bx, int by )
+{   // never evaluated by slicetype_slice_cost (slicetype.c:823-828)
+    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
+    return border && !P.do_edges && P.mbw > 2 && P.mbh > 2;
 }
 
-// ------------------------------------------------------------------------------------------------
-// mode decision + sums
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int bidir_cost( uint2 fenc, const uint8_t *r0, const uint8_t *r1, const LaParams &P, const Grp &g,
-                                           int mv0x, int mv0y, int mv1x, int mv1y, int w )
-{   // TRY_BIDIR without the penalty (slicetype.c:579-603)
-    uint2 a, b;
-    if( !P.b_satd )
-    {   // subme <= 1: hpel planes addressed directly (slicetype.c:582-589)
-        int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
-        a = load8u( r0 + i0*P.plane_size + ( mv0x >> 2 ) + (int64_t)( mv0y >> 2 ) * P.stride );
-        b = load8u( r1 + i1*P.plane_size + ( mv1x >> 2 ) + (int64_t)( mv1y >> 2 ) * P.stride );
-    }
-    else
-    {
-        a = qpel_row( r0, P, mv0x, mv0y, 0, -1, 0 );
-        b = qpel_row( r1, P, mv1x, mv1y, 0, -1, 0 );
-    }
-    uint2 p = make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) );
-    return cmp_rows( fenc, p, g, P.b_satd );
-}
-
-__global__ void __launch_bounds__(CTA_THREADS) final_kernel( const FinalJob *__restrict__ jobs, LaParams P )
+__global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob *__restrict__ jobs, LaParams P )
 {
-    const FinalJob J = jobs[blockIdx.y];
-    Grp g; g.r = threadIdx.x & 7; g.mask = 0xffu << ( threadIdx.x & 24 );
+    extern __shared__ uint16_t s_tab[];
+    for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
+    __syncthreads();
+    const SearchJob J = jobs[blockIdx.y];
+    GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
     const int blk = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );
     if( blk >= P.nmb ) return;
     const int bx = blk % P.mbw, by = blk / P.mbw;
-    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
-    const bool tiny = P.mbw <= 2 || P.mbh <= 2;
-    if( border && !P.do_edges && !tiny )
-    {
-        if( g.r == 0 && !J.b_intra_only ) J.lowres_costs[blk] = 0;
+    if( skipped_border( P, bx, by ) )
+    {   // the field keeps frame_new's zeros (frame.c:283-285)
+        if( be.g.r == 0 ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; }
         return;
     }
+    const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
+    be.fenc = *(const uint2 *)( J.fenc + pel );
+    be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
+    search_block( be, J, P, s_tab, bx, by, blk );
+}
+
+#define T_TILE_W 32
+#define T_TILE_H 4
+__global__ void __launch_bounds__(T_TILE_W*T_TILE_H) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
+{
+    extern __shared__ uint16_t s_tab[];
+    for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
+    __syncthreads();
+    const SearchJob J = jobs[blockIdx.z];
+    const int bx = blockIdx.x * T_TILE_W + ( threadIdx.x & ( T_TILE_W-1 ) ), by = blockIdx.y * T_TILE_H + threadIdx.x / T_TILE_W;
+    if( bx >= P.mbw || by >= P.mbh ) return;
+    const int blk = by * P.mbw + bx;
+    if( skipped_border( P, bx, by ) ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; return; }
+    ThreadBE be; be.P = &P;
+    const int64_t pel = (int64_t)( by*8 ) * P.stride + bx*8;
+    const uint8_t *src = J.fenc + pel;
+#pragma unroll
+    for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + (size_t)r * P.stride ) );
+    be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
+    search_block( be, J, P, s_tab, bx, by, blk );
+}
+
+static bool use_thread_mapping( const LaParams &P, int njobs )
+{
+    if( P.lanes_per_block == 1 ) return true;
+    if( P.lanes_per_block == 8 ) return false;
+    return (int64_t)njobs * P.nmb >= 4 * 8160;     // wide launches: enough blocks to fill the SMs one thread each
+}
+
+void launch_search( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
+{
+    size_t smem = ( P.cost_mv_n + 1 ) * sizeof(uint16_t);
+    if( use_thread_mapping( P, njobs ) )
+    {
+        dim3 grid( ( P.mbw + T_TILE_W - 1 ) / T_TILE_W, ( P.mbh + T_TILE_H - 1 ) / T_TILE_H, njobs );
+        search_kernel_t<<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
+    }
+    else
+    {
+        dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
+        search_kernel_g<<<grid, CTA_THREADS, smem, st>>>( d_jobs, P );
+    }
+}
+
+// ---- mode decision + sums: the tail of slicetype_mb_cost for one block ----------------------------
+template<class BE>
+__device__ __forceinline__ void final_block( const BE &be, const FinalJob &J, const LaParams &P, int bx, int by, int blk )
+{
+    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
+    const bool tiny = P.mbw <= 2 || P.mbh <= 2;
     int bcost = X264CU_COST_MAX, list_used = 0;
     if( !J.b_intra_only )
     {
-        const int64_t pel = (int64_t)( by*8 + g.r ) * P.stride + bx*8;
-        const uint2 fenc = *(const uint2 *)( J.fenc + pel );
-        int mv[2][2] = {{0,0},{0,0}}, mc[2] = { X264CU_COST_MAX, X264CU_COST_MAX };
-        for( int l = 0; l < 1 + J.b_bidir; l++ )
+        int mv0x, mv0y, mv1x = 0, mv1y = 0, mc0, mc1 = X264CU_COST_MAX;
         {
-            int v = __ldg( (const int *)J.mv[l] + blk );
-            mv[l][0] = (int16_t)( v & 0xffff ); mv[l][1] = v >> 16;
-            mc[l] = __ldg( J.mvcost[l] + blk );
+            int v = __ldg( (const int *)J.mv[0] + blk );
+            mv0x = (int16_t)( v & 0xffff ); mv0y = v >> 16;
+            mc0 = __ldg( J.mvcost[0] + blk );
         }
         if( J.b_bidir )
         {   // slicetype.c:616-652
-            const int sminx = max( 4*( -8*bx - 12 ), -P.mv_range2 ), smaxx = min( 4*( 8*( P.mbw - bx - 1 ) + 12 ), P.mv_range2 - 1 );
-            const int sminy = max( 4*( -8*by - 12 ), -P.mv_range2 ), smaxy = min( 4*( 8*( P.mbh - by - 1 ) + 12 ), P.mv_range2 - 1 );
+            int v = __ldg( (const int *)J.mv[1] + blk );
+            mv1x = (int16_t)( v & 0xffff ); mv1y = v >> 16;
+            mc1 = __ldg( J.mvcost[1] + blk );
+            MeGeo m;
+            me_limits( m, P, bx, by );
             int d0x = 0, d0y = 0, d1x = 0, d1y = 0;
             if( J.dmv_src )
             {
-                int v = __ldg( (const int *)J.dmv_src + blk );
-                int mrx = (int16_t)( v & 0xffff ), mry = v >> 16;
+                int w = __ldg( (const int *)J.dmv_src + blk );
+                int mrx = (int16_t)( w & 0xffff ), mry = w >> 16;
                 d0x = ( mrx * J.dist_scale_factor + 128 ) >> 8;
                 d0y = ( mry * J.dist_scale_factor + 128 ) >> 8;
                 d1x = d0x - mrx; d1y = d0y - mry;
-                d0x = iclip3( d0x, sminx, smaxx ); d0y = iclip3( d0y, sminy, smaxy );
-                d1x = iclip3( d1x, sminx, smaxx ); d1y = iclip3( d1y, sminy, smaxy );
+                d0x = iclip3( d0x, m.sminx, m.smaxx ); d0y = iclip3( d0y, m.sminy, m.smaxy );
+                d1x = iclip3( d1x, m.sminx, m.smaxx ); d1y = iclip3( d1y, m.sminy, m.smaxy );
                 if( !P.b_satd ) { d0x &= ~1; d0y &= ~1; d1x &= ~1; d1y &= ~1; }
             }
-            int cost = bidir_cost( fenc, J.ref0 + pel, J.ref1 + pel, P, g, d0x, d0y, d1x, d1y, J.bipred_weight );
+            int cost = be.bidir( d0x, d0y, d1x, d1y, J.bipred_weight );
             if( cost < bcost ) { bcost = cost; list_used = 3; }
             if( d0x | d0y | d1x | d1y )
             {
-                uint2 a = load8u( J.ref0 + pel ), b = load8u( J.ref1 + pel );
-                uint2 p = make_uint2( biavg4( a.x, b.x, J.bipred_weight ), biavg4( a.y, b.y, J.bipred_weight ) );
-                cost = cmp_rows( fenc, p, g, P.b_satd );
+                cost = be.bidir_zero( J.bipred_weight );
                 if( cost < bcost ) { bcost = cost; list_used = 3; }
             }
         }
-        for( int l = 0; l < 1 + J.b_bidir; l++ )
-            if( mc[l] < bcost ) { bcost = mc[l]; list_used = l+1; }
-        if( J.b_bidir && ( mv[0][0] | mv[0][1] | mv[1][0] | mv[1][1] ) )
-        {   // slicetype.c:711-712
-            int cost = 5 + bidir_cost( fenc, J.ref0 + pel, J.ref1 + pel, P, g, mv[0][0], mv[0][1], mv[1][0], mv[1][1], J.bipred_weight );
-            if( cost < bcost ) { bcost = cost; list_used = 3; }
+        if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
+        if( J.b_bidir )
+        {
+            if( mc1 < bcost ) { bcost = mc1; list_used = 2; }
+            if( mv0x | mv0y | mv1x | mv1y )
+            {   // slicetype.c:711-712
+                int cost = 5 + be.bidir( mv0x, mv0y, mv1x, mv1y, J.bipred_weight );
+                if( cost < bcost ) { bcost = cost; list_used = 3; }
+            }
         }
     }
-    if( g.r != 0 ) return;
+    if( !be.leader() ) return;
     bcost += 4;                                         // lowres_penalty (slicetype.c:758)
     const bool score = !border || tiny;
     if( !J.b_bidir )
@@ -722,10 +945,55 @@ __global__ void __launch_bounds__(CTA_THREADS) final_kernel( const FinalJob *__r
     J.lowres_costs[blk] = (uint16_t)( min( bcost, 0x3FFF ) + ( list_used << 14 ) );     // slicetype.c:790
 }
 
+__global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *__restrict__ jobs, LaParams P )
+{
+    const FinalJob J = jobs[blockIdx.y];
+    GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
+    const int blk = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );
+    if( blk >= P.nmb ) return;
+    const int bx = blk % P.mbw, by = blk / P.mbw;
+    if( skipped_border( P, bx, by ) )
+    {
+        if( be.g.r == 0 && !J.b_intra_only ) J.lowres_costs[blk] = 0;
+        return;
+    }
+    const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
+    be.fenc = *(const uint2 *)( J.fenc + pel );
+    be.ref0 = J.ref0 + pel; be.ref1 = J.ref1 + pel; be.ref_w = be.ref0;
+    final_block( be, J, P, bx, by, blk );
+}
+
+__global__ void __launch_bounds__(T_TILE_W*T_TILE_H) final_kernel_t( const FinalJob *__restrict__ jobs, LaParams P )
+{
+    const FinalJob J = jobs[blockIdx.z];
+    const int bx = blockIdx.x * T_TILE_W + ( threadIdx.x & ( T_TILE_W-1 ) ), by = blockIdx.y * T_TILE_H + threadIdx.x / T_TILE_W;
+    if( bx >= P.mbw || by >= P.mbh ) return;
+    const int blk = by * P.mbw + bx;
+    if( skipped_border( P, bx, by ) ) { if( !J.b_intra_only ) J.lowres_costs[blk] = 0; return; }
+    ThreadBE be; be.P = &P;
+    const int64_t pel = (int64_t)( by*8 ) * P.stride + bx*8;
+    const uint8_t *src = J.fenc + pel;
+    if( !J.b_intra_only )
+    {
+#pragma unroll
+        for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + (size_t)r * P.stride ) );
+    }
+    be.ref0 = J.ref0 + pel; be.ref1 = J.ref1 + pel; be.ref_w = be.ref0;
+    final_block( be, J, P, bx, by, blk );
+}
+
 void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
 {
-    dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
-    final_kernel<<<grid, CTA_THREADS, 0, st>>>( d_jobs, P );
+    if( use_thread_mapping( P, njobs ) )
+    {
+        dim3 grid( ( P.mbw + T_TILE_W - 1 ) / T_TILE_W, ( P.mbh + T_TILE_H - 1 ) / T_TILE_H, njobs );
+        final_kernel_t<<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
+    }
+    else
+    {
+        dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
+        final_kernel_g<<<grid, CTA_THREADS, 0, st>>>( d_jobs, P );
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

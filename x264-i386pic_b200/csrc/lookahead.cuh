@@ -16,6 +16,7 @@ struct LaParams
     int do_edges;
     int aq;
     int weighted_bipred;
+    int lanes_per_block;        // tuning: 0 auto, 1 thread-per-block kernels, 8 eight-lanes-per-block kernels
     int cost_mv_n;              // table covers |d| <= cost_mv_n
     const uint16_t *cost_mv;    // device table indexed by |mvd| in qpel
 };
