@@ -504,7 +504,9 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
             const SearchJob *d;
             if( push_jobs( c, sj, &d ) ) return -1;
             Span s( c, K_SEARCH, 1 );
-            launch_search( d, (int)sj.size(), P, c->st );
+            bool anyw = false;
+            for( const SearchTask &t : tasks ) anyw = anyw || t.w.enabled;
+            launch_search( d, (int)sj.size(), anyw, P, c->st );
         }
     }
     return 0;

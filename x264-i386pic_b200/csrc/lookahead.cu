@@ -178,18 +178,17 @@ __device__ __forceinline__ uint2 qpel_row( const uint8_t *ref, const LaParams &P
     return v;
 }
 
-// pixel_avg_8x8 with weight (mc.c:63-99)
+// pixel_avg_8x8 with weight (mc.c:63-99): (a*w + b*(64-w) + 32) >> 6 on 4 packed pixels.  The lookahead's
+// weights are 64 - (dist_scale_factor>>2) in [1,63] (slicetype.c:529) or 32, a convex combination, so the clip of
+// mc.c:86 never acts and two pixels fit one 16:16 multiply-add without carries between the halves.
 __device__ __forceinline__ u32 biavg4( u32 a, u32 b, int w )
 {
     if( w == 32 ) return avg4( a, b );
-    u32 r = 0;
-#pragma unroll
-    for( int k = 0; k < 4; k++ )
-    {
-        int v = ( (int)byte_of( a, k ) * w + (int)byte_of( b, k ) * ( 64 - w ) + 32 ) >> 6;
-        r |= (u32)min( max( v, 0 ), 255 ) << ( 8*k );
-    }
-    return r;
+    const u32 w2 = 64 - w;
+    u32 ae = a & 0x00ff00ffu, ao = ( a >> 8 ) & 0x00ff00ffu, be = b & 0x00ff00ffu, bo = ( b >> 8 ) & 0x00ff00ffu;
+    u32 re = ( ( ae * w + be * w2 + 0x00200020u ) >> 6 ) & 0x00ff00ffu;
+    u32 ro = ( ( ao * w + bo * w2 + 0x00200020u ) << 2 ) & 0xff00ff00u;
+    return re | ro;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -367,23 +366,41 @@ struct GroupBE
     const LaParams *P;
 
     __device__ __forceinline__ bool leader() const { return g.r == 0; }
-    __device__ __forceinline__ int zero_cmp( int b_satd ) const { return cmp_rows( fenc, load8u( ref0 ), g, b_satd ); }
-    template<int N> __device__ __forceinline__ void fpel( const int ( &mx )[N], const int ( &my )[N], int ( &c )[N] ) const
+    __device__ __forceinline__ bool satd() const { return P->b_satd != 0; }
+    __device__ __forceinline__ int zero_cmp() const { return cmp_rows( fenc, load8u( ref0 ), g, P->b_satd ); }
+    // candidates k = 0..n-1 in order, strict '<' (the reference's COPY*_IF_LT tie-breaking); two candidates share
+    // one 3-shuffle reduction (16:16 packed partial sums)
+    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const uint16_t *tab, const MeGeo &m, int &bcost, int &best ) const
     {
-#pragma unroll
-        for( int k = 0; k < N; k++ ) c[k] = (int)sad8( fenc, load8u( ref_w + (int64_t)my[k] * P->stride + mx[k] ) );
-#pragma unroll
-        for( int k = 0; k + 1 < N; k += 2 ) red8x2( c[k], c[k+1], g );
-        if( N & 1 ) c[N-1] = red8( c[N-1], g );
+        for( int k = 0; k < n; k += 2 )
+        {
+            int x0, y0, x1, y1;
+            xy( k, x0, y0 ); xy( min( k+1, n-1 ), x1, y1 );
+            int c0 = (int)sad8( fenc, load8u( ref_w + (int64_t)y0 * P->stride + x0 ) );
+            int c1 = (int)sad8( fenc, load8u( ref_w + (int64_t)y1 * P->stride + x1 ) );
+            red8x2( c0, c1, g );
+            c0 += mvcost( tab, m, x0*4, y0*4 ); c1 += mvcost( tab, m, x1*4, y1*4 );
+            if( c0 < bcost ) { bcost = c0; best = k; }
+            if( k+1 < n && c1 < bcost ) { bcost = c1; best = k+1; }
+        }
     }
-    template<int N> __device__ __forceinline__ void qsad( const MeGeo &m, const int ( &mx )[N], const int ( &my )[N], int ( &c )[N] ) const
+    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const uint16_t *tab, const MeGeo &m, int &bcost, int &best ) const
     {
-#pragma unroll
-        for( int k = 0; k < N; k++ ) c[k] = (int)sad8( fenc, qpel_row( ref0, *P, mx[k], my[k], m.wscale, m.wdenom, m.woffset ) );
-#pragma unroll
-        for( int k = 0; k + 1 < N; k += 2 ) red8x2( c[k], c[k+1], g );
-        if( N & 1 ) c[N-1] = red8( c[N-1], g );
+        for( int k = 0; k < n; k += 2 )
+        {
+            int x0, y0, x1, y1;
+            xy( k, x0, y0 ); xy( min( k+1, n-1 ), x1, y1 );
+            int c0 = (int)sad8( fenc, qpel_row( ref0, *P, x0, y0, m.wscale, m.wdenom, m.woffset ) );
+            int c1 = (int)sad8( fenc, qpel_row( ref0, *P, x1, y1, m.wscale, m.wdenom, m.woffset ) );
+            red8x2( c0, c1, g );
+            c0 += mvcost( tab, m, x0, y0 ); c1 += mvcost( tab, m, x1, y1 );
+            if( c0 < bcost ) { bcost = c0; best = k; }
+            if( k+1 < n && c1 < bcost ) { bcost = c1; best = k+1; }
+        }
     }
+    __device__ __forceinline__ int fpel1( int mx, int my ) const { return red8( (int)sad8( fenc, load8u( ref_w + (int64_t)my * P->stride + mx ) ), g ); }
+    __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const
+    { return red8( (int)sad8( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ), g ); }
     __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
     {
         return satd_rows( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ), g );
@@ -451,6 +468,7 @@ __device__ __forceinline__ int satd8x8_t( const uint2 ( &fenc )[8], RowFn pred )
 }
 
 // get_ref (mc.c:221-249) as a row generator: plane/offset selection hoisted out of the row loop
+template<bool WEIGHTED>
 struct QpelRows
 {
     const u32 *q1, *q2;      // word pointers of the two source planes at row 0
@@ -478,11 +496,12 @@ struct QpelRows
             uint2 w = ld8w( q2 + r*stride4, sh2 );
             v.x = avg4( v.x, w.x ); v.y = avg4( v.y, w.y );
         }
-        if( wdenom >= 0 ) { v.x = weight4( v.x, wscale, wdenom, woffset ); v.y = weight4( v.y, wscale, wdenom, woffset ); }
+        if( WEIGHTED && wdenom >= 0 ) { v.x = weight4( v.x, wscale, wdenom, woffset ); v.y = weight4( v.y, wscale, wdenom, woffset ); }
         return v;
     }
 };
 
+template<bool SATD, bool WEIGHTED>
 struct ThreadBE
 {
     uint2 fenc[8];
@@ -490,35 +509,52 @@ struct ThreadBE
     const LaParams *P;
 
     __device__ __forceinline__ bool leader() const { return true; }
-    __device__ __forceinline__ int zero_cmp( int b_satd ) const
+    __device__ __forceinline__ bool satd() const { return SATD; }
+    __device__ __forceinline__ int zero_cmp() const
     {
         const u32 *q = (const u32 *)ref0; const int s4 = P->stride >> 2;
         auto rows = [&]( int r ) { return __ldg( (const uint2 *)( q + r*s4 ) ); };
-        return b_satd ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
+        return SATD ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
     }
-    template<int N> __device__ __forceinline__ void fpel( const int ( &mx )[N], const int ( &my )[N], int ( &c )[N] ) const
+    __device__ __forceinline__ int fpel1( int mx, int my ) const
     {
-        const int s4 = P->stride >> 2;
-#pragma unroll
-        for( int k = 0; k < N; k++ )
+        const int s4 = P->stride >> 2, off = my * P->stride + mx;
+        const u32 *q = (const u32 *)ref_w + ( off >> 2 ); const u32 sh = ( off & 3 ) * 8;
+        return sad8x8_t( fenc, [&]( int r ) { return ld8w( q + r*s4, sh ); } );
+    }
+    __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const
+    { return sad8x8_t( fenc, QpelRows<WEIGHTED>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ); }
+    // candidate loops are NOT unrolled: one copy of the 8-row body per call site keeps the kernel inside the
+    // instruction cache (ncu r01: the fully unrolled form had 25k SASS lines and 53 % no-instruction stalls)
+    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const uint16_t *tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+#pragma unroll 1
+        for( int k = 0; k < n; k++ )
         {
-            int off = my[k] * P->stride + mx[k];
-            const u32 *q = (const u32 *)ref_w + ( off >> 2 ); const u32 sh = ( off & 3 ) * 8;
-            c[k] = sad8x8_t( fenc, [&]( int r ) { return ld8w( q + r*s4, sh ); } );
+            int x, y;
+            xy( k, x, y );
+            int c = fpel1( x, y ) + mvcost( tab, m, x*4, y*4 );
+            if( c < bcost ) { bcost = c; best = k; }
         }
     }
-    template<int N> __device__ __forceinline__ void qsad( const MeGeo &m, const int ( &mx )[N], const int ( &my )[N], int ( &c )[N] ) const
+    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const uint16_t *tab, const MeGeo &m, int &bcost, int &best ) const
     {
-#pragma unroll
-        for( int k = 0; k < N; k++ ) c[k] = sad8x8_t( fenc, QpelRows( ref0, *P, mx[k], my[k], m.wscale, m.wdenom, m.woffset ) );
+#pragma unroll 1
+        for( int k = 0; k < n; k++ )
+        {
+            int x, y;
+            xy( k, x, y );
+            int c = qsad1( m, x, y ) + mvcost( tab, m, x, y );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
     }
     __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
     {
-        return satd8x8_t( fenc, QpelRows( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) );
+        return satd8x8_t( fenc, QpelRows<WEIGHTED>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) );
     }
     __device__ __forceinline__ int bidir( int mv0x, int mv0y, int mv1x, int mv1y, int w ) const
     {
-        if( !P->b_satd )
+        if( !SATD )
         {
             const int s4 = P->stride >> 2;
             int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
@@ -528,7 +564,7 @@ struct ThreadBE
             return sad8x8_t( fenc, [&]( int r ) { uint2 a = ld8w( q0 + r*s4, h0 ), b = ld8w( q1 + r*s4, h1 );
                                                   return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
         }
-        QpelRows r0( ref0, *P, mv0x, mv0y, 0, -1, 0 ), r1( ref1, *P, mv1x, mv1y, 0, -1, 0 );
+        QpelRows<false> r0( ref0, *P, mv0x, mv0y, 0, -1, 0 ), r1( ref1, *P, mv1x, mv1y, 0, -1, 0 );
         return satd8x8_t( fenc, [&]( int r ) { uint2 a = r0( r ), b = r1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
     }
     __device__ __forceinline__ int bidir_zero( int w ) const
@@ -536,7 +572,7 @@ struct ThreadBE
         const u32 *q0 = (const u32 *)ref0, *q1 = (const u32 *)ref1; const int s4 = P->stride >> 2;
         auto rows = [&]( int r ) { uint2 a = __ldg( (const uint2 *)( q0 + r*s4 ) ), b = __ldg( (const uint2 *)( q1 + r*s4 ) );
                                    return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); };
-        return P->b_satd ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
+        return SATD ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
     }
 };
 
@@ -552,43 +588,35 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
 {
     if( hpel_iters )
     {
-        if( !P.b_satd )
+        if( !be.satd() )
         {   // la subme 2 (< 3): try the subpel component of the predictor (me.c:889-895)
-            int mx[1] = { iclip3( m.mvpx, m.sminx + 2, m.smaxx - 2 ) };
-            int my[1] = { iclip3( m.mvpy, m.sminy + 2, m.smaxy - 2 ) };
-            if( ( mx[0] - bmx ) | ( my[0] - bmy ) )
+            int mx = iclip3( m.mvpx, m.sminx + 2, m.smaxx - 2 );
+            int my = iclip3( m.mvpy, m.sminy + 2, m.smaxy - 2 );
+            if( ( mx - bmx ) | ( my - bmy ) )
             {
-                int c[1];
-                be.qsad( m, mx, my, c );
-                int cost = c[0] + mvcost( tab, m, mx[0], my[0] );
-                if( cost < bcost ) { bcost = cost; bmx = mx[0]; bmy = my[0]; }
+                int cost = be.qsad1( m, mx, my ) + mvcost( tab, m, mx, my );
+                if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
             }
         }
         for( int i = hpel_iters; i > 0; i-- )
         {   // me.c:898-921, tie order: up, down, left, right
             const int omx = bmx, omy = bmy;
-            int mx[4] = { omx, omx, omx-2, omx+2 }, my[4] = { omy-2, omy+2, omy, omy }, c[4];
-            be.qsad( m, mx, my, c );
             int best = -1;
-#pragma unroll
-            for( int k = 0; k < 4; k++ )
-            {
-                int cost = c[k] + mvcost( tab, m, mx[k], my[k] );
-                if( cost < bcost ) { bcost = cost; best = k; }
-            }
+            be.qsad_best( 4, [&]( int k, int &x, int &y ) { x = omx + ( k == 2 ? -2 : k == 3 ? 2 : 0 ); y = omy + ( k == 0 ? -2 : k == 1 ? 2 : 0 ); },
+                          tab, m, bcost, best );
             if( best < 0 ) break;
             bmx = omx + ( best == 2 ? -2 : best == 3 ? 2 : 0 );
             bmy = omy + ( best == 0 ? -2 : best == 1 ? 2 : 0 );
         }
     }
-    if( P.b_satd )   // mbcmp != fpelcmp: re-measure the winner with SATD (me.c:925-929)
+    if( be.satd() )   // mbcmp != fpelcmp: re-measure the winner with SATD (me.c:925-929)
         bcost = be.qsatd( m, bmx, bmy ) + mvcost( tab, m, bmx, bmy );
     int bdir = -1;
     for( int i = qpel_iters; i > 0; i-- )
     {   // me.c:947-963
         if( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx ) break;
         const int odir = bdir, omx = bmx, omy = bmy;
-#pragma unroll
+#pragma unroll 1
         for( int k = 0; k < 4; k++ )
             if( ( k ^ 1 ) != odir )
             {
@@ -606,58 +634,69 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
                                            const int (*mvc)[2], int i_mvc, int &out_mx, int &out_my, int &out_cost )
 {
     int bmx, bmy, bcost = X264CU_COST_MAX, bpred_cost = X264CU_COST_MAX, bpred_mx = 0, bpred_my = 0, pmvx, pmvy;
-#define COST_MV( mx_, my_ ) { int x_[1] = { mx_ }, y_[1] = { my_ }, c_[1]; be.fpel( x_, y_, c_ ); \
-                              c_[0] += mvcost( tab, m, (mx_)*4, (my_)*4 ); \
-                              if( c_[0] < bcost ) { bcost = c_[0]; bmx = mx_; bmy = my_; } }
-    if( P.b_satd )
+#define COST_MV( mx_, my_ ) { int c_ = be.fpel1( mx_, my_ ) + mvcost( tab, m, (mx_)*4, (my_)*4 ); \
+                              if( c_ < bcost ) { bcost = c_; bmx = mx_; bmy = my_; } }
+    if( be.satd() )
     {   // la subme 4 (>= 3): subpel predictors (me.c:216-275)
         bpred_mx = iclip3( m.mvpx, 4*m.fminx, 4*m.fmaxx );
         bpred_my = iclip3( m.mvpy, 4*m.fminy, 4*m.fmaxy );
         pmvx = bpred_mx; pmvy = bpred_my;
-        {
-            int x_[1] = { bpred_mx }, y_[1] = { bpred_my }, c_[1];
-            be.qsad( m, x_, y_, c_ );
-            bpred_cost = c_[0] + mvcost( tab, m, bpred_mx, bpred_my );
-        }
+        bpred_cost = be.qsad1( m, bpred_mx, bpred_my ) + mvcost( tab, m, bpred_mx, bpred_my );
         const int pmv_cost = bpred_cost;
+#pragma unroll 1
         for( int i = 0; i < i_mvc; i++ )
         {   // x264_predictor_clip (common.h:790-805): drop zero and == pmv, clip the rest
             int mx = mvc[i][0], my = mvc[i][1];
             if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
-            int x_[1] = { iclip3( mx, 4*m.fminx, 4*m.fmaxx ) }, y_[1] = { iclip3( my, 4*m.fminy, 4*m.fmaxy ) }, c_[1];
-            be.qsad( m, x_, y_, c_ );
-            int cost = c_[0] + mvcost( tab, m, x_[0], y_[0] );
-            if( cost < bpred_cost ) { bpred_cost = cost; bpred_mx = x_[0]; bpred_my = y_[0]; }
+            mx = iclip3( mx, 4*m.fminx, 4*m.fmaxx ); my = iclip3( my, 4*m.fminy, 4*m.fmaxy );
+            int cost = be.qsad1( m, mx, my ) + mvcost( tab, m, mx, my );
+            if( cost < bpred_cost ) { bpred_cost = cost; bpred_mx = mx; bpred_my = my; }
         }
         bmx = FPEL( bpred_mx ); bmy = FPEL( bpred_my );
-        if( ( bpred_mx & 3 ) | ( bpred_my & 3 ) ) COST_MV( bmx, bmy )
-        else bcost = bpred_cost;
-        if( pmvx | pmvy ) { if( bmx | bmy ) COST_MV( 0, 0 ) }
-        else if( pmv_cost < bcost ) { bcost = pmv_cost; bmx = 0; bmy = 0; }
+        // me.c:258-274 with the two possible fullpel probes folded into one call site
+        const bool probe_start = ( bpred_mx & 3 ) | ( bpred_my & 3 );
+        if( !probe_start ) bcost = bpred_cost;
+        const bool probe_zero = ( pmvx | pmvy ) && ( bmx | bmy );
+        const int sx = bmx, sy = bmy;
+#pragma unroll 1
+        for( int t = 0; t < 2; t++ )
+        {
+            if( t == 0 ? !probe_start : !probe_zero ) continue;
+            const int x = t == 0 ? sx : 0, y = t == 0 ? sy : 0;
+            COST_MV( x, y )
+        }
+        if( !( pmvx | pmvy ) && pmv_cost < bcost ) { bcost = pmv_cost; bmx = 0; bmy = 0; }
     }
     else
     {   // la subme 2: fullpel predictors (me.c:278-317)
         bmx = iclip3( FPEL( m.mvpx ), m.fminx, m.fmaxx );
         bmy = iclip3( FPEL( m.mvpy ), m.fminy, m.fmaxy );
         pmvx = bmx; pmvy = bmy;
-        {
-            int x_[1] = { bmx }, y_[1] = { bmy }, c_[1];
-            be.fpel( x_, y_, c_ );
-            bcost = c_[0];
-        }
         int sx = bmx, sy = bmy;
-        for( int i = 0; i < i_mvc; i++ )
-        {   // x264_predictor_roundclip (common.h:774-788)
-            int mx = ( mvc[i][0] + 2 ) >> 2, my = ( mvc[i][1] + 2 ) >> 2;
-            if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
-            int x_[1] = { iclip3( mx, m.fminx, m.fmaxx ) }, y_[1] = { iclip3( my, m.fminy, m.fmaxy ) }, c_[1];
-            be.fpel( x_, y_, c_ );
-            int cost = c_[0] + mvcost( tab, m, x_[0]*4, y_[0]*4 );
-            if( cost < bcost ) { bcost = cost; sx = x_[0]; sy = y_[0]; }
+        // the start point (no mv cost, me.c:291), the rounded candidates (:293-313) and zero (:316-317) share one call site
+#pragma unroll 1
+        for( int i = -1; i <= i_mvc; i++ )
+        {
+            int mx, my, add;
+            if( i < 0 ) { mx = bmx; my = bmy; add = 0; }
+            else if( i < i_mvc )
+            {   // x264_predictor_roundclip (common.h:774-788)
+                mx = ( mvc[i][0] + 2 ) >> 2; my = ( mvc[i][1] + 2 ) >> 2;
+                if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
+                mx = iclip3( mx, m.fminx, m.fmaxx ); my = iclip3( my, m.fminy, m.fmaxy );
+                add = mvcost( tab, m, mx*4, my*4 );
+            }
+            else
+            {
+                if( !( pmvx | pmvy ) ) continue;
+                mx = 0; my = 0; add = mvcost( tab, m, 0, 0 );
+            }
+            int cost = be.fpel1( mx, my ) + add;
+            if( cost < bcost ) { bcost = cost; sx = mx; sy = my; }
         }
         bmx = sx; bmy = sy;
-        if( pmvx | pmvy ) COST_MV( 0, 0 )
     }
+#undef COST_MV
 
     if( P.me_method == 0 )
     {   // DIA (me.c:322-342): tie order up, down, left, right
@@ -665,75 +704,46 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
         do
         {
             const int ox = bmx, oy = bmy;
-            int mx[4] = { ox, ox, ox-1, ox+1 }, my[4] = { oy-1, oy+1, oy, oy }, c[4];
-            be.fpel( mx, my, c );
             int best = -1;
-#pragma unroll
-            for( int k = 0; k < 4; k++ )
-            {
-                int cost = c[k] + mvcost( tab, m, mx[k]*4, my[k]*4 );
-                if( cost < bcost ) { bcost = cost; best = k; }
-            }
+            be.fpel_best( 4, [&]( int k, int &x, int &y ) { x = ox + ( k == 2 ? -1 : k == 3 ? 1 : 0 ); y = oy + ( k == 0 ? -1 : k == 1 ? 1 : 0 ); },
+                          tab, m, bcost, best );
             if( best < 0 ) break;
             bmx = ox + ( best == 2 ? -1 : best == 3 ? 1 : 0 );
             bmy = oy + ( best == 0 ? -1 : best == 1 ? 1 : 0 );
         } while( --i && in_range( m, bmx, bmy ) );
     }
     else
-    {   // HEX (me.c:344-420)
-        int mx[6], my[6], c[6];
-#pragma unroll
-        for( int k = 0; k < 6; k++ ) { mx[k] = bmx + c_hex2[k+1][0]; my[k] = bmy + c_hex2[k+1][1]; }
-        be.fpel( mx, my, c );
-        int best = -1;
-#pragma unroll
-        for( int k = 0; k < 6; k++ )
+    {   // HEX (me.c:344-420): the full hexagon, then half hexagons that do not overlap the previous one;
+        // both go through ONE call site (first = 6 points from hex2[1], later = 3 points from hex2[dir])
+        int dir = 0, npts = 6, first = 1;
+        for( int i = P.me_range >> 1; i > 0; i-- )
         {
-            int cost = c[k] + mvcost( tab, m, mx[k]*4, my[k]*4 );
-            if( cost < bcost ) { bcost = cost; best = k; }
-        }
-        if( best >= 0 )
-        {
-            int dir = best;
-            bmx += c_hex2[dir+1][0]; bmy += c_hex2[dir+1][1];
-            for( int i = ( P.me_range >> 1 ) - 1; i > 0 && in_range( m, bmx, bmy ); i-- )
-            {   // half hexagon not overlapping the previous one
-                int hx[3], hy[3], hc[3];
-#pragma unroll
-                for( int k = 0; k < 3; k++ ) { hx[k] = bmx + c_hex2[dir+k][0]; hy[k] = bmy + c_hex2[dir+k][1]; }
-                be.fpel( hx, hy, hc );
-                int b2 = -1;
-#pragma unroll
-                for( int k = 0; k < 3; k++ )
-                {
-                    int cost = hc[k] + mvcost( tab, m, hx[k]*4, hy[k]*4 );
-                    if( cost < bcost ) { bcost = cost; b2 = k; }
-                }
-                if( b2 < 0 ) break;
-                dir += b2 - 1;
+            if( !first && !in_range( m, bmx, bmy ) ) break;
+            const int ox = bmx, oy = bmy, base = first ? 1 : dir;
+            int best = -1;
+            be.fpel_best( npts, [&]( int k, int &x, int &y ) { x = ox + c_hex2[base+k][0]; y = oy + c_hex2[base+k][1]; }, tab, m, bcost, best );
+            if( best < 0 ) break;
+            if( first ) dir = best;
+            else
+            {
+                dir += best - 1;
                 dir = dir < 0 ? dir + 6 : dir >= 6 ? dir - 6 : dir;      // mod6m1 (me.c:53)
-                bmx += c_hex2[dir+1][0]; bmy += c_hex2[dir+1][1];
             }
+            bmx = ox + c_hex2[dir+1][0]; bmy = oy + c_hex2[dir+1][1];
+            first = 0; npts = 3;
         }
         // square refine (me.c:404-418)
-        int sx[8], sy[8], sc[8];
-#pragma unroll
-        for( int k = 0; k < 8; k++ ) { sx[k] = bmx + c_sq1[k+1][0]; sy[k] = bmy + c_sq1[k+1][1]; }
-        be.fpel( sx, sy, sc );
-        int bs = 0;
-#pragma unroll
-        for( int k = 0; k < 8; k++ )
         {
-            int cost = sc[k] + mvcost( tab, m, sx[k]*4, sy[k]*4 );
-            if( cost < bcost ) { bcost = cost; bs = k+1; }
+            const int ox = bmx, oy = bmy;
+            int bs = -1;
+            be.fpel_best( 8, [&]( int k, int &x, int &y ) { x = ox + c_sq1[k+1][0]; y = oy + c_sq1[k+1][1]; }, tab, m, bcost, bs );
+            bmx = ox + c_sq1[bs+1][0]; bmy = oy + c_sq1[bs+1][1];
         }
-        bmx += c_sq1[bs][0]; bmy += c_sq1[bs][1];
     }
-#undef COST_MV
 
     // -> qpel mv (me.c:774-797)
     int mx, my, cost;
-    if( !P.b_satd )
+    if( !be.satd() )
     {
         cost = bcost;
         if( bmx == pmvx && bmy == pmvy ) cost += mvcost( tab, m, bmx*4, bmy*4 );
@@ -783,7 +793,7 @@ __device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, 
     bool skip = false;
     if( !( m.mvpx | m.mvpy ) )
     {   // zero-predictor shortcut (slicetype.c:684-692): unweighted F plane at mv 0
-        cost = be.zero_cmp( P.b_satd );
+        cost = be.zero_cmp();
         skip = cost < 64;
     }
     if( !skip )
@@ -828,6 +838,7 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob 
 
 #define T_TILE_W 32
 #define T_TILE_H 4
+template<bool SATD, bool WEIGHTED>
 __global__ void __launch_bounds__(T_TILE_W*T_TILE_H) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
 {
     extern __shared__ uint16_t s_tab[];
@@ -838,7 +849,7 @@ __global__ void __launch_bounds__(T_TILE_W*T_TILE_H) search_kernel_t( const Sear
     if( bx >= P.mbw || by >= P.mbh ) return;
     const int blk = by * P.mbw + bx;
     if( skipped_border( P, bx, by ) ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; return; }
-    ThreadBE be; be.P = &P;
+    ThreadBE<SATD, WEIGHTED> be; be.P = &P;
     const int64_t pel = (int64_t)( by*8 ) * P.stride + bx*8;
     const uint8_t *src = J.fenc + pel;
 #pragma unroll
@@ -854,13 +865,22 @@ static bool use_thread_mapping( const LaParams &P, int njobs )
     return (int64_t)njobs * P.nmb >= 4 * 8160;     // wide launches: enough blocks to fill the SMs one thread each
 }
 
-void launch_search( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
+void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
 {
     size_t smem = ( P.cost_mv_n + 1 ) * sizeof(uint16_t);
     if( use_thread_mapping( P, njobs ) )
     {
         dim3 grid( ( P.mbw + T_TILE_W - 1 ) / T_TILE_W, ( P.mbh + T_TILE_H - 1 ) / T_TILE_H, njobs );
-        search_kernel_t<<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
+        if( P.b_satd )
+        {
+            if( any_weighted ) search_kernel_t<true, true><<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
+            else               search_kernel_t<true, false><<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
+        }
+        else
+        {
+            if( any_weighted ) search_kernel_t<false, true><<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
+            else               search_kernel_t<false, false><<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
+        }
     }
     else
     {
@@ -903,24 +923,27 @@ __device__ __forceinline__ void final_block( const BE &be, const FinalJob &J, co
                 d1x = iclip3( d1x, m.sminx, m.smaxx ); d1y = iclip3( d1y, m.sminy, m.smaxy );
                 if( !P.b_satd ) { d0x &= ~1; d0y &= ~1; d1x &= ~1; d1y &= ~1; }
             }
-            int cost = be.bidir( d0x, d0y, d1x, d1y, J.bipred_weight );
-            if( cost < bcost ) { bcost = cost; list_used = 3; }
-            if( d0x | d0y | d1x | d1y )
+            // candidates in the reference's order (ties keep the earlier one): temporal direct, zero (both :644-652),
+            // L0, L1 (:708), L0+L1 with penalty 5*lambda (:711-712).  The two qpel bidir costs share one call site.
+#pragma unroll 1
+            for( int t = 0; t < 2; t++ )
             {
-                cost = be.bidir_zero( J.bipred_weight );
+                if( t == 1 )
+                {
+                    if( d0x | d0y | d1x | d1y )
+                    {
+                        int cz = be.bidir_zero( J.bipred_weight );
+                        if( cz < bcost ) { bcost = cz; list_used = 3; }
+                    }
+                    if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
+                    if( mc1 < bcost ) { bcost = mc1; list_used = 2; }
+                    if( !( mv0x | mv0y | mv1x | mv1y ) ) break;
+                }
+                int cost = ( t ? 5 : 0 ) + be.bidir( t ? mv0x : d0x, t ? mv0y : d0y, t ? mv1x : d1x, t ? mv1y : d1y, J.bipred_weight );
                 if( cost < bcost ) { bcost = cost; list_used = 3; }
             }
         }
-        if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
-        if( J.b_bidir )
-        {
-            if( mc1 < bcost ) { bcost = mc1; list_used = 2; }
-            if( mv0x | mv0y | mv1x | mv1y )
-            {   // slicetype.c:711-712
-                int cost = 5 + be.bidir( mv0x, mv0y, mv1x, mv1y, J.bipred_weight );
-                if( cost < bcost ) { bcost = cost; list_used = 3; }
-            }
-        }
+        else if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
     }
     if( !be.leader() ) return;
     bcost += 4;                                         // lowres_penalty (slicetype.c:758)
@@ -963,6 +986,7 @@ __global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *_
     final_block( be, J, P, bx, by, blk );
 }
 
+template<bool SATD>
 __global__ void __launch_bounds__(T_TILE_W*T_TILE_H) final_kernel_t( const FinalJob *__restrict__ jobs, LaParams P )
 {
     const FinalJob J = jobs[blockIdx.z];
@@ -970,7 +994,7 @@ __global__ void __launch_bounds__(T_TILE_W*T_TILE_H) final_kernel_t( const Final
     if( bx >= P.mbw || by >= P.mbh ) return;
     const int blk = by * P.mbw + bx;
     if( skipped_border( P, bx, by ) ) { if( !J.b_intra_only ) J.lowres_costs[blk] = 0; return; }
-    ThreadBE be; be.P = &P;
+    ThreadBE<SATD, false> be; be.P = &P;
     const int64_t pel = (int64_t)( by*8 ) * P.stride + bx*8;
     const uint8_t *src = J.fenc + pel;
     if( !J.b_intra_only )
@@ -987,7 +1011,8 @@ void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStr
     if( use_thread_mapping( P, njobs ) )
     {
         dim3 grid( ( P.mbw + T_TILE_W - 1 ) / T_TILE_W, ( P.mbh + T_TILE_H - 1 ) / T_TILE_H, njobs );
-        final_kernel_t<<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
+        if( P.b_satd ) final_kernel_t<true><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
+        else           final_kernel_t<false><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
     }
     else
     {
