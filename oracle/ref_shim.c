@@ -548,7 +548,7 @@ EXPORT int ref_la_slicetype_analyse( void *ctx, int first, int n, int intra_mini
 {
     ref_la_t *c = ctx;
     x264_t *h = c->h;
-    if( n < 2 ) return -1;
+    if( n < 2 || n - 1 > h->lookahead->next.i_max_size ) return -1;
     h->lookahead->last_nonb = c->frames[first];
     c->frames[first]->i_type = X264_TYPE_I;
     h->lookahead->next.i_size = 0;
@@ -563,6 +563,62 @@ EXPORT int ref_la_slicetype_analyse( void *ctx, int first, int n, int intra_mini
         types_out[i] = c->frames[first+i]->i_type;
     h->lookahead->next.i_size = 0;
     h->lookahead->next.list[0] = NULL;
+    h->lookahead->last_nonb = NULL;       /* x264_lookahead_delete would free it (lookahead.c) */
+    return 0;
+}
+
+/* Pre-populate the cost caches of frame idx so that the reference's own decision logic runs on externally
+ * supplied costs (every slicetype_frame_cost becomes a cache hit, slicetype.c:848). */
+EXPORT int ref_la_inject_cost( void *ctx, int idx, int d0, int d1, int cost_est, int cost_est_aq, int intra_mbs )
+{
+    ref_la_t *c = ctx;
+    x264_frame_t *f = c->frames[idx];
+    if( !f ) return -1;
+    f->i_cost_est[d0][d1] = cost_est;
+    f->i_cost_est_aq[d0][d1] = cost_est_aq;
+    if( d1 == 0 ) f->i_intra_mbs[d0] = intra_mbs;
+    f->i_row_satds[d0][d1][0] = 0;
+    return 0;
+}
+
+/* x264_slicetype_analyse (slicetype.c:1473) over frames[first..first+n): frames[first] is the last non-B frame.
+ * forced[i] = forced type of frames[first+i] (0 = auto).  Writes the types after the call and the frames' i_type
+ * as decided; returns 0. */
+EXPORT int ref_la_analyse2( void *ctx, int first, int n, int intra_minigop, int last_keyframe, const uint8_t *forced, uint8_t *types_out )
+{
+    ref_la_t *c = ctx;
+    x264_t *h = c->h;
+    if( n < 1 || n - 1 > h->lookahead->next.i_max_size ) return -1;   /* the real lookahead never holds more */
+    h->lookahead->last_nonb = c->frames[first];
+    h->lookahead->i_last_keyframe = last_keyframe;
+    h->lookahead->next.i_size = 0;
+    for( int i = 1; i < n; i++ )
+    {
+        x264_frame_t *f = c->frames[first+i];
+        f->i_forced_type = forced ? forced[i] : X264_TYPE_AUTO;
+        f->i_type = f->i_forced_type;
+        f->b_scenecut = 1;
+        h->lookahead->next.list[h->lookahead->next.i_size++] = f;
+    }
+    h->lookahead->next.list[h->lookahead->next.i_size] = NULL;
+    x264_slicetype_analyse( h, intra_minigop );
+    for( int i = 0; i < n; i++ )
+        types_out[i] = c->frames[first+i]->i_type;
+    h->lookahead->next.i_size = 0;
+    h->lookahead->next.list[0] = NULL;
+    h->lookahead->last_nonb = NULL;       /* x264_lookahead_delete would free it (lookahead.c) */
+    return 0;
+}
+
+EXPORT int ref_la_param( void *ctx, int *out )
+{
+    ref_la_t *c = ctx;
+    x264_t *h = c->h;
+    out[0] = h->param.i_bframe; out[1] = h->param.i_bframe_adaptive; out[2] = h->param.i_bframe_pyramid;
+    out[3] = h->param.i_scenecut_threshold; out[4] = h->param.i_keyint_max; out[5] = h->param.i_keyint_min;
+    out[6] = h->param.b_open_gop; out[7] = h->param.b_intra_refresh;
+    out[8] = (h->param.analyse.b_psy && h->param.rc.b_mb_tree) || (h->param.rc.i_vbv_buffer_size && h->param.rc.i_lookahead);
+    out[9] = h->lookahead->i_slicetype_length; out[10] = h->param.b_deterministic;
     return 0;
 }
 
