@@ -141,10 +141,20 @@ def run_cuda_pass(x264cu, ctx, frames, streams_n, warmup, steps, e2e, pinned=Non
     ctx.timer_begin()
     t0 = time.perf_counter()
     evals = 0
+    # software pipeline of depth 1: the next stream's frame is enqueued before this step's results are awaited, so
+    # the device never idles while the host builds job tables; every step's results are complete on the host
+    # (x264cu_stream_sync = device work + deferred copies of that push) before the step after next is enqueued
+    prev = None
     for k in range(steps):
         s = (warmup + k) % streams_n
         evals += push(s)
-        x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")      # results of this step are on the host here
+        if prev is not None:
+            x264cu.check(L.x264cu_stream_sync(wins[prev]), "sync")
+        prev = s if streams_n > 1 else None
+        if streams_n == 1:
+            x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")
+    if prev is not None:
+        x264cu.check(L.x264cu_stream_sync(wins[prev]), "sync")
     ms = ctx.timer_end()
     wall_ms = (time.perf_counter() - t0) * 1e3
     barrier_sync(dist, local)
@@ -245,7 +255,7 @@ def main():
     config = {"workload": "lowres lookahead frame-cost matrix, 1080p, bframes=16, b-adapt 2 (BASELINE.json configs[2])",
               "width": W, "height": H, "bframes": BFRAMES, "search_passes": 2, "subme": 7, "mbtree_edges": 1, "aq": 1,
               "evals_per_step": 154, "new_search_fields_per_step": 33, "streams_per_gpu": args.streams,
-              "sharding": "independent encode streams per GPU, no collective",
+              "sharding": "independent encode streams per GPU, no collective", "host_pipeline_depth": 1,
               "l2": "inputs larger than L2: %d windows x 18 frames x ~10 MB of planes+cost arrays per GPU" % args.streams}
 
     if args.impl == "reference":

@@ -114,6 +114,11 @@ int x264cu_motionsearch( x264cu_ctx *ctx, x264cu_frame *fenc, x264cu_frame *fref
 int x264cu_frame_cost_batch( x264cu_ctx *ctx, const x264cu_job *jobs, int n_jobs );
 /* x264_opencl_flush (slicetype-cl.c:58-70): wait for the stream, then complete the queued copies. */
 int x264cu_flush( x264cu_ctx *ctx );
+/* Pipelining: every enqueueing call is a batch with an increasing sequence number; up to 3 further batches may
+ * be enqueued before the host has to wait for the oldest one.  x264cu_wait completes (device work + host copies)
+ * every batch up to `seq` only -- the tail keeps running -- whereas x264cu_flush completes everything. */
+uint64_t x264cu_last_batch( x264cu_ctx *ctx );
+int x264cu_wait( x264cu_ctx *ctx, uint64_t seq );
 /* number of kernels launched by this context so far */
 int64_t x264cu_launch_count( x264cu_ctx *ctx );
 /* device-side time of the kernels between the last two flushes, in milliseconds, per kernel class:

@@ -23,7 +23,8 @@ static thread_local char g_err[512] = "";
 
 enum { K_LOWRES, K_INTRA, K_SEARCH, K_FINAL, K_NCLASS };
 
-struct PendingCopy { void *dst; const void *src; size_t bytes; int kind, bias; };   // kind < 0: raw copy; 0/1/2: I/P/B stats fix-up
+struct PendingCopy { void *dst; const void *src; size_t bytes; int kind, bias; uint64_t seq; };   // kind < 0: raw copy; 0/1/2: I/P/B stats fix-up
+#define NSLOT 4      // batches that may be in flight before the host has to wait (pipeline depth)
 struct TimedSpan { cudaEvent_t a, b; int cls; };
 
 struct x264cu_frame
@@ -46,7 +47,9 @@ struct x264cu_ctx
     x264cu_cfg cfg;
     LaParams P;
     int sm_count;
-    cudaStream_t st;
+    cudaStream_t st;                 // compute stream (the in-order queue every kernel runs on)
+    cudaStream_t st_in, st_out;      // copy streams: luma H2D ahead of the compute, results D2H behind it
+    cudaEvent_t ev_up[2], ev_res;
     uint16_t *d_cost_mv;
     int stat_pitch;
     size_t plane_alloc;      // bytes of the 4 planes + slack
@@ -54,12 +57,17 @@ struct x264cu_ctx
     uint8_t *d_luma[2]; int luma_pitch; int luma_sel;
     cudaEvent_t luma_free[2];
     // pinned staging (H2D inputs, D2H results) and the deferred copy list
-    uint8_t *pin; size_t pin_size, pin_used;
-    std::vector<PendingCopy> copies;
+    // Every enqueueing entry point is one "batch"; batch k uses region k % NSLOT of each pool below, and a
+    // region is recycled only after the CUDA event of the batch that used it last has completed and its
+    // deferred copies have been drained -- so up to NSLOT batches are in flight while the host keeps enqueueing.
+    uint8_t *pin; size_t pin_size, pin_used[NSLOT];
+    std::vector<PendingCopy> copies; size_t copies_head;
     // job tables: pinned host ring mirrored to a device ring
-    uint8_t *h_jobs, *d_jobs; size_t jobs_size, jobs_used;
-    // device workspace arena for per-batch temporaries (MV ping-pong fields, weighted planes)
-    uint8_t *arena; size_t arena_size, arena_used;
+    uint8_t *h_jobs, *d_jobs; size_t jobs_size, jobs_used[NSLOT];
+    // device workspace arena for per-batch temporaries (MV ping-pong fields, weighted planes, result gather)
+    uint8_t *arena; size_t arena_size, arena_used[NSLOT];
+    uint64_t seq; int slot; bool batch_out;      // batch_out: this batch ends on the D2H stream
+    cudaEvent_t slot_done[NSLOT]; uint64_t slot_seq[NSLOT]; bool slot_pending[NSLOT];
     int64_t launches;
     // timing
     bool profiling;
@@ -120,6 +128,10 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
     c->plane_alloc = 4 * (size_t)P.plane_size + 256;
     c->stat_pitch = (int)align_up( P.mbh + 4, 4 );
     CUP( cudaStreamCreateWithFlags( &c->st, cudaStreamNonBlocking ) );
+    CUP( cudaStreamCreateWithFlags( &c->st_in, cudaStreamNonBlocking ) );
+    CUP( cudaStreamCreateWithFlags( &c->st_out, cudaStreamNonBlocking ) );
+    CUP( cudaEventCreateWithFlags( &c->ev_res, cudaEventDisableTiming ) );
+    for( int i = 0; i < 2; i++ ) CUP( cudaEventCreateWithFlags( &c->ev_up[i], cudaEventDisableTiming ) );
     // mv cost table: lambda * (log2(|d|+1)*2 + 1.718) rounded, lambda = 1 at X264_LOOKAHEAD_QP (analyse.c:153-157,186-188)
     {
         std::vector<uint16_t> tab( P.cost_mv_n + 1 );
@@ -149,8 +161,18 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
     c->jobs_size = (size_t)1 << 20;
     CUP( cudaHostAlloc( &c->h_jobs, c->jobs_size, cudaHostAllocDefault ) );
     CUP( cudaMalloc( &c->d_jobs, c->jobs_size ) );
-    c->arena_size = (size_t)P.nmb * 4 * 2 * 128 + 8 * (size_t)P.plane_size;
+    {   // per region: MV ping-pong fields of 2B+1 searches, a few weighted planes, the result gather block
+        size_t region = (size_t)P.nmb * 4 * 2 * 40 + 4 * (size_t)P.plane_size + (size_t)P.nmb * 2 * 200;
+        c->arena_size = NSLOT * align_up( region, 1 << 20 );
+    }
     CUP( cudaMalloc( &c->arena, c->arena_size ) );
+    for( int i = 0; i < NSLOT; i++ )
+    {
+        CUP( cudaEventCreateWithFlags( &c->slot_done[i], cudaEventDisableTiming ) );
+        c->slot_pending[i] = false; c->slot_seq[i] = 0;
+        c->pin_used[i] = c->jobs_used[i] = c->arena_used[i] = 0;
+    }
+    c->seq = 0; c->slot = 0; c->copies_head = 0;
     CUP( cudaEventCreate( &c->tm_a ) );
     CUP( cudaEventCreate( &c->tm_b ) );
     g_err[0] = 0;
@@ -187,7 +209,9 @@ extern "C" void x264cu_close( x264cu_ctx *c )
     cudaFree( c->d_cost_mv ); cudaFree( c->d_jobs ); cudaFree( c->arena );
     cudaFreeHost( c->pin ); cudaFreeHost( c->h_jobs );
     cudaEventDestroy( c->tm_a ); cudaEventDestroy( c->tm_b );
-    cudaStreamDestroy( c->st );
+    for( int i = 0; i < NSLOT; i++ ) cudaEventDestroy( c->slot_done[i] );
+    cudaEventDestroy( c->ev_res ); cudaEventDestroy( c->ev_up[0] ); cudaEventDestroy( c->ev_up[1] );
+    cudaStreamDestroy( c->st_in ); cudaStreamDestroy( c->st_out ); cudaStreamDestroy( c->st );
     delete c;
 }
 
@@ -251,16 +275,64 @@ static void finish_stats( int32_t *dst, const uint8_t *p, int kind, int bias )
     }
 }
 
-static int ctx_sync( x264cu_ctx *c )
-{
-    CU( cudaStreamSynchronize( c->st ) );
-    for( const PendingCopy &p : c->copies )
+static void drain_copies( x264cu_ctx *c, uint64_t upto )
+{   // the deferred host-side completion of x264_opencl_flush (slicetype-cl.c:64-69), in enqueue order
+    while( c->copies_head < c->copies.size() && c->copies[c->copies_head].seq <= upto )
     {
+        const PendingCopy &p = c->copies[c->copies_head++];
         if( p.kind < 0 ) memcpy( p.dst, p.src, p.bytes );
         else finish_stats( (int32_t *)p.dst, (const uint8_t *)p.src, p.kind, p.bias );
     }
-    c->copies.clear();
-    c->pin_used = 0; c->jobs_used = 0; c->arena_used = 0;
+    if( c->copies_head == c->copies.size() ) { c->copies.clear(); c->copies_head = 0; }
+}
+
+static int wait_slot( x264cu_ctx *c, int i )
+{
+    if( !c->slot_pending[i] ) return 0;
+    CU( cudaEventSynchronize( c->slot_done[i] ) );
+    drain_copies( c, c->slot_seq[i] );
+    c->slot_pending[i] = false;
+    c->pin_used[i] = c->jobs_used[i] = c->arena_used[i] = 0;
+    return 0;
+}
+
+// wait for every batch with sequence number <= seq, oldest first
+static int wait_upto( x264cu_ctx *c, uint64_t seq )
+{
+    for( ;; )
+    {
+        int best = -1;
+        for( int i = 0; i < NSLOT; i++ )
+            if( c->slot_pending[i] && c->slot_seq[i] <= seq && ( best < 0 || c->slot_seq[i] < c->slot_seq[best] ) ) best = i;
+        if( best < 0 ) return 0;
+        if( wait_slot( c, best ) ) return -1;
+    }
+}
+
+static int begin_batch( x264cu_ctx *c )
+{
+    c->seq++;
+    c->batch_out = false;
+    c->slot = (int)( c->seq % NSLOT );
+    if( wait_upto( c, c->slot_pending[c->slot] ? c->slot_seq[c->slot] : 0 ) ) return -1;
+    c->slot_seq[c->slot] = c->seq;
+    return 0;
+}
+
+static int end_batch( x264cu_ctx *c, cudaStream_t last = NULL )
+{
+    CU( cudaEventRecord( c->slot_done[c->slot], last ? last : c->st ) );
+    c->slot_pending[c->slot] = true;
+    return 0;
+}
+
+static int ctx_sync( x264cu_ctx *c )
+{
+    CU( cudaStreamSynchronize( c->st_in ) );
+    CU( cudaStreamSynchronize( c->st ) );
+    CU( cudaStreamSynchronize( c->st_out ) );
+    drain_copies( c, ~0ULL );
+    for( int i = 0; i < NSLOT; i++ ) { c->slot_pending[i] = false; c->pin_used[i] = c->jobs_used[i] = c->arena_used[i] = 0; }
     for( TimedSpan &s : c->spans )
     {
         float ms = 0;
@@ -286,6 +358,7 @@ extern "C" int64_t x264cu_launch_count( x264cu_ctx *c ) { return c ? c->launches
 extern "C" int x264cu_kernel_times( x264cu_ctx *c, float *ms4, int *n4 )
 {
     if( !c ) FAIL( "null context" );
+    if( !c->spans.empty() && ctx_sync( c ) ) return -1;
     for( int i = 0; i < K_NCLASS; i++ )
     {
         if( ms4 ) ms4[i] = c->class_ms[i];
@@ -302,13 +375,14 @@ extern "C" int x264cu_set_profiling( x264cu_ctx *c, int on )
     return 0;
 }
 
-// pinned staging: returns NULL when full (caller syncs and retries)
+// pinned staging of the current batch's region: returns NULL when full (caller syncs everything and retries)
 static uint8_t *pin_alloc( x264cu_ctx *c, size_t bytes )
 {
-    size_t a = align_up( c->pin_used, 256 );
-    if( a + bytes > c->pin_size ) return NULL;
-    c->pin_used = a + bytes;
-    return c->pin + a;
+    const size_t region = c->pin_size / NSLOT;
+    size_t a = align_up( c->pin_used[c->slot], 256 );
+    if( a + bytes > region ) return NULL;
+    c->pin_used[c->slot] = a + bytes;
+    return c->pin + c->slot * region + a;
 }
 static uint8_t *pin_alloc_sync( x264cu_ctx *c, size_t bytes )
 {
@@ -332,7 +406,7 @@ static int queue_d2h( x264cu_ctx *c, void *dst, const void *dsrc, size_t bytes )
     uint8_t *p = pin_alloc_sync( c, bytes );
     if( !p ) return -1;
     CU( cudaMemcpyAsync( p, dsrc, bytes, cudaMemcpyDeviceToHost, c->st ) );
-    c->copies.push_back( { dst, p, bytes, -1, 0 } );
+    c->copies.push_back( { dst, p, bytes, -1, 0, c->seq } );
     return 0;
 }
 
@@ -368,6 +442,7 @@ extern "C" int x264cu_frame_upload( x264cu_ctx *c, x264cu_frame *f, const uint8_
 {
     if( !c || !f || !luma ) FAIL( "x264cu_frame_upload: null argument" );
     CU( cudaSetDevice( c->device ) );
+    if( begin_batch( c ) ) return -1;
     const LaParams &P = c->P;
     const int W = c->cfg.width, H = c->cfg.height;
     int sel = c->luma_sel; c->luma_sel ^= 1;
@@ -379,8 +454,12 @@ extern "C" int x264cu_frame_upload( x264cu_ctx *c, x264cu_frame *f, const uint8_
         for( int y = 0; y < H; y++ ) memcpy( p + (size_t)y*W, luma + (size_t)y*stride, W );
         src = p; spitch = W;
     }
-    CU( cudaStreamWaitEvent( c->st, c->luma_free[sel], 0 ) );
-    CU( cudaMemcpy2DAsync( c->d_luma[sel], c->luma_pitch, src, spitch, W, H, cudaMemcpyHostToDevice, c->st ) );
+    // the luma crosses PCIe on its own stream, ahead of the compute queue: it only has to wait until the lowres
+    // kernel that last read this staging buffer is done, and the compute queue only waits for this copy
+    CU( cudaStreamWaitEvent( c->st_in, c->luma_free[sel], 0 ) );
+    CU( cudaMemcpy2DAsync( c->d_luma[sel], c->luma_pitch, src, spitch, W, H, cudaMemcpyHostToDevice, c->st_in ) );
+    CU( cudaEventRecord( c->ev_up[sel], c->st_in ) );
+    CU( cudaStreamWaitEvent( c->st, c->ev_up[sel], 0 ) );
     if( inv_qscale )
     {
         const uint16_t *q = inv_qscale;
@@ -397,18 +476,20 @@ extern "C" int x264cu_frame_upload( x264cu_ctx *c, x264cu_frame *f, const uint8_
         launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );         // memset_int16 (downscale.cl:132)
     if( upload_common( c, f, c->d_luma[sel], c->luma_pitch ) ) return -1;
     CU( cudaEventRecord( c->luma_free[sel], c->st ) );
-    return 0;
+    return end_batch( c );
 }
 
 extern "C" int x264cu_frame_upload_device( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint16_t *d_inv_qscale )
 {
     if( !c || !f || !d_luma ) FAIL( "x264cu_frame_upload_device: null argument" );
     CU( cudaSetDevice( c->device ) );
+    if( begin_batch( c ) ) return -1;
     if( d_inv_qscale )
         CU( cudaMemcpyAsync( f->inv_qscale, d_inv_qscale, (size_t)c->P.nmb * 2, cudaMemcpyDeviceToDevice, c->st ) );
     else
         launch_fill_u16( f->inv_qscale, 256, c->P.nmb, c->st );
-    return upload_common( c, f, d_luma, stride );
+    if( upload_common( c, f, d_luma, stride ) ) return -1;
+    return end_batch( c );
 }
 
 extern "C" int x264cu_frame_get_lowres( x264cu_ctx *c, x264cu_frame *f, int plane, uint8_t *out )
@@ -425,27 +506,42 @@ extern "C" int x264cu_frame_get_lowres( x264cu_ctx *c, x264cu_frame *f, int plan
 // ---- job tables and workspace ----
 template<typename T> static int push_jobs( x264cu_ctx *c, const std::vector<T> &v, const T **d_out )
 {
-    size_t bytes = v.size() * sizeof(T);
-    size_t a = align_up( c->jobs_used, 16 );
-    if( a + bytes > c->jobs_size )
+    const size_t region = c->jobs_size / NSLOT, bytes = v.size() * sizeof(T);
+    size_t a = align_up( c->jobs_used[c->slot], 16 );
+    if( a + bytes > region )
     {
-        if( bytes > c->jobs_size ) FAIL( "job table too large" );
+        if( bytes > region ) FAIL( "job table too large" );
         if( ctx_sync( c ) ) return -1;
         a = 0;
     }
-    memcpy( c->h_jobs + a, v.data(), bytes );
-    CU( cudaMemcpyAsync( c->d_jobs + a, c->h_jobs + a, bytes, cudaMemcpyHostToDevice, c->st ) );
-    c->jobs_used = a + bytes;
-    *d_out = (const T *)( c->d_jobs + a );
+    uint8_t *h = c->h_jobs + c->slot * region + a, *d = c->d_jobs + c->slot * region + a;
+    memcpy( h, v.data(), bytes );
+    CU( cudaMemcpyAsync( d, h, bytes, cudaMemcpyHostToDevice, c->st ) );
+    c->jobs_used[c->slot] = a + bytes;
+    *d_out = (const T *)d;
     return 0;
 }
 
+// device workspace of the current batch's region; grows the arena (when idle) if one batch needs more
 static uint8_t *arena_alloc( x264cu_ctx *c, size_t bytes )
 {
-    size_t a = align_up( c->arena_used, 256 );
-    if( a + bytes > c->arena_size ) return NULL;
-    c->arena_used = a + bytes;
-    return c->arena + a;
+    size_t region = c->arena_size / NSLOT;
+    size_t a = align_up( c->arena_used[c->slot], 256 );
+    if( a + bytes > region )
+    {
+        if( ctx_sync( c ) ) return NULL;
+        a = 0;
+        if( bytes > region )
+        {
+            cudaFree( c->arena );
+            c->arena_size = NSLOT * align_up( bytes * 2, 1 << 20 );
+            if( cudaMalloc( &c->arena, c->arena_size ) != cudaSuccess )
+            { snprintf( g_err, sizeof(g_err), "workspace allocation of %zu bytes failed", c->arena_size ); c->arena = NULL; c->arena_size = 0; return NULL; }
+            region = c->arena_size / NSLOT;
+        }
+    }
+    c->arena_used[c->slot] = a + bytes;
+    return c->arena + c->slot * region + a;
 }
 
 struct SearchTask { x264cu_frame *fenc, *fref; int list, dist; x264cu_weight w; };
@@ -462,26 +558,18 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
     const int K = c->cfg.search_passes;
     if( !tasks.empty() )
     {
-        size_t field_bytes = (size_t)P.nmb * 4;
-        size_t need = tasks.size() * 2 * align_up( field_bytes, 256 );
-        for( const SearchTask &t : tasks ) if( t.w.enabled ) need += align_up( (size_t)P.plane_size, 256 );
-        if( c->arena_used + need + 4096 > c->arena_size )
-        {
-            if( ctx_sync( c ) ) return -1;
-            if( need + 4096 > c->arena_size )
-            {
-                cudaFree( c->arena );
-                c->arena_size = need * 2;
-                CU( cudaMalloc( &c->arena, c->arena_size ) );
-            }
-        }
+        const size_t field_bytes = align_up( (size_t)P.nmb * 4, 256 ), plane_bytes = align_up( (size_t)P.plane_size, 256 );
+        size_t need = tasks.size() * 2 * field_bytes;
+        for( const SearchTask &t : tasks ) if( t.w.enabled ) need += plane_bytes;
+        uint8_t *ws = arena_alloc( c, need );
+        if( !ws ) return -1;
         std::vector<uint8_t *> tmp0( tasks.size() ), tmp1( tasks.size() ), wpl( tasks.size(), NULL );
         for( size_t t = 0; t < tasks.size(); t++ )
         {
-            tmp0[t] = arena_alloc( c, field_bytes ); tmp1[t] = arena_alloc( c, field_bytes );
+            tmp0[t] = ws; ws += field_bytes; tmp1[t] = ws; ws += field_bytes;
             if( tasks[t].w.enabled )
             {
-                wpl[t] = arena_alloc( c, (size_t)P.plane_size );
+                wpl[t] = ws; ws += plane_bytes;
                 c->launches++;
                 launch_weight_plane( tasks[t].fref->planes, wpl[t], P.plane_size, tasks[t].w.scale, tasks[t].w.denom, tasks[t].w.offset, c->st );
             }
@@ -619,22 +707,8 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
     }
     if( segs.empty() && sts.empty() ) return 0;
     const size_t baseS = align_up( offA, 256 ), total = baseS + offS;
-    if( c->arena_used + total + 4096 > c->arena_size )
-    {
-        if( ctx_sync( c ) ) return -1;
-        if( total + 4096 > c->arena_size )
-        {
-            cudaFree( c->arena );
-            c->arena_size = total * 2;
-            CU( cudaMalloc( &c->arena, c->arena_size ) );
-        }
-    }
     uint8_t *dstage = arena_alloc( c, total );
-    for( const HostOut &h : sts )
-    {
-        // recover the job: raw sums live right behind its row sums, intra sums behind the frame's intra rows
-        (void)h;
-    }
+    if( !dstage ) return -1;
     {
         size_t k = 0;
         for( int i = 0; i < n; i++ )
@@ -653,13 +727,17 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
     c->launches++;
     launch_gather( dsegs, (int)segs.size(), dstage, c->st );
     CU( cudaGetLastError() );
+    // the results cross PCIe behind the compute queue, on their own stream, so the next batch's kernels overlap them
+    CU( cudaEventRecord( c->ev_res, c->st ) );
+    CU( cudaStreamWaitEvent( c->st_out, c->ev_res, 0 ) );
+    c->batch_out = true;
     if( offA )
     {
         bool direct = is_pinned( arrs[0].dst );
         uint8_t *base = (uint8_t *)arrs[0].dst - arrs[0].off;
         for( const HostOut &h : arrs ) direct = direct && (uint8_t *)h.dst == base + h.off;
         if( direct )
-            CU( cudaMemcpyAsync( base, dstage, offA, cudaMemcpyDeviceToHost, c->st ) );
+            CU( cudaMemcpyAsync( base, dstage, offA, cudaMemcpyDeviceToHost, c->st_out ) );
         else
         {
             uint8_t *p = pin_alloc( c, offA );
@@ -670,8 +748,8 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
                 if( !p ) FAIL( "staging buffer too small for %zu result bytes", offA );
                 // the arena was recycled by the sync but its contents are intact until the next batch
             }
-            CU( cudaMemcpyAsync( p, dstage, offA, cudaMemcpyDeviceToHost, c->st ) );
-            for( const HostOut &h : arrs ) c->copies.push_back( { h.dst, p + h.off, h.bytes, -1, 0 } );
+            CU( cudaMemcpyAsync( p, dstage, offA, cudaMemcpyDeviceToHost, c->st_out ) );
+            for( const HostOut &h : arrs ) c->copies.push_back( { h.dst, p + h.off, h.bytes, -1, 0, c->seq } );
         }
     }
     if( offS )
@@ -683,8 +761,8 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
             p = pin_alloc( c, offS );
             if( !p ) FAIL( "staging buffer too small" );
         }
-        CU( cudaMemcpyAsync( p, dstage + baseS, offS, cudaMemcpyDeviceToHost, c->st ) );
-        for( const HostOut &h : sts ) c->copies.push_back( { h.dst, p + h.off, 32, h.kind, c->cfg.bframe_bias } );
+        CU( cudaMemcpyAsync( p, dstage + baseS, offS, cudaMemcpyDeviceToHost, c->st_out ) );
+        for( const HostOut &h : sts ) c->copies.push_back( { h.dst, p + h.off, 32, h.kind, c->cfg.bframe_bias, c->seq } );
     }
     return 0;
 }
@@ -693,7 +771,9 @@ extern "C" int x264cu_frame_cost_batch( x264cu_ctx *c, const x264cu_job *jobs, i
 {
     if( !c || ( !jobs && n ) ) FAIL( "x264cu_frame_cost_batch: null argument" );
     CU( cudaSetDevice( c->device ) );
-    return run_batch( c, jobs, n );
+    if( begin_batch( c ) ) return -1;
+    if( run_batch( c, jobs, n ) ) return -1;
+    return end_batch( c, c->batch_out ? c->st_out : c->st );
 }
 
 extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_frame *fref, int list, int dist,
@@ -702,6 +782,7 @@ extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_fr
     if( !c || !fenc || !fref || list < 0 || list > 1 || dist < 1 || dist > c->cfg.bframes + 1 ) FAIL( "x264cu_motionsearch: bad argument" );
     if( !fenc->uploaded || !fref->uploaded ) FAIL( "x264cu_motionsearch: frame not uploaded" );
     CU( cudaSetDevice( c->device ) );
+    if( begin_batch( c ) ) return -1;
     if( !fenc->searched[list][dist-1] )
     {
         fenc->searched[list][dist-1] = 1;
@@ -714,7 +795,17 @@ extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_fr
     int fi = field_index( c, list, dist );
     if( queue_d2h( c, mvs, fenc->mvs + (size_t)fi * c->P.nmb * 2, (size_t)c->P.nmb * 4 ) ) return -1;
     if( queue_d2h( c, mv_costs, fenc->mvcosts + (size_t)fi * c->P.nmb, (size_t)c->P.nmb * 4 ) ) return -1;
-    return 0;
+    return end_batch( c );
+}
+
+// sequence number of the most recently enqueued batch / wait for everything up to a sequence number:
+// lets a caller keep NSLOT-1 batches in flight and still pick up results in order (x264cu_stream_sync)
+extern "C" uint64_t x264cu_last_batch( x264cu_ctx *c ) { return c ? c->seq : 0; }
+extern "C" int x264cu_wait( x264cu_ctx *c, uint64_t seq )
+{
+    if( !c ) FAIL( "null context" );
+    CU( cudaSetDevice( c->device ) );
+    return wait_upto( c, seq );
 }
 
 extern "C" int x264cu_frame_cost( x264cu_ctx *c, const x264cu_job *job ) { return x264cu_frame_cost_batch( c, job, 1 ); }
@@ -766,6 +857,8 @@ extern "C" float x264cu_timer_end( x264cu_ctx *c )
     if( !c ) return -1.f;
     cudaSetDevice( c->device );
     float ms = -1.f;
+    // everything enqueued so far, including result copies on the D2H stream
+    if( cudaEventRecord( c->ev_res, c->st_out ) != cudaSuccess || cudaStreamWaitEvent( c->st, c->ev_res, 0 ) != cudaSuccess ) return -1.f;
     if( cudaEventRecord( c->tm_b, c->st ) != cudaSuccess ) return -1.f;
     if( cudaEventSynchronize( c->tm_b ) != cudaSuccess ) return -1.f;
     cudaEventElapsedTime( &ms, c->tm_a, c->tm_b );

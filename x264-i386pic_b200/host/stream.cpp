@@ -21,6 +21,7 @@ struct x264cu_stream
     int want_arrays;                    // also bring lowres_costs / row_satds / MVs back (the full hook protocol)
     std::vector<x264cu_frame *> ring;   // frame n lives in ring[n % depth]
     int64_t n_pushed;
+    uint64_t last_seq;                  // batch sequence number of the most recent push (x264cu_wait target)
     // host results of the most recent push: stats[d0][d1][4] for p1 = newest
     std::vector<int32_t> stats;         // (B+2)*(B+2)*4, indexed [d0*(B+2)+d1]
     std::vector<int32_t> intra_stats;   // 2
@@ -40,7 +41,7 @@ extern "C" x264cu_stream *x264cu_stream_open( x264cu_ctx *ctx, int bframes, int 
     s->ctx = ctx; s->bframes = bframes; s->depth = bframes + 2;
     s->mbw = info[0]; s->mbh = info[1]; s->nmb = info[0] * info[1];
     s->want_arrays = want_arrays;
-    s->n_pushed = 0;
+    s->n_pushed = 0; s->last_seq = 0;
     s->stats.assign( (size_t)( bframes+2 ) * ( bframes+2 ) * 4, -1 );
     s->intra_stats.assign( 2, -1 );
     s->arr = NULL; s->arr_bytes = 0; s->arr_pinned = false;
@@ -118,11 +119,13 @@ extern "C" int x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int st
             s->jobs.push_back( j );
         }
     if( x264cu_frame_cost_batch( s->ctx, s->jobs.data(), (int)s->jobs.size() ) ) return -1;
+    s->last_seq = x264cu_last_batch( s->ctx );
     s->n_pushed++;
     return (int)s->jobs.size();
 }
 
-extern "C" int x264cu_stream_sync( x264cu_stream *s ) { return s ? x264cu_flush( s->ctx ) : -1; }
+// completes this window's most recent push only; pushes of other windows enqueued after it keep running
+extern "C" int x264cu_stream_sync( x264cu_stream *s ) { return s ? x264cu_wait( s->ctx, s->last_seq ) : -1; }
 
 // stats of slicetype_frame_cost( p0 = n-d0-d1.., ) for the newest frame n as p1: d0 = b-p0, d1 = n-b.
 // out4: cost_est (B: scaled), cost_est_aq, intra_mbs, raw cost; -1 when not evaluated.

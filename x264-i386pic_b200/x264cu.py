@@ -65,6 +65,9 @@ def load():
     L.x264cu_frame_cost_batch.argtypes = [vp, C.POINTER(Job), C.c_int]
     L.x264cu_motionsearch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
     L.x264cu_flush.argtypes = [vp]
+    L.x264cu_last_batch.argtypes = [vp]
+    L.x264cu_last_batch.restype = C.c_uint64
+    L.x264cu_wait.argtypes = [vp, C.c_uint64]
     L.x264cu_launch_count.argtypes = [vp]
     L.x264cu_launch_count.restype = C.c_int64
     L.x264cu_kernel_times.argtypes = [vp, vp, vp]
