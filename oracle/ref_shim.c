@@ -50,9 +50,10 @@ static x264_t *open_encoder( int width, int height, int bframes, int subme, int 
     param.i_height = height;
     param.i_csp = X264_CSP_I420;
     param.i_bitdepth = 8;
-    param.i_threads = 1;
+    /* lookahead slices need i_threads > 1 (encoder.c:580-584); sliced threads keep i_thread_frames == 1 */
+    param.i_threads = la_threads > 1 ? la_threads : 1;
     param.i_lookahead_threads = la_threads;
-    param.b_sliced_threads = 0;
+    param.b_sliced_threads = la_threads > 1;
     param.i_sync_lookahead = 0;
     param.i_bframe = bframes;
     param.i_bframe_adaptive = b_adapt;
@@ -302,7 +303,7 @@ EXPORT int ref_la_info( void *ctx, int *out )
     out[6] = c->a.i_lambda; out[7] = h->param.i_bframe_bias;
     out[8] = h->param.analyse.b_weighted_bipred;
     out[9] = h->param.rc.b_mb_tree || h->param.rc.i_vbv_buffer_size || h->mb.i_mb_width <= 2 || h->mb.i_mb_height <= 2;
-    return 0;
+    return h->param.i_lookahead_threads;
 }
 
 /* copy of the lookahead mv-cost table centre +-n (analyse.c:143-157), qp = X264_LOOKAHEAD_QP */
