@@ -340,10 +340,13 @@ def main():
         alg = per_block * nmb * fields
         avg_ms = s_ms / s_n
         ach = alg / avg_ms / 1e6
-        out["roofline"] = {"kernel": "search_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
-                           "frac": round(ach / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch from the committed
+        # `ncu --set full` capture (profiles/r01/ncu_summary_v3.md: 40.62 MB + 0.35 MB); below the algorithmic bytes
+        # because the 18 frames of a window are shared by the 33 fields of a launch and stay in L2
+        out["roofline"] = {"kernel": "search_kernel_t<SATD,unweighted>", "bound": "hbm", "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
+                           "frac": round(ach / peak_gbs, 4), "traffic": 40.97e6, "peak_source": peak_src,
                            "avg_launch_ms": round(avg_ms, 4), "launches_timed": s_n, "algorithmic_bytes_per_launch": alg,
-                           "note": "compulsory bytes are tiny; the kernel is integer-pipe/latency bound (see profiles/)"}
+                           "note": "compulsory bytes are tiny; ncu: L1TEX wavefronts 59 %, ALU pipe 51 %, long-scoreboard stalls 42 % (profiles/r01)"}
         out["kernel_ms_per_step"] = {k: round(v[0] / args.steps, 4) for k, v in kt.items()}
     if rank == 0:
         if not args.no_primitives:

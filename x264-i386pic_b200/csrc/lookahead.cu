@@ -838,8 +838,14 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob 
 
 #define T_TILE_W 32
 #define T_TILE_H 4
+#ifndef X264CU_MINB_SEARCH
+#define X264CU_MINB_SEARCH 5
+#endif
+#ifndef X264CU_MINB_FINAL
+#define X264CU_MINB_FINAL 4
+#endif
 template<bool SATD, bool WEIGHTED>
-__global__ void __launch_bounds__(T_TILE_W*T_TILE_H) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
+__global__ void __launch_bounds__(T_TILE_W*T_TILE_H, X264CU_MINB_SEARCH) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
 {
     extern __shared__ uint16_t s_tab[];
     for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
@@ -987,7 +993,7 @@ __global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *_
 }
 
 template<bool SATD>
-__global__ void __launch_bounds__(T_TILE_W*T_TILE_H) final_kernel_t( const FinalJob *__restrict__ jobs, LaParams P )
+__global__ void __launch_bounds__(T_TILE_W*T_TILE_H, X264CU_MINB_FINAL) final_kernel_t( const FinalJob *__restrict__ jobs, LaParams P )
 {
     const FinalJob J = jobs[blockIdx.z];
     const int bx = blockIdx.x * T_TILE_W + ( threadIdx.x & ( T_TILE_W-1 ) ), by = blockIdx.y * T_TILE_H + threadIdx.x / T_TILE_W;

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libx264cuda.so")
+LIB_PATH = os.environ.get("X264CU_LIB", os.path.join(HERE, "libx264cuda.so"))     # X264CU_LIB: tuning builds only
 
 vp = C.c_void_p
 BFRAME_MAX = 16
