@@ -176,6 +176,32 @@ typedef int (*x264cu_cost_fn)( void *user, int p0, int p1, int b, int32_t *stats
 int x264cu_slicetype_analyse( const x264cu_slicetype_cfg *cfg, x264cu_slicetype_frame *frames, int n_lookahead,
                               int i_last_keyframe, int intra_minigop, x264cu_cost_fn cost, void *user );
 
+/* ---- MB-tree (the consumer right after the path): macroblock_tree_propagate =
+ *      mbtree_propagate_cost + mbtree_propagate_list (common/mc.c:511-598) and macroblock_tree_finish
+ *      (encoder/slicetype.c:1029-1089) on the device, the frame walk of macroblock_tree (:1091-1188) on the host. ---- */
+int x264cu_mbtree_reset( x264cu_ctx *ctx, x264cu_frame *f );                         /* i_propagate_cost = 0 */
+int x264cu_mbtree_swap( x264cu_ctx *ctx, x264cu_frame *a, x264cu_frame *b );         /* XCHG of the two i_propagate_cost arrays */
+/* frame b = fb evaluated as (d0 = b-p0, d1 = p1-b) propagates into fp0 / fp1; fps_factor as slicetype.c:1065 */
+int x264cu_mbtree_propagate( x264cu_ctx *ctx, x264cu_frame *fb, x264cu_frame *fp0, x264cu_frame *fp1, int d0, int d1,
+                             float fps_factor, int referenced );
+/* qp_offset_aq / qp_offset: host float[mb_count]; qp_offset is read-modify-write (blocks with intra_cost 0 keep their value) */
+int x264cu_mbtree_finish( x264cu_ctx *ctx, x264cu_frame *f, int fps_factor, float weightdelta, float strength,
+                          const float *qp_offset_aq, float *qp_offset );
+int x264cu_mbtree_get_propagate( x264cu_ctx *ctx, x264cu_frame *f, uint16_t *out );   /* i_propagate_cost, host u16[mb_count] */
+
+typedef struct
+{
+    x264cu_frame *f;
+    int type;                                   /* decided X264_TYPE_* */
+    float duration;                             /* f_duration */
+    const float *qp_offset_aq;                  /* f_qp_offset_aq, host float[mb_count] */
+    float *qp_offset;                           /* f_qp_offset, host float[mb_count] (out) */
+    float weighted_cost_delta[X264CU_BFRAME_MAX+2];   /* f_weighted_cost_delta */
+} x264cu_mbtree_frame;
+typedef struct { int rc_lookahead, bframe_pyramid, vbv, vbv_lookahead; float qcompress; } x264cu_mbtree_cfg;
+/* macroblock_tree( h, a, frames, num_frames, b_intra ): frames[0..num_frames] */
+int x264cu_macroblock_tree( x264cu_ctx *ctx, const x264cu_mbtree_cfg *cfg, x264cu_mbtree_frame *frames, int num_frames, int b_intra );
+
 /* ---- batched pixel primitives (config "checkasm-style"): x264_pixel_function_t sad/satd/sa8d/
  *      hadamard_ac (pixel.h:82-103), x264_dct_function_t sub4x4/8x8/16x16_dct (dct.h:28-33),
  *      x264_quant_function_t quant_4x4/8x8 (quant.h:30-33), frame_init_lowres_core (mc.h:303).

@@ -623,6 +623,65 @@ EXPORT int ref_la_param( void *ctx, int *out )
     return 0;
 }
 
+/* ---- MB-tree ---- */
+EXPORT void ref_mbtree_propagate_cost( int16_t *dst, uint16_t *propagate_in, uint16_t *intra_costs, uint16_t *inter_costs,
+                                       uint16_t *inv_qscales, float fps, int len )
+{
+    ensure_tables();
+    g_mc.mbtree_propagate_cost( dst, propagate_in, intra_costs, inter_costs, inv_qscales, &fps, len );
+}
+EXPORT void ref_mbtree_propagate_list( void *ctx, uint16_t *ref_costs, int16_t *mvs, int16_t *propagate_amount, uint16_t *lowres_costs,
+                                       int bipred_weight, int mb_y, int len, int list )
+{
+    ref_la_t *c = ctx;
+    ensure_tables();
+    g_mc.mbtree_propagate_list( c->h, ref_costs, (int16_t(*)[2])mvs, propagate_amount, lowres_costs, bipred_weight, mb_y, len, list );
+}
+EXPORT int ref_log2_lut( float *out128 ) { memcpy( out128, x264_log2_lut, 128*sizeof(float) ); return 0; }
+
+/* like ref_la_put_frame, but runs the reference's adaptive quantisation first (x264_adaptive_quant_frame,
+ * ratecontrol.c:304, as encoder.c:3417 does before x264_frame_init_lowres): fills f_qp_offset_aq and
+ * i_inv_qscale_factor from the picture itself */
+EXPORT int ref_la_put_frame_aq( void *ctx, int idx, const uint8_t *luma, int stride )
+{
+    ref_la_t *c = ctx;
+    x264_t *h = c->h;
+    if( ref_la_put_frame( ctx, idx, luma, stride, NULL ) ) return -1;
+    x264_frame_t *f = c->frames[idx];
+    for( int y = 0; y < f->i_lines[1]; y++ )
+        memset( f->plane[1] + (intptr_t)y*f->i_stride[1], 128, f->i_width[1] );
+    x264_adaptive_quant_frame( h, f, NULL );
+    return 0;
+}
+
+/* what: 0 f_qp_offset_aq, 1 f_qp_offset (float x n), 2 i_propagate_cost (u16 x n) */
+EXPORT int ref_la_get_mbtree( void *ctx, int idx, int what, void *out )
+{
+    ref_la_t *c = ctx;
+    x264_frame_t *f = c->frames[idx];
+    int n = c->h->mb.i_mb_count;
+    if( what == 0 ) memcpy( out, f->f_qp_offset_aq, n*sizeof(float) );
+    else if( what == 1 ) memcpy( out, f->f_qp_offset, n*sizeof(float) );
+    else if( what == 2 ) memcpy( out, f->i_propagate_cost, n*sizeof(uint16_t) );
+    else return -1;
+    return 0;
+}
+
+/* the reference's own macroblock_tree (slicetype.c:1091) over frames[first..first+num_frames]; every
+ * slicetype_frame_cost inside it is a cache hit when the caller has evaluated the triples beforehand */
+EXPORT int ref_la_macroblock_tree( void *ctx, int first, int num_frames, int b_intra, const uint8_t *types, const float *durations )
+{
+    ref_la_t *c = ctx;
+    for( int i = 0; i <= num_frames; i++ )
+    {
+        c->frames[first+i]->i_type = types[i];
+        c->frames[first+i]->f_duration = durations[i];
+        memset( c->frames[first+i]->f_weighted_cost_delta, 0, sizeof(c->frames[first+i]->f_weighted_cost_delta) );
+    }
+    macroblock_tree( c->h, &c->a, c->frames + first, num_frames, b_intra );
+    return 0;
+}
+
 EXPORT double ref_now( void )
 {
     struct timespec ts;

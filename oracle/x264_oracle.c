@@ -536,6 +536,7 @@ typedef struct
     int cost_est[XO_MAXB+2][XO_MAXB+2];
     int cost_est_aq[XO_MAXB+2][XO_MAXB+2];
     int intra_mbs[XO_MAXB+2];
+    uint16_t *propagate;          /* i_propagate_cost */
 } xo_frame;
 
 struct xo_ctx
@@ -578,7 +579,7 @@ xo_ctx *xo_open( const xo_cfg *cfg )
 
 static void free_frame( xo_frame *f )
 {
-    free( f->buf ); free( f->wbuf ); free( f->inv_qscale );
+    free( f->buf ); free( f->wbuf ); free( f->inv_qscale ); free( f->propagate );
     for( int i = 0; i < XO_MAXB+2; i++ )
         for( int j = 0; j < XO_MAXB+2; j++ ) { free( f->lowres_costs[i][j] ); free( f->row_satds[i][j] ); }
     for( int l = 0; l < 2; l++ )
@@ -1216,3 +1217,129 @@ int xo_get( xo_ctx *c, int idx, int what, int i, int j, void *out )
 }
 
 void xo_counters( xo_ctx *c, int64_t *out ) { memcpy( out, c->cnt, sizeof(c->cnt) ); }
+
+/* ================================================================================================ */
+/* MB-tree                                                                   */
+/* ================================================================================================ */
+
+/* mc.c:511-525 */
+void xo_mbtree_propagate_cost( int16_t *dst, const uint16_t *propagate_in, const uint16_t *intra_costs, const uint16_t *inter_costs,
+                               const uint16_t *inv_qscales, float fps, int len )
+{
+    for( int i = 0; i < len; i++ )
+    {
+        int intra_cost = intra_costs[i];
+        int inter_cost = imin( intra_costs[i], inter_costs[i] & 0x3FFF );
+        float propagate_intra  = intra_cost * inv_qscales[i];
+        float propagate_amount = propagate_in[i] + propagate_intra*fps;
+        float propagate_num    = intra_cost - inter_cost;
+        float propagate_denom  = intra_cost;
+        dst[i] = imin( (int)( propagate_amount * propagate_num / propagate_denom + 0.5f ), 32767 );
+    }
+}
+
+#define CLIP_ADD(s,x) (s) = imin( (s)+(x), (1<<15)-1 )       /* MC_CLIP_ADD, mc.h:29 */
+
+/* mc.c:527-598 */
+void xo_mbtree_propagate_list( int mbw, int mbh, uint16_t *ref_costs, const int16_t (*mvs)[2], const int16_t *propagate_amount,
+                               const uint16_t *lowres_costs, int bipred_weight, int mb_y, int len, int list )
+{
+    unsigned stride = mbw, width = mbw, height = mbh;
+    for( int i = 0; i < len; i++ )
+    {
+        int lists_used = lowres_costs[i] >> 14;
+        if( !( lists_used & ( 1 << list ) ) ) continue;
+        int listamount = propagate_amount[i];
+        if( lists_used == 3 ) listamount = ( listamount * bipred_weight + 32 ) >> 6;
+        if( !mvs[i][0] && !mvs[i][1] ) { CLIP_ADD( ref_costs[mb_y*stride + i], listamount ); continue; }
+        int x = mvs[i][0], y = mvs[i][1];
+        unsigned mbx = (unsigned)( ( x >> 5 ) + i ), mby = (unsigned)( ( y >> 5 ) + mb_y );
+        unsigned idx0 = mbx + mby * stride, idx2 = idx0 + stride;
+        x &= 31; y &= 31;
+        int w0 = ( ( 32-y ) * ( 32-x ) * listamount + 512 ) >> 10, w1 = ( ( 32-y ) * x * listamount + 512 ) >> 10;
+        int w2 = ( y * ( 32-x ) * listamount + 512 ) >> 10, w3 = ( y * x * listamount + 512 ) >> 10;
+        if( mby < height )
+        {
+            if( mbx < width ) CLIP_ADD( ref_costs[idx0], w0 );
+            if( mbx+1 < width ) CLIP_ADD( ref_costs[idx0+1], w1 );
+        }
+        if( mby+1 < height )
+        {
+            if( mbx < width ) CLIP_ADD( ref_costs[idx2], w2 );
+            if( mbx+1 < width ) CLIP_ADD( ref_costs[idx2+1], w3 );
+        }
+    }
+}
+
+static uint16_t *prop_of( xo_ctx *c, int idx )
+{
+    xo_frame *f = &c->fr[idx];
+    if( !f->propagate ) f->propagate = calloc( c->nmb, sizeof(uint16_t) );
+    return f->propagate;
+}
+
+int xo_mbtree_reset( xo_ctx *c, int idx ) { memset( prop_of( c, idx ), 0, c->nmb * sizeof(uint16_t) ); return 0; }
+int xo_mbtree_get( xo_ctx *c, int idx, uint16_t *out ) { memcpy( out, prop_of( c, idx ), c->nmb * sizeof(uint16_t) ); return 0; }
+int xo_mbtree_swap( xo_ctx *c, int a, int b )
+{
+    uint16_t *pa = prop_of( c, a ), *pb = prop_of( c, b );
+    c->fr[a].propagate = pb; c->fr[b].propagate = pa;
+    return 0;
+}
+
+/* macroblock_tree_propagate, slicetype.c:1051-1089 (without the VBV-lookahead finish) */
+int xo_mbtree_propagate( xo_ctx *c, int p0, int p1, int b, float fps_factor, int referenced )
+{
+    xo_frame *fb = &c->fr[b];
+    if( !fb->valid || !fb->lowres_costs[b-p0][p1-b] ) return -1;
+    uint16_t *ref_costs[2] = { prop_of( c, p0 ), prop_of( c, p1 ) };
+    int dsf = ( ( ( b-p0 ) << 8 ) + ( ( p1-p0 ) >> 1 ) ) / ( p1-p0 );
+    int w = c->cfg.weighted_bipred ? 64 - ( dsf >> 2 ) : 32;
+    int bw[2] = { w, 64 - w };
+    const int16_t (*mvs[2])[2] = { b != p0 ? (const int16_t(*)[2])fb->lowres_mvs[0][b-p0-1] : NULL,
+                                   b != p1 ? (const int16_t(*)[2])fb->lowres_mvs[1][p1-b-1] : NULL };
+    uint16_t *propagate_cost = prop_of( c, b );
+    const uint16_t *lowres_costs = fb->lowres_costs[b-p0][p1-b];
+    int16_t *buf = malloc( c->mbw * sizeof(int16_t) );
+    if( !referenced ) memset( propagate_cost, 0, c->mbw * sizeof(uint16_t) );
+    for( int y = 0; y < c->mbh; y++ )
+    {
+        int mb_index = y * c->mbw;
+        xo_mbtree_propagate_cost( buf, propagate_cost, fb->lowres_costs[0][0] + mb_index, lowres_costs + mb_index,
+                                  fb->inv_qscale + mb_index, fps_factor, c->mbw );
+        if( referenced ) propagate_cost += c->mbw;
+        xo_mbtree_propagate_list( c->mbw, c->mbh, ref_costs[0], mvs[0] + mb_index, buf, lowres_costs + mb_index, bw[0], y, c->mbw, 0 );
+        if( b != p1 )
+            xo_mbtree_propagate_list( c->mbw, c->mbh, ref_costs[1], mvs[1] + mb_index, buf, lowres_costs + mb_index, bw[1], y, c->mbw, 1 );
+    }
+    free( buf );
+    return 0;
+}
+
+/* x264_log2, base.h:226-230 with the tables of tables.c:66-90 */
+static float xo_log2( uint32_t x )
+{
+    static float lut[128];
+    static int init;
+    if( !init ) { for( int i = 0; i < 128; i++ ) lut[i] = (float)( round( log2( 1.0 + i / 128.0 ) * 1e5 ) / 1e5 ); init = 1; }
+    int lz = __builtin_clz( x );
+    return lut[( x << lz >> 24 ) & 0x7f] + (float)( 31 - lz );
+}
+
+/* macroblock_tree_finish, slicetype.c:1029-1049 */
+int xo_mbtree_finish( xo_ctx *c, int idx, int fps_factor, float weightdelta, float strength, const float *qp_offset_aq, float *qp_offset )
+{
+    xo_frame *f = &c->fr[idx];
+    const uint16_t *prop = prop_of( c, idx );
+    for( int i = 0; i < c->nmb; i++ )
+    {
+        int intra_cost = ( f->lowres_costs[0][0][i] * f->inv_qscale[i] + 128 ) >> 8;
+        if( intra_cost )
+        {
+            int propagate_cost = ( prop[i] * fps_factor + 128 ) >> 8;
+            float log2_ratio = xo_log2( intra_cost + propagate_cost ) - xo_log2( intra_cost ) + weightdelta;
+            qp_offset[i] = qp_offset_aq[i] - strength * log2_ratio;
+        }
+    }
+    return 0;
+}

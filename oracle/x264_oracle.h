@@ -70,6 +70,17 @@ int     xo_get( xo_ctx *, int idx, int what, int i, int j, void *out );   /* sam
 /* counters of the last xo_frame_cost: [0] fullpel SAD candidates, [1] subpel SAD, [2] SATD 8x8 */
 void    xo_counters( xo_ctx *, int64_t *out );
 
+/* ---- MB-tree: mc.c:511-598, slicetype.c:1029-1089 ---- */
+void    xo_mbtree_propagate_cost( int16_t *dst, const uint16_t *propagate_in, const uint16_t *intra_costs, const uint16_t *inter_costs,
+                                  const uint16_t *inv_qscales, float fps, int len );
+void    xo_mbtree_propagate_list( int mbw, int mbh, uint16_t *ref_costs, const int16_t (*mvs)[2], const int16_t *propagate_amount,
+                                  const uint16_t *lowres_costs, int bipred_weight, int mb_y, int len, int list );
+int     xo_mbtree_reset( xo_ctx *, int idx );
+int     xo_mbtree_swap( xo_ctx *, int a, int b );
+int     xo_mbtree_get( xo_ctx *, int idx, uint16_t *out );
+int     xo_mbtree_propagate( xo_ctx *, int p0, int p1, int b, float fps_factor, int referenced );
+int     xo_mbtree_finish( xo_ctx *, int idx, int fps_factor, float weightdelta, float strength, const float *qp_offset_aq, float *qp_offset );
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,8 @@ struct x264cu_frame
     int16_t  *mvs;           // [2*(B+1)][nmb][2]
     int32_t  *mvcosts;       // [2*(B+1)][nmb]
     int32_t  *stats;         // [(B+2)*(B+2)][stat_pitch]: row_satds[mbh], cost_est, cost_est_aq, intra_mbs
+    uint32_t *prop;          // i_propagate_cost accumulators (MB-tree), clamped to 32767 on read
+    float    *qp_aq, *qp;    // f_qp_offset_aq (in) / f_qp_offset (out) staging for macroblock_tree_finish
     uint8_t   searched[2][X264CU_BFRAME_MAX+1];
     uint8_t   evaluated[X264CU_BFRAME_MAX+2][X264CU_BFRAME_MAX+2];
     bool      uploaded;
@@ -51,6 +53,7 @@ struct x264cu_ctx
     cudaStream_t st_in, st_out;      // copy streams: luma H2D ahead of the compute, results D2H behind it
     cudaEvent_t ev_up[2], ev_res;
     uint16_t *d_cost_mv;
+    float *d_log2_lut;
     int stat_pitch;
     size_t plane_alloc;      // bytes of the 4 planes + slack
     // full-resolution luma staging on the device (double buffered)
@@ -149,6 +152,12 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
         CUP( cudaMemcpy( c->d_cost_mv, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice ) );
         P.cost_mv = c->d_cost_mv;
     }
+    {   // x264_log2_lut (tables.c:66-85) is log2(1 + i/128) printed with 5 decimals
+        float lut[128];
+        for( int i = 0; i < 128; i++ ) lut[i] = (float)( round( log2( 1.0 + i / 128.0 ) * 1e5 ) / 1e5 );
+        CUP( cudaMalloc( &c->d_log2_lut, sizeof(lut) ) );
+        CUP( cudaMemcpy( c->d_log2_lut, lut, sizeof(lut), cudaMemcpyHostToDevice ) );
+    }
     c->luma_pitch = (int)align_up( cfg->width, 256 );
     for( int i = 0; i < 2; i++ )
     {
@@ -193,6 +202,7 @@ extern "C" void x264cu_frame_free( x264cu_ctx *c, x264cu_frame *f )
     ctx_sync( c );
     cudaFree( f->planes ); cudaFree( f->inv_qscale ); cudaFree( f->costs );
     cudaFree( f->mvs ); cudaFree( f->mvcosts ); cudaFree( f->stats );
+    cudaFree( f->prop ); cudaFree( f->qp_aq ); cudaFree( f->qp );
     for( size_t i = 0; i < c->frames.size(); i++ )
         if( c->frames[i] == f ) { c->frames.erase( c->frames.begin() + i ); break; }
     delete f;
@@ -206,7 +216,7 @@ extern "C" void x264cu_close( x264cu_ctx *c )
     while( !c->frames.empty() ) x264cu_frame_free( c, c->frames.back() );
     for( cudaEvent_t e : c->ev_pool ) cudaEventDestroy( e );
     for( int i = 0; i < 2; i++ ) { cudaFree( c->d_luma[i] ); cudaEventDestroy( c->luma_free[i] ); }
-    cudaFree( c->d_cost_mv ); cudaFree( c->d_jobs ); cudaFree( c->arena );
+    cudaFree( c->d_cost_mv ); cudaFree( c->d_log2_lut ); cudaFree( c->d_jobs ); cudaFree( c->arena );
     cudaFreeHost( c->pin ); cudaFreeHost( c->h_jobs );
     cudaEventDestroy( c->tm_a ); cudaEventDestroy( c->tm_b );
     for( int i = 0; i < NSLOT; i++ ) cudaEventDestroy( c->slot_done[i] );
@@ -229,14 +239,18 @@ extern "C" x264cu_frame *x264cu_frame_new( x264cu_ctx *c )
         cudaMalloc( &f->costs, ntri * P.nmb * 2 ) != cudaSuccess ||
         cudaMalloc( &f->mvs, nfield * P.nmb * 4 ) != cudaSuccess ||
         cudaMalloc( &f->mvcosts, nfield * P.nmb * 4 ) != cudaSuccess ||
-        cudaMalloc( &f->stats, ntri * c->stat_pitch * 4 ) != cudaSuccess )
+        cudaMalloc( &f->stats, ntri * c->stat_pitch * 4 ) != cudaSuccess ||
+        cudaMalloc( &f->prop, (size_t)P.nmb * 4 ) != cudaSuccess ||
+        cudaMalloc( &f->qp_aq, (size_t)P.nmb * 4 ) != cudaSuccess || cudaMalloc( &f->qp, (size_t)P.nmb * 4 ) != cudaSuccess )
     {
         snprintf( g_err, sizeof(g_err), "x264cu_frame_new: out of device memory" );
         cudaGetLastError();
         cudaFree( f->planes ); cudaFree( f->inv_qscale ); cudaFree( f->costs ); cudaFree( f->mvs ); cudaFree( f->mvcosts ); cudaFree( f->stats );
+        cudaFree( f->prop ); cudaFree( f->qp_aq ); cudaFree( f->qp );
         delete f;
         return NULL;
     }
+    cudaMemset( f->prop, 0, (size_t)P.nmb * 4 );
     c->frames.push_back( f );
     return f;
 }
@@ -809,6 +823,77 @@ extern "C" int x264cu_wait( x264cu_ctx *c, uint64_t seq )
 }
 
 extern "C" int x264cu_frame_cost( x264cu_ctx *c, const x264cu_job *job ) { return x264cu_frame_cost_batch( c, job, 1 ); }
+
+// ------------------------------------------------------------------------------------------------
+// MB-tree: macroblock_tree_propagate / macroblock_tree_finish on the device
+// ------------------------------------------------------------------------------------------------
+extern "C" int x264cu_mbtree_reset( x264cu_ctx *c, x264cu_frame *f )
+{   // memset( i_propagate_cost, 0, ... ) (slicetype.c:1128,1139,1145)
+    if( !c || !f ) FAIL( "x264cu_mbtree_reset: null argument" );
+    CU( cudaSetDevice( c->device ) );
+    CU( cudaMemsetAsync( f->prop, 0, (size_t)c->P.nmb * 4, c->st ) );
+    return 0;
+}
+
+extern "C" int x264cu_mbtree_swap( x264cu_ctx *c, x264cu_frame *a, x264cu_frame *b )
+{   // XCHG( uint16_t*, frames[last_nonb]->i_propagate_cost, frames[0]->i_propagate_cost ) (slicetype.c:1127,1180)
+    if( !c || !a || !b ) FAIL( "x264cu_mbtree_swap: null argument" );
+    uint32_t *t = a->prop; a->prop = b->prop; b->prop = t;
+    return 0;
+}
+
+extern "C" int x264cu_mbtree_propagate( x264cu_ctx *c, x264cu_frame *fb, x264cu_frame *fp0, x264cu_frame *fp1, int d0, int d1,
+                                        float fps_factor, int referenced )
+{
+    if( !c || !fb || !fp0 || !fp1 || d0 < 1 || d1 < 0 || d0 + d1 > c->cfg.bframes + 1 ) FAIL( "x264cu_mbtree_propagate: bad argument" );
+    if( !fb->evaluated[d0][d1] ) FAIL( "x264cu_mbtree_propagate: evaluation (%d,%d) has not been computed", d0, d1 );
+    CU( cudaSetDevice( c->device ) );
+    const LaParams &P = c->P;
+    MbtreeJob J;
+    J.intra = fb->costs;
+    J.lowres_costs = fb->costs + (size_t)tri_index( c, d0, d1 ) * P.nmb;
+    J.inv_qscale = fb->inv_qscale;
+    J.prop_b = fb->prop;
+    J.prop_ref[0] = fp0->prop; J.prop_ref[1] = fp1->prop;
+    J.mvs[0] = fb->mvs + (size_t)field_index( c, 0, d0 ) * P.nmb * 2;
+    J.mvs[1] = d1 ? fb->mvs + (size_t)field_index( c, 1, d1 ) * P.nmb * 2 : NULL;
+    int dsf = ( ( d0 << 8 ) + ( ( d0 + d1 ) >> 1 ) ) / ( d0 + d1 );                  // slicetype.c:1054
+    int w = P.weighted_bipred ? 64 - ( dsf >> 2 ) : 32;
+    J.bipred_weight[0] = w; J.bipred_weight[1] = 64 - w;
+    J.fps_factor = fps_factor;
+    J.referenced = referenced;
+    c->launches++;
+    launch_mbtree_propagate( J, P, c->st );
+    CU( cudaGetLastError() );
+    return 0;
+}
+
+extern "C" int x264cu_mbtree_finish( x264cu_ctx *c, x264cu_frame *f, int fps_factor, float weightdelta, float strength,
+                                     const float *qp_offset_aq, float *qp_offset )
+{   // host arrays of mb_count floats; qp_offset must be initialised by the caller (blocks with intra_cost == 0 keep their value)
+    if( !c || !f || !qp_offset_aq || !qp_offset ) FAIL( "x264cu_mbtree_finish: null argument" );
+    CU( cudaSetDevice( c->device ) );
+    const size_t bytes = (size_t)c->P.nmb * 4;
+    CU( cudaMemcpyAsync( f->qp_aq, qp_offset_aq, bytes, cudaMemcpyHostToDevice, c->st ) );
+    CU( cudaMemcpyAsync( f->qp, qp_offset, bytes, cudaMemcpyHostToDevice, c->st ) );
+    c->launches++;
+    launch_mbtree_finish( f->costs, f->inv_qscale, f->prop, f->qp_aq, f->qp, c->d_log2_lut, fps_factor, weightdelta, strength, c->P.nmb, c->st );
+    CU( cudaGetLastError() );
+    CU( cudaMemcpyAsync( qp_offset, f->qp, bytes, cudaMemcpyDeviceToHost, c->st ) );
+    CU( cudaStreamSynchronize( c->st ) );
+    return 0;
+}
+
+extern "C" int x264cu_mbtree_get_propagate( x264cu_ctx *c, x264cu_frame *f, uint16_t *out )
+{
+    if( !c || !f || !out ) FAIL( "x264cu_mbtree_get_propagate: null argument" );
+    CU( cudaSetDevice( c->device ) );
+    std::vector<uint32_t> tmp( c->P.nmb );
+    CU( cudaMemcpyAsync( tmp.data(), f->prop, (size_t)c->P.nmb * 4, cudaMemcpyDeviceToHost, c->st ) );
+    CU( cudaStreamSynchronize( c->st ) );
+    for( int i = 0; i < c->P.nmb; i++ ) out[i] = (uint16_t)( tmp[i] < 32767u ? tmp[i] : 32767u );
+    return 0;
+}
 
 // ---- small helpers exported for callers that keep data resident ----
 extern "C" void *x264cu_malloc( x264cu_ctx *c, size_t bytes )

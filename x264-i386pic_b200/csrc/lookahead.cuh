@@ -60,3 +60,18 @@ void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *
                    int32_t *stats, const LaParams &P, cudaStream_t st );
 void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st );
 void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );
+
+// One macroblock_tree_propagate step (slicetype.c:1051-1089) of frame b towards its references.
+struct MbtreeJob
+{
+    const uint16_t *intra, *lowres_costs, *inv_qscale;   // of frame b: i_intra_cost, lowres_costs[b-p0][p1-b], i_inv_qscale_factor
+    const u32 *prop_b;                                     // frame b's own accumulated propagate cost (read when referenced)
+    u32 *prop_ref[2];                                      // accumulators of frames p0 / p1
+    const int16_t *mvs[2];                                 // lowres_mvs[l][dist-1] of frame b (NULL: list unused)
+    int bipred_weight[2];
+    float fps_factor;
+    int referenced;
+};
+void launch_mbtree_propagate( const MbtreeJob &J, const LaParams &P, cudaStream_t st );
+void launch_mbtree_finish( const uint16_t *intra, const uint16_t *inv_qscale, const u32 *prop, const float *qp_offset_aq, float *qp_offset,
+                           const float *log2_lut, int fps_factor, float weightdelta, float strength, int nmb, cudaStream_t st );
