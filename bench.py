@@ -247,13 +247,14 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--streams", type=int, default=4, help="independent encode streams per GPU (round-robin)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--search-passes", type=int, default=2, help="K of the dependency-free schedule; 0 = exact raster-serial wavefront mode")
     ap.add_argument("--no-primitives", action="store_true", help="skip the SATD/SAD primitive roofline section")
     ap.add_argument("--value-only", action="store_true", help="profiling aid: skip the end-to-end pass")
     args = ap.parse_args()
     warmup = max(args.warmup, 3)
     nproc = os.cpu_count() or 1
     config = {"workload": "lowres lookahead frame-cost matrix, 1080p, bframes=16, b-adapt 2 (BASELINE.json configs[2])",
-              "width": W, "height": H, "bframes": BFRAMES, "search_passes": 2, "subme": 7, "mbtree_edges": 1, "aq": 1,
+              "width": W, "height": H, "bframes": BFRAMES, "search_passes": args.search_passes, "subme": 7, "mbtree_edges": 1, "aq": 1,
               "evals_per_step": 154, "new_search_fields_per_step": 33, "streams_per_gpu": args.streams,
               "sharding": "independent encode streams per GPU, no collective", "host_pipeline_depth": 1,
               "l2": "inputs larger than L2: %d windows x 18 frames x ~10 MB of planes+cost arrays per GPU" % args.streams}
@@ -280,7 +281,7 @@ def main():
     rank, world, local, dist = dist_setup(args.gpus)
     S = args.streams
     per_stream = RAMP + (warmup + args.steps + S - 1) // S + 1
-    ctx = x264cu.Context(W, H, bframes=BFRAMES, subme=7, do_edges=1, aq=1, passes=2, device=local)
+    ctx = x264cu.Context(W, H, bframes=BFRAMES, subme=7, do_edges=1, aq=1, passes=args.search_passes, device=local)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

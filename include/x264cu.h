@@ -44,7 +44,9 @@ typedef struct
     int aq;                   /* rc.i_aq_mode != 0 (slicetype.c:749,779)                                  */
     int weighted_bipred;      /* analyse.b_weighted_bipred (slicetype.c:529)                              */
     int bframe_bias;          /* i_bframe_bias (slicetype.c:985)                                          */
-    int search_passes;        /* K of the dependency-free schedule; >= 1, default 2           */
+    int search_passes;        /* K >= 1: passes of the dependency-free schedule, default 2;
+                               * 0: exact raster-serial search (one launch per anti-diagonal wave): results
+                               * identical to the reference's own slicetype_frame_cost with 1 lookahead thread */
     int max_frames;           /* frame handles that may be alive at once (rc.i_lookahead + bframes + 3)   */
     const uint16_t *cost_mv;  /* optional: host pointer to the CENTRE of h->cost_mv[X264_LOOKAHEAD_QP]
                                * (analyse.c:143-157), valid for +-8*mv_range; NULL: rebuilt with the same

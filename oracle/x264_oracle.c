@@ -557,7 +557,7 @@ xo_ctx *xo_open( const xo_cfg *cfg )
     xo_ctx *c = calloc( 1, sizeof(*c) );
     if( !c ) return NULL;
     c->cfg = *cfg;
-    if( c->cfg.search_passes < 1 ) c->cfg.search_passes = 1;
+    if( c->cfg.search_passes < 0 ) c->cfg.search_passes = 1;      /* 0: the reference's own raster-serial schedule */
     c->mbw = ( cfg->width + 15 ) / 16;
     c->mbh = ( cfg->height + 15 ) / 16;
     c->nmb = c->mbw * c->mbh;
@@ -1151,7 +1151,8 @@ int xo_frame_cost( xo_ctx *c, int p0, int p1, int b, int w_scale, int w_denom, i
     int do_edges = c->cfg.do_edges || c->mbw <= 2 || c->mbh <= 2;
     int start_y = imin( c->mbh-1, c->mbh-2+do_edges ), end_y = imax( 0, 1-do_edges );
     int start_x = c->mbw-2+do_edges, end_x = 1-do_edges;
-    int n_pass = ( e.do_search[0] || e.do_search[1] ) ? c->cfg.search_passes : 1;
+    const int serial = c->cfg.search_passes == 0;
+    int n_pass = ( e.do_search[0] || e.do_search[1] ) && !serial ? c->cfg.search_passes : 1;
     int64_t cnt_total[3] = {0,0,0};
 
     for( int l = 0; l < 2; l++ )
@@ -1159,9 +1160,10 @@ int xo_frame_cost( xo_ctx *c, int p0, int p1, int b, int w_scale, int w_denom, i
 
     for( int pass = 0; pass < n_pass; pass++ )
     {
-        int16_t (*nb[2])[2] = { c->snap[0], c->snap[1] };
+        /* serial: neighbours come from the field being written, as in slicetype.c:662-680 (reverse raster order) */
+        int16_t (*nb[2])[2] = { serial ? e.mvs[0] : c->snap[0], serial ? e.mvs[1] : c->snap[1] };
         for( int l = 0; l < 2; l++ )
-            if( e.do_search[l] ) memcpy( c->snap[l], e.mvs[l], c->nmb*4 );
+            if( e.do_search[l] && !serial ) memcpy( c->snap[l], e.mvs[l], c->nmb*4 );
         e.final_pass = pass == n_pass-1;
         if( e.final_pass )
         {

@@ -179,6 +179,38 @@ def test_frame_costs_match_reference_build():
         gpu.close()
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libx264ref.so not built")
+@pytest.mark.parametrize("W,H,subme,mbtree", [(352, 288, 7, 1), (208, 160, 7, 0), (352, 288, 1, 1)])
+def test_exact_raster_mode_matches_unmodified_reference(W, H, subme, mbtree):
+    """search_passes = 0 (one launch per anti-diagonal wave): bit-exact with the reference's OWN raster-serial
+    slicetype_frame_cost (slicetype.c:836) -- no schedule change, nothing modified, one lookahead thread."""
+    x264cu = _cu()
+    frames = synth_frames(W, H, 5, seed=12, pan=(-4, 3), noise=5)
+    rng = np.random.default_rng(2)
+    ref = Lookahead(RefLib(), "ref_serial", W, H, bframes=3, subme=subme, mbtree=mbtree, aq=1)
+    gpu = x264cu.CudaLookahead(W, H, bframes=3, subme=subme, mbtree=mbtree, aq=1, passes=0, mv_range=ref.mv_range)
+    try:
+        for i, f in enumerate(frames):
+            q = rng.integers(64, 1024, ref.nmb).astype(np.uint16)
+            ref.put_frame(i, f, q)
+            gpu.put_frame(i, f, q)
+        for (p0, p1, b) in [(0, 0, 0), (0, 1, 1), (0, 3, 3), (0, 3, 1), (0, 3, 2), (1, 4, 4), (1, 4, 2), (1, 4, 3), (2, 4, 4), (2, 4, 3)]:
+            sr = ref.frame_cost(p0, p1, b)
+            sg = gpu.frame_cost(p0, p1, b)
+            r = gpu.results[(b, b - p0, p1 - b)]
+            i, j = b - p0, p1 - b
+            np.testing.assert_array_equal(r["lowres_costs"], ref.get(b, GET_LOWRES_COSTS, i, j), err_msg=f"({p0},{p1},{b})")
+            if i:
+                np.testing.assert_array_equal(r["mvs0"], ref.get(b, GET_MVS, 0, i - 1))
+                np.testing.assert_array_equal(r["mv_costs0"], ref.get(b, GET_MV_COSTS, 0, i - 1))
+            if j:
+                np.testing.assert_array_equal(r["mvs1"], ref.get(b, GET_MVS, 1, j - 1))
+            assert sr == sg
+    finally:
+        ref.close()
+        gpu.close()
+
+
 def test_1080p_properties():
     """full-size run: properties that do not need the (slow) CPU oracle at 1080p."""
     x264cu = _cu()

@@ -100,6 +100,35 @@ def test_lookahead_random(libs, W, H, subme, mbtree, aq, passes, bframes):
         B.close()
 
 
+@pytest.mark.parametrize("subme,mbtree", [(7, 1), (7, 0), (1, 1)])
+def test_serial_mode_equals_unmodified_reference(libs, subme, mbtree):
+    """search_passes = 0: the oracle in the reference's raster-serial schedule against the reference's OWN
+    slicetype_frame_cost (slicetype.c:836), nothing modified, one lookahead thread."""
+    ref, orc = libs
+    W, H = 208, 160
+    frames = synth_frames(W, H, 5, seed=12, pan=(-4, 3), noise=5)
+    rng = np.random.default_rng(2)
+    A = Lookahead(ref, "ref_serial", W, H, bframes=3, subme=subme, mbtree=mbtree, aq=1)
+    B = Lookahead(orc, "oracle", W, H, bframes=3, subme=subme, mbtree=mbtree, aq=1, passes=0, mv_range=A.mv_range)
+    try:
+        for i, f in enumerate(frames):
+            q = rng.integers(64, 1024, A.nmb).astype(np.uint16)
+            A.put_frame(i, f, q)
+            B.put_frame(i, f, q)
+        for (p0, p1, b) in [(0, 0, 0), (0, 1, 1), (0, 3, 3), (0, 3, 1), (0, 3, 2), (1, 4, 4), (1, 4, 2), (1, 4, 3), (2, 4, 4), (2, 4, 3)]:
+            assert A.frame_cost(p0, p1, b) == B.frame_cost(p0, p1, b), (p0, p1, b)
+            i, j = b - p0, p1 - b
+            np.testing.assert_array_equal(A.get(b, GET_LOWRES_COSTS, i, j), B.get(b, GET_LOWRES_COSTS, i, j))
+            if i:
+                np.testing.assert_array_equal(A.get(b, GET_MVS, 0, i - 1), B.get(b, GET_MVS, 0, i - 1))
+                np.testing.assert_array_equal(A.get(b, GET_MV_COSTS, 0, i - 1), B.get(b, GET_MV_COSTS, 0, i - 1))
+            if j:
+                np.testing.assert_array_equal(A.get(b, GET_MVS, 1, j - 1), B.get(b, GET_MVS, 1, j - 1))
+    finally:
+        A.close()
+        B.close()
+
+
 def test_jacobi_tracks_raster_serial_quality(libs):
     """sanity (not parity): the dependency-free schedule with K=2 stays close to the reference's
     own raster-serial search on panning content (secondary oracle)."""

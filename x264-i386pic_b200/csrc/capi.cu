@@ -105,7 +105,7 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
     x264cu_ctx *c = new x264cu_ctx();
     c->device = device;
     c->cfg = *cfg;
-    if( c->cfg.search_passes < 1 ) c->cfg.search_passes = 2;
+    if( c->cfg.search_passes < 0 ) c->cfg.search_passes = 2;      // 0 selects the exact raster-serial wavefront mode
     if( c->cfg.me_range < 4 ) c->cfg.me_range = 16;
     if( c->cfg.max_frames < 4 ) c->cfg.max_frames = 64;
     cudaDeviceProp prop;
@@ -587,6 +587,29 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
                 c->launches++;
                 launch_weight_plane( tasks[t].fref->planes, wpl[t], P.plane_size, tasks[t].w.scale, tasks[t].w.denom, tasks[t].w.offset, c->st );
             }
+        }
+        if( K == 0 )
+        {   // exact raster-serial mode: neighbours are read from the field being written, wave by wave
+            std::vector<SearchJob> sj( tasks.size() );
+            for( size_t t = 0; t < tasks.size(); t++ )
+            {
+                const SearchTask &T = tasks[t];
+                int fi = field_index( c, T.list, T.dist );
+                SearchJob &S = sj[t];
+                S.fenc = planeF( c, T.fenc ); S.ref = planeF( c, T.fref );
+                S.ref_w = wpl[t] ? wpl[t] + (size_t)X264CU_PAD * P.stride + X264CU_PAD : S.ref;
+                S.mv_out = T.fenc->mvs + (size_t)fi * P.nmb * 2;
+                S.mv_in = S.mv_out;
+                S.cost_out = T.fenc->mvcosts + (size_t)fi * P.nmb;
+                S.wscale = T.w.scale; S.wdenom = T.w.enabled ? T.w.denom : -1; S.woffset = T.w.offset;
+                CU( cudaMemsetAsync( S.mv_out, 0, (size_t)P.nmb * 4, c->st ) );
+                CU( cudaMemsetAsync( S.cost_out, 0, (size_t)P.nmb * 4, c->st ) );
+            }
+            const SearchJob *d;
+            if( push_jobs( c, sj, &d ) ) return -1;
+            const int nwaves = P.mbw + 2 * ( P.mbh - 1 );
+            Span s( c, K_SEARCH, nwaves );
+            launch_search_waves( d, (int)sj.size(), P, c->st );
         }
         for( int pass = 0; pass < K; pass++ )
         {

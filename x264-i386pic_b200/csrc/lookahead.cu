@@ -864,6 +864,38 @@ __global__ void __launch_bounds__(T_TILE_W*T_TILE_H, X264CU_MINB_SEARCH) search_
     search_block( be, J, P, s_tab, bx, by, blk );
 }
 
+// Exact raster-serial mode: the reference evaluates blocks in reverse raster order and
+// each block reads the MVs of its right / below / below-left / below-right neighbours from the SAME pass
+// (slicetype.c:662-680,830-833).  Blocks with equal w = (mbw-1-x) + 2*(mbh-1-y) depend only on blocks of smaller w,
+// so one launch per anti-diagonal wave reproduces the serial result exactly; mv_in == mv_out (in place).
+__global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJob *__restrict__ jobs, LaParams P, int wave )
+{
+    extern __shared__ uint16_t s_tab[];
+    for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
+    __syncthreads();
+    const SearchJob J = jobs[blockIdx.y];
+    GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
+    const int by = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );       // one candidate block per row
+    if( by >= P.mbh ) return;
+    const int bx = P.mbw - 1 - ( wave - 2 * ( P.mbh - 1 - by ) );
+    if( bx < 0 || bx >= P.mbw ) return;
+    if( skipped_border( P, bx, by ) ) return;                                 // the field was zeroed before the first wave
+    const int blk = by * P.mbw + bx;
+    const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
+    be.fenc = *(const uint2 *)( J.fenc + pel );
+    be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
+    search_block( be, J, P, s_tab, bx, by, blk );
+}
+
+void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
+{
+    size_t smem = ( P.cost_mv_n + 1 ) * sizeof(uint16_t);
+    dim3 grid( ( P.mbh + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
+    const int nwaves = P.mbw + 2 * ( P.mbh - 1 );
+    for( int w = 0; w < nwaves; w++ )
+        search_kernel_wave<<<grid, CTA_THREADS, smem, st>>>( d_jobs, P, w );
+}
+
 static bool use_thread_mapping( const LaParams &P, int njobs )
 {
     if( P.lanes_per_block == 1 ) return true;

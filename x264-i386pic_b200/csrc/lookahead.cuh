@@ -60,6 +60,7 @@ void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *
                    int32_t *stats, const LaParams &P, cudaStream_t st );
 void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st );
 void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );
+void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );
 
 // One macroblock_tree_propagate step (slicetype.c:1051-1089) of frame b towards its references.
 struct MbtreeJob
