@@ -114,7 +114,14 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
     LaParams &P = c->P;
     P.mbw = ( cfg->width + 15 ) / 16; P.mbh = ( cfg->height + 15 ) / 16; P.nmb = P.mbw * P.mbh;
     P.lw = P.mbw * 8; P.lh = P.mbh * 8;
-    P.stride = (int)align_up( P.lw + 2*X264CU_PAD, 128 );
+    // plane pitch: 1024 or 2048 whenever the padded width fits, so that the search/decision kernels run their
+    // compile-time-pitch instantiations (row addresses become immediates); wider frames use a run-time pitch
+    {
+        const int padded = P.lw + 2*X264CU_PAD;
+        const char *e = getenv( "X264CU_RUNTIME_PITCH" );      // testing aid: forces the run-time-pitch kernels
+        P.stride = ( e && atoi( e ) ) || padded > 2048 ? (int)align_up( padded, 128 ) + ( e && atoi( e ) && ( padded == 1024 || padded == 2048 ) ? 128 : 0 )
+                 : padded <= 1024 ? 1024 : 2048;
+    }
     P.plane_size = (int64_t)P.stride * ( P.lh + 2*X264CU_PAD );
     P.mv_range2 = 2 * cfg->mv_range;
     P.me_range = c->cfg.me_range;

@@ -19,10 +19,13 @@ typedef uint32_t u32;
 __device__ __forceinline__ int iclip3( int v, int lo, int hi ) { return min( max( v, lo ), hi ); }
 __device__ __forceinline__ int imedian( int a, int b, int c ) { return max( min( a, b ), min( max( a, b ), c ) ); }
 
-// pixel.c:255-259 abs2(): per-lane absolute value of a true-sum packed word.
+// pixel.c:255-259 abs2(): per-lane absolute value of a true-sum packed word.  The reference's mask
+// s = ((a>>15)&0x10001)*0xffff is 0xffff in each half whose bit 15 is set; PRMT's sign-replicate mode builds the
+// same word in one instruction (bytes 0,1 <- sign of byte 1; bytes 2,3 <- sign of byte 3).
 __device__ __forceinline__ u32 abs2( u32 a )
 {
-    u32 s = ( ( a >> 15 ) & 0x10001u ) * 0xffffu;
+    u32 s;
+    asm( "prmt.b32 %0, %1, 0, 0xbb99;" : "=r"( s ) : "r"( a ) );
     return ( a + s ) ^ s;
 }
 
@@ -61,7 +64,13 @@ __device__ __forceinline__ uint4 load16u( const uint8_t *p )
 }
 
 // rounding byte average (a+b+1)>>1 on 4 packed pixels: mc.c:56 / FILTER of mc.c:494
-__device__ __forceinline__ u32 avg4( u32 a, u32 b ) { return __vavgu4( a, b ); }
+// = (a|b) - (((a^b) & 0xfe..fe) >> 1) per byte; the explicit LOP3 keeps it at 4 instructions (__vavgu4 expands to 5)
+__device__ __forceinline__ u32 avg4( u32 a, u32 b )
+{
+    u32 t;
+    asm( "lop3.b32 %0, %1, %2, 0xfefefefe, 0x28;" : "=r"( t ) : "r"( a ), "r"( b ) );     // (a ^ b) & c
+    return ( a | b ) - ( t >> 1 );
+}
 
 // SAD of 8 pixels held as two words each
 __device__ __forceinline__ u32 sad8( uint2 a, uint2 b ) { return __vsadu4( a.x, b.x ) + __vsadu4( a.y, b.y ); }

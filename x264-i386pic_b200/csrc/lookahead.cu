@@ -339,7 +339,24 @@ __device__ __forceinline__ void me_limits( MeGeo &m, const LaParams &P, int bx, 
     m.fminx = m.sminx >> 2; m.fmaxx = m.smaxx >> 2; m.fminy = m.sminy >> 2; m.fmaxy = m.smaxy >> 2;
 }
 
-__device__ __forceinline__ int mvcost( const uint16_t *tab, const MeGeo &m, int mx, int my )
+// cost_mv table (analyse.c:153-157): the first S_TAB_N entries (|mvd| < 128 px) are staged in shared memory per CTA,
+// the rare larger deltas read the global table through L1 (ncu r01: copying all 8*mv_range+1 entries per CTA was
+// 14 % of the search kernel's stall samples)
+#define S_TAB_N 512
+struct CostTab
+{
+    const uint16_t *s, *g;
+    __device__ __forceinline__ int operator[]( int d ) const { return d < S_TAB_N ? (int)s[d] : (int)__ldg( g + d ); }
+};
+__device__ __forceinline__ CostTab stage_cost_tab( uint16_t *s_tab, const LaParams &P )
+{
+    for( int i = threadIdx.x; i < S_TAB_N && i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = __ldg( P.cost_mv + i );
+    __syncthreads();
+    CostTab t; t.s = s_tab; t.g = P.cost_mv;
+    return t;
+}
+
+__device__ __forceinline__ int mvcost( const CostTab &tab, const MeGeo &m, int mx, int my )
 {   // p_cost_mvx[mx] + p_cost_mvy[my] (me.c:211-212); the table is symmetric (analyse.c:153-157)
     return tab[abs( mx - m.mvpx )] + tab[abs( my - m.mvpy )];
 }
@@ -354,6 +371,9 @@ __device__ __forceinline__ uint2 ld8w( const u32 *q, u32 sh )
     u32 w0 = __ldg( q ), w1 = __ldg( q + 1 ), w2 = __ldg( q + 2 );
     return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
 }
+
+__constant__ int8_t c_hex2[8][2] = {{-1,-2}, {-2,0}, {-1,2}, {1,2}, {2,0}, {1,-2}, {-1,-2}, {-2,0}};   // me.c:55
+__constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1}, {-1,1}, {1,-1}, {1,1}}; // me.c:56
 
 // ---- 8 lanes per block -------------------------------------------------------------------------------
 struct GroupBE
@@ -370,7 +390,7 @@ struct GroupBE
     __device__ __forceinline__ int zero_cmp() const { return cmp_rows( fenc, load8u( ref0 ), g, P->b_satd ); }
     // candidates k = 0..n-1 in order, strict '<' (the reference's COPY*_IF_LT tie-breaking); two candidates share
     // one 3-shuffle reduction (16:16 packed partial sums)
-    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const uint16_t *tab, const MeGeo &m, int &bcost, int &best ) const
+    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
     {
         for( int k = 0; k < n; k += 2 )
         {
@@ -384,7 +404,7 @@ struct GroupBE
             if( k+1 < n && c1 < bcost ) { bcost = c1; best = k+1; }
         }
     }
-    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const uint16_t *tab, const MeGeo &m, int &bcost, int &best ) const
+    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
     {
         for( int k = 0; k < n; k += 2 )
         {
@@ -398,6 +418,10 @@ struct GroupBE
             if( k+1 < n && c1 < bcost ) { bcost = c1; best = k+1; }
         }
     }
+    __device__ __forceinline__ void hex6( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    { fpel_best( 6, [&]( int k, int &x, int &y ) { x = ox + c_hex2[k+1][0]; y = oy + c_hex2[k+1][1]; }, tab, m, bcost, best ); }
+    __device__ __forceinline__ void square8( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    { fpel_best( 8, [&]( int k, int &x, int &y ) { x = ox + c_sq1[k+1][0]; y = oy + c_sq1[k+1][1]; }, tab, m, bcost, best ); }
     __device__ __forceinline__ int fpel1( int mx, int my ) const { return red8( (int)sad8( fenc, load8u( ref_w + (int64_t)my * P->stride + mx ) ), g ); }
     __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const
     { return red8( (int)sad8( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ), g ); }
@@ -430,12 +454,15 @@ struct GroupBE
 };
 
 // ---- 1 thread per block ---------------------------------------------------------------------------
+// PITCH is the device plane pitch as a compile-time constant (0: read it from LaParams).  With a constant pitch the
+// eight row loads of a candidate are one base address plus immediates; with a run-time pitch every row costs two
+// 64-bit address instructions (ncu r01: address arithmetic was ~40 % of the executed instructions).
 template<class RowFn>
 __device__ __forceinline__ int sad8x8_t( const uint2 ( &fenc )[8], RowFn pred )
 {
     u32 s0 = 0, s1 = 0;
 #pragma unroll
-    for( int r = 0; r < 8; r++ ) { uint2 p = pred( r ); s0 += __vsadu4( fenc[r].x, p.x ); s1 += __vsadu4( fenc[r].y, p.y ); }
+    for( int r = 0; r < 8; r++ ) { uint2 p = pred( r ); s0 = __vsadu4( fenc[r].x, p.x ) + s0; s1 = __vsadu4( fenc[r].y, p.y ) + s1; }
     return (int)( s0 + s1 );
 }
 // x264_pixel_satd_8x8 = two satd_8x4 (pixel.c:290-330), all in registers
@@ -467,8 +494,15 @@ __device__ __forceinline__ int satd8x8_t( const uint2 ( &fenc )[8], RowFn pred )
     return total;
 }
 
+// 12 consecutive pixels starting at word pointer q (aligned) + sh bits, as three words
+__device__ __forceinline__ void ld12w( const u32 *q, u32 sh, u32 &a0, u32 &a1, u32 &a2 )
+{
+    u32 w0 = __ldg( q ), w1 = __ldg( q + 1 ), w2 = __ldg( q + 2 ), w3 = __ldg( q + 3 );
+    a0 = __funnelshift_r( w0, w1, sh ); a1 = __funnelshift_r( w1, w2, sh ); a2 = __funnelshift_r( w2, w3, sh );
+}
+
 // get_ref (mc.c:221-249) as a row generator: plane/offset selection hoisted out of the row loop
-template<bool WEIGHTED>
+template<bool WEIGHTED, int PITCH>
 struct QpelRows
 {
     const u32 *q1, *q2;      // word pointers of the two source planes at row 0
@@ -477,23 +511,25 @@ struct QpelRows
     bool avg;
     int wscale, wdenom, woffset;
     __device__ __forceinline__ QpelRows( const uint8_t *ref, const LaParams &P, int mvx, int mvy, int ws, int wd, int wo )
-    {   // ref: 8-byte aligned block origin in the F plane; plane_size and stride are multiples of 4
-        int qidx = ( ( mvy & 3 ) << 2 ) + ( mvx & 3 );
-        int off = ( mvy >> 2 ) * P.stride + ( mvx >> 2 );
-        int o1 = off + ( ( mvy & 3 ) == 3 ? P.stride : 0 );
-        int o2 = off + ( ( mvx & 3 ) == 3 );
-        q1 = (const u32 *)( ref + c_hpel_ref0[qidx] * P.plane_size ) + ( o1 >> 2 ); sh1 = ( o1 & 3 ) * 8;
-        q2 = (const u32 *)( ref + c_hpel_ref1[qidx] * P.plane_size ) + ( o2 >> 2 ); sh2 = ( o2 & 3 ) * 8;
-        stride4 = P.stride >> 2;
+    {   // ref: 8-byte aligned block origin in the F plane; plane_size and the pitch are multiples of 4
+        const int pitch = PITCH ? PITCH : P.stride, psz = (int)P.plane_size;
+        const int qidx = ( ( mvy & 3 ) << 2 ) + ( mvx & 3 );
+        const int off = ( mvy >> 2 ) * pitch + ( mvx >> 2 );
+        const int o1 = off + ( ( mvy & 3 ) == 3 ? pitch : 0 ) + c_hpel_ref0[qidx] * psz;
+        const int o2 = off + ( ( mvx & 3 ) == 3 ) + c_hpel_ref1[qidx] * psz;
+        q1 = (const u32 *)ref + ( o1 >> 2 ); sh1 = ( o1 & 3 ) * 8;
+        q2 = (const u32 *)ref + ( o2 >> 2 ); sh2 = ( o2 & 3 ) * 8;
+        stride4 = pitch >> 2;
         avg = ( qidx & 5 ) != 0;
         wscale = ws; wdenom = wd; woffset = wo;
     }
     __device__ __forceinline__ uint2 operator()( int r ) const
     {
-        uint2 v = ld8w( q1 + r*stride4, sh1 );
+        const int s4 = PITCH ? PITCH >> 2 : stride4;
+        uint2 v = ld8w( q1 + r*s4, sh1 );
         if( avg )
         {
-            uint2 w = ld8w( q2 + r*stride4, sh2 );
+            uint2 w = ld8w( q2 + r*s4, sh2 );
             v.x = avg4( v.x, w.x ); v.y = avg4( v.y, w.y );
         }
         if( WEIGHTED && wdenom >= 0 ) { v.x = weight4( v.x, wscale, wdenom, woffset ); v.y = weight4( v.y, wscale, wdenom, woffset ); }
@@ -501,32 +537,33 @@ struct QpelRows
     }
 };
 
-template<bool SATD, bool WEIGHTED>
+template<bool SATD, bool WEIGHTED, int PITCH>
 struct ThreadBE
 {
     uint2 fenc[8];
     const uint8_t *ref0, *ref1, *ref_w;      // block origins (8-byte aligned)
     const LaParams *P;
 
+    __device__ __forceinline__ int pitch() const { return PITCH ? PITCH : P->stride; }
     __device__ __forceinline__ bool leader() const { return true; }
     __device__ __forceinline__ bool satd() const { return SATD; }
     __device__ __forceinline__ int zero_cmp() const
     {
-        const u32 *q = (const u32 *)ref0; const int s4 = P->stride >> 2;
+        const u32 *q = (const u32 *)ref0; const int s4 = pitch() >> 2;
         auto rows = [&]( int r ) { return __ldg( (const uint2 *)( q + r*s4 ) ); };
         return SATD ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
     }
     __device__ __forceinline__ int fpel1( int mx, int my ) const
     {
-        const int s4 = P->stride >> 2, off = my * P->stride + mx;
+        const int s4 = pitch() >> 2, off = my * pitch() + mx;
         const u32 *q = (const u32 *)ref_w + ( off >> 2 ); const u32 sh = ( off & 3 ) * 8;
         return sad8x8_t( fenc, [&]( int r ) { return ld8w( q + r*s4, sh ); } );
     }
     __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const
-    { return sad8x8_t( fenc, QpelRows<WEIGHTED>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ); }
+    { return sad8x8_t( fenc, QpelRows<WEIGHTED, PITCH>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ); }
     // candidate loops are NOT unrolled: one copy of the 8-row body per call site keeps the kernel inside the
     // instruction cache (ncu r01: the fully unrolled form had 25k SASS lines and 53 % no-instruction stalls)
-    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const uint16_t *tab, const MeGeo &m, int &bcost, int &best ) const
+    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
     {
 #pragma unroll 1
         for( int k = 0; k < n; k++ )
@@ -537,7 +574,7 @@ struct ThreadBE
             if( c < bcost ) { bcost = c; best = k; }
         }
     }
-    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const uint16_t *tab, const MeGeo &m, int &bcost, int &best ) const
+    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
     {
 #pragma unroll 1
         for( int k = 0; k < n; k++ )
@@ -548,42 +585,122 @@ struct ThreadBE
             if( c < bcost ) { bcost = c; best = k; }
         }
     }
+    // The full hexagon (me.c:354-362) with shared row loads: the six points touch rows oy-2..oy+9 and columns
+    // ox-2..ox+9, so each of the 12 rows is loaded once (4 words), aligned once to column ox-2, and the dx = -1/+1
+    // candidates are immediate funnel shifts of it.  96 + 36 row loads become 48; costs are then compared in the
+    // reference's order with strict '<'.
+    __device__ __forceinline__ void hex6( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        const int s4 = pitch() >> 2, off = ( oy - 2 ) * pitch() + ox - 2;
+        const u32 *q = (const u32 *)ref_w + ( off >> 2 ); const u32 sh = ( off & 3 ) * 8;
+        u32 acc[6] = {0, 0, 0, 0, 0, 0};      // hex2[1..6]: (-2,0) (-1,2) (1,2) (2,0) (1,-2) (-1,-2)
+#pragma unroll
+        for( int r = 0; r < 12; r++ )
+        {
+            u32 a0, a1, a2;
+            ld12w( q + r*s4, sh, a0, a1, a2 );
+            if( r <= 7 || r >= 4 )
+            {
+                const u32 m0 = __funnelshift_r( a0, a1, 8 ),  m1 = __funnelshift_r( a1, a2, 8 );      // column ox-1
+                const u32 p0 = __funnelshift_r( a0, a1, 24 ), p1 = __funnelshift_r( a1, a2, 24 );     // column ox+1
+                if( r <= 7 )
+                {   // dy = -2: block row r
+                    acc[5] = __vsadu4( fenc[r].x, m0 ) + __vsadu4( fenc[r].y, m1 ) + acc[5];
+                    acc[4] = __vsadu4( fenc[r].x, p0 ) + __vsadu4( fenc[r].y, p1 ) + acc[4];
+                }
+                if( r >= 4 )
+                {   // dy = +2: block row r-4
+                    acc[1] = __vsadu4( fenc[r-4].x, m0 ) + __vsadu4( fenc[r-4].y, m1 ) + acc[1];
+                    acc[2] = __vsadu4( fenc[r-4].x, p0 ) + __vsadu4( fenc[r-4].y, p1 ) + acc[2];
+                }
+            }
+            if( r >= 2 && r <= 9 )
+            {   // dy = 0: block row r-2, columns ox-2 and ox+2
+                acc[0] = __vsadu4( fenc[r-2].x, a0 ) + __vsadu4( fenc[r-2].y, a1 ) + acc[0];
+                acc[3] = __vsadu4( fenc[r-2].x, a1 ) + __vsadu4( fenc[r-2].y, a2 ) + acc[3];
+            }
+        }
+#pragma unroll
+        for( int k = 0; k < 6; k++ )
+        {
+            const int x = ox + c_hex2[k+1][0], y = oy + c_hex2[k+1][1];
+            const int c = (int)acc[k] + mvcost( tab, m, x*4, y*4 );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
+    }
+    // The square refine (me.c:404-418): rows oy-1..oy+8, columns ox-1..ox+8, 10 shared row loads for 8 candidates
+    __device__ __forceinline__ void square8( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        const int s4 = pitch() >> 2, off = ( oy - 1 ) * pitch() + ox - 1;
+        const u32 *q = (const u32 *)ref_w + ( off >> 2 ); const u32 sh = ( off & 3 ) * 8;
+        u32 acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // square1[1..8]: (0,-1) (0,1) (-1,0) (1,0) (-1,-1) (-1,1) (1,-1) (1,1)
+#pragma unroll
+        for( int r = 0; r < 10; r++ )
+        {
+            u32 a0, a1, a2;
+            ld12w( q + r*s4, sh, a0, a1, a2 );
+            const u32 c0 = __funnelshift_r( a0, a1, 8 ),  c1 = __funnelshift_r( a1, a2, 8 );       // column ox
+            const u32 p0 = __funnelshift_r( a0, a1, 16 ), p1 = __funnelshift_r( a1, a2, 16 );      // column ox+1
+            if( r <= 7 )
+            {   // dy = -1: block row r
+                acc[0] = __vsadu4( fenc[r].x, c0 ) + __vsadu4( fenc[r].y, c1 ) + acc[0];
+                acc[4] = __vsadu4( fenc[r].x, a0 ) + __vsadu4( fenc[r].y, a1 ) + acc[4];
+                acc[6] = __vsadu4( fenc[r].x, p0 ) + __vsadu4( fenc[r].y, p1 ) + acc[6];
+            }
+            if( r >= 1 && r <= 8 )
+            {   // dy = 0: block row r-1
+                acc[2] = __vsadu4( fenc[r-1].x, a0 ) + __vsadu4( fenc[r-1].y, a1 ) + acc[2];
+                acc[3] = __vsadu4( fenc[r-1].x, p0 ) + __vsadu4( fenc[r-1].y, p1 ) + acc[3];
+            }
+            if( r >= 2 )
+            {   // dy = +1: block row r-2
+                acc[1] = __vsadu4( fenc[r-2].x, c0 ) + __vsadu4( fenc[r-2].y, c1 ) + acc[1];
+                acc[5] = __vsadu4( fenc[r-2].x, a0 ) + __vsadu4( fenc[r-2].y, a1 ) + acc[5];
+                acc[7] = __vsadu4( fenc[r-2].x, p0 ) + __vsadu4( fenc[r-2].y, p1 ) + acc[7];
+            }
+        }
+#pragma unroll
+        for( int k = 0; k < 8; k++ )
+        {
+            const int x = ox + c_sq1[k+1][0], y = oy + c_sq1[k+1][1];
+            const int c = (int)acc[k] + mvcost( tab, m, x*4, y*4 );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
+    }
     __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
     {
-        return satd8x8_t( fenc, QpelRows<WEIGHTED>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) );
+        return satd8x8_t( fenc, QpelRows<WEIGHTED, PITCH>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) );
     }
     __device__ __forceinline__ int bidir( int mv0x, int mv0y, int mv1x, int mv1y, int w ) const
     {
         if( !SATD )
         {
-            const int s4 = P->stride >> 2;
-            int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
-            int o0 = ( mv0x >> 2 ) + ( mv0y >> 2 ) * P->stride, o1 = ( mv1x >> 2 ) + ( mv1y >> 2 ) * P->stride;
-            const u32 *q0 = (const u32 *)( ref0 + i0*P->plane_size ) + ( o0 >> 2 ), *q1 = (const u32 *)( ref1 + i1*P->plane_size ) + ( o1 >> 2 );
+            const int s4 = pitch() >> 2, psz = (int)P->plane_size;
+            const int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
+            const int o0 = ( mv0x >> 2 ) + ( mv0y >> 2 ) * pitch() + i0*psz, o1 = ( mv1x >> 2 ) + ( mv1y >> 2 ) * pitch() + i1*psz;
+            const u32 *q0 = (const u32 *)ref0 + ( o0 >> 2 ), *q1 = (const u32 *)ref1 + ( o1 >> 2 );
             const u32 h0 = ( o0 & 3 ) * 8, h1 = ( o1 & 3 ) * 8;
             return sad8x8_t( fenc, [&]( int r ) { uint2 a = ld8w( q0 + r*s4, h0 ), b = ld8w( q1 + r*s4, h1 );
                                                   return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
         }
-        QpelRows<false> r0( ref0, *P, mv0x, mv0y, 0, -1, 0 ), r1( ref1, *P, mv1x, mv1y, 0, -1, 0 );
+        QpelRows<false, PITCH> r0( ref0, *P, mv0x, mv0y, 0, -1, 0 ), r1( ref1, *P, mv1x, mv1y, 0, -1, 0 );
         return satd8x8_t( fenc, [&]( int r ) { uint2 a = r0( r ), b = r1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
     }
     __device__ __forceinline__ int bidir_zero( int w ) const
     {
-        const u32 *q0 = (const u32 *)ref0, *q1 = (const u32 *)ref1; const int s4 = P->stride >> 2;
+        const u32 *q0 = (const u32 *)ref0, *q1 = (const u32 *)ref1; const int s4 = pitch() >> 2;
         auto rows = [&]( int r ) { uint2 a = __ldg( (const uint2 *)( q0 + r*s4 ) ), b = __ldg( (const uint2 *)( q1 + r*s4 ) );
                                    return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); };
         return SATD ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
     }
 };
 
-__constant__ int8_t c_hex2[8][2] = {{-1,-2}, {-2,0}, {-1,2}, {1,2}, {2,0}, {1,-2}, {-1,-2}, {-2,0}};   // me.c:55
-__constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1}, {-1,1}, {1,-1}, {1,1}}; // me.c:56
 
 #define FPEL(v) (((v)+2)>>2)
 
 // refine_subpel (me.c:865-992), p_halfpel_thresh == NULL, b_refine_qpel == 0, no chroma
 template<class BE>
-__device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, const LaParams &P, const uint16_t *tab,
+__device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, const LaParams &P, const CostTab &tab,
                                                int &bmx, int &bmy, int &bcost, int hpel_iters, int qpel_iters )
 {
     if( hpel_iters )
@@ -630,7 +747,7 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
 
 // x264_me_search_ref (me.c:182-420,774-797) for one block; result mv (qpel) and cost
 template<class BE>
-__device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const LaParams &P, const uint16_t *tab,
+__device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const LaParams &P, const CostTab &tab,
                                            const int (*mvc)[2], int i_mvc, int &out_mx, int &out_my, int &out_cost )
 {
     int bmx, bmy, bcost = X264CU_COST_MAX, bpred_cost = X264CU_COST_MAX, bpred_mx = 0, bpred_my = 0, pmvx, pmvy;
@@ -713,30 +830,29 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
         } while( --i && in_range( m, bmx, bmy ) );
     }
     else
-    {   // HEX (me.c:344-420): the full hexagon, then half hexagons that do not overlap the previous one;
-        // both go through ONE call site (first = 6 points from hex2[1], later = 3 points from hex2[dir])
-        int dir = 0, npts = 6, first = 1;
-        for( int i = P.me_range >> 1; i > 0; i-- )
+    {   // HEX (me.c:344-420): the full hexagon, then half hexagons that do not overlap the previous one
+        int best = -1;
+        be.hex6( bmx, bmy, tab, m, bcost, best );
+        if( best >= 0 )
         {
-            if( !first && !in_range( m, bmx, bmy ) ) break;
-            const int ox = bmx, oy = bmy, base = first ? 1 : dir;
-            int best = -1;
-            be.fpel_best( npts, [&]( int k, int &x, int &y ) { x = ox + c_hex2[base+k][0]; y = oy + c_hex2[base+k][1]; }, tab, m, bcost, best );
-            if( best < 0 ) break;
-            if( first ) dir = best;
-            else
+            int dir = best;
+            bmx += c_hex2[dir+1][0]; bmy += c_hex2[dir+1][1];
+            for( int i = ( P.me_range >> 1 ) - 1; i > 0 && in_range( m, bmx, bmy ); i-- )
             {
+                const int ox = bmx, oy = bmy, base = dir;
+                best = -1;
+                be.fpel_best( 3, [&]( int k, int &x, int &y ) { x = ox + c_hex2[base+k][0]; y = oy + c_hex2[base+k][1]; }, tab, m, bcost, best );
+                if( best < 0 ) break;
                 dir += best - 1;
                 dir = dir < 0 ? dir + 6 : dir >= 6 ? dir - 6 : dir;      // mod6m1 (me.c:53)
+                bmx = ox + c_hex2[dir+1][0]; bmy = oy + c_hex2[dir+1][1];
             }
-            bmx = ox + c_hex2[dir+1][0]; bmy = oy + c_hex2[dir+1][1];
-            first = 0; npts = 3;
         }
         // square refine (me.c:404-418)
         {
             const int ox = bmx, oy = bmy;
             int bs = -1;
-            be.fpel_best( 8, [&]( int k, int &x, int &y ) { x = ox + c_sq1[k+1][0]; y = oy + c_sq1[k+1][1]; }, tab, m, bcost, bs );
+            be.square8( ox, oy, tab, m, bcost, bs );
             bmx = ox + c_sq1[bs+1][0]; bmy = oy + c_sq1[bs+1][1];
         }
     }
@@ -762,7 +878,7 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
 
 // one block of one search pass (slicetype.c:654-702)
 template<class BE>
-__device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, const LaParams &P, const uint16_t *tab,
+__device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, const LaParams &P, const CostTab &tab,
                                               int bx, int by, int blk )
 {
     MeGeo m;
@@ -817,9 +933,8 @@ __device__ __forceinline__ bool skipped_border( const LaParams &P, int bx, int b
 
 __global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob *__restrict__ jobs, LaParams P )
 {
-    extern __shared__ uint16_t s_tab[];
-    for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
-    __syncthreads();
+    __shared__ uint16_t s_tab[S_TAB_N];
+    const CostTab tab = stage_cost_tab( s_tab, P );
     const SearchJob J = jobs[blockIdx.y];
     GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
     const int blk = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );
@@ -833,7 +948,7 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob 
     const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
     be.fenc = *(const uint2 *)( J.fenc + pel );
     be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
-    search_block( be, J, P, s_tab, bx, by, blk );
+    search_block( be, J, P, tab, bx, by, blk );
 }
 
 #define T_TILE_W 32
@@ -844,24 +959,23 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob 
 #ifndef X264CU_MINB_FINAL
 #define X264CU_MINB_FINAL 4
 #endif
-template<bool SATD, bool WEIGHTED>
+template<bool SATD, bool WEIGHTED, int PITCH>
 __global__ void __launch_bounds__(T_TILE_W*T_TILE_H, X264CU_MINB_SEARCH) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
 {
-    extern __shared__ uint16_t s_tab[];
-    for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
-    __syncthreads();
+    __shared__ uint16_t s_tab[S_TAB_N];
+    const CostTab tab = stage_cost_tab( s_tab, P );
     const SearchJob J = jobs[blockIdx.z];
     const int bx = blockIdx.x * T_TILE_W + ( threadIdx.x & ( T_TILE_W-1 ) ), by = blockIdx.y * T_TILE_H + threadIdx.x / T_TILE_W;
     if( bx >= P.mbw || by >= P.mbh ) return;
     const int blk = by * P.mbw + bx;
     if( skipped_border( P, bx, by ) ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; return; }
-    ThreadBE<SATD, WEIGHTED> be; be.P = &P;
-    const int64_t pel = (int64_t)( by*8 ) * P.stride + bx*8;
+    ThreadBE<SATD, WEIGHTED, PITCH> be; be.P = &P;
+    const int pel = ( by*8 ) * be.pitch() + bx*8;
     const uint8_t *src = J.fenc + pel;
 #pragma unroll
-    for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + (size_t)r * P.stride ) );
+    for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * be.pitch() ) );
     be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
-    search_block( be, J, P, s_tab, bx, by, blk );
+    search_block( be, J, P, tab, bx, by, blk );
 }
 
 // Exact raster-serial mode: the reference evaluates blocks in reverse raster order and
@@ -870,9 +984,8 @@ __global__ void __launch_bounds__(T_TILE_W*T_TILE_H, X264CU_MINB_SEARCH) search_
 // so one launch per anti-diagonal wave reproduces the serial result exactly; mv_in == mv_out (in place).
 __global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJob *__restrict__ jobs, LaParams P, int wave )
 {
-    extern __shared__ uint16_t s_tab[];
-    for( int i = threadIdx.x; i <= P.cost_mv_n; i += blockDim.x ) s_tab[i] = P.cost_mv[i];
-    __syncthreads();
+    __shared__ uint16_t s_tab[S_TAB_N];
+    const CostTab tab = stage_cost_tab( s_tab, P );
     const SearchJob J = jobs[blockIdx.y];
     GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
     const int by = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );       // one candidate block per row
@@ -884,16 +997,15 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJ
     const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
     be.fenc = *(const uint2 *)( J.fenc + pel );
     be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
-    search_block( be, J, P, s_tab, bx, by, blk );
+    search_block( be, J, P, tab, bx, by, blk );
 }
 
 void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
 {
-    size_t smem = ( P.cost_mv_n + 1 ) * sizeof(uint16_t);
     dim3 grid( ( P.mbh + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
     const int nwaves = P.mbw + 2 * ( P.mbh - 1 );
     for( int w = 0; w < nwaves; w++ )
-        search_kernel_wave<<<grid, CTA_THREADS, smem, st>>>( d_jobs, P, w );
+        search_kernel_wave<<<grid, CTA_THREADS, 0, st>>>( d_jobs, P, w );
 }
 
 static bool use_thread_mapping( const LaParams &P, int njobs )
@@ -903,27 +1015,35 @@ static bool use_thread_mapping( const LaParams &P, int njobs )
     return (int64_t)njobs * P.nmb >= 4 * 8160;     // wide launches: enough blocks to fill the SMs one thread each
 }
 
+template<int PITCH>
+static void launch_search_t( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
+{
+    dim3 grid( ( P.mbw + T_TILE_W - 1 ) / T_TILE_W, ( P.mbh + T_TILE_H - 1 ) / T_TILE_H, njobs );
+    if( P.b_satd )
+    {
+        if( any_weighted ) search_kernel_t<true, true, PITCH><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
+        else               search_kernel_t<true, false, PITCH><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
+    }
+    else
+    {
+        if( any_weighted ) search_kernel_t<false, true, PITCH><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
+        else               search_kernel_t<false, false, PITCH><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
+    }
+}
+
 void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
 {
-    size_t smem = ( P.cost_mv_n + 1 ) * sizeof(uint16_t);
     if( use_thread_mapping( P, njobs ) )
-    {
-        dim3 grid( ( P.mbw + T_TILE_W - 1 ) / T_TILE_W, ( P.mbh + T_TILE_H - 1 ) / T_TILE_H, njobs );
-        if( P.b_satd )
-        {
-            if( any_weighted ) search_kernel_t<true, true><<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
-            else               search_kernel_t<true, false><<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
-        }
-        else
-        {
-            if( any_weighted ) search_kernel_t<false, true><<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
-            else               search_kernel_t<false, false><<<grid, T_TILE_W*T_TILE_H, smem, st>>>( d_jobs, P );
-        }
+    {   // the context picks the pitch from {1024, 2048} whenever the padded width fits (capi.cu), anything wider runs the
+        // run-time-pitch instantiation
+        if( P.stride == 1024 )      launch_search_t<1024>( d_jobs, njobs, any_weighted, P, st );
+        else if( P.stride == 2048 ) launch_search_t<2048>( d_jobs, njobs, any_weighted, P, st );
+        else                        launch_search_t<0>( d_jobs, njobs, any_weighted, P, st );
     }
     else
     {
         dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
-        search_kernel_g<<<grid, CTA_THREADS, smem, st>>>( d_jobs, P );
+        search_kernel_g<<<grid, CTA_THREADS, 0, st>>>( d_jobs, P );
     }
 }
 
@@ -1024,7 +1144,7 @@ __global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *_
     final_block( be, J, P, bx, by, blk );
 }
 
-template<bool SATD>
+template<bool SATD, int PITCH>
 __global__ void __launch_bounds__(T_TILE_W*T_TILE_H, X264CU_MINB_FINAL) final_kernel_t( const FinalJob *__restrict__ jobs, LaParams P )
 {
     const FinalJob J = jobs[blockIdx.z];
@@ -1032,13 +1152,13 @@ __global__ void __launch_bounds__(T_TILE_W*T_TILE_H, X264CU_MINB_FINAL) final_ke
     if( bx >= P.mbw || by >= P.mbh ) return;
     const int blk = by * P.mbw + bx;
     if( skipped_border( P, bx, by ) ) { if( !J.b_intra_only ) J.lowres_costs[blk] = 0; return; }
-    ThreadBE<SATD, false> be; be.P = &P;
-    const int64_t pel = (int64_t)( by*8 ) * P.stride + bx*8;
+    ThreadBE<SATD, false, PITCH> be; be.P = &P;
+    const int pel = ( by*8 ) * be.pitch() + bx*8;
     const uint8_t *src = J.fenc + pel;
     if( !J.b_intra_only )
     {
 #pragma unroll
-        for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + (size_t)r * P.stride ) );
+        for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * be.pitch() ) );
     }
     be.ref0 = J.ref0 + pel; be.ref1 = J.ref1 + pel; be.ref_w = be.ref0;
     final_block( be, J, P, bx, by, blk );
@@ -1049,8 +1169,12 @@ void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStr
     if( use_thread_mapping( P, njobs ) )
     {
         dim3 grid( ( P.mbw + T_TILE_W - 1 ) / T_TILE_W, ( P.mbh + T_TILE_H - 1 ) / T_TILE_H, njobs );
-        if( P.b_satd ) final_kernel_t<true><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
-        else           final_kernel_t<false><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P );
+#define FINAL_T( PITCH ) { if( P.b_satd ) final_kernel_t<true, PITCH><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P ); \
+                           else           final_kernel_t<false, PITCH><<<grid, T_TILE_W*T_TILE_H, 0, st>>>( d_jobs, P ); }
+        if( P.stride == 1024 )      FINAL_T( 1024 )
+        else if( P.stride == 2048 ) FINAL_T( 2048 )
+        else                        FINAL_T( 0 )
+#undef FINAL_T
     }
     else
     {
