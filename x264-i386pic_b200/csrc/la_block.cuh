@@ -1,0 +1,599 @@
+// la_block.cuh -- per-block cost machinery shared by the search and decision kernels (search.cu, final.cu):
+// row-lane and whole-block SAD/SATD, the qpel fetch of get_ref, and the two "backends" that say how a block's pixels
+// are spread over lanes.  Everything here is inline device code; each kernel file is its own translation unit so that
+// the code generation of one kernel family cannot perturb the other's (r01: register allocation of the decision
+// kernel changed with unrelated edits of the search kernel while both lived in one file).
+#pragma once
+#include "lookahead.cuh"
+
+// ---- tuning knobs, all measured on B200 (profiles/r01/tuning.md).  The thread-per-block kernels are sensitive to
+// ptxas's choices under register pressure (if-conversion of the second-plane fetch, rematerialised row addresses), so
+// the knobs are per kernel family and each family is its own translation unit.
+// CTA tiles in blocks: one block row per warp for the search kernels; 16x8 for the decision kernels (squarer tile =
+// less halo in the L2->L1 fill traffic that bounds them)
+#ifndef S_TILE_W
+#define S_TILE_W 32
+#define S_TILE_H 4
+#endif
+#ifndef F_TILE_W
+#define F_TILE_W 16
+#define F_TILE_H 8
+#endif
+// row loads as two aligned 64-bit words (1) or three 32-bit words (0)
+#ifndef X264CU_SEARCH_LD64
+#define X264CU_SEARCH_LD64 1
+#endif
+#ifndef X264CU_FINAL_LD64
+#define X264CU_FINAL_LD64 0
+#endif
+// second-plane fetch of get_ref as PTX-predicated loads (1) or a C++ branch (0)
+#ifndef X264CU_SEARCH_PTXPRED
+#define X264CU_SEARCH_PTXPRED 1
+#endif
+#ifndef X264CU_FINAL_PTXPRED
+#define X264CU_FINAL_PTXPRED 0
+#endif
+// __launch_bounds__ minimum CTAs per SM: 3 leaves ptxas at ~115 registers (4 resident CTAs of 128 threads)
+#ifndef X264CU_MINB_SEARCH
+#define X264CU_MINB_SEARCH 3
+#endif
+#ifndef X264CU_MINB_FINAL
+#define X264CU_MINB_FINAL 5
+#endif
+
+#define GROUPS_PER_CTA 32
+#define CTA_THREADS (GROUPS_PER_CTA*8)
+
+static __constant__ uint8_t c_hpel_ref0[16] = {0,1,1,1,0,1,1,1,2,3,3,3,0,1,1,1};   // tables.c:183
+static __constant__ uint8_t c_hpel_ref1[16] = {0,0,1,0,2,2,3,2,2,2,3,2,2,2,3,2};   // tables.c:184
+
+__device__ __forceinline__ int weight_px( int v, int scale, int denom, int offset )
+{   // mc.c:117-118
+    int r = denom >= 1 ? ( ( v*scale + ( 1 << ( denom-1 ) ) ) >> denom ) + offset : v*scale + offset;
+    return min( max( r, 0 ), 255 );
+}
+__device__ __forceinline__ u32 weight4( u32 w, int scale, int denom, int offset )
+{
+    return (u32)weight_px( w & 0xff, scale, denom, offset ) | ( (u32)weight_px( ( w >> 8 ) & 0xff, scale, denom, offset ) << 8 )
+         | ( (u32)weight_px( ( w >> 16 ) & 0xff, scale, denom, offset ) << 16 ) | ( (u32)weight_px( w >> 24, scale, denom, offset ) << 24 );
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-lane metrics
+// ------------------------------------------------------------------------------------------------
+struct Grp
+{
+    unsigned mask;    // the 8 lanes of this block
+    int r;            // row owned by this lane
+};
+
+__device__ __forceinline__ int red8( int v, const Grp &g )
+{
+    v += __shfl_xor_sync( g.mask, v, 1 );
+    v += __shfl_xor_sync( g.mask, v, 2 );
+    v += __shfl_xor_sync( g.mask, v, 4 );
+    return v;
+}
+// two partial sums (each < 2^16 after reduction) per shuffle
+__device__ __forceinline__ void red8x2( int &a, int &b, const Grp &g )
+{
+    u32 v = (u32)a | ( (u32)b << 16 );
+    v += __shfl_xor_sync( g.mask, v, 1 );
+    v += __shfl_xor_sync( g.mask, v, 2 );
+    v += __shfl_xor_sync( g.mask, v, 4 );
+    a = v & 0xffff; b = v >> 16;
+}
+
+// x264_pixel_satd_8x8 = satd_8x4(top) + satd_8x4(bottom) (pixel.c:290-330), rows across lanes
+__device__ __forceinline__ int satd_rows( uint2 a, uint2 b, const Grp &g )
+{
+    u32 d[4], h0, h1, h2, h3;
+    diff_row8( a, b, d );
+    HADAMARD4( h0, h1, h2, h3, d[0], d[1], d[2], d[3] );
+#define VSTAGE( v, bit ) { u32 o_ = __shfl_xor_sync( g.mask, v, bit ); v = ( g.r & bit ) ? o_ - v : v + o_; }
+    VSTAGE( h0, 1 ) VSTAGE( h1, 1 ) VSTAGE( h2, 1 ) VSTAGE( h3, 1 )
+    VSTAGE( h0, 2 ) VSTAGE( h1, 2 ) VSTAGE( h2, 2 ) VSTAGE( h3, 2 )
+#undef VSTAGE
+    u32 s = abs2( h0 ) + abs2( h1 ) + abs2( h2 ) + abs2( h3 );
+    s += __shfl_xor_sync( g.mask, s, 1 );
+    s += __shfl_xor_sync( g.mask, s, 2 );
+    int v = (int)( ( ( s & 0xffff ) + ( s >> 16 ) ) >> 1 );
+    v += __shfl_xor_sync( g.mask, v, 4 );
+    return v;
+}
+
+__device__ __forceinline__ int cmp_rows( uint2 a, uint2 b, const Grp &g, int b_satd )
+{
+    return b_satd ? satd_rows( a, b, g ) : red8( (int)sad8( a, b ), g );
+}
+
+// get_ref (mc.c:221-249) for this lane's row: `ref` points at this lane's row of the F plane at mv 0
+__device__ __forceinline__ uint2 qpel_row( const uint8_t *ref, const LaParams &P, int mvx, int mvy, int wscale, int wdenom, int woffset )
+{
+    int qidx = ( ( mvy & 3 ) << 2 ) + ( mvx & 3 );
+    int64_t off = (int64_t)( mvy >> 2 ) * P.stride + ( mvx >> 2 );
+    const uint8_t *s1 = ref + c_hpel_ref0[qidx] * P.plane_size + off + ( ( mvy & 3 ) == 3 ? P.stride : 0 );
+    uint2 v = load8u( s1 );
+    if( qidx & 5 )
+    {
+        const uint8_t *s2 = ref + c_hpel_ref1[qidx] * P.plane_size + off + ( ( mvx & 3 ) == 3 );
+        uint2 w = load8u( s2 );
+        v.x = avg4( v.x, w.x ); v.y = avg4( v.y, w.y );
+    }
+    if( wdenom >= 0 )
+    {
+        v.x = weight4( v.x, wscale, wdenom, woffset );
+        v.y = weight4( v.y, wscale, wdenom, woffset );
+    }
+    return v;
+}
+
+// pixel_avg_8x8 with weight (mc.c:63-99): (a*w + b*(64-w) + 32) >> 6 on 4 packed pixels.  The lookahead's
+// weights are 64 - (dist_scale_factor>>2) in [1,63] (slicetype.c:529) or 32, a convex combination, so the clip of
+// mc.c:86 never acts and two pixels fit one 16:16 multiply-add without carries between the halves.
+__device__ __forceinline__ u32 biavg4( u32 a, u32 b, int w )
+{
+    if( w == 32 ) return avg4( a, b );
+    const u32 w2 = 64 - w;
+    u32 ae = a & 0x00ff00ffu, ao = ( a >> 8 ) & 0x00ff00ffu, be = b & 0x00ff00ffu, bo = ( b >> 8 ) & 0x00ff00ffu;
+    u32 re = ( ( ae * w + be * w2 + 0x00200020u ) >> 6 ) & 0x00ff00ffu;
+    u32 ro = ( ( ao * w + bo * w2 + 0x00200020u ) << 2 ) & 0xff00ff00u;
+    return re | ro;
+}
+
+// ------------------------------------------------------------------------------------------------
+// motion search and mode decision
+//
+// The control flow (x264_me_search_ref, refine_subpel, the tail of slicetype_mb_cost) is written ONCE,
+// templated on a cost "backend" that says how a block's pixels are spread over lanes:
+//   GroupBE  -- 8 lanes per block (lane = pixel row): lowest latency, used when a launch has few
+//               blocks (single evaluations through the per-call hook);
+//   ThreadBE -- 1 thread per block, 32 horizontally adjacent blocks per warp: a warp-wide row load
+//               touches 2-3 cache lines instead of 8 and nothing is recomputed per lane; used for
+//               the wide launches of the batched path (ncu r01: the 8-lane form was L1TEX-wavefront
+//               bound at 91 %).
+// Both produce identical results (tests run each mapping against the oracle).
+// ------------------------------------------------------------------------------------------------
+struct MeGeo
+{
+    int wscale, wdenom, woffset;
+    int mvpx, mvpy;
+    int fminx, fminy, fmaxx, fmaxy;     // mv_limit_fpel
+    int sminx, sminy, smaxx, smaxy;     // mv_min_spel / mv_max_spel
+};
+
+__device__ __forceinline__ void me_limits( MeGeo &m, const LaParams &P, int bx, int by )
+{   // slicetype.c:550-562 (the y limits are refreshed at every row start, so they depend on by only)
+    m.sminx = max( 4*( -8*bx - 12 ), -P.mv_range2 );
+    m.smaxx = min( 4*( 8*( P.mbw - bx - 1 ) + 12 ), P.mv_range2 - 1 );
+    m.sminy = max( 4*( -8*by - 12 ), -P.mv_range2 );
+    m.smaxy = min( 4*( 8*( P.mbh - by - 1 ) + 12 ), P.mv_range2 - 1 );
+    m.fminx = m.sminx >> 2; m.fmaxx = m.smaxx >> 2; m.fminy = m.sminy >> 2; m.fmaxy = m.smaxy >> 2;
+}
+
+// cost_mv table (analyse.c:153-157), read from global memory through L1: two 16-bit loads per candidate that issue
+// ahead of the pixel loads.  (r01 history: a full per-CTA shared-memory copy cost 14 % of the search kernel's stall
+// samples in the fill; a 512-entry copy with a global fallback cost ~25 instructions per candidate in address
+// selection.)
+struct CostTab
+{
+    const uint16_t *g;
+    __device__ __forceinline__ int operator[]( int d ) const { return (int)__ldg( g + d ); }
+};
+__device__ __forceinline__ CostTab stage_cost_tab( const LaParams &P )
+{
+    CostTab t; t.g = P.cost_mv;
+    return t;
+}
+
+__device__ __forceinline__ int mvcost( const CostTab &tab, const MeGeo &m, int mx, int my )
+{   // p_cost_mvx[mx] + p_cost_mvy[my] (me.c:211-212); the table is symmetric (analyse.c:153-157)
+    return tab[abs( mx - m.mvpx )] + tab[abs( my - m.mvpy )];
+}
+__device__ __forceinline__ bool in_range( const MeGeo &m, int mx, int my )
+{   // CHECK_MVRANGE (me.c:209)
+    return mx >= m.fminx && mx <= m.fmaxx && my >= m.fminy && my <= m.fmaxy;
+}
+
+// Row loader of ThreadBE: 8 pixels at byte offset `off` (any alignment) from an 8-byte aligned origin.
+// LD32: three aligned words + two funnel shifts.  LD64: two aligned 64-bit loads cover the 8 pixels at any alignment
+// (4 L1 wavefronts per warp instead of 6) at the price of three selects.  B200 measurements (profiles/r01): the search
+// kernels gain from LD64, the decision kernels -- bound by L2->L1 fill traffic, which the wider window increases --
+// lose 28 %, so it is a per-kernel choice.  The pointer is aligned ONCE per candidate; rows are immediates off it.
+template<bool LD64>
+struct RowSrc
+{
+    const u32 *q;
+    u32 sh;
+    bool k;
+    __device__ __forceinline__ RowSrc( const uint8_t *origin, int off )
+    {
+        if( LD64 ) { q = (const u32 *)origin + ( ( off >> 3 ) << 1 ); k = ( off & 4 ) != 0; }
+        else       { q = (const u32 *)origin + ( off >> 2 ); k = false; }
+        sh = ( off & 3 ) * 8;
+        // pin the row-0 pointer in a register pair: under register pressure ptxas otherwise rematerialises the whole
+        // address (plane select, 64-bit add) for every row instead of using the row immediates
+        asm( "" : "+l"( q ) );
+    }
+    __device__ __forceinline__ uint2 row( int w4 ) const      // w4: row offset in words (a multiple of 2)
+    {
+        if( LD64 )
+        {
+            const uint2 A = __ldg( (const uint2 *)( q + w4 ) ), B = __ldg( (const uint2 *)( q + w4 ) + 1 );
+            const u32 a = k ? A.y : A.x, b = k ? B.x : A.y, c = k ? B.y : B.x;
+            return make_uint2( __funnelshift_r( a, b, sh ), __funnelshift_r( b, c, sh ) );
+        }
+        const u32 w0 = __ldg( q + w4 ), w1 = __ldg( q + w4 + 1 ), w2 = __ldg( q + w4 + 2 );
+        return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+    }
+    // The same fetch under a per-thread predicate, written in PTX so that it stays predicated: get_ref reads a second
+    // plane only at quarter-pel positions, and whether the compiler turns `if( avg )` into predication or into two
+    // specialised copies of the 8-row body flips with unrelated edits (r01: the branchy form runs 13 % slower, because
+    // a warp whose blocks disagree on `avg` executes both copies).  When p is 0 nothing is loaded and junk derived
+    // from `v` comes back (the caller discards it).
+    __device__ __forceinline__ uint2 row_if( int p, int w4, uint2 v ) const
+    {
+        if( LD64 )
+        {
+            u32 a0 = v.x, a1 = v.y, b0 = v.x, b1 = v.y;
+            asm( "{ .reg .pred p;\n setp.ne.s32 p, %4, 0;\n @p ld.global.nc.v2.u32 {%0,%1}, [%5];\n @p ld.global.nc.v2.u32 {%2,%3}, [%5+8];\n}"
+                 : "+r"( a0 ), "+r"( a1 ), "+r"( b0 ), "+r"( b1 ) : "r"( p ), "l"( q + w4 ) );
+            const u32 a = k ? a1 : a0, b = k ? b0 : a1, c = k ? b1 : b0;
+            return make_uint2( __funnelshift_r( a, b, sh ), __funnelshift_r( b, c, sh ) );
+        }
+        u32 w0 = v.x, w1 = v.y, w2 = v.x;
+        asm( "{ .reg .pred p;\n setp.ne.s32 p, %3, 0;\n @p ld.global.nc.u32 %0, [%4];\n @p ld.global.nc.u32 %1, [%4+4];\n @p ld.global.nc.u32 %2, [%4+8];\n}"
+             : "+r"( w0 ), "+r"( w1 ), "+r"( w2 ) : "r"( p ), "l"( q + w4 ) );
+        return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+    }
+};
+
+static __constant__ int8_t c_hex2[8][2] = {{-1,-2}, {-2,0}, {-1,2}, {1,2}, {2,0}, {1,-2}, {-1,-2}, {-2,0}};   // me.c:55
+// the same table as two immediates (4 bits per entry, value + 2): no indexed constant load on the candidate path
+__device__ __forceinline__ int hex2x( int i ) { return (int)( ( 0x01343101u >> ( 4*i ) ) & 7u ) - 2; }
+__device__ __forceinline__ int hex2y( int i ) { return (int)( ( 0x20024420u >> ( 4*i ) ) & 7u ) - 2; }
+static __constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1}, {-1,1}, {1,-1}, {1,1}}; // me.c:56
+
+// ---- 8 lanes per block -------------------------------------------------------------------------------
+struct GroupBE
+{
+    Grp g;
+    uint2 fenc;              // this lane's row of the block
+    const uint8_t *ref0;     // this lane's row of reference 0's F plane at mv 0
+    const uint8_t *ref1;     // same for reference 1 (decision kernel only)
+    const uint8_t *ref_w;    // this lane's row of the fullpel (possibly weighted) plane of reference 0
+    const LaParams *P;
+
+    __device__ __forceinline__ bool leader() const { return g.r == 0; }
+    __device__ __forceinline__ bool satd() const { return P->b_satd != 0; }
+    __device__ __forceinline__ int zero_cmp() const { return cmp_rows( fenc, load8u( ref0 ), g, P->b_satd ); }
+    // candidates k = 0..n-1 in order, strict '<' (the reference's COPY*_IF_LT tie-breaking); two candidates share
+    // one 3-shuffle reduction (16:16 packed partial sums)
+    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        for( int k = 0; k < n; k += 2 )
+        {
+            int x0, y0, x1, y1;
+            xy( k, x0, y0 ); xy( min( k+1, n-1 ), x1, y1 );
+            int c0 = (int)sad8( fenc, load8u( ref_w + (int64_t)y0 * P->stride + x0 ) );
+            int c1 = (int)sad8( fenc, load8u( ref_w + (int64_t)y1 * P->stride + x1 ) );
+            red8x2( c0, c1, g );
+            c0 += mvcost( tab, m, x0*4, y0*4 ); c1 += mvcost( tab, m, x1*4, y1*4 );
+            if( c0 < bcost ) { bcost = c0; best = k; }
+            if( k+1 < n && c1 < bcost ) { bcost = c1; best = k+1; }
+        }
+    }
+    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        for( int k = 0; k < n; k += 2 )
+        {
+            int x0, y0, x1, y1;
+            xy( k, x0, y0 ); xy( min( k+1, n-1 ), x1, y1 );
+            int c0 = (int)sad8( fenc, qpel_row( ref0, *P, x0, y0, m.wscale, m.wdenom, m.woffset ) );
+            int c1 = (int)sad8( fenc, qpel_row( ref0, *P, x1, y1, m.wscale, m.wdenom, m.woffset ) );
+            red8x2( c0, c1, g );
+            c0 += mvcost( tab, m, x0, y0 ); c1 += mvcost( tab, m, x1, y1 );
+            if( c0 < bcost ) { bcost = c0; best = k; }
+            if( k+1 < n && c1 < bcost ) { bcost = c1; best = k+1; }
+        }
+    }
+    __device__ __forceinline__ void hex6( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    { fpel_best( 6, [&]( int k, int &x, int &y ) { x = ox + c_hex2[k+1][0]; y = oy + c_hex2[k+1][1]; }, tab, m, bcost, best ); }
+    __device__ __forceinline__ void square8( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    { fpel_best( 8, [&]( int k, int &x, int &y ) { x = ox + c_sq1[k+1][0]; y = oy + c_sq1[k+1][1]; }, tab, m, bcost, best ); }
+    __device__ __forceinline__ int fpel1( int mx, int my ) const { return red8( (int)sad8( fenc, load8u( ref_w + (int64_t)my * P->stride + mx ) ), g ); }
+    __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const
+    { return red8( (int)sad8( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ), g ); }
+    __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
+    {
+        return satd_rows( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ), g );
+    }
+    // TRY_BIDIR without the penalty (slicetype.c:579-603)
+    __device__ __forceinline__ int bidir( int mv0x, int mv0y, int mv1x, int mv1y, int w ) const
+    {
+        uint2 a, b;
+        if( !P->b_satd )
+        {   // subme <= 1: hpel planes addressed directly (slicetype.c:582-589)
+            int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
+            a = load8u( ref0 + i0*P->plane_size + ( mv0x >> 2 ) + (int64_t)( mv0y >> 2 ) * P->stride );
+            b = load8u( ref1 + i1*P->plane_size + ( mv1x >> 2 ) + (int64_t)( mv1y >> 2 ) * P->stride );
+        }
+        else
+        {
+            a = qpel_row( ref0, *P, mv0x, mv0y, 0, -1, 0 );
+            b = qpel_row( ref1, *P, mv1x, mv1y, 0, -1, 0 );
+        }
+        return cmp_rows( fenc, make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ), g, P->b_satd );
+    }
+    __device__ __forceinline__ int bidir_zero( int w ) const
+    {   // slicetype.c:648-649
+        uint2 a = load8u( ref0 ), b = load8u( ref1 );
+        return cmp_rows( fenc, make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ), g, P->b_satd );
+    }
+};
+
+// ---- 1 thread per block ---------------------------------------------------------------------------
+// PITCH is the device plane pitch as a compile-time constant (0: read it from LaParams).  With a constant pitch the
+// eight row loads of a candidate are one base address plus immediates; with a run-time pitch every row costs two
+// 64-bit address instructions (ncu r01: address arithmetic was ~40 % of the executed instructions).
+template<class RowFn>
+__device__ __forceinline__ int sad8x8_t( const uint2 ( &fenc )[8], RowFn pred )
+{
+    u32 s0 = 0, s1 = 0;
+#pragma unroll
+    for( int r = 0; r < 8; r++ ) { uint2 p = pred( r ); s0 = __vsadu4( fenc[r].x, p.x ) + s0; s1 = __vsadu4( fenc[r].y, p.y ) + s1; }
+    return (int)( s0 + s1 );
+}
+// x264_pixel_satd_8x8 = two satd_8x4 (pixel.c:290-330), all in registers
+template<class RowFn>
+__device__ __forceinline__ int satd8x8_t( const uint2 ( &fenc )[8], RowFn pred )
+{
+    int total = 0;
+#pragma unroll
+    for( int h = 0; h < 2; h++ )
+    {
+        u32 t[4][4];
+#pragma unroll
+        for( int i = 0; i < 4; i++ )
+        {
+            u32 d[4];
+            diff_row8( fenc[4*h+i], pred( 4*h+i ), d );
+            HADAMARD4( t[i][0], t[i][1], t[i][2], t[i][3], d[0], d[1], d[2], d[3] );
+        }
+        // second half of the vertical transform folded into the absolute sum: |u+v| + |u-v| == 2*max(|u|,|v|)
+        // per 16-bit half (lane sums stay below 2^15 for 8-bit pixels), so the result equals pixel.c:300-306's
+        u32 sum = 0;
+#pragma unroll
+        for( int i = 0; i < 4; i++ )
+        {
+            const u32 u0 = t[0][i] + t[1][i], u1 = t[0][i] - t[1][i], u2 = t[2][i] + t[3][i], u3 = t[2][i] - t[3][i];
+            sum += __vmaxu2( abs2( u0 ), abs2( u2 ) ) + __vmaxu2( abs2( u1 ), abs2( u3 ) );
+        }
+        total += (int)( ( sum & 0xffff ) + ( sum >> 16 ) );
+    }
+    return total;
+}
+
+// 12 consecutive pixels starting at word pointer q (aligned) + sh bits, as three words
+__device__ __forceinline__ void ld12w( const u32 *q, u32 sh, u32 &a0, u32 &a1, u32 &a2 )
+{
+    u32 w0 = __ldg( q ), w1 = __ldg( q + 1 ), w2 = __ldg( q + 2 ), w3 = __ldg( q + 3 );
+    a0 = __funnelshift_r( w0, w1, sh ); a1 = __funnelshift_r( w1, w2, sh ); a2 = __funnelshift_r( w2, w3, sh );
+}
+
+// get_ref (mc.c:221-249) as a row generator: plane/offset selection hoisted out of the row loop
+template<bool WEIGHTED, int PITCH, bool LD64, bool PTXPRED>
+struct QpelRows
+{
+    RowSrc<LD64> s1, s2;     // the two source planes at row 0
+    int stride4;             // plane pitch in words
+    int avg;
+    int wscale, wdenom, woffset;
+    __device__ __forceinline__ static int off1( const LaParams &P, int mvx, int mvy )
+    {
+        const int pitch = PITCH ? PITCH : P.stride;
+        return ( mvy >> 2 ) * pitch + ( mvx >> 2 ) + ( ( mvy & 3 ) == 3 ? pitch : 0 ) + c_hpel_ref0[( ( mvy & 3 ) << 2 ) + ( mvx & 3 )] * (int)P.plane_size;
+    }
+    __device__ __forceinline__ static int off2( const LaParams &P, int mvx, int mvy )
+    {
+        const int pitch = PITCH ? PITCH : P.stride;
+        return ( mvy >> 2 ) * pitch + ( mvx >> 2 ) + ( ( mvx & 3 ) == 3 ) + c_hpel_ref1[( ( mvy & 3 ) << 2 ) + ( mvx & 3 )] * (int)P.plane_size;
+    }
+    // ref: 8-byte aligned block origin in the F plane; plane_size and the pitch are multiples of 8
+    __device__ __forceinline__ QpelRows( const uint8_t *ref, const LaParams &P, int mvx, int mvy, int ws, int wd, int wo )
+        : s1( ref, off1( P, mvx, mvy ) ), s2( ref, off2( P, mvx, mvy ) )
+    {
+        stride4 = ( PITCH ? PITCH : P.stride ) >> 2;
+        avg = ( ( ( ( mvy & 3 ) << 2 ) + ( mvx & 3 ) ) & 5 ) != 0;
+        wscale = ws; wdenom = wd; woffset = wo;
+    }
+    __device__ __forceinline__ uint2 operator()( int r ) const
+    {
+        const int s4 = PITCH ? PITCH >> 2 : stride4;
+        uint2 v = s1.row( r*s4 );
+        if( PTXPRED )
+        {
+            const uint2 w = s2.row_if( avg, r*s4, v );
+            v.x = avg ? avg4( v.x, w.x ) : v.x; v.y = avg ? avg4( v.y, w.y ) : v.y;
+        }
+        else if( avg )
+        {
+            const uint2 w = s2.row( r*s4 );
+            v.x = avg4( v.x, w.x ); v.y = avg4( v.y, w.y );
+        }
+        if( WEIGHTED && wdenom >= 0 ) { v.x = weight4( v.x, wscale, wdenom, woffset ); v.y = weight4( v.y, wscale, wdenom, woffset ); }
+        return v;
+    }
+};
+
+template<bool SATD, bool WEIGHTED, int PITCH, bool LD64, bool PTXPRED>
+struct ThreadBE
+{
+    uint2 fenc[8];
+    const uint8_t *ref0, *ref1, *ref_w;      // block origins (8-byte aligned)
+    const LaParams *P;
+
+    __device__ __forceinline__ int pitch() const { return PITCH ? PITCH : P->stride; }
+    __device__ __forceinline__ bool leader() const { return true; }
+    __device__ __forceinline__ bool satd() const { return SATD; }
+    __device__ __forceinline__ int zero_cmp() const
+    {
+        const u32 *q = (const u32 *)ref0; const int s4 = pitch() >> 2;
+        auto rows = [&]( int r ) { return __ldg( (const uint2 *)( q + r*s4 ) ); };
+        return SATD ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
+    }
+    __device__ __forceinline__ int fpel1( int mx, int my ) const
+    {
+        const int s4 = pitch() >> 2;
+        const RowSrc<LD64> src( ref_w, my * pitch() + mx );
+        return sad8x8_t( fenc, [&]( int r ) { return src.row( r*s4 ); } );
+    }
+    __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const
+    { return sad8x8_t( fenc, QpelRows<WEIGHTED, PITCH, LD64, PTXPRED>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ); }
+    // candidate loops are NOT unrolled: one copy of the 8-row body per call site keeps the kernel inside the
+    // instruction cache (ncu r01: the fully unrolled form had 25k SASS lines and 53 % no-instruction stalls)
+    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+#pragma unroll 1
+        for( int k = 0; k < n; k++ )
+        {
+            int x, y;
+            xy( k, x, y );
+            int c = fpel1( x, y ) + mvcost( tab, m, x*4, y*4 );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
+    }
+    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+#pragma unroll 1
+        for( int k = 0; k < n; k++ )
+        {
+            int x, y;
+            xy( k, x, y );
+            int c = qsad1( m, x, y ) + mvcost( tab, m, x, y );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
+    }
+    // The full hexagon (me.c:354-362) with shared row loads: the six points touch rows oy-2..oy+9 and columns
+    // ox-2..ox+9, so each of the 12 rows is loaded once (4 words), aligned once to column ox-2, and the dx = -1/+1
+    // candidates are immediate funnel shifts of it.  96 + 36 row loads become 48; costs are then compared in the
+    // reference's order with strict '<'.
+    __device__ __forceinline__ void hex6( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        const int s4 = pitch() >> 2, off = ( oy - 2 ) * pitch() + ox - 2;
+        const u32 *q = (const u32 *)ref_w + ( off >> 2 ); const u32 sh = ( off & 3 ) * 8;
+        u32 acc[6] = {0, 0, 0, 0, 0, 0};      // hex2[1..6]: (-2,0) (-1,2) (1,2) (2,0) (1,-2) (-1,-2)
+#pragma unroll
+        for( int r = 0; r < 12; r++ )
+        {
+            u32 a0, a1, a2;
+            ld12w( q + r*s4, sh, a0, a1, a2 );
+            if( r <= 7 || r >= 4 )
+            {
+                const u32 m0 = __funnelshift_r( a0, a1, 8 ),  m1 = __funnelshift_r( a1, a2, 8 );      // column ox-1
+                const u32 p0 = __funnelshift_r( a0, a1, 24 ), p1 = __funnelshift_r( a1, a2, 24 );     // column ox+1
+                if( r <= 7 )
+                {   // dy = -2: block row r
+                    acc[5] = __vsadu4( fenc[r].x, m0 ) + __vsadu4( fenc[r].y, m1 ) + acc[5];
+                    acc[4] = __vsadu4( fenc[r].x, p0 ) + __vsadu4( fenc[r].y, p1 ) + acc[4];
+                }
+                if( r >= 4 )
+                {   // dy = +2: block row r-4
+                    acc[1] = __vsadu4( fenc[r-4].x, m0 ) + __vsadu4( fenc[r-4].y, m1 ) + acc[1];
+                    acc[2] = __vsadu4( fenc[r-4].x, p0 ) + __vsadu4( fenc[r-4].y, p1 ) + acc[2];
+                }
+            }
+            if( r >= 2 && r <= 9 )
+            {   // dy = 0: block row r-2, columns ox-2 and ox+2
+                acc[0] = __vsadu4( fenc[r-2].x, a0 ) + __vsadu4( fenc[r-2].y, a1 ) + acc[0];
+                acc[3] = __vsadu4( fenc[r-2].x, a1 ) + __vsadu4( fenc[r-2].y, a2 ) + acc[3];
+            }
+        }
+#pragma unroll
+        for( int k = 0; k < 6; k++ )
+        {
+            const int x = ox + c_hex2[k+1][0], y = oy + c_hex2[k+1][1];
+            const int c = (int)acc[k] + mvcost( tab, m, x*4, y*4 );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
+    }
+    // The square refine (me.c:404-418): rows oy-1..oy+8, columns ox-1..ox+8, 10 shared row loads for 8 candidates
+    __device__ __forceinline__ void square8( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        const int s4 = pitch() >> 2, off = ( oy - 1 ) * pitch() + ox - 1;
+        const u32 *q = (const u32 *)ref_w + ( off >> 2 ); const u32 sh = ( off & 3 ) * 8;
+        u32 acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // square1[1..8]: (0,-1) (0,1) (-1,0) (1,0) (-1,-1) (-1,1) (1,-1) (1,1)
+#pragma unroll
+        for( int r = 0; r < 10; r++ )
+        {
+            u32 a0, a1, a2;
+            ld12w( q + r*s4, sh, a0, a1, a2 );
+            const u32 c0 = __funnelshift_r( a0, a1, 8 ),  c1 = __funnelshift_r( a1, a2, 8 );       // column ox
+            const u32 p0 = __funnelshift_r( a0, a1, 16 ), p1 = __funnelshift_r( a1, a2, 16 );      // column ox+1
+            if( r <= 7 )
+            {   // dy = -1: block row r
+                acc[0] = __vsadu4( fenc[r].x, c0 ) + __vsadu4( fenc[r].y, c1 ) + acc[0];
+                acc[4] = __vsadu4( fenc[r].x, a0 ) + __vsadu4( fenc[r].y, a1 ) + acc[4];
+                acc[6] = __vsadu4( fenc[r].x, p0 ) + __vsadu4( fenc[r].y, p1 ) + acc[6];
+            }
+            if( r >= 1 && r <= 8 )
+            {   // dy = 0: block row r-1
+                acc[2] = __vsadu4( fenc[r-1].x, a0 ) + __vsadu4( fenc[r-1].y, a1 ) + acc[2];
+                acc[3] = __vsadu4( fenc[r-1].x, p0 ) + __vsadu4( fenc[r-1].y, p1 ) + acc[3];
+            }
+            if( r >= 2 )
+            {   // dy = +1: block row r-2
+                acc[1] = __vsadu4( fenc[r-2].x, c0 ) + __vsadu4( fenc[r-2].y, c1 ) + acc[1];
+                acc[5] = __vsadu4( fenc[r-2].x, a0 ) + __vsadu4( fenc[r-2].y, a1 ) + acc[5];
+                acc[7] = __vsadu4( fenc[r-2].x, p0 ) + __vsadu4( fenc[r-2].y, p1 ) + acc[7];
+            }
+        }
+#pragma unroll
+        for( int k = 0; k < 8; k++ )
+        {
+            const int x = ox + c_sq1[k+1][0], y = oy + c_sq1[k+1][1];
+            const int c = (int)acc[k] + mvcost( tab, m, x*4, y*4 );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
+    }
+    __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
+    {
+        return satd8x8_t( fenc, QpelRows<WEIGHTED, PITCH, LD64, PTXPRED>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) );
+    }
+    __device__ __forceinline__ int bidir( int mv0x, int mv0y, int mv1x, int mv1y, int w ) const
+    {
+        if( !SATD )
+        {
+            const int s4 = pitch() >> 2, psz = (int)P->plane_size;
+            const int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
+            const int o0 = ( mv0x >> 2 ) + ( mv0y >> 2 ) * pitch() + i0*psz, o1 = ( mv1x >> 2 ) + ( mv1y >> 2 ) * pitch() + i1*psz;
+            const RowSrc<LD64> q0( ref0, o0 ), q1( ref1, o1 );
+            return sad8x8_t( fenc, [&]( int r ) { uint2 a = q0.row( r*s4 ), b = q1.row( r*s4 );
+                                                  return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+        }
+        QpelRows<false, PITCH, LD64, PTXPRED> r0( ref0, *P, mv0x, mv0y, 0, -1, 0 ), r1( ref1, *P, mv1x, mv1y, 0, -1, 0 );
+        return satd8x8_t( fenc, [&]( int r ) { uint2 a = r0( r ), b = r1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+    }
+    __device__ __forceinline__ int bidir_zero( int w ) const
+    {
+        const u32 *q0 = (const u32 *)ref0, *q1 = (const u32 *)ref1; const int s4 = pitch() >> 2;
+        auto rows = [&]( int r ) { uint2 a = __ldg( (const uint2 *)( q0 + r*s4 ) ), b = __ldg( (const uint2 *)( q1 + r*s4 ) );
+                                   return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); };
+        return SATD ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
+    }
+};
+
+
+__device__ __forceinline__ bool skipped_border( const LaParams &P, int bx, int by )
+{   // never evaluated by slicetype_slice_cost (slicetype.c:823-828)
+    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
+    return border && !P.do_edges && P.mbw > 2 && P.mbh > 2;
+}
+
+static inline bool use_thread_mapping( const LaParams &P, int njobs )
+{
+    if( P.lanes_per_block == 1 ) return true;
+    if( P.lanes_per_block == 8 ) return false;
+    return (int64_t)njobs * P.nmb >= 4 * 8160;     // wide launches: enough blocks to fill the SMs one thread each
+}
+

@@ -1,0 +1,333 @@
+// search.cu -- motion search kernels of the lookahead cost engine (sm_100a).
+//
+//   search_kernel_t / _g   x264_me_search_ref for PIXEL_8x8 (me.c:182-420,774-797,865-992) under the MV-predictor
+//                          rule of slicetype.c:658-697, one pass of the dependency-free schedule
+//   search_kernel_wave     the same block search in the reference's raster-serial order, one anti-diagonal per launch
+#include "la_block.cuh"
+
+#define FPEL(v) (((v)+2)>>2)
+
+// refine_subpel (me.c:865-992), p_halfpel_thresh == NULL, b_refine_qpel == 0, no chroma
+template<class BE>
+__device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, const LaParams &P, const CostTab &tab,
+                                               int &bmx, int &bmy, int &bcost, int hpel_iters, int qpel_iters )
+{
+    if( hpel_iters )
+    {
+        if( !be.satd() )
+        {   // la subme 2 (< 3): try the subpel component of the predictor (me.c:889-895)
+            int mx = iclip3( m.mvpx, m.sminx + 2, m.smaxx - 2 );
+            int my = iclip3( m.mvpy, m.sminy + 2, m.smaxy - 2 );
+            if( ( mx - bmx ) | ( my - bmy ) )
+            {
+                int cost = be.qsad1( m, mx, my ) + mvcost( tab, m, mx, my );
+                if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
+            }
+        }
+        for( int i = hpel_iters; i > 0; i-- )
+        {   // me.c:898-921, tie order: up, down, left, right
+            const int omx = bmx, omy = bmy;
+            int best = -1;
+            be.qsad_best( 4, [&]( int k, int &x, int &y ) { x = omx + ( k == 2 ? -2 : k == 3 ? 2 : 0 ); y = omy + ( k == 0 ? -2 : k == 1 ? 2 : 0 ); },
+                          tab, m, bcost, best );
+            if( best < 0 ) break;
+            bmx = omx + ( best == 2 ? -2 : best == 3 ? 2 : 0 );
+            bmy = omy + ( best == 0 ? -2 : best == 1 ? 2 : 0 );
+        }
+    }
+    if( be.satd() )   // mbcmp != fpelcmp: re-measure the winner with SATD (me.c:925-929)
+        bcost = be.qsatd( m, bmx, bmy ) + mvcost( tab, m, bmx, bmy );
+    int bdir = -1;
+    for( int i = qpel_iters; i > 0; i-- )
+    {   // me.c:947-963
+        if( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx ) break;
+        const int odir = bdir, omx = bmx, omy = bmy;
+#pragma unroll 1
+        for( int k = 0; k < 4; k++ )
+            if( ( k ^ 1 ) != odir )
+            {
+                int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
+                int cost = be.qsatd( m, mx, my ) + mvcost( tab, m, mx, my );
+                if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; bdir = k; }
+            }
+        if( bmx == omx && bmy == omy ) break;
+    }
+}
+
+// x264_me_search_ref (me.c:182-420,774-797) for one block; result mv (qpel) and cost
+template<class BE>
+__device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const LaParams &P, const CostTab &tab,
+                                           const int (*mvc)[2], int i_mvc, int &out_mx, int &out_my, int &out_cost )
+{
+    int bmx, bmy, bcost = X264CU_COST_MAX, bpred_cost = X264CU_COST_MAX, bpred_mx = 0, bpred_my = 0, pmvx, pmvy;
+#define COST_MV( mx_, my_ ) { int c_ = be.fpel1( mx_, my_ ) + mvcost( tab, m, (mx_)*4, (my_)*4 ); \
+                              if( c_ < bcost ) { bcost = c_; bmx = mx_; bmy = my_; } }
+    if( be.satd() )
+    {   // la subme 4 (>= 3): subpel predictors (me.c:216-275)
+        bpred_mx = iclip3( m.mvpx, 4*m.fminx, 4*m.fmaxx );
+        bpred_my = iclip3( m.mvpy, 4*m.fminy, 4*m.fmaxy );
+        pmvx = bpred_mx; pmvy = bpred_my;
+        bpred_cost = be.qsad1( m, bpred_mx, bpred_my ) + mvcost( tab, m, bpred_mx, bpred_my );
+        const int pmv_cost = bpred_cost;
+#pragma unroll 1
+        for( int i = 0; i < i_mvc; i++ )
+        {   // x264_predictor_clip (common.h:790-805): drop zero and == pmv, clip the rest
+            int mx = mvc[i][0], my = mvc[i][1];
+            if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
+            mx = iclip3( mx, 4*m.fminx, 4*m.fmaxx ); my = iclip3( my, 4*m.fminy, 4*m.fmaxy );
+            int cost = be.qsad1( m, mx, my ) + mvcost( tab, m, mx, my );
+            if( cost < bpred_cost ) { bpred_cost = cost; bpred_mx = mx; bpred_my = my; }
+        }
+        bmx = FPEL( bpred_mx ); bmy = FPEL( bpred_my );
+        // me.c:258-274 with the two possible fullpel probes folded into one call site
+        const bool probe_start = ( bpred_mx & 3 ) | ( bpred_my & 3 );
+        if( !probe_start ) bcost = bpred_cost;
+        const bool probe_zero = ( pmvx | pmvy ) && ( bmx | bmy );
+        const int sx = bmx, sy = bmy;
+#pragma unroll 1
+        for( int t = 0; t < 2; t++ )
+        {
+            if( t == 0 ? !probe_start : !probe_zero ) continue;
+            const int x = t == 0 ? sx : 0, y = t == 0 ? sy : 0;
+            COST_MV( x, y )
+        }
+        if( !( pmvx | pmvy ) && pmv_cost < bcost ) { bcost = pmv_cost; bmx = 0; bmy = 0; }
+    }
+    else
+    {   // la subme 2: fullpel predictors (me.c:278-317)
+        bmx = iclip3( FPEL( m.mvpx ), m.fminx, m.fmaxx );
+        bmy = iclip3( FPEL( m.mvpy ), m.fminy, m.fmaxy );
+        pmvx = bmx; pmvy = bmy;
+        int sx = bmx, sy = bmy;
+        // the start point (no mv cost, me.c:291), the rounded candidates (:293-313) and zero (:316-317) share one call site
+#pragma unroll 1
+        for( int i = -1; i <= i_mvc; i++ )
+        {
+            int mx, my, add;
+            if( i < 0 ) { mx = bmx; my = bmy; add = 0; }
+            else if( i < i_mvc )
+            {   // x264_predictor_roundclip (common.h:774-788)
+                mx = ( mvc[i][0] + 2 ) >> 2; my = ( mvc[i][1] + 2 ) >> 2;
+                if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
+                mx = iclip3( mx, m.fminx, m.fmaxx ); my = iclip3( my, m.fminy, m.fmaxy );
+                add = mvcost( tab, m, mx*4, my*4 );
+            }
+            else
+            {
+                if( !( pmvx | pmvy ) ) continue;
+                mx = 0; my = 0; add = mvcost( tab, m, 0, 0 );
+            }
+            int cost = be.fpel1( mx, my ) + add;
+            if( cost < bcost ) { bcost = cost; sx = mx; sy = my; }
+        }
+        bmx = sx; bmy = sy;
+    }
+#undef COST_MV
+
+    if( P.me_method == 0 )
+    {   // DIA (me.c:322-342): tie order up, down, left, right
+        int i = P.me_range;
+        do
+        {
+            const int ox = bmx, oy = bmy;
+            int best = -1;
+            be.fpel_best( 4, [&]( int k, int &x, int &y ) { x = ox + ( k == 2 ? -1 : k == 3 ? 1 : 0 ); y = oy + ( k == 0 ? -1 : k == 1 ? 1 : 0 ); },
+                          tab, m, bcost, best );
+            if( best < 0 ) break;
+            bmx = ox + ( best == 2 ? -1 : best == 3 ? 1 : 0 );
+            bmy = oy + ( best == 0 ? -1 : best == 1 ? 1 : 0 );
+        } while( --i && in_range( m, bmx, bmy ) );
+    }
+    else
+    {   // HEX (me.c:344-420): the full hexagon, then half hexagons that do not overlap the previous one
+        int best = -1;
+        be.hex6( bmx, bmy, tab, m, bcost, best );
+        if( best >= 0 )
+        {
+            int dir = best;
+            bmx += hex2x( dir+1 ); bmy += hex2y( dir+1 );
+            for( int i = ( P.me_range >> 1 ) - 1; i > 0 && in_range( m, bmx, bmy ); i-- )
+            {
+                const int ox = bmx, oy = bmy, base = dir;
+                best = -1;
+                be.fpel_best( 3, [&]( int k, int &x, int &y ) { x = ox + hex2x( base+k ); y = oy + hex2y( base+k ); }, tab, m, bcost, best );
+                if( best < 0 ) break;
+                dir += best - 1;
+                dir = dir < 0 ? dir + 6 : dir >= 6 ? dir - 6 : dir;      // mod6m1 (me.c:53)
+                bmx = ox + hex2x( dir+1 ); bmy = oy + hex2y( dir+1 );
+            }
+        }
+        // square refine (me.c:404-418)
+        {
+            const int ox = bmx, oy = bmy;
+            int bs = -1;
+            be.square8( ox, oy, tab, m, bcost, bs );
+            bmx = ox + c_sq1[bs+1][0]; bmy = oy + c_sq1[bs+1][1];
+        }
+    }
+
+    // -> qpel mv (me.c:774-797)
+    int mx, my, cost;
+    if( !be.satd() )
+    {
+        cost = bcost;
+        if( bmx == pmvx && bmy == pmvy ) cost += mvcost( tab, m, bmx*4, bmy*4 );
+        mx = bmx*4; my = bmy*4;
+        refine_subpel( be, m, P, tab, mx, my, cost, 1, 0 );      // subpel_iterations[2] = {0,1,1,0}
+    }
+    else
+    {
+        if( bpred_cost < bcost ) { mx = bpred_mx; my = bpred_my; }
+        else                     { mx = bmx*4;    my = bmy*4; }
+        cost = min( bpred_cost, bcost );
+        refine_subpel( be, m, P, tab, mx, my, cost, 1, 1 );      // subpel_iterations[4] = {0,2,1,1}
+    }
+    out_mx = mx; out_my = my; out_cost = cost;
+}
+
+// one block of one search pass (slicetype.c:654-702)
+template<class BE>
+__device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, const LaParams &P, const CostTab &tab,
+                                              int bx, int by, int blk )
+{
+    MeGeo m;
+    m.wscale = J.wscale; m.wdenom = J.wdenom; m.woffset = J.woffset;
+    me_limits( m, P, bx, by );
+    // MV predictor from the previous pass's field (slicetype.c:658-680): right, below, below-left, below-right
+    int mvc[4][2] = {{0,0},{0,0},{0,0},{0,0}}, i_mvc = 0;
+    if( J.mv_in )
+    {
+        const int *f = (const int *)J.mv_in + blk;
+#define MVC( o ) { int v_ = __ldg( f + (o) ); mvc[i_mvc][0] = (int16_t)( v_ & 0xffff ); mvc[i_mvc][1] = v_ >> 16; i_mvc++; }
+        if( bx < P.mbw-1 ) MVC( 1 )
+        if( by < P.mbh-1 )
+        {
+            MVC( P.mbw )
+            if( bx > 0 ) MVC( P.mbw-1 )
+            if( bx < P.mbw-1 ) MVC( P.mbw+1 )
+        }
+#undef MVC
+    }
+    if( i_mvc <= 1 ) { m.mvpx = mvc[0][0]; m.mvpy = mvc[0][1]; }
+    else
+    {
+        m.mvpx = imedian( mvc[0][0], mvc[1][0], mvc[2][0] );
+        m.mvpy = imedian( mvc[0][1], mvc[1][1], mvc[2][1] );
+    }
+    int mx = 0, my = 0, cost = 0;
+    bool skip = false;
+    if( !( m.mvpx | m.mvpy ) )
+    {   // zero-predictor shortcut (slicetype.c:684-692): unweighted F plane at mv 0
+        cost = be.zero_cmp();
+        skip = cost < 64;
+    }
+    if( !skip )
+    {
+        me_search( be, m, P, tab, mvc, i_mvc, mx, my, cost );
+        cost -= tab[0];                                // slicetype.c:695
+        if( mx | my ) cost += 5;                       // 5 * lambda (:696-697)
+    }
+    if( be.leader() )
+    {
+        ( (int *)J.mv_out )[blk] = ( mx & 0xffff ) | ( my << 16 );
+        J.cost_out[blk] = cost;
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob *__restrict__ jobs, LaParams P )
+{
+    const CostTab tab = stage_cost_tab( P );
+    const SearchJob J = jobs[blockIdx.y];
+    GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
+    const int blk = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );
+    if( blk >= P.nmb ) return;
+    const int bx = blk % P.mbw, by = blk / P.mbw;
+    if( skipped_border( P, bx, by ) )
+    {   // the field keeps frame_new's zeros (frame.c:283-285)
+        if( be.g.r == 0 ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; }
+        return;
+    }
+    const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
+    be.fenc = *(const uint2 *)( J.fenc + pel );
+    be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
+    search_block( be, J, P, tab, bx, by, blk );
+}
+
+template<bool SATD, bool WEIGHTED, int PITCH>
+__global__ void __launch_bounds__(S_TILE_W*S_TILE_H, X264CU_MINB_SEARCH) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
+{
+    const CostTab tab = stage_cost_tab( P );
+    const SearchJob J = jobs[blockIdx.z];
+    const int bx = blockIdx.x * S_TILE_W + threadIdx.x % S_TILE_W, by = blockIdx.y * S_TILE_H + threadIdx.x / S_TILE_W;
+    if( bx >= P.mbw || by >= P.mbh ) return;
+    const int blk = by * P.mbw + bx;
+    if( skipped_border( P, bx, by ) ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; return; }
+    ThreadBE<SATD, WEIGHTED, PITCH, X264CU_SEARCH_LD64 != 0, X264CU_SEARCH_PTXPRED != 0> be; be.P = &P;
+    const int pel = ( by*8 ) * be.pitch() + bx*8;
+    const uint8_t *src = J.fenc + pel;
+#pragma unroll
+    for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * be.pitch() ) );
+    be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
+    search_block( be, J, P, tab, bx, by, blk );
+}
+
+// Exact raster-serial mode: the reference evaluates blocks in reverse raster order and
+// each block reads the MVs of its right / below / below-left / below-right neighbours from the SAME pass
+// (slicetype.c:662-680,830-833).  Blocks with equal w = (mbw-1-x) + 2*(mbh-1-y) depend only on blocks of smaller w,
+// so one launch per anti-diagonal wave reproduces the serial result exactly; mv_in == mv_out (in place).
+__global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJob *__restrict__ jobs, LaParams P, int wave )
+{
+    const CostTab tab = stage_cost_tab( P );
+    const SearchJob J = jobs[blockIdx.y];
+    GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
+    const int by = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );       // one candidate block per row
+    if( by >= P.mbh ) return;
+    const int bx = P.mbw - 1 - ( wave - 2 * ( P.mbh - 1 - by ) );
+    if( bx < 0 || bx >= P.mbw ) return;
+    if( skipped_border( P, bx, by ) ) return;                                 // the field was zeroed before the first wave
+    const int blk = by * P.mbw + bx;
+    const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
+    be.fenc = *(const uint2 *)( J.fenc + pel );
+    be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
+    search_block( be, J, P, tab, bx, by, blk );
+}
+
+void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
+{
+    dim3 grid( ( P.mbh + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
+    const int nwaves = P.mbw + 2 * ( P.mbh - 1 );
+    for( int w = 0; w < nwaves; w++ )
+        search_kernel_wave<<<grid, CTA_THREADS, 0, st>>>( d_jobs, P, w );
+}
+
+template<int PITCH>
+static void launch_search_t( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
+{
+    dim3 grid( ( P.mbw + S_TILE_W - 1 ) / S_TILE_W, ( P.mbh + S_TILE_H - 1 ) / S_TILE_H, njobs );
+    if( P.b_satd )
+    {
+        if( any_weighted ) search_kernel_t<true, true, PITCH><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
+        else               search_kernel_t<true, false, PITCH><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
+    }
+    else
+    {
+        if( any_weighted ) search_kernel_t<false, true, PITCH><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
+        else               search_kernel_t<false, false, PITCH><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
+    }
+}
+
+void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
+{
+    if( use_thread_mapping( P, njobs ) )
+    {   // the context picks the pitch from {1024, 2048} whenever the padded width fits (capi.cu), anything wider runs the
+        // run-time-pitch instantiation
+        if( P.stride == 1024 )      launch_search_t<1024>( d_jobs, njobs, any_weighted, P, st );
+        else if( P.stride == 2048 ) launch_search_t<2048>( d_jobs, njobs, any_weighted, P, st );
+        else                        launch_search_t<0>( d_jobs, njobs, any_weighted, P, st );
+    }
+    else
+    {
+        dim3 grid( ( P.nmb + GROUPS_PER_CTA - 1 ) / GROUPS_PER_CTA, njobs );
+        search_kernel_g<<<grid, CTA_THREADS, 0, st>>>( d_jobs, P );
+    }
+}
