@@ -682,6 +682,50 @@ EXPORT int ref_la_macroblock_tree( void *ctx, int first, int num_frames, int b_i
     return 0;
 }
 
+/* ---- adaptive quantisation + weighted-prediction analysis ---- */
+/* like ref_la_put_frame_aq with the real interleaved NV12 chroma plane: x264_adaptive_quant_frame (ratecontrol.c:304)
+ * needs both chroma components for ac_energy_mb (:262-294) */
+EXPORT int ref_la_put_frame_yuv( void *ctx, int idx, const uint8_t *luma, int stride, const uint8_t *chroma, int cstride,
+                                 const float *quant_offsets )
+{
+    ref_la_t *c = ctx;
+    x264_t *h = c->h;
+    if( ref_la_put_frame( ctx, idx, luma, stride, NULL ) ) return -1;
+    x264_frame_t *f = c->frames[idx];
+    for( int y = 0; y < h->param.i_height/2; y++ )
+        memcpy( f->plane[1] + (intptr_t)y*f->i_stride[1], chroma + (intptr_t)y*cstride, h->param.i_width );
+    if( h->param.i_width != 16*h->mb.i_mb_width || h->param.i_height != 16*h->mb.i_mb_height )
+        x264_frame_expand_border_mod16( h, f );
+    x264_adaptive_quant_frame( h, f, (float *)quant_offsets );
+    return 0;
+}
+
+/* f_qp_offset, i_inv_qscale_factor, {i_pixel_sum[p], i_pixel_ssd[p]} p = 0..2 */
+EXPORT int ref_la_get_aq( void *ctx, int idx, float *qp_offset, uint16_t *inv_qscale, uint64_t *sums6 )
+{
+    ref_la_t *c = ctx;
+    x264_frame_t *f = c->frames[idx];
+    int n = c->h->mb.i_mb_count;
+    if( qp_offset ) memcpy( qp_offset, f->f_qp_offset, n*sizeof(float) );
+    if( inv_qscale ) memcpy( inv_qscale, f->i_inv_qscale_factor, n*sizeof(uint16_t) );
+    if( sums6 ) for( int i = 0; i < 3; i++ ) { sums6[2*i] = f->i_pixel_sum[i]; sums6[2*i+1] = f->i_pixel_ssd[i]; }
+    return 0;
+}
+
+/* the reference's own x264_weights_analyse( h, frames[b], frames[ref], b_lookahead = 1 ) (slicetype.c:284);
+ * out: [0] weightfn != NULL [1] i_scale [2] i_denom [3] i_offset */
+EXPORT int ref_la_weights_analyse( void *ctx, int b, int ref, int *out )
+{
+    ref_la_t *c = ctx;
+    x264_frame_t *fenc = c->frames[b];
+    x264_weights_analyse( c->h, fenc, c->frames[ref], 1 );
+    out[0] = fenc->weight[0][0].weightfn != NULL;
+    out[1] = fenc->weight[0][0].i_scale; out[2] = fenc->weight[0][0].i_denom; out[3] = fenc->weight[0][0].i_offset;
+    return 0;
+}
+
+EXPORT int ref_exp2_lut( uint8_t *out64 ) { memcpy( out64, x264_exp2_lut, 64 ); return 0; }
+
 EXPORT double ref_now( void )
 {
     struct timespec ts;

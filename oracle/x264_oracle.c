@@ -537,6 +537,9 @@ typedef struct
     int cost_est_aq[XO_MAXB+2][XO_MAXB+2];
     int intra_mbs[XO_MAXB+2];
     uint16_t *propagate;          /* i_propagate_cost */
+    uint64_t pixel_sum[3], pixel_ssd[3];   /* i_pixel_sum / i_pixel_ssd after the mean removal (ratecontrol.c:406-414) */
+    float *qp_offset_aq;          /* f_qp_offset_aq == f_qp_offset right after x264_adaptive_quant_frame */
+    int have_aq;
 } xo_frame;
 
 struct xo_ctx
@@ -579,7 +582,7 @@ xo_ctx *xo_open( const xo_cfg *cfg )
 
 static void free_frame( xo_frame *f )
 {
-    free( f->buf ); free( f->wbuf ); free( f->inv_qscale ); free( f->propagate );
+    free( f->buf ); free( f->wbuf ); free( f->inv_qscale ); free( f->propagate ); free( f->qp_offset_aq );
     for( int i = 0; i < XO_MAXB+2; i++ )
         for( int j = 0; j < XO_MAXB+2; j++ ) { free( f->lowres_costs[i][j] ); free( f->row_satds[i][j] ); }
     for( int l = 0; l < 2; l++ )
@@ -1326,6 +1329,192 @@ static float xo_log2( uint32_t x )
     if( !init ) { for( int i = 0; i < 128; i++ ) lut[i] = (float)( round( log2( 1.0 + i / 128.0 ) * 1e5 ) / 1e5 ); init = 1; }
     int lz = __builtin_clz( x );
     return lut[( x << lz >> 24 ) & 0x7f] + (float)( 31 - lz );
+}
+
+/* ================================================================================================ */
+/* adaptive quantisation and explicit weighted prediction analysis: the producers right before the  */
+/* path                                                             */
+/* ================================================================================================ */
+
+/* x264_exp2fix8, base.h:216-224; x264_exp2_lut[i] (tables.c:58-64) is round( 256 * ( 2^(i/64) - 1 ) ) */
+static int xo_exp2fix8( float x )
+{
+    static uint8_t lut[64];
+    static int init;
+    if( !init ) { for( int i = 0; i < 64; i++ ) lut[i] = (uint8_t)lround( 256.0 * ( pow( 2.0, i / 64.0 ) - 1.0 ) ); init = 1; }
+    int i = x * ( -64.f / 6.f ) + 512.5f;
+    if( i < 0 ) return 0;
+    if( i > 1023 ) return 0xffff;
+    return ( lut[i&63] + 256 ) << ( i >> 6 ) >> 8;
+}
+void xo_exp2_lut( uint8_t *out64 ) { for( int i = 0; i < 64; i++ ) out64[i] = (uint8_t)lround( 256.0 * ( pow( 2.0, i / 64.0 ) - 1.0 ) ); }
+
+/* pixel_var_16x16 / _8x8 (pixel.c:158-175) over a plane with replicated mod-16 padding (frame.c:640-668):
+ * step is 1 for luma, 2 for one component of the interleaved NV12 chroma plane */
+static uint32_t ac_energy_var( const uint8_t *p, int stride, int x0, int y0, int n, int step, int wmax, int hmax, int shift,
+                               uint64_t *acc_sum, uint64_t *acc_ssd )
+{
+    uint32_t sum = 0, sqr = 0;
+    for( int y = 0; y < n; y++ )
+        for( int x = 0; x < n; x++ )
+        {
+            int v = p[(intptr_t)imin( y0+y, hmax ) * stride + imin( x0+x, wmax ) * step];
+            sum += v; sqr += v*v;
+        }
+    *acc_sum += sum; *acc_ssd += sqr;                                  /* ac_energy_var b_store, ratecontrol.c:226-236 */
+    return sqr - (uint32_t)( ( (uint64_t)sum * sum ) >> shift );
+}
+
+/* x264_adaptive_quant_frame (ratecontrol.c:304-415) for a progressive 4:2:0 frame, aq-mode 0 or 1 (mode 2/3 go through
+ * powf and are not restated), followed by x264_frame_init_lowres through xo_put_frame -- the order of encoder.c:3417-3421 */
+int xo_put_frame_aq( xo_ctx *c, int idx, const uint8_t *luma, int stride, const uint8_t *chroma, int cstride,
+                     int aq_mode, float aq_strength, const float *quant_offsets )
+{
+    if( aq_mode < 0 || aq_mode > 1 ) return -1;
+    const int W = c->cfg.width, H = c->cfg.height;
+    uint64_t sum[3] = {0,0,0}, ssd[3] = {0,0,0};
+    float *qp = calloc( c->nmb, sizeof(float) );
+    uint16_t *inv = malloc( c->nmb * sizeof(uint16_t) );
+    const float strength = aq_strength * 1.0397f;                      /* ratecontrol.c:371 */
+    for( int i = 0; i < c->nmb; i++ ) inv[i] = 256;
+    for( int my = 0; my < c->mbh; my++ )
+        for( int mx = 0; mx < c->mbw; mx++ )
+        {   /* ac_energy_mb (ratecontrol.c:262-294): luma 16x16 + both 8x8 chroma blocks */
+            uint32_t energy = ac_energy_var( luma, stride, 16*mx, 16*my, 16, 1, W-1, H-1, 8, &sum[0], &ssd[0] );
+            energy += ac_energy_var( chroma,   cstride, 8*mx, 8*my, 8, 2, W/2-1, H/2-1, 6, &sum[1], &ssd[1] );
+            energy += ac_energy_var( chroma+1, cstride, 8*mx, 8*my, 8, 2, W/2-1, H/2-1, 6, &sum[2], &ssd[2] );
+            if( aq_mode == 1 && aq_strength != 0 )
+            {   /* ratecontrol.c:388-399 */
+                float qp_adj = strength * ( xo_log2( energy > 1 ? energy : 1 ) - 14.427f );
+                if( quant_offsets ) qp_adj += quant_offsets[mx + my*c->mbw];
+                qp[mx + my*c->mbw] = qp_adj;
+                inv[mx + my*c->mbw] = xo_exp2fix8( qp_adj );
+            }
+            else if( aq_mode && quant_offsets )
+            {   /* ratecontrol.c:318-325 */
+                qp[mx + my*c->mbw] = quant_offsets[mx + my*c->mbw];
+                inv[mx + my*c->mbw] = xo_exp2fix8( quant_offsets[mx + my*c->mbw] );
+            }
+        }
+    if( xo_put_frame( c, idx, luma, stride, aq_mode ? inv : NULL ) ) { free( qp ); free( inv ); return -1; }
+    xo_frame *f = &c->fr[idx];
+    for( int i = 0; i < 3; i++ )
+    {   /* remove the mean from the SSD (ratecontrol.c:406-414) */
+        uint64_t width = 16*c->mbw >> !!i, height = 16*c->mbh >> !!i;
+        f->pixel_sum[i] = sum[i];
+        f->pixel_ssd[i] = ssd[i] - ( sum[i] * sum[i] + width * height / 2 ) / ( width * height );
+    }
+    f->qp_offset_aq = qp;
+    f->have_aq = 1;
+    free( inv );
+    return 0;
+}
+
+int xo_get_aq( xo_ctx *c, int idx, float *qp_offset, uint16_t *inv_qscale, uint64_t *sums6 )
+{
+    xo_frame *f = &c->fr[idx];
+    if( !f->valid || !f->have_aq ) return -1;
+    if( qp_offset ) memcpy( qp_offset, f->qp_offset_aq, c->nmb * sizeof(float) );
+    if( inv_qscale ) memcpy( inv_qscale, f->inv_qscale, c->nmb * sizeof(uint16_t) );
+    if( sums6 ) for( int i = 0; i < 3; i++ ) { sums6[2*i] = f->pixel_sum[i]; sums6[2*i+1] = f->pixel_ssd[i]; }
+    return 0;
+}
+
+/* bs_size_ue / bs_size_se (bitstream.h:278-299); x264_ue_size_tab[i] is 2*floor(log2(i))+1, and 1 for i = 0 */
+static int ue_size_tab( int i ) { return i ? 2 * ( 31 - __builtin_clz( i ) ) + 1 : 1; }
+static int bs_size_ue( unsigned v ) { return ue_size_tab( v + 1 ); }
+static int bs_size_se( int v )
+{
+    int tmp = 1 - v*2;
+    if( tmp < 0 ) tmp = v*2;
+    return tmp < 256 ? ue_size_tab( tmp ) : ue_size_tab( tmp >> 8 ) + 16;
+}
+
+/* weight_cost_luma (slicetype.c:191-222): src is the reference's plane 0 or its motion-compensated copy (stride 8*mbw) */
+static unsigned weight_cost_luma( xo_ctx *c, xo_frame *fenc, const uint8_t *src, int sstride, int weighted, int scale, int denom, int offset, int numslices )
+{
+    unsigned cost = 0;
+    uint8_t buf[64];
+    for( int y = 0, i_mb = 0; y < c->lh; y += 8 )
+        for( int x = 0; x < c->lw; x += 8, i_mb++ )
+        {
+            const uint8_t *s = src + (intptr_t)y*sstride + x, *e = fenc->plane[0] + (intptr_t)y*c->stride + x;
+            int cmp;
+            if( weighted )
+            {
+                for( int j = 0; j < 8; j++ )
+                    for( int i = 0; i < 8; i++ ) buf[8*j+i] = weight_px( s[j*sstride+i], scale, denom, offset );
+                cmp = c->b_satd ? xo_satd( XO_8x8, buf, 8, e, c->stride ) : xo_sad( XO_8x8, buf, 8, e, c->stride );
+            }
+            else
+                cmp = c->b_satd ? xo_satd( XO_8x8, s, sstride, e, c->stride ) : xo_sad( XO_8x8, s, sstride, e, c->stride );
+            cost += imin( cmp, fenc->lowres_costs[0][0][i_mb] );
+        }
+    if( weighted )    /* weight_slice_header_cost (slicetype.c:170-189), lambda 1, luma */
+        cost += numslices * ( 10 + bs_size_ue( denom ) * 2 + 2 * ( bs_size_se( scale ) + bs_size_se( offset ) ) );
+    return cost;
+}
+
+/* x264_weights_analyse( h, fenc, ref, b_lookahead = 1 ) (slicetype.c:284-501): luma only, one candidate.
+ * out: [0] enabled [1] scale [2] denom [3] offset [4] minscore [5] origscore */
+int xo_weights_analyse( xo_ctx *c, int b, int ref, int numslices, int *out )
+{
+    xo_frame *fenc = &c->fr[b], *fref = &c->fr[ref];
+    if( !fenc->valid || !fref->valid || !fenc->have_aq || !fref->have_aq || b <= ref || b-ref > c->cfg.bframes+1 ) return -1;
+    const float epsilon = 1.f/128.f;
+    out[0] = 0; out[1] = 1; out[2] = 0; out[3] = 0; out[4] = out[5] = 0;
+    int zero_bias = !fref->pixel_ssd[0];
+    float fenc_var = fenc->pixel_ssd[0] + zero_bias;
+    float ref_var  = fref->pixel_ssd[0] + zero_bias;
+    float guess_scale = sqrtf( fenc_var / ref_var );
+    float fenc_mean = (float)( fenc->pixel_sum[0] + zero_bias ) / ( ( 16*c->mbh ) * ( 16*c->mbw ) ) / ( 1 << 0 );
+    float ref_mean  = (float)( fref->pixel_sum[0] + zero_bias ) / ( ( 16*c->mbh ) * ( 16*c->mbw ) ) / ( 1 << 0 );
+    if( fabsf( ref_mean - fenc_mean ) < 0.5f && fabsf( 1.f - guess_scale ) < epsilon )
+        return 0;                                                      /* early termination, :335-339 */
+    /* weight_get_h264( round( guess_scale * 128 ), 0, w ), :62-74 */
+    int mindenom = 7, minscale = round( guess_scale * 128 ), minoff = 0, found = 0;
+    while( mindenom > 0 && minscale > 127 ) { mindenom--; minscale >>= 1; }
+    minscale = imin( minscale, 127 );
+    if( !fenc->b_intra_calculated ) xo_frame_cost( c, b, b, b, 0, -1, 0 );     /* :361-366 */
+    /* weight_cost_init_luma (:76-103): motion-compensate the reference when the field has been searched */
+    const uint8_t *mcbuf = fref->plane[0]; int mcstride = c->stride;
+    uint8_t *tmp = NULL;
+    if( fenc->searched[0][b-ref-1] )
+    {
+        tmp = malloc( (size_t)c->lw * c->lh );
+        for( int y = 0, i = 0; y < c->lh; y += 8 )
+            for( int x = 0; x < c->lw; x += 8, i++ )
+            {
+                const uint8_t *pl[4];
+                for( int k = 0; k < 4; k++ ) pl[k] = fref->plane[k] + (intptr_t)y*c->stride + x;
+                xo_mc_luma( tmp + (size_t)y*c->lw + x, c->lw, pl, c->stride, fenc->lowres_mvs[0][b-ref-1][i][0], fenc->lowres_mvs[0][b-ref-1][i][1], 8, 8, 1, -1, 0 );
+            }
+        mcbuf = tmp; mcstride = c->lw;
+    }
+    unsigned origscore, minscore;
+    origscore = minscore = weight_cost_luma( c, fenc, mcbuf, mcstride, 0, 0, 0, 0, numslices );
+    out[4] = out[5] = origscore;
+    if( !minscore ) { free( tmp ); return 0; }
+    {   /* the lookahead checks one scale and one offset (scale_dist = offset_dist = 0), :399-441 */
+        int cur_scale = minscale;
+        int cur_offset = fenc_mean - ref_mean * cur_scale / ( 1 << mindenom ) + 0.5f * 1;
+        if( cur_offset < -128 || cur_offset > 127 )
+        {
+            cur_offset = cur_offset < -128 ? -128 : 127;
+            float v = ( 1 << mindenom ) * ( fenc_mean - cur_offset ) / ref_mean + 0.5f;
+            cur_scale = v < 0 ? 0 : v > 127 ? 127 : v;
+        }
+        int i_off = cur_offset < -128 ? -128 : cur_offset > 127 ? 127 : cur_offset;
+        unsigned s = weight_cost_luma( c, fenc, mcbuf, mcstride, 1, cur_scale, mindenom, i_off, numslices );
+        if( s < minscore ) { minscore = s; minscale = cur_scale; minoff = i_off; found = 1; }
+    }
+    free( tmp );
+    while( mindenom > 0 && !( minscale & 1 ) ) { mindenom--; minscale >>= 1; }       /* :444-451 */
+    out[4] = minscore;
+    if( !found || ( minscale == 1 << mindenom && minoff == 0 ) || (float)minscore / origscore > 0.998f )
+        return 0;
+    out[0] = 1; out[1] = minscale; out[2] = mindenom; out[3] = minoff;
+    return 0;
 }
 
 /* macroblock_tree_finish, slicetype.c:1029-1049 */

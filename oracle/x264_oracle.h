@@ -81,6 +81,16 @@ int     xo_mbtree_get( xo_ctx *, int idx, uint16_t *out );
 int     xo_mbtree_propagate( xo_ctx *, int p0, int p1, int b, float fps_factor, int referenced );
 int     xo_mbtree_finish( xo_ctx *, int idx, int fps_factor, float weightdelta, float strength, const float *qp_offset_aq, float *qp_offset );
 
+/* ---- adaptive quantisation + weighted-prediction analysis: ratecontrol.c:226-415 (aq-mode 0/1), slicetype.c:62-501 ---- */
+/* x264_adaptive_quant_frame followed by x264_frame_init_lowres (encoder.c:3417-3421); chroma is the interleaved NV12 plane */
+int     xo_put_frame_aq( xo_ctx *, int idx, const uint8_t *luma, int stride, const uint8_t *chroma_nv12, int cstride,
+                         int aq_mode, float aq_strength, const float *quant_offsets );
+/* f_qp_offset (float x mb_count), i_inv_qscale_factor (u16 x mb_count), {i_pixel_sum[p], i_pixel_ssd[p]} p = 0..2 */
+int     xo_get_aq( xo_ctx *, int idx, float *qp_offset, uint16_t *inv_qscale, uint64_t *sums6 );
+/* x264_weights_analyse( h, frames[b], frames[ref], 1 ); out: enabled, scale, denom, offset, minscore, origscore */
+int     xo_weights_analyse( xo_ctx *, int b, int ref, int numslices, int *out6 );
+void    xo_exp2_lut( uint8_t *out64 );
+
 #ifdef __cplusplus
 }
 #endif

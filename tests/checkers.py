@@ -234,11 +234,11 @@ class Lookahead:
     'ref_serial': the reference's own raster-serial slicetype_frame_cost) and OracleLib ('oracle')."""
 
     def __init__(self, lib, kind, width, height, bframes=3, subme=7, mbtree=1, aq=1, passes=2,
-                 b_adapt=2, rc_lookahead=40, la_threads=1, mv_range=None):
+                 b_adapt=2, rc_lookahead=40, la_threads=1, mv_range=None, weightp=0):
         self.lib, self.kind = lib, kind
         self.W, self.H, self.passes = width, height, passes
         if kind.startswith("ref"):
-            self.ctx = lib.lib.ref_la_open(width, height, bframes, subme, mbtree, aq, 0, b_adapt, la_threads, rc_lookahead, 0)
+            self.ctx = lib.lib.ref_la_open(width, height, bframes, subme, mbtree, aq, weightp, b_adapt, la_threads, rc_lookahead, 0)
             assert self.ctx
             info = (C.c_int * 10)()
             lib.lib.ref_la_info(self.ctx, info)
@@ -266,6 +266,42 @@ class Lookahead:
         f = self.lib.lib.ref_la_put_frame if self.kind.startswith("ref") else self.lib.lib.xo_put_frame
         assert f(self.ctx, idx, _ptr(luma), self.W, q) == 0
 
+    # ---- adaptive quantisation + weighted-prediction analysis ----
+    def put_frame_yuv(self, idx, luma, chroma, aq_mode=1, aq_strength=1.0, quant_offsets=None):
+        """x264_adaptive_quant_frame + x264_frame_init_lowres; chroma: interleaved NV12, (H/2, W) uint8"""
+        luma = np.ascontiguousarray(luma, dtype=np.uint8)
+        chroma = np.ascontiguousarray(chroma, dtype=np.uint8)
+        assert luma.shape == (self.H, self.W) and chroma.shape == (self.H // 2, self.W)
+        qo = None if quant_offsets is None else _ptr(np.ascontiguousarray(quant_offsets, dtype=np.float32))
+        if self.kind.startswith("ref"):      # aq mode / strength are the encoder's parameters (ref_la_open)
+            L = self.lib.lib
+            L.ref_la_put_frame_yuv.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]
+            assert L.ref_la_put_frame_yuv(self.ctx, idx, _ptr(luma), self.W, _ptr(chroma), self.W, qo) == 0
+        else:
+            L = self.lib.lib
+            L.xo_put_frame_aq.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, vp]
+            assert L.xo_put_frame_aq(self.ctx, idx, _ptr(luma), self.W, _ptr(chroma), self.W, aq_mode, aq_strength, qo) == 0
+
+    def get_aq(self, idx):
+        qp = np.zeros(self.nmb, dtype=np.float32)
+        inv = np.zeros(self.nmb, dtype=np.uint16)
+        sums = np.zeros(6, dtype=np.uint64)
+        f = self.lib.lib.ref_la_get_aq if self.kind.startswith("ref") else self.lib.lib.xo_get_aq
+        f.argtypes = [vp, C.c_int, vp, vp, vp]
+        assert f(self.ctx, idx, _ptr(qp), _ptr(inv), _ptr(sums)) == 0
+        return qp, inv, sums
+
+    def weights_analyse(self, b, ref, numslices=1):
+        """x264_weights_analyse(h, frames[b], frames[ref], 1) -> (enabled, scale, denom, offset)"""
+        out = (C.c_int * 6)()
+        if self.kind.startswith("ref"):
+            self.lib.lib.ref_la_weights_analyse.argtypes = [vp, C.c_int, C.c_int, vp]
+            assert self.lib.lib.ref_la_weights_analyse(self.ctx, b, ref, out) == 0
+        else:
+            self.lib.lib.xo_weights_analyse.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+            assert self.lib.lib.xo_weights_analyse(self.ctx, b, ref, numslices, out) == 0
+        return tuple(out[:4]) if out[0] else (0, 1, 0, 0)
+
     def lowres(self, idx, plane):
         w, h = self.mbw * 8 + 64, self.mbh * 8 + 64
         out = np.zeros((h, w), dtype=np.uint8)
@@ -273,7 +309,11 @@ class Lookahead:
         assert f(self.ctx, idx, plane, _ptr(out)) == 0
         return out
 
-    def frame_cost(self, p0, p1, b):
+    def frame_cost(self, p0, p1, b, weight=None):
+        """weight (oracle only): (enabled, scale, denom, offset) for list 0 of a P evaluation; the reference analyses
+        its own weights inside slicetype_frame_cost when it was opened with weightp"""
+        if self.kind == "oracle" and weight is not None and weight[0]:
+            return self.lib.lib.xo_frame_cost(self.ctx, p0, p1, b, weight[1], weight[2], weight[3])
         if self.kind == "ref":
             return self.lib.lib.ref_la_frame_cost_jacobi(self.ctx, p0, p1, b, self.passes)
         if self.kind == "ref_serial":
@@ -326,3 +366,16 @@ def synth_frames(width, height, n, seed=7, pan=(3, 1), noise=3, scene_cut_at=Non
         f = f + rng.integers(-noise, noise + 1, f.shape)
         frames.append(np.clip(f, 0, 255).astype(np.uint8))
     return frames
+
+
+def synth_chroma(width, height, n, seed=11):
+    """interleaved NV12 chroma planes (H/2, W) that follow the luma generator's pan: smooth field + noise"""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(64, 192, (height // 16 + 4, width // 16 + 4, 2)).astype(np.float32)
+    base = np.kron(base, np.ones((8, 8, 1), dtype=np.float32))
+    out = []
+    for i in range(n):
+        c = base[i:i + height // 2, 2 * i:2 * i + width // 2, :]
+        c = c + rng.integers(-6, 7, c.shape)
+        out.append(np.clip(c, 0, 255).astype(np.uint8).reshape(height // 2, width))
+    return out
