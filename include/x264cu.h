@@ -53,7 +53,10 @@ typedef struct
                                * formula                                                                  */
 } x264cu_cfg;
 
-/* explicit weighted prediction of list 0 of a P evaluation: x264_weight_t (common/mc.h:235-245) */
+/* explicit weighted prediction of list 0 of a P evaluation: x264_weight_t (common/mc.h:235-245).
+ * enabled == X264CU_WEIGHT_DEVICE: use the result that x264cu_weights_analyse( fenc, fref0 ) left in device memory
+ * (no host round trip between the analysis and the search, slicetype.c:859-867) */
+#define X264CU_WEIGHT_DEVICE 2
 typedef struct { int enabled, scale, denom, offset; } x264cu_weight;
 
 /* Host destinations of one evaluation: the x264_frame_t lookahead fields (common/frame.h:103-127).
@@ -100,6 +103,29 @@ void          x264cu_frame_free( x264cu_ctx *ctx, x264cu_frame *f );
  * `luma`/`inv_qscale` are HOST pointers; the _device variant takes DEVICE pointers (no PCIe copy). */
 int x264cu_frame_upload( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *luma, int stride, const uint16_t *inv_qscale );
 int x264cu_frame_upload_device( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint16_t *d_inv_qscale );
+
+/* ---- adaptive quantisation + weighted-prediction analysis: the two producers right before the path ----
+ * x264_adaptive_quant_frame (ratecontrol.c:304-415) followed by x264_frame_init_lowres, the order of
+ * encoder.c:3417-3421: upload luma and the interleaved NV12 chroma plane (width x height/2 bytes), compute on the
+ * device the per-macroblock AC energy (luma 16x16 + both chroma 8x8), f_qp_offset / f_qp_offset_aq,
+ * i_inv_qscale_factor and the frame's i_pixel_sum / i_pixel_ssd, then everything x264cu_frame_upload does.
+ * aq_mode 0 (X264_AQ_NONE: sums only) and 1 (X264_AQ_VARIANCE) are computed bit-exactly; the auto-variance modes 2/3
+ * go through powf and are refused (compute them on the host and use x264cu_frame_upload). */
+typedef struct { int mode; float strength; } x264cu_aq_cfg;                      /* rc.i_aq_mode, rc.f_aq_strength */
+typedef struct
+{
+    float    *qp_offset;      /* f_qp_offset == f_qp_offset_aq        float x mb_count                 */
+    uint16_t *inv_qscale;     /* i_inv_qscale_factor                  u16 x mb_count                   */
+    uint64_t *pixel_stats;    /* {i_pixel_sum[p], i_pixel_ssd[p]} for p = Y,U,V after the mean removal */
+} x264cu_aq_out;              /* host destinations, filled when x264cu_flush returns; NULL members are skipped */
+int x264cu_frame_upload_aq( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *luma, int stride, const uint8_t *chroma_nv12, int cstride,
+                            const x264cu_aq_cfg *aq, const float *quant_offsets, const x264cu_aq_out *out );
+/* x264_weights_analyse( h, fenc, fref, b_lookahead = 1 ) (slicetype.c:284-501): luma weight of `fenc` against `fref`
+ * (dist = frame distance, 1..bframes+1) from the frames' pixel statistics, the intra costs and -- when the list-0 field
+ * has already been searched -- the motion-compensated reference.  Both frames must come from x264cu_frame_upload_aq.
+ * The result stays in device memory for a following evaluation with weight.enabled == X264CU_WEIGHT_DEVICE and is
+ * copied to `out` (host, may be NULL) when x264cu_flush returns.  numslices: weight_slice_header_cost (:170-189). */
+int x264cu_weights_analyse( x264cu_ctx *ctx, x264cu_frame *fenc, x264cu_frame *fref, int dist, int numslices, x264cu_weight *out );
 
 /* slicetype_frame_cost through the GPU hook (slicetype.c:878-897): enqueue, asynchronously, the
  * searches this evaluation still needs (x264_opencl_motionsearch), the mode decision and sums
@@ -186,7 +212,8 @@ int x264cu_mbtree_swap( x264cu_ctx *ctx, x264cu_frame *a, x264cu_frame *b );    
 /* frame b = fb evaluated as (d0 = b-p0, d1 = p1-b) propagates into fp0 / fp1; fps_factor as slicetype.c:1065 */
 int x264cu_mbtree_propagate( x264cu_ctx *ctx, x264cu_frame *fb, x264cu_frame *fp0, x264cu_frame *fp1, int d0, int d1,
                              float fps_factor, int referenced );
-/* qp_offset_aq / qp_offset: host float[mb_count]; qp_offset is read-modify-write (blocks with intra_cost 0 keep their value) */
+/* qp_offset_aq / qp_offset: host float[mb_count]; qp_offset is read-modify-write (blocks with intra_cost 0 keep their value).
+ * qp_offset_aq == NULL: use the device copy that x264cu_frame_upload_aq computed for this frame */
 int x264cu_mbtree_finish( x264cu_ctx *ctx, x264cu_frame *f, int fps_factor, float weightdelta, float strength,
                           const float *qp_offset_aq, float *qp_offset );
 int x264cu_mbtree_get_propagate( x264cu_ctx *ctx, x264cu_frame *f, uint16_t *out );   /* i_propagate_cost, host u16[mb_count] */

@@ -6,7 +6,7 @@ cd "$(dirname "$0")/../../x264-i386pic_b200"
 mkdir -p build/var
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --split-compile=0 $3 -c csrc/$2.cu -o build/var/$2_$1.o
 OBJS=""
-for o in lookahead search final mbtree primitives capi stream slicetype mbtree_host; do
+for o in lookahead search final aq_weights mbtree primitives capi stream slicetype mbtree_host; do
   if [ $o = $2 ]; then OBJS="$OBJS build/var/$2_$1.o"; else OBJS="$OBJS build/$o.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/var/lib_$1.so $OBJS -cudart static

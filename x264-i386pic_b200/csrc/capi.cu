@@ -37,6 +37,10 @@ struct x264cu_frame
     int32_t  *stats;         // [(B+2)*(B+2)][stat_pitch]: row_satds[mbh], cost_est, cost_est_aq, intra_mbs
     uint32_t *prop;          // i_propagate_cost accumulators (MB-tree), clamped to 32767 on read
     float    *qp_aq, *qp;    // f_qp_offset_aq (in) / f_qp_offset (out) staging for macroblock_tree_finish
+    unsigned long long *pixstats;   // raw {sum, ssd} of Y, U, V (x264cu_frame_upload_aq); [6..7] unused
+    int32_t  *wres;          // [bframes+1][8]: device-side result of x264cu_weights_analyse per list-0 distance
+    bool      have_aq;       // pixstats / qp_aq were produced by the device AQ kernel
+    uint8_t   wanalysed[X264CU_BFRAME_MAX+1];   // wres[dist-1] holds a result
     uint8_t   searched[2][X264CU_BFRAME_MAX+1];
     uint8_t   evaluated[X264CU_BFRAME_MAX+2][X264CU_BFRAME_MAX+2];
     bool      uploaded;
@@ -54,6 +58,8 @@ struct x264cu_ctx
     cudaEvent_t ev_up[2], ev_res;
     uint16_t *d_cost_mv;
     float *d_log2_lut;
+    uint8_t *d_exp2_lut;
+    uint8_t *d_chroma[2]; int chroma_pitch;      // NV12 chroma staging, paired with d_luma[]
     int stat_pitch;
     size_t plane_alloc;      // bytes of the 4 planes + slack
     // full-resolution luma staging on the device (double buffered)
@@ -165,10 +171,18 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
         CUP( cudaMalloc( &c->d_log2_lut, sizeof(lut) ) );
         CUP( cudaMemcpy( c->d_log2_lut, lut, sizeof(lut), cudaMemcpyHostToDevice ) );
     }
+    {   // x264_exp2_lut (tables.c:58-64) is round( 256 * ( 2^(i/64) - 1 ) )
+        uint8_t lut[64];
+        for( int i = 0; i < 64; i++ ) lut[i] = (uint8_t)lround( 256.0 * ( pow( 2.0, i / 64.0 ) - 1.0 ) );
+        CUP( cudaMalloc( &c->d_exp2_lut, sizeof(lut) ) );
+        CUP( cudaMemcpy( c->d_exp2_lut, lut, sizeof(lut), cudaMemcpyHostToDevice ) );
+    }
+    c->chroma_pitch = (int)align_up( cfg->width, 256 );
     c->luma_pitch = (int)align_up( cfg->width, 256 );
     for( int i = 0; i < 2; i++ )
     {
         CUP( cudaMalloc( &c->d_luma[i], (size_t)c->luma_pitch * cfg->height + 256 ) );
+        c->d_chroma[i] = NULL;                    // allocated by the first x264cu_frame_upload_aq
         CUP( cudaEventCreateWithFlags( &c->luma_free[i], cudaEventDisableTiming ) );
     }
     c->pin_size = (size_t)64 << 20;            // cf. PAGE_LOCKED_BUF_SIZE 32 MiB (opencl.h:715)
@@ -209,7 +223,7 @@ extern "C" void x264cu_frame_free( x264cu_ctx *c, x264cu_frame *f )
     ctx_sync( c );
     cudaFree( f->planes ); cudaFree( f->inv_qscale ); cudaFree( f->costs );
     cudaFree( f->mvs ); cudaFree( f->mvcosts ); cudaFree( f->stats );
-    cudaFree( f->prop ); cudaFree( f->qp_aq ); cudaFree( f->qp );
+    cudaFree( f->prop ); cudaFree( f->qp_aq ); cudaFree( f->qp ); cudaFree( f->pixstats ); cudaFree( f->wres );
     for( size_t i = 0; i < c->frames.size(); i++ )
         if( c->frames[i] == f ) { c->frames.erase( c->frames.begin() + i ); break; }
     delete f;
@@ -223,6 +237,7 @@ extern "C" void x264cu_close( x264cu_ctx *c )
     while( !c->frames.empty() ) x264cu_frame_free( c, c->frames.back() );
     for( cudaEvent_t e : c->ev_pool ) cudaEventDestroy( e );
     for( int i = 0; i < 2; i++ ) { cudaFree( c->d_luma[i] ); cudaEventDestroy( c->luma_free[i] ); }
+    cudaFree( c->d_exp2_lut ); cudaFree( c->d_chroma[0] ); cudaFree( c->d_chroma[1] );
     cudaFree( c->d_cost_mv ); cudaFree( c->d_log2_lut ); cudaFree( c->d_jobs ); cudaFree( c->arena );
     cudaFreeHost( c->pin ); cudaFreeHost( c->h_jobs );
     cudaEventDestroy( c->tm_a ); cudaEventDestroy( c->tm_b );
@@ -248,12 +263,13 @@ extern "C" x264cu_frame *x264cu_frame_new( x264cu_ctx *c )
         cudaMalloc( &f->mvcosts, nfield * P.nmb * 4 ) != cudaSuccess ||
         cudaMalloc( &f->stats, ntri * c->stat_pitch * 4 ) != cudaSuccess ||
         cudaMalloc( &f->prop, (size_t)P.nmb * 4 ) != cudaSuccess ||
-        cudaMalloc( &f->qp_aq, (size_t)P.nmb * 4 ) != cudaSuccess || cudaMalloc( &f->qp, (size_t)P.nmb * 4 ) != cudaSuccess )
+        cudaMalloc( &f->qp_aq, (size_t)P.nmb * 4 ) != cudaSuccess || cudaMalloc( &f->qp, (size_t)P.nmb * 4 ) != cudaSuccess ||
+        cudaMalloc( &f->pixstats, 8 * sizeof(unsigned long long) ) != cudaSuccess || cudaMalloc( &f->wres, (size_t)( B+1 ) * 8 * 4 ) != cudaSuccess )
     {
         snprintf( g_err, sizeof(g_err), "x264cu_frame_new: out of device memory" );
         cudaGetLastError();
         cudaFree( f->planes ); cudaFree( f->inv_qscale ); cudaFree( f->costs ); cudaFree( f->mvs ); cudaFree( f->mvcosts ); cudaFree( f->stats );
-        cudaFree( f->prop ); cudaFree( f->qp_aq ); cudaFree( f->qp );
+        cudaFree( f->prop ); cudaFree( f->qp_aq ); cudaFree( f->qp ); cudaFree( f->pixstats ); cudaFree( f->wres );
         delete f;
         return NULL;
     }
@@ -302,6 +318,16 @@ static void drain_copies( x264cu_ctx *c, uint64_t upto )
     {
         const PendingCopy &p = c->copies[c->copies_head++];
         if( p.kind < 0 ) memcpy( p.dst, p.src, p.bytes );
+        else if( p.kind == 3 )
+        {   // i_pixel_sum / i_pixel_ssd with the mean removed (ratecontrol.c:406-414); bias = mbw | mbh << 16
+            const uint64_t *raw = (const uint64_t *)p.src; uint64_t *dst = (uint64_t *)p.dst;
+            for( int i = 0; i < 3; i++ )
+            {
+                const uint64_t w = (uint64_t)( 16 * ( p.bias & 0xffff ) ) >> !!i, h = (uint64_t)( 16 * ( p.bias >> 16 ) ) >> !!i;
+                dst[2*i] = raw[2*i];
+                dst[2*i+1] = raw[2*i+1] - ( raw[2*i] * raw[2*i] + w * h / 2 ) / ( w * h );
+            }
+        }
         else finish_stats( (int32_t *)p.dst, (const uint8_t *)p.src, p.kind, p.bias );
     }
     if( c->copies_head == c->copies.size() ) { c->copies.clear(); c->copies_head = 0; }
@@ -431,10 +457,18 @@ static int queue_d2h( x264cu_ctx *c, void *dst, const void *dsrc, size_t bytes )
     return 0;
 }
 
+static inline uint8_t *planeF( x264cu_ctx *c, x264cu_frame *f ) { return f->planes + (size_t)X264CU_PAD * c->P.stride + X264CU_PAD; }
+static inline int tri_index( x264cu_ctx *c, int d0, int d1 ) { return d0 * ( c->cfg.bframes + 2 ) + d1; }
+static inline int field_index( x264cu_ctx *c, int list, int dist ) { return list * ( c->cfg.bframes + 1 ) + dist - 1; }
+
+// h->param.rc.f_aq_strength * 1.0397f as one single-precision product (ratecontrol.c:371)
+static float aq_strength_f32( float s ) { volatile float r = s * 1.0397f; return r; }
+
 static void reset_caches( x264cu_frame *f )
 {   // mc.c:473-481: i_cost_est = -1, MV sentinels = 0x7FFF
     memset( f->searched, 0, sizeof(f->searched) );
     memset( f->evaluated, 0, sizeof(f->evaluated) );
+    memset( f->wanalysed, 0, sizeof(f->wanalysed) );
     f->any_eval = false;
 }
 
@@ -497,6 +531,102 @@ extern "C" int x264cu_frame_upload( x264cu_ctx *c, x264cu_frame *f, const uint8_
         launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );         // memset_int16 (downscale.cl:132)
     if( upload_common( c, f, c->d_luma[sel], c->luma_pitch ) ) return -1;
     CU( cudaEventRecord( c->luma_free[sel], c->st ) );
+    return end_batch( c );
+}
+
+// x264_adaptive_quant_frame + x264_frame_init_lowres (encoder.c:3417-3421), SURVEY.md section 8f row 3
+extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uint8_t *luma, int stride, const uint8_t *chroma, int cstride,
+                                       const x264cu_aq_cfg *aq, const float *quant_offsets, const x264cu_aq_out *out )
+{
+    if( !c || !f || !luma || !chroma || !aq ) FAIL( "x264cu_frame_upload_aq: null argument" );
+    if( aq->mode < 0 || aq->mode > 1 )
+        FAIL( "x264cu_frame_upload_aq: aq-mode %d goes through powf and is not computed on the device (use x264cu_frame_upload with host inv_qscale)", aq->mode );
+    if( ( c->cfg.width | c->cfg.height ) & 1 ) FAIL( "x264cu_frame_upload_aq: 4:2:0 needs even dimensions" );
+    CU( cudaSetDevice( c->device ) );
+    const LaParams &P = c->P;
+    const int W = c->cfg.width, H = c->cfg.height;
+    for( int i = 0; i < 2; i++ )
+        if( !c->d_chroma[i] ) CU( cudaMalloc( &c->d_chroma[i], (size_t)c->chroma_pitch * ( H / 2 ) + 256 ) );
+    if( begin_batch( c ) ) return -1;
+    int sel = c->luma_sel; c->luma_sel ^= 1;
+    const uint8_t *src = luma, *csrc = chroma; int spitch = stride, cpitch = cstride;
+    if( !is_pinned( luma ) )
+    {
+        uint8_t *p = pin_alloc_sync( c, (size_t)W * H );
+        if( !p ) return -1;
+        for( int y = 0; y < H; y++ ) memcpy( p + (size_t)y*W, luma + (size_t)y*stride, W );
+        src = p; spitch = W;
+    }
+    if( !is_pinned( chroma ) )
+    {
+        uint8_t *p = pin_alloc_sync( c, (size_t)W * ( H / 2 ) );
+        if( !p ) return -1;
+        for( int y = 0; y < H / 2; y++ ) memcpy( p + (size_t)y*W, chroma + (size_t)y*cstride, W );
+        csrc = p; cpitch = W;
+    }
+    CU( cudaStreamWaitEvent( c->st_in, c->luma_free[sel], 0 ) );
+    CU( cudaMemcpy2DAsync( c->d_luma[sel], c->luma_pitch, src, spitch, W, H, cudaMemcpyHostToDevice, c->st_in ) );
+    CU( cudaMemcpy2DAsync( c->d_chroma[sel], c->chroma_pitch, csrc, cpitch, W, H / 2, cudaMemcpyHostToDevice, c->st_in ) );
+    CU( cudaEventRecord( c->ev_up[sel], c->st_in ) );
+    CU( cudaStreamWaitEvent( c->st, c->ev_up[sel], 0 ) );
+    const float *d_qo = NULL;
+    if( quant_offsets && aq->mode )
+    {   // f->qp doubles as the device staging of the caller's quant_offsets (x264_picture_t.prop.quant_offsets)
+        const float *q = quant_offsets;
+        if( !is_pinned( q ) )
+        {
+            uint8_t *p = pin_alloc_sync( c, (size_t)P.nmb * 4 );
+            if( !p ) return -1;
+            memcpy( p, quant_offsets, (size_t)P.nmb * 4 );
+            q = (const float *)p;
+        }
+        CU( cudaMemcpyAsync( f->qp, q, (size_t)P.nmb * 4, cudaMemcpyHostToDevice, c->st ) );
+        d_qo = f->qp;
+    }
+    CU( cudaMemsetAsync( f->pixstats, 0, 8 * sizeof(unsigned long long), c->st ) );
+    launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );
+    c->launches += 2;
+    launch_aq( c->d_luma[sel], c->luma_pitch, c->d_chroma[sel], c->chroma_pitch, W, H, P, aq->mode, aq_strength_f32( aq->strength ),
+               d_qo, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats, c->st );
+    f->have_aq = true;
+    if( upload_common( c, f, c->d_luma[sel], c->luma_pitch ) ) return -1;
+    CU( cudaEventRecord( c->luma_free[sel], c->st ) );
+    if( out )
+    {
+        if( queue_d2h( c, out->qp_offset, f->qp_aq, (size_t)P.nmb * 4 ) ) return -1;
+        if( queue_d2h( c, out->inv_qscale, f->inv_qscale, (size_t)P.nmb * 2 ) ) return -1;
+        if( out->pixel_stats )
+        {
+            uint8_t *p = pin_alloc_sync( c, 64 );
+            if( !p ) return -1;
+            CU( cudaMemcpyAsync( p, f->pixstats, 48, cudaMemcpyDeviceToHost, c->st ) );
+            c->copies.push_back( { out->pixel_stats, p, 48, 3, P.mbw | ( P.mbh << 16 ), c->seq } );
+        }
+    }
+    return end_batch( c );
+}
+
+// x264_weights_analyse( h, fenc, fref, 1 ) (slicetype.c:284-501), SURVEY.md section 8f row 2
+extern "C" int x264cu_weights_analyse( x264cu_ctx *c, x264cu_frame *fenc, x264cu_frame *fref, int dist, int numslices, x264cu_weight *out )
+{
+    if( !c || !fenc || !fref || dist < 1 || dist > c->cfg.bframes + 1 ) FAIL( "x264cu_weights_analyse: bad argument" );
+    if( !fenc->uploaded || !fref->uploaded || !fenc->have_aq || !fref->have_aq )
+        FAIL( "x264cu_weights_analyse: both frames need the pixel statistics of x264cu_frame_upload_aq" );
+    CU( cudaSetDevice( c->device ) );
+    if( begin_batch( c ) ) return -1;
+    const LaParams &P = c->P;
+    int *wres = fenc->wres + 8 * ( dist - 1 );
+    // weight_cost_init_luma (:76-103): motion-compensate the reference when the list-0 field has been searched
+    const int16_t *mvs = fenc->searched[0][dist-1] ? fenc->mvs + (size_t)field_index( c, 0, dist ) * P.nmb * 2 : NULL;
+    // the intra costs exist since upload; the reference computes them here if need be (:361-366), which also makes a
+    // later I evaluation a cache hit
+    fenc->any_eval = true;
+    fenc->wanalysed[dist-1] = 1;
+    c->launches += 3;
+    launch_weights_analyse( planeF( c, fenc ), planeF( c, fref ), mvs, fenc->costs, fenc->pixstats, fref->pixstats, wres,
+                            numslices > 0 ? numslices : 1, P, c->st );
+    CU( cudaGetLastError() );
+    if( queue_d2h( c, out, wres, sizeof(x264cu_weight) ) ) return -1;
     return end_batch( c );
 }
 
@@ -565,11 +695,8 @@ static uint8_t *arena_alloc( x264cu_ctx *c, size_t bytes )
     return c->arena + c->slot * region + a;
 }
 
-struct SearchTask { x264cu_frame *fenc, *fref; int list, dist; x264cu_weight w; };
+struct SearchTask { x264cu_frame *fenc, *fref; int list, dist; x264cu_weight w; };      // w.enabled == X264CU_WEIGHT_DEVICE: fenc->wres[dist-1]
 
-static inline uint8_t *planeF( x264cu_ctx *c, x264cu_frame *f ) { return f->planes + (size_t)X264CU_PAD * c->P.stride + X264CU_PAD; }
-static inline int tri_index( x264cu_ctx *c, int d0, int d1 ) { return d0 * ( c->cfg.bframes + 2 ) + d1; }
-static inline int field_index( x264cu_ctx *c, int list, int dist ) { return list * ( c->cfg.bframes + 1 ) + dist - 1; }
 
 // K passes of the dependency-free schedule over a set of (fenc, ref, list, dist) fields, each pass
 // ONE launch over all fields (x264_opencl_motionsearch batched as in x264_opencl_slicetype_prep).
@@ -592,7 +719,10 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
             {
                 wpl[t] = ws; ws += plane_bytes;
                 c->launches++;
-                launch_weight_plane( tasks[t].fref->planes, wpl[t], P.plane_size, tasks[t].w.scale, tasks[t].w.denom, tasks[t].w.offset, c->st );
+                if( tasks[t].w.enabled == X264CU_WEIGHT_DEVICE )
+                    launch_weight_plane_dev( tasks[t].fref->planes, wpl[t], P.plane_size, tasks[t].fenc->wres + 8 * ( tasks[t].dist - 1 ), c->st );
+                else
+                    launch_weight_plane( tasks[t].fref->planes, wpl[t], P.plane_size, tasks[t].w.scale, tasks[t].w.denom, tasks[t].w.offset, c->st );
             }
         }
         if( K == 0 )
@@ -609,6 +739,7 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
                 S.mv_in = S.mv_out;
                 S.cost_out = T.fenc->mvcosts + (size_t)fi * P.nmb;
                 S.wscale = T.w.scale; S.wdenom = T.w.enabled ? T.w.denom : -1; S.woffset = T.w.offset;
+                S.wdev = T.w.enabled == X264CU_WEIGHT_DEVICE ? T.fenc->wres + 8 * ( T.dist - 1 ) : NULL;
                 CU( cudaMemsetAsync( S.mv_out, 0, (size_t)P.nmb * 4, c->st ) );
                 CU( cudaMemsetAsync( S.cost_out, 0, (size_t)P.nmb * 4, c->st ) );
             }
@@ -632,6 +763,7 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
                 S.mv_out = pass == K-1 ? T.fenc->mvs + (size_t)fi * P.nmb * 2 : (int16_t *)( ( pass & 1 ) ? tmp1[t] : tmp0[t] );
                 S.cost_out = T.fenc->mvcosts + (size_t)fi * P.nmb;
                 S.wscale = T.w.scale; S.wdenom = T.w.enabled ? T.w.denom : -1; S.woffset = T.w.offset;
+                S.wdev = T.w.enabled == X264CU_WEIGHT_DEVICE ? T.fenc->wres + 8 * ( T.dist - 1 ) : NULL;
             }
             const SearchJob *d;
             if( push_jobs( c, sj, &d ) ) return -1;
@@ -676,7 +808,12 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
             {   // do_search[l] (slicetype.c:855-867)
                 j.fenc->searched[l][dist-1] = 1;
                 SearchTask t = { j.fenc, l ? j.fref1 : j.fref0, l, dist, { 0, 0, 0, 0 } };
-                if( l == 0 && j.d1 == 0 && j.weight.enabled ) t.w = j.weight;      // w only when b == p1 (:859-864)
+                if( l == 0 && j.d1 == 0 && j.weight.enabled )                      // w only when b == p1 (:859-864)
+                {
+                    if( j.weight.enabled == X264CU_WEIGHT_DEVICE && !j.fenc->wanalysed[dist-1] )
+                        FAIL( "x264cu_frame_cost: X264CU_WEIGHT_DEVICE without a preceding x264cu_weights_analyse for distance %d", dist );
+                    t.w = j.weight;
+                }
                 tasks.push_back( t );
             }
             F.mv[l] = j.fenc->mvs + (size_t)fi * P.nmb * 2;
@@ -901,10 +1038,11 @@ extern "C" int x264cu_mbtree_propagate( x264cu_ctx *c, x264cu_frame *fb, x264cu_
 extern "C" int x264cu_mbtree_finish( x264cu_ctx *c, x264cu_frame *f, int fps_factor, float weightdelta, float strength,
                                      const float *qp_offset_aq, float *qp_offset )
 {   // host arrays of mb_count floats; qp_offset must be initialised by the caller (blocks with intra_cost == 0 keep their value)
-    if( !c || !f || !qp_offset_aq || !qp_offset ) FAIL( "x264cu_mbtree_finish: null argument" );
+    if( !c || !f || !qp_offset ) FAIL( "x264cu_mbtree_finish: null argument" );
+    if( !qp_offset_aq && !f->have_aq ) FAIL( "x264cu_mbtree_finish: no f_qp_offset_aq (pass it, or upload the frame with x264cu_frame_upload_aq)" );
     CU( cudaSetDevice( c->device ) );
     const size_t bytes = (size_t)c->P.nmb * 4;
-    CU( cudaMemcpyAsync( f->qp_aq, qp_offset_aq, bytes, cudaMemcpyHostToDevice, c->st ) );
+    if( qp_offset_aq ) CU( cudaMemcpyAsync( f->qp_aq, qp_offset_aq, bytes, cudaMemcpyHostToDevice, c->st ) );
     CU( cudaMemcpyAsync( f->qp, qp_offset, bytes, cudaMemcpyHostToDevice, c->st ) );
     c->launches++;
     launch_mbtree_finish( f->costs, f->inv_qscale, f->prop, f->qp_aq, f->qp, c->d_log2_lut, fps_factor, weightdelta, strength, c->P.nmb, c->st );

@@ -31,6 +31,8 @@ struct SearchJob
     int16_t *mv_out;            // MV field written by this pass (x,y int16 per block, qpel)
     int32_t *cost_out;          // lowres_mv_costs written by this pass
     int wscale, wdenom, woffset;// wdenom < 0: unweighted
+    const int *wdev;            // != NULL: the weight is the device-side result of x264cu_weights_analyse
+                                // ([0] enabled [1] scale [2] denom [3] offset); ref_w is used only when enabled
 };
 
 // Mode decision + sums of one (b,p0,p1) evaluation: the tail of slicetype_mb_cost.
@@ -60,6 +62,13 @@ void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *
                    int32_t *stats, const LaParams &P, cudaStream_t st );
 void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st );
 void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );
+void launch_aq( const uint8_t *luma, int ls, const uint8_t *chroma, int cs, int W, int H, const LaParams &P, int mode, float strength,
+                const float *quant_offsets, const float *log2_lut, const uint8_t *exp2_lut, float *qp_offset, uint16_t *inv_qscale,
+                unsigned long long *pixstats, cudaStream_t st );
+void launch_weights_analyse( const uint8_t *fencF, const uint8_t *refF, const int16_t *mvs, const uint16_t *intra,
+                             const unsigned long long *st_fenc, const unsigned long long *st_ref, int *wres, int numslices,
+                             const LaParams &P, cudaStream_t st );
+void launch_weight_plane_dev( const uint8_t *src, uint8_t *dst, int64_t bytes, const int *wres, cudaStream_t st );
 void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );
 
 // One macroblock_tree_propagate step (slicetype.c:1051-1089) of frame b towards its references.

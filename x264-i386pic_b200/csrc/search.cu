@@ -234,10 +234,19 @@ __device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, 
     }
 }
 
+// a job whose weight lives in device memory (x264cu_weights_analyse ran on the same stream, no host round trip)
+__device__ __forceinline__ void resolve_device_weight( SearchJob &J )
+{
+    if( !J.wdev ) return;
+    if( __ldg( J.wdev ) ) { J.wscale = __ldg( J.wdev + 1 ); J.wdenom = __ldg( J.wdev + 2 ); J.woffset = __ldg( J.wdev + 3 ); }
+    else                  { J.wdenom = -1; J.ref_w = J.ref; }
+}
+
 __global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob *__restrict__ jobs, LaParams P )
 {
     const CostTab tab = stage_cost_tab( P );
-    const SearchJob J = jobs[blockIdx.y];
+    SearchJob J = jobs[blockIdx.y];
+    resolve_device_weight( J );
     GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
     const int blk = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );
     if( blk >= P.nmb ) return;
@@ -257,7 +266,8 @@ template<bool SATD, bool WEIGHTED, int PITCH>
 __global__ void __launch_bounds__(S_TILE_W*S_TILE_H, X264CU_MINB_SEARCH) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
 {
     const CostTab tab = stage_cost_tab( P );
-    const SearchJob J = jobs[blockIdx.z];
+    SearchJob J = jobs[blockIdx.z];
+    resolve_device_weight( J );
     const int bx = blockIdx.x * S_TILE_W + threadIdx.x % S_TILE_W, by = blockIdx.y * S_TILE_H + threadIdx.x / S_TILE_W;
     if( bx >= P.mbw || by >= P.mbh ) return;
     const int blk = by * P.mbw + bx;
@@ -278,7 +288,8 @@ __global__ void __launch_bounds__(S_TILE_W*S_TILE_H, X264CU_MINB_SEARCH) search_
 __global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJob *__restrict__ jobs, LaParams P, int wave )
 {
     const CostTab tab = stage_cost_tab( P );
-    const SearchJob J = jobs[blockIdx.y];
+    SearchJob J = jobs[blockIdx.y];
+    resolve_device_weight( J );
     GroupBE be; be.g.r = threadIdx.x & 7; be.g.mask = 0xffu << ( threadIdx.x & 24 ); be.P = &P;
     const int by = blockIdx.x * GROUPS_PER_CTA + ( threadIdx.x >> 3 );       // one candidate block per row
     if( by >= P.mbh ) return;

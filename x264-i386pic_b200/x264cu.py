@@ -37,6 +37,17 @@ class Job(C.Structure):
                 ("weight", Weight), ("out", Out)]
 
 
+class AqCfg(C.Structure):
+    _fields_ = [("mode", C.c_int), ("strength", C.c_float)]
+
+
+class AqOut(C.Structure):
+    _fields_ = [("qp_offset", vp), ("inv_qscale", vp), ("pixel_stats", vp)]
+
+
+WEIGHT_DEVICE = 2
+
+
 def _ptr(a):
     return a.ctypes.data_as(vp) if a is not None else None
 
@@ -61,6 +72,8 @@ def load():
     L.x264cu_frame_free.argtypes = [vp, vp]
     L.x264cu_frame_upload.argtypes = [vp, vp, vp, C.c_int, vp]
     L.x264cu_frame_upload_device.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.x264cu_frame_upload_aq.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(AqCfg), vp, C.POINTER(AqOut)]
+    L.x264cu_weights_analyse.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(Weight)]
     L.x264cu_frame_cost.argtypes = [vp, C.POINTER(Job)]
     L.x264cu_frame_cost_batch.argtypes = [vp, C.POINTER(Job), C.c_int]
     L.x264cu_motionsearch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]
@@ -198,6 +211,32 @@ class Context:
                 qp = inv_qscale
         check(self.L.x264cu_frame_upload(self.ctx, f, lp, st, qp), "x264cu_frame_upload")
 
+    def upload_aq(self, f, luma, chroma, aq_mode=1, aq_strength=1.0, quant_offsets=None):
+        """x264cu_frame_upload_aq: luma (H, W), chroma interleaved NV12 (H/2, W).  Returns the arrays filled at flush:
+        qp_offset (f32), inv_qscale (u16), pixel_stats (u64 x 6: sum/ssd of Y, U, V)."""
+        assert luma.dtype == np.uint8 and luma.shape == (self.H, self.W) and luma.flags.c_contiguous
+        assert chroma.dtype == np.uint8 and chroma.shape == (self.H // 2, self.W) and chroma.flags.c_contiguous
+        res = {"qp_offset": np.zeros(self.nmb, np.float32), "inv_qscale": np.zeros(self.nmb, np.uint16),
+               "pixel_stats": np.zeros(6, np.uint64)}
+        out = AqOut(res["qp_offset"].ctypes.data, res["inv_qscale"].ctypes.data, res["pixel_stats"].ctypes.data)
+        cfg = AqCfg(aq_mode, aq_strength)
+        qo = None
+        if quant_offsets is not None:
+            qo = np.ascontiguousarray(quant_offsets, dtype=np.float32)
+            self._keep.append(qo)
+        self._keep.extend([luma, chroma, res, out, cfg])
+        check(self.L.x264cu_frame_upload_aq(self.ctx, f, luma.ctypes.data, self.W, chroma.ctypes.data, self.W, C.byref(cfg),
+                                            _ptr(qo), C.byref(out)), "x264cu_frame_upload_aq")
+        return res
+
+    def weights_analyse(self, fenc, fref, dist, numslices=1):
+        """x264cu_weights_analyse; returns a Weight that is filled at flush (and stays on the device for
+        make_job(..., weight='device'))"""
+        w = Weight(0, 0, 0, 0)
+        self._keep.append(w)
+        check(self.L.x264cu_weights_analyse(self.ctx, fenc, fref, dist, numslices, C.byref(w)), "x264cu_weights_analyse")
+        return w
+
     def upload_device(self, f, d_luma, stride, d_inv_qscale=None):
         check(self.L.x264cu_frame_upload_device(self.ctx, f, d_luma, stride, d_inv_qscale), "x264cu_frame_upload_device")
 
@@ -227,7 +266,9 @@ class Context:
             res["intra_row_satds"] = np.zeros(self.mbh, dtype=np.int32); o.intra_row_satds = res["intra_row_satds"].ctypes.data
             res["intra_stats"] = np.zeros(2, dtype=np.int32); o.intra_stats = res["intra_stats"].ctypes.data
         w = Weight(0, 0, 0, 0)
-        if weight is not None:
+        if isinstance(weight, str) and weight == "device":
+            w = Weight(WEIGHT_DEVICE, 0, 0, 0)
+        elif weight is not None:
             w = Weight(1, weight[0], weight[1], weight[2])
         return Job(fenc, fref0, fref1, d0, d1, w, o), res
 
@@ -387,12 +428,34 @@ class CudaLookahead:
         for k in [k for k in self.results if k[0] == idx]:
             del self.results[k]
 
+    def put_frame_yuv(self, idx, luma, chroma, aq_mode=1, aq_strength=1.0, quant_offsets=None):
+        if idx not in self.frames:
+            self.frames[idx] = self.ctx.frame_new()
+        r = self.ctx.upload_aq(self.frames[idx], np.ascontiguousarray(luma), np.ascontiguousarray(chroma), aq_mode, aq_strength, quant_offsets)
+        self.ctx.flush()
+        self.aq = getattr(self, "aq", {})
+        self.aq[idx] = r
+        for k in [k for k in self.results if k[0] == idx]:
+            del self.results[k]
+
+    def get_aq(self, idx):
+        r = self.aq[idx]
+        return r["qp_offset"], r["inv_qscale"], r["pixel_stats"]
+
+    def weights_analyse(self, b, ref, numslices=1, flush=True):
+        w = self.ctx.weights_analyse(self.frames[b], self.frames[ref], b - ref, numslices)
+        if not flush:
+            return w
+        self.ctx.flush()
+        return (w.enabled, w.scale, w.denom, w.offset) if w.enabled else (0, 1, 0, 0)
+
     def lowres(self, idx, plane):
         return self.ctx.get_lowres(self.frames[idx], plane)
 
     ALL = ("lowres_costs", "mvs", "row_satds", "stats", "intra")
 
     def frame_cost(self, p0, p1, b, weight=None):
+        """weight: None, (scale, denom, offset), or 'device' (the result of the last weights_analyse(b, p0))"""
         r = self.ctx.frame_cost(self.frames[b], self.frames[p0], self.frames[p1], b - p0, p1 - b, want=self.ALL, weight=weight)
         self.results[(b, b - p0, p1 - b)] = r
         return int(r["stats"][0])
