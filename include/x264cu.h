@@ -120,6 +120,9 @@ typedef struct
 } x264cu_aq_out;              /* host destinations, filled when x264cu_flush returns; NULL members are skipped */
 int x264cu_frame_upload_aq( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *luma, int stride, const uint8_t *chroma_nv12, int cstride,
                             const x264cu_aq_cfg *aq, const float *quant_offsets, const x264cu_aq_out *out );
+/* the same with DEVICE pointers (no PCIe copy); results stay on the device */
+int x264cu_frame_upload_aq_device( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint8_t *d_chroma_nv12,
+                                   int cstride, const x264cu_aq_cfg *aq, const float *d_quant_offsets );
 /* x264_weights_analyse( h, fenc, fref, b_lookahead = 1 ) (slicetype.c:284-501): luma weight of `fenc` against `fref`
  * (dist = frame distance, 1..bframes+1) from the frames' pixel statistics, the intra costs and -- when the list-0 field
  * has already been searched -- the motion-compensated reference.  Both frames must come from x264cu_frame_upload_aq.

@@ -606,6 +606,24 @@ extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uin
     return end_batch( c );
 }
 
+extern "C" int x264cu_frame_upload_aq_device( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint8_t *d_chroma, int cstride,
+                                              const x264cu_aq_cfg *aq, const float *d_quant_offsets )
+{
+    if( !c || !f || !d_luma || !d_chroma || !aq ) FAIL( "x264cu_frame_upload_aq_device: null argument" );
+    if( aq->mode < 0 || aq->mode > 1 ) FAIL( "x264cu_frame_upload_aq_device: aq-mode %d goes through powf and is not computed on the device", aq->mode );
+    CU( cudaSetDevice( c->device ) );
+    if( begin_batch( c ) ) return -1;
+    const LaParams &P = c->P;
+    CU( cudaMemsetAsync( f->pixstats, 0, 8 * sizeof(unsigned long long), c->st ) );
+    launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );
+    c->launches += 2;
+    launch_aq( d_luma, stride, d_chroma, cstride, c->cfg.width, c->cfg.height, P, aq->mode, aq_strength_f32( aq->strength ),
+               aq->mode ? d_quant_offsets : NULL, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats, c->st );
+    f->have_aq = true;
+    if( upload_common( c, f, d_luma, stride ) ) return -1;
+    return end_batch( c );
+}
+
 // x264_weights_analyse( h, fenc, fref, 1 ) (slicetype.c:284-501), SURVEY.md section 8f row 2
 extern "C" int x264cu_weights_analyse( x264cu_ctx *c, x264cu_frame *fenc, x264cu_frame *fref, int dist, int numslices, x264cu_weight *out )
 {

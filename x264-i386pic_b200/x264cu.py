@@ -73,6 +73,7 @@ def load():
     L.x264cu_frame_upload.argtypes = [vp, vp, vp, C.c_int, vp]
     L.x264cu_frame_upload_device.argtypes = [vp, vp, vp, C.c_int, vp]
     L.x264cu_frame_upload_aq.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(AqCfg), vp, C.POINTER(AqOut)]
+    L.x264cu_frame_upload_aq_device.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(AqCfg), vp]
     L.x264cu_weights_analyse.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(Weight)]
     L.x264cu_frame_cost.argtypes = [vp, C.POINTER(Job)]
     L.x264cu_frame_cost_batch.argtypes = [vp, C.POINTER(Job), C.c_int]
