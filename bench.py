@@ -109,10 +109,13 @@ def barrier_sync(dist, local):
         torch.cuda.synchronize(local)
 
 
-def run_cuda_pass(x264cu, ctx, frames, streams_n, warmup, steps, e2e, pinned=None, dev=None, profile=False, dist=None, local=0):
-    """ramp (untimed) -> warmup -> timed steps; returns (ms, evals per step, launches, kernel times, bytes)."""
-    L = ctx.L
-    wins = [L.x264cu_stream_open(ctx.ctx, BFRAMES, 1 if e2e else 0) for _ in range(streams_n)]
+def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=None, dev=None, profile=False, dist=None, local=0):
+    """ramp (untimed) -> warmup -> timed steps; returns (ms, evals per step, launches, kernel times, bytes).
+    ctxs: one context for all streams (they then share its in-order CUDA stream), or one context per encode stream
+    (--contexts: kernels of different streams overlap on the device; this is how concurrent encoders would run)."""
+    L = ctxs[0].L
+    cx = [ctxs[s % len(ctxs)] for s in range(streams_n)]
+    wins = [L.x264cu_stream_open(cx[s].ctx, BFRAMES, 1 if e2e else 0) for s in range(streams_n)]
     assert all(wins), x264cu.last_error()
     pos = [0] * streams_n
 
@@ -134,33 +137,40 @@ def run_cuda_pass(x264cu, ctx, frames, streams_n, warmup, steps, e2e, pinned=Non
     for k in range(warmup):
         push(k % streams_n)
         x264cu.check(L.x264cu_stream_sync(wins[k % streams_n]), "sync")
-    ctx.kernel_times()
-    ctx.set_profiling(profile)
-    l0 = ctx.launches()
+    for c in ctxs:
+        c.kernel_times()
+        c.set_profiling(profile)
+    l0 = sum(c.launches() for c in ctxs)
     barrier_sync(dist, local)
-    ctx.timer_begin()
+    ctxs[0].timer_begin()
     t0 = time.perf_counter()
     evals = 0
-    # software pipeline of depth 1: the next stream's frame is enqueued before this step's results are awaited, so
-    # the device never idles while the host builds job tables; every step's results are complete on the host
-    # (x264cu_stream_sync = device work + deferred copies of that push) before the step after next is enqueued
-    prev = None
+    # software pipeline: a stream's previous step is awaited only when that stream gets its next frame, so up to
+    # min(streams, 2) steps (one context) or `streams` steps (one context per stream) are in flight and the device never
+    # idles while the host builds job tables; every step's results are complete on the host (x264cu_stream_sync =
+    # device work + deferred copies of that push) before the same stream is pushed again
+    depth = streams_n if len(ctxs) > 1 else min(streams_n, 2)
+    pending = []
     for k in range(steps):
         s = (warmup + k) % streams_n
-        evals += push(s)
-        if prev is not None:
-            x264cu.check(L.x264cu_stream_sync(wins[prev]), "sync")
-        prev = s if streams_n > 1 else None
-        if streams_n == 1:
+        if s in pending:
+            pending.remove(s)
             x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")
-    if prev is not None:
-        x264cu.check(L.x264cu_stream_sync(wins[prev]), "sync")
-    ms = ctx.timer_end()
+        evals += push(s)
+        pending.append(s)
+        while len(pending) >= depth:
+            x264cu.check(L.x264cu_stream_sync(wins[pending.pop(0)]), "sync")
+    for s in pending:
+        x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")
+    ms = ctxs[0].timer_end()        # every context is idle again: the bracket on context 0 spans all of them
     wall_ms = (time.perf_counter() - t0) * 1e3
     barrier_sync(dist, local)
-    ctx.set_profiling(False)
-    kt = ctx.kernel_times()
-    launches = ctx.launches() - l0
+    kt = {}
+    for c in ctxs:
+        c.set_profiling(False)
+        for k, v in c.kernel_times().items():
+            kt[k] = (kt.get(k, (0.0, 0))[0] + v[0], kt.get(k, (0.0, 0))[1] + v[1])
+    launches = sum(c.launches() for c in ctxs) - l0
     res_bytes = int(L.x264cu_stream_result_bytes(wins[0])) if e2e else 0
     # a result the caller would read: the P cost of the newest frame against its predecessor
     st = (x264cu.C.c_int32 * 4)()
@@ -283,6 +293,8 @@ def main():
     ap.add_argument("--search-passes", type=int, default=2, help="K of the dependency-free schedule; 0 = exact raster-serial wavefront mode")
     ap.add_argument("--no-primitives", action="store_true", help="skip the SATD/SAD primitive roofline section")
     ap.add_argument("--value-only", action="store_true", help="profiling aid: skip the end-to-end pass")
+    ap.add_argument("--contexts", type=int, default=0, help="contexts per GPU; 0 (default): one context (own CUDA streams) per encode stream, "
+                    "as concurrent encoders would run; 1: all streams share one in-order context")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k", "64streams"],
                     help="1080p: BASELINE.json configs[2] (the headline); 4k: configs[3] (3840x2160, 62 live frames per window); "
                          "64streams: configs[4] (8 independent 1080p encode streams per GPU)")
@@ -301,7 +313,7 @@ def main():
     config = {"workload": wl,
               "width": W, "height": H, "bframes": BFRAMES, "search_passes": args.search_passes, "subme": 7, "mbtree_edges": 1, "aq": 1,
               "evals_per_step": 154, "new_search_fields_per_step": 33, "streams_per_gpu": args.streams,
-              "sharding": "independent encode streams per GPU, no collective", "host_pipeline_depth": 1,
+              "sharding": "independent encode streams per GPU, no collective", "host_pipeline_depth": "one outstanding step per stream",
               "l2": "inputs larger than L2: %d windows x 18 frames x ~10 MB of planes+cost arrays per GPU" % args.streams}
 
     if args.impl == "reference":
@@ -326,7 +338,10 @@ def main():
     rank, world, local, dist = dist_setup(args.gpus)
     S = args.streams
     per_stream = RAMP + (warmup + args.steps + S - 1) // S + 1
-    ctx = x264cu.Context(W, H, bframes=BFRAMES, subme=7, do_edges=1, aq=1, passes=args.search_passes, device=local)
+    n_ctx = S if args.contexts == 0 else max(1, min(args.contexts, S))
+    ctxs = [x264cu.Context(W, H, bframes=BFRAMES, subme=7, do_edges=1, aq=1, passes=args.search_passes, device=local) for _ in range(n_ctx)]
+    ctx = ctxs[0]
+    config["contexts_per_gpu"] = n_ctx
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -351,12 +366,15 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     # device-resident pass ("value"): inputs already in HBM, only the cost scalars come back
-    ms_v, wall_v, evals, launches, kt, _, chk_v = run_cuda_pass(x264cu, ctx, frames, S, warmup, args.steps, False, dev=dev, profile=True, dist=dist, local=local)
+    # (kernel timing pass first: ONE context, so that the per-kernel CUDA events do not span kernels of other streams)
+    psteps = min(args.steps, 16)
+    _, _, _, _, kt, _, _ = run_cuda_pass(x264cu, ctxs[:1], frames, S, warmup, psteps, False, dev=dev, profile=True, dist=dist, local=local)
+    ms_v, wall_v, evals, launches, _, _, chk_v = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, False, dev=dev, profile=False, dist=dist, local=local)
     # end-to-end pass: pinned host luma in, every result array of the hook protocol out, per step
     if args.value_only:
         ms_e, wall_e, res_bytes, chk_e = ms_v, wall_v, 0, chk_v
     else:
-        ms_e, wall_e, _, _, _, res_bytes, chk_e = run_cuda_pass(x264cu, ctx, frames, S, warmup, args.steps, True, pinned=pinned, dist=dist, local=local)
+        ms_e, wall_e, _, _, _, res_bytes, chk_e = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, True, pinned=pinned, dist=dist, local=local)
     clocks = sampler.summary()
     assert chk_v > 0 and chk_e > 0
 
@@ -380,7 +398,7 @@ def main():
     nmb = ctx.nmb
     s_ms, s_n = kt["search"]
     if s_n and args.workload != "1080p":
-        out["kernel_ms_per_step"] = {k: round(v[0] / args.steps, 4) for k, v in kt.items()}
+        out["kernel_ms_per_step"] = {k: round(v[0] / psteps, 4) for k, v in kt.items()}
     elif s_n:
         # algorithmic bytes of one block-field search pass: fenc 64 B + 4 reference phase planes 256 B
         # + MV/cost out 8 B + previous-pass MV in 4 B; one launch = 33 fields x 8160 blocks in steady state
@@ -395,11 +413,14 @@ def main():
         out["roofline"] = {"kernel": "search_kernel_t<SATD,unweighted>", "bound": "hbm", "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
                            "frac": round(ach / peak_gbs, 4), "traffic": 41.39e6, "peak_source": peak_src,
                            "avg_launch_ms": round(avg_ms, 4), "launches_timed": s_n, "algorithmic_bytes_per_launch": alg,
+                           "timed": "CUDA events around every launch in a separate %d-step pass on one context (no overlap with other streams' kernels)" % psteps,
                            "integer_pipe": {"alu_pipe_pct": 62.8, "issue_active_pct": 53.4, "l1tex_wavefronts_pct": 58.0,
                                             "source": "ncu --set full, profiles/r01/ncu_summary_v5.md (not measured in this run)"},
                            "note": "compulsory bytes are tiny: the kernel is bound by integer issue (6 SATD 8x8 + ~35 SAD 8x8 per block and pass) "
                                    "and L1 wavefronts, not by HBM; the HBM-streaming kernels of the path are in `primitives`"}
-        out["kernel_ms_per_step"] = {k: round(v[0] / args.steps, 4) for k, v in kt.items()}
+        out["kernel_ms_per_step"] = {k: round(v[0] / psteps, 4) for k, v in kt.items()}
+        if args.search_passes == 0:
+            out["roofline"]["kernel"] = "search_kernel_serial (exact raster-serial mode: latency-bound wavefront, one launch per step)"
     if rank == 0:
         if not args.no_primitives and args.workload == "1080p":
             out["primitives"] = bench_satd(x264cu, ctx, peak_gbs)
@@ -409,7 +430,8 @@ def main():
             out["cpu_baseline"] = {"value": round(2 / dt, 4), "unit": "frames/s", "cores": thr, "kind": kind,
                                    "sample": "2 steady-state steps of stream 0 after an untimed 17-frame window fill; C-only build of the reference (no nasm)"}
         print(json.dumps(out))
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -59,6 +59,7 @@ struct x264cu_ctx
     uint16_t *d_cost_mv;
     float *d_log2_lut;
     uint8_t *d_exp2_lut;
+    bool exact_waves; int serial_ctas_per_sm; int serial_error;      // exact raster-serial mode (search_passes == 0)
     uint8_t *d_chroma[2]; int chroma_pitch;      // NV12 chroma staging, paired with d_luma[]
     int stat_pitch;
     size_t plane_alloc;      // bytes of the 4 planes + slack
@@ -176,6 +177,13 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
         for( int i = 0; i < 64; i++ ) lut[i] = (uint8_t)lround( 256.0 * ( pow( 2.0, i / 64.0 ) - 1.0 ) );
         CUP( cudaMalloc( &c->d_exp2_lut, sizeof(lut) ) );
         CUP( cudaMemcpy( c->d_exp2_lut, lut, sizeof(lut), cudaMemcpyHostToDevice ) );
+    }
+    {
+        const char *e = getenv( "X264CU_EXACT_WAVES" );
+        c->exact_waves = e && atoi( e );
+        c->serial_ctas_per_sm = search_serial_max_ctas_per_sm();
+        if( c->serial_ctas_per_sm < 1 ) c->serial_ctas_per_sm = 1;
+        c->serial_error = 0;
     }
     c->chroma_pitch = (int)align_up( cfg->width, 256 );
     c->luma_pitch = (int)align_up( cfg->width, 256 );
@@ -318,6 +326,7 @@ static void drain_copies( x264cu_ctx *c, uint64_t upto )
     {
         const PendingCopy &p = c->copies[c->copies_head++];
         if( p.kind < 0 ) memcpy( p.dst, p.src, p.bytes );
+        else if( p.kind == 4 ) { if( *(const int *)p.src ) *(int *)p.dst = 1; }      // error flag of the serial search kernel
         else if( p.kind == 3 )
         {   // i_pixel_sum / i_pixel_ssd with the mean removed (ratecontrol.c:406-414); bias = mbw | mbh << 16
             const uint64_t *raw = (const uint64_t *)p.src; uint64_t *dst = (uint64_t *)p.dst;
@@ -396,6 +405,7 @@ extern "C" int x264cu_flush( x264cu_ctx *c )
     if( !c ) FAIL( "null context" );
     CU( cudaSetDevice( c->device ) );
     if( ctx_sync( c ) ) return -1;
+    if( c->serial_error ) FAIL( "exact-mode search kernel: a row waited too long for the row below (launch not fully resident?)" );
     CU( cudaGetLastError() );
     return 0;
 }
@@ -763,9 +773,26 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
             }
             const SearchJob *d;
             if( push_jobs( c, sj, &d ) ) return -1;
-            const int nwaves = P.mbw + 2 * ( P.mbh - 1 );
-            Span s( c, K_SEARCH, nwaves );
-            launch_search_waves( d, (int)sj.size(), P, c->st );
+            if( c->exact_waves )
+            {   // one launch per anti-diagonal wave (the first implementation; kept as a cross-check, X264CU_EXACT_WAVES=1)
+                const int nwaves = P.mbw + 2 * ( P.mbh - 1 );
+                Span s( c, K_SEARCH, nwaves );
+                launch_search_waves( d, (int)sj.size(), P, c->st );
+            }
+            else
+            {   // one persistent launch: every MV word of the field is its own "ready" flag (search_kernel_serial)
+                for( const SearchJob &S : sj ) CU( cudaMemsetAsync( S.mv_out, 0x7F, (size_t)P.nmb * 4, c->st ) );
+                int *derr = (int *)arena_alloc( c, 256 );
+                if( !derr ) return -1;
+                CU( cudaMemsetAsync( derr, 0, 4, c->st ) );
+                Span s( c, K_SEARCH, 0 );
+                int nl = launch_search_serial( d, (int)sj.size(), P, derr, c->sm_count * c->serial_ctas_per_sm, c->st );
+                c->launches += nl; c->class_n[K_SEARCH] += nl;
+                uint8_t *p = pin_alloc_sync( c, 4 );
+                if( !p ) return -1;
+                CU( cudaMemcpyAsync( p, derr, 4, cudaMemcpyDeviceToHost, c->st ) );
+                c->copies.push_back( { &c->serial_error, p, 4, 4, 0, c->seq } );
+            }
         }
         for( int pass = 0; pass < K; pass++ )
         {
@@ -1004,7 +1031,9 @@ extern "C" int x264cu_wait( x264cu_ctx *c, uint64_t seq )
 {
     if( !c ) FAIL( "null context" );
     CU( cudaSetDevice( c->device ) );
-    return wait_upto( c, seq );
+    if( wait_upto( c, seq ) ) return -1;
+    if( c->serial_error ) FAIL( "exact-mode search kernel: a row waited too long for the row below (launch not fully resident?)" );
+    return 0;
 }
 
 extern "C" int x264cu_frame_cost( x264cu_ctx *c, const x264cu_job *job ) { return x264cu_frame_cost_batch( c, job, 1 ); }

@@ -205,15 +205,15 @@ struct RowSrc
 {
     const u32 *q;
     u32 sh;
-    bool k;
+    int k;
     __device__ __forceinline__ RowSrc( const uint8_t *origin, int off )
     {
-        if( LD64 ) { q = (const u32 *)origin + ( ( off >> 3 ) << 1 ); k = ( off & 4 ) != 0; }
-        else       { q = (const u32 *)origin + ( off >> 2 ); k = false; }
+        if( LD64 ) { q = (const u32 *)origin + ( ( off >> 3 ) << 1 ); k = off & 4; }
+        else       { q = (const u32 *)origin + ( off >> 2 ); k = 0; }
         sh = ( off & 3 ) * 8;
-        // pin the row-0 pointer in a register pair: under register pressure ptxas otherwise rematerialises the whole
-        // address (plane select, 64-bit add) for every row instead of using the row immediates
-        asm( "" : "+l"( q ) );
+        // pin the row-0 pointer, the shift and the word select in registers: under register pressure the compiler
+        // otherwise rematerialises the whole offset computation (plane table lookup, multiply, 64-bit add) for every row
+        asm volatile( "" : "+l"( q ), "+r"( sh ), "+r"( k ) );
     }
     __device__ __forceinline__ uint2 row( int w4 ) const      // w4: row offset in words (a multiple of 2)
     {
@@ -257,6 +257,7 @@ static __constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {
 // ---- 8 lanes per block -------------------------------------------------------------------------------
 struct GroupBE
 {
+    static constexpr bool PAR4 = false;
     Grp g;
     uint2 fenc;              // this lane's row of the block
     const uint8_t *ref0;     // this lane's row of reference 0's F plane at mv 0
@@ -330,6 +331,96 @@ struct GroupBE
         uint2 a = load8u( ref0 ), b = load8u( ref1 );
         return cmp_rows( fenc, make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ), g, P->b_satd );
     }
+};
+
+// ---- 32 lanes per block: 4 candidates x 8 pixel rows ---------------------------------------------------
+// The latency-oriented mapping of the exact raster-serial mode (search_kernel_serial): every candidate round of
+// x264_me_search scores up to FOUR candidates at once, one per 8-lane subgroup (lane & 7 = pixel row, lane >> 3 =
+// candidate slot); the winner is the minimum of (cost << 2 | slot) over the subgroups, which is the reference's
+// "strict <, earlier candidate wins ties" rule.  Single evaluations are computed redundantly by the four subgroups.
+struct WarpBE
+{
+    static constexpr bool PAR4 = true;
+    Grp g;                   // mask: the whole warp; r: pixel row
+    int sub;                 // candidate slot of this lane
+    uint2 fenc;
+    const uint8_t *ref0, *ref1, *ref_w;      // this lane's row at mv 0
+    const LaParams *P;
+    int *err;                // error flag of the launch (bounded spins)
+
+    // an MV word of the row below: spin (L1-bypassing loads) until its producer has replaced the "not ready" pattern
+    __device__ __forceinline__ int wait_mv( const int *p ) const
+    {
+        int v;
+        for( int spins = 1; ; spins++ )
+        {
+            asm volatile( "ld.volatile.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+            if( v != 0x7F7F7F7F ) break;
+            if( ( spins & 1023 ) == 0 && ( *(volatile int *)err || spins > ( 1 << 22 ) ) ) { *(volatile int *)err = 1; v = 0; break; }
+            __nanosleep( 20 );
+        }
+        return v;
+    }
+    __device__ __forceinline__ bool leader() const { return ( threadIdx.x & 31 ) == 0; }
+    __device__ __forceinline__ bool satd() const { return P->b_satd != 0; }
+    __device__ __forceinline__ int zero_cmp() const { return cmp_rows( fenc, load8u( ref0 ), g, P->b_satd ); }
+    // slot s scores candidate k0 + s; `c` is this subgroup's full cost (identical in its 8 lanes)
+    __device__ __forceinline__ void take_min4( int c, bool valid, int k0, int &bcost, int &best ) const
+    {
+        u32 key = valid ? ( (u32)c << 2 ) | (u32)sub : 0xffffffffu;
+        key = min( key, __shfl_xor_sync( 0xffffffffu, key, 8 ) );
+        key = min( key, __shfl_xor_sync( 0xffffffffu, key, 16 ) );
+        if( key != 0xffffffffu && (int)( key >> 2 ) < bcost ) { bcost = (int)( key >> 2 ); best = k0 + (int)( key & 3 ); }
+    }
+    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        for( int k0 = 0; k0 < n; k0 += 4 )
+        {
+            int x, y;
+            xy( min( k0 + sub, n-1 ), x, y );
+            const int c = red8( (int)sad8( fenc, load8u( ref_w + (int64_t)y * P->stride + x ) ), g ) + mvcost( tab, m, x*4, y*4 );
+            take_min4( c, k0 + sub < n, k0, bcost, best );
+        }
+    }
+    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        for( int k0 = 0; k0 < n; k0 += 4 )
+        {
+            int x, y;
+            xy( min( k0 + sub, n-1 ), x, y );
+            const int c = red8( (int)sad8( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ) ), g ) + mvcost( tab, m, x, y );
+            take_min4( c, k0 + sub < n, k0, bcost, best );
+        }
+    }
+    // qsad_best that also reports the cost of candidate 0 (the predictor of me.c:216-275)
+    template<class XY> __device__ __forceinline__ void qsad_best0( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best, int &cost0 ) const
+    {
+        for( int k0 = 0; k0 < n; k0 += 4 )
+        {
+            int x, y;
+            xy( min( k0 + sub, n-1 ), x, y );
+            const int c = red8( (int)sad8( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ) ), g ) + mvcost( tab, m, x, y );
+            if( k0 == 0 ) cost0 = __shfl_sync( 0xffffffffu, c, 0 );
+            take_min4( c, k0 + sub < n, k0, bcost, best );
+        }
+    }
+    // four SATD candidates at once; bit k of `skip` drops candidate k (me.c:947-963)
+    template<class XY> __device__ __forceinline__ void qsatd_best4( XY xy, int skip, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        int x, y;
+        xy( sub, x, y );
+        const int c = satd_rows( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ), g ) + mvcost( tab, m, x, y );
+        take_min4( c, !( ( skip >> sub ) & 1 ), 0, bcost, best );
+    }
+    __device__ __forceinline__ void hex6( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    { fpel_best( 6, [&]( int k, int &x, int &y ) { x = ox + hex2x( k+1 ); y = oy + hex2y( k+1 ); }, tab, m, bcost, best ); }
+    __device__ __forceinline__ void square8( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    { fpel_best( 8, [&]( int k, int &x, int &y ) { x = ox + c_sq1[k+1][0]; y = oy + c_sq1[k+1][1]; }, tab, m, bcost, best ); }
+    __device__ __forceinline__ int fpel1( int mx, int my ) const { return red8( (int)sad8( fenc, load8u( ref_w + (int64_t)my * P->stride + mx ) ), g ); }
+    __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const
+    { return red8( (int)sad8( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ), g ); }
+    __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
+    { return satd_rows( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ), g ); }
 };
 
 // ---- 1 thread per block ---------------------------------------------------------------------------
@@ -429,6 +520,7 @@ struct QpelRows
 template<bool SATD, bool WEIGHTED, int PITCH, bool LD64, bool PTXPRED>
 struct ThreadBE
 {
+    static constexpr bool PAR4 = false;
     uint2 fenc[8];
     const uint8_t *ref0, *ref1, *ref_w;      // block origins (8-byte aligned)
     const LaParams *P;

@@ -69,6 +69,8 @@ void launch_weights_analyse( const uint8_t *fencF, const uint8_t *refF, const in
                              const unsigned long long *st_fenc, const unsigned long long *st_ref, int *wres, int numslices,
                              const LaParams &P, cudaStream_t st );
 void launch_weight_plane_dev( const uint8_t *src, uint8_t *dst, int64_t bytes, const int *wres, cudaStream_t st );
+int  launch_search_serial( const SearchJob *d_jobs, int njobs, const LaParams &P, int *d_err, int max_resident_ctas, cudaStream_t st );
+int  search_serial_max_ctas_per_sm();
 void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );
 
 // One macroblock_tree_propagate step (slicetype.c:1051-1089) of frame b towards its references.

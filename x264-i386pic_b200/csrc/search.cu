@@ -42,6 +42,14 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
     {   // me.c:947-963
         if( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx ) break;
         const int odir = bdir, omx = bmx, omy = bmy;
+        if constexpr( BE::PAR4 )
+        {   // the four quarter-pel neighbours in one round
+            int best = -1;
+            be.qsatd_best4( [&]( int k, int &x, int &y ) { x = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ); y = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 ); },
+                            odir >= 0 ? 1 << ( odir ^ 1 ) : 0, tab, m, bcost, best );
+            if( best >= 0 ) { bmx = omx + ( best == 2 ? -1 : best == 3 ? 1 : 0 ); bmy = omy + ( best == 0 ? -1 : best == 1 ? 1 : 0 ); bdir = best; }
+        }
+        else
 #pragma unroll 1
         for( int k = 0; k < 4; k++ )
             if( ( k ^ 1 ) != odir )
@@ -67,8 +75,26 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
         bpred_mx = iclip3( m.mvpx, 4*m.fminx, 4*m.fmaxx );
         bpred_my = iclip3( m.mvpy, 4*m.fminy, 4*m.fmaxy );
         pmvx = bpred_mx; pmvy = bpred_my;
+        int pmv_cost;
+        if constexpr( BE::PAR4 )
+        {   // the predictor and its candidates in one round of four (two when all four neighbours survive the filter)
+            int cx[5], cy[5], nc = 1;
+            cx[0] = bpred_mx; cy[0] = bpred_my;
+#pragma unroll
+            for( int i = 0; i < 4; i++ )
+            {
+                int mx = mvc[i][0], my = mvc[i][1];
+                if( i >= i_mvc || ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
+                cx[nc] = iclip3( mx, 4*m.fminx, 4*m.fmaxx ); cy[nc] = iclip3( my, 4*m.fminy, 4*m.fmaxy ); nc++;
+            }
+            int best = 0;
+            be.qsad_best0( nc, [&]( int k, int &x, int &y ) { x = cx[k]; y = cy[k]; }, tab, m, bpred_cost, best, pmv_cost );
+            bpred_mx = cx[best]; bpred_my = cy[best];
+        }
+        else
+        {
         bpred_cost = be.qsad1( m, bpred_mx, bpred_my ) + mvcost( tab, m, bpred_mx, bpred_my );
-        const int pmv_cost = bpred_cost;
+        pmv_cost = bpred_cost;
 #pragma unroll 1
         for( int i = 0; i < i_mvc; i++ )
         {   // x264_predictor_clip (common.h:790-805): drop zero and == pmv, clip the rest
@@ -78,12 +104,24 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
             int cost = be.qsad1( m, mx, my ) + mvcost( tab, m, mx, my );
             if( cost < bpred_cost ) { bpred_cost = cost; bpred_mx = mx; bpred_my = my; }
         }
+        }
         bmx = FPEL( bpred_mx ); bmy = FPEL( bpred_my );
         // me.c:258-274 with the two possible fullpel probes folded into one call site
         const bool probe_start = ( bpred_mx & 3 ) | ( bpred_my & 3 );
         if( !probe_start ) bcost = bpred_cost;
         const bool probe_zero = ( pmvx | pmvy ) && ( bmx | bmy );
         const int sx = bmx, sy = bmy;
+        if constexpr( BE::PAR4 )
+        {
+            const int np = (int)probe_start + (int)probe_zero;
+            if( np )
+            {
+                int best = -1;
+                be.fpel_best( np, [&]( int k, int &x, int &y ) { const bool z = k || !probe_start; x = z ? 0 : sx; y = z ? 0 : sy; }, tab, m, bcost, best );
+                if( best >= 0 ) { const bool z = best || !probe_start; bmx = z ? 0 : sx; bmy = z ? 0 : sy; }
+            }
+        }
+        else
 #pragma unroll 1
         for( int t = 0; t < 2; t++ )
         {
@@ -187,8 +225,8 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
 
 // one block of one search pass (slicetype.c:654-702)
 template<class BE>
-__device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, const LaParams &P, const CostTab &tab,
-                                              int bx, int by, int blk )
+__device__ __forceinline__ int search_block( const BE &be, const SearchJob &J, const LaParams &P, const CostTab &tab,
+                                             int bx, int by, int blk, int right_mv = 0 )
 {
     MeGeo m;
     m.wscale = J.wscale; m.wdenom = J.wdenom; m.woffset = J.woffset;
@@ -198,15 +236,29 @@ __device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, 
     if( J.mv_in )
     {
         const int *f = (const int *)J.mv_in + blk;
-#define MVC( o ) { int v_ = __ldg( f + (o) ); mvc[i_mvc][0] = (int16_t)( v_ & 0xffff ); mvc[i_mvc][1] = v_ >> 16; i_mvc++; }
-        if( bx < P.mbw-1 ) MVC( 1 )
-        if( by < P.mbh-1 )
-        {
-            MVC( P.mbw )
-            if( bx > 0 ) MVC( P.mbw-1 )
-            if( bx < P.mbw-1 ) MVC( P.mbw+1 )
+#define MVC_SET( v ) { int v_ = (v); mvc[i_mvc][0] = (int16_t)( v_ & 0xffff ); mvc[i_mvc][1] = v_ >> 16; i_mvc++; }
+        if constexpr( BE::PAR4 )
+        {   // serial kernel: the right neighbour is this warp's previous block; the row below is written by another
+            // warp of the same launch and each MV word is its own "ready" flag (see search_kernel_serial)
+            if( bx < P.mbw-1 ) MVC_SET( right_mv )
+            if( by < P.mbh-1 )
+            {
+                MVC_SET( be.wait_mv( f + P.mbw ) )
+                if( bx > 0 ) MVC_SET( be.wait_mv( f + P.mbw-1 ) )
+                if( bx < P.mbw-1 ) MVC_SET( be.wait_mv( f + P.mbw+1 ) )
+            }
         }
-#undef MVC
+        else
+        {
+            if( bx < P.mbw-1 ) MVC_SET( __ldg( f + 1 ) )
+            if( by < P.mbh-1 )
+            {
+                MVC_SET( __ldg( f + P.mbw ) )
+                if( bx > 0 ) MVC_SET( __ldg( f + P.mbw-1 ) )
+                if( bx < P.mbw-1 ) MVC_SET( __ldg( f + P.mbw+1 ) )
+            }
+        }
+#undef MVC_SET
     }
     if( i_mvc <= 1 ) { m.mvpx = mvc[0][0]; m.mvpy = mvc[0][1]; }
     else
@@ -227,11 +279,14 @@ __device__ __forceinline__ void search_block( const BE &be, const SearchJob &J, 
         cost -= tab[0];                                // slicetype.c:695
         if( mx | my ) cost += 5;                       // 5 * lambda (:696-697)
     }
+    const int packed = ( mx & 0xffff ) | ( my << 16 );
     if( be.leader() )
     {
-        ( (int *)J.mv_out )[blk] = ( mx & 0xffff ) | ( my << 16 );
         J.cost_out[blk] = cost;
+        if constexpr( BE::PAR4 ) __stcg( (int *)J.mv_out + blk, packed );      // straight to L2, where the row above polls it
+        else ( (int *)J.mv_out )[blk] = packed;
     }
+    return packed;
 }
 
 // a job whose weight lives in device memory (x264cu_weights_analyse ran on the same stream, no host round trip)
@@ -301,6 +356,82 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJ
     be.fenc = *(const uint2 *)( J.fenc + pel );
     be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
     search_block( be, J, P, tab, bx, by, blk );
+}
+
+// Exact raster-serial mode as ONE launch per batch: a warp owns one block row of one field and walks it right to left.
+// Block x of a row needs the MVs of the below, below-left and below-right blocks (slicetype.c:662-680).  The field is
+// pre-filled with an impossible MV (0x7F7F7F7F); every MV word is stored once, straight to L2 (st.cg), and is its own
+// "ready" flag: the row above polls the three words it needs with L1-bypassing loads -- no counters, no fences, and
+// the immutable pixel planes keep their L1 residency (an ld.acquire poll invalidated the whole L1: first ncu capture,
+// 17 % of the stall samples in CCTL and a 65 % L1 hit rate).  Rows are numbered bottom-up, so a warp only waits for a
+// lower-numbered warp, which the hardware dispatched earlier: no deadlock; a bounded spin turns a violated assumption
+// into an error flag instead of a hang.
+#define X264CU_MV_NOT_READY 0x7F7F7F7F
+#define SERIAL_WARPS 4
+__global__ void __launch_bounds__(SERIAL_WARPS*32) search_kernel_serial( const SearchJob *__restrict__ jobs, LaParams P, int first_job, int njobs,
+                                                                          int *__restrict__ err )
+{
+    const CostTab tab = stage_cost_tab( P );
+    const int worker = blockIdx.x * SERIAL_WARPS + ( threadIdx.x >> 5 ), lane = threadIdx.x & 31;
+    if( worker >= njobs * P.mbh ) return;
+    const int ji = first_job + worker / P.mbh, by = P.mbh - 1 - worker % P.mbh;      // bottom rows first
+    SearchJob J = jobs[ji];
+    resolve_device_weight( J );
+    WarpBE be; be.g.r = lane & 7; be.g.mask = 0xffffffffu; be.sub = lane >> 3; be.P = &P; be.ref1 = NULL; be.err = err;
+    int right_mv = 0;
+    for( int i = 0; i < P.mbw; i++ )
+    {
+        const int bx = P.mbw - 1 - i, blk = by * P.mbw + bx;
+        if( !skipped_border( P, bx, by ) )
+        {
+            const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
+            be.fenc = *(const uint2 *)( J.fenc + pel );
+            be.ref0 = J.ref + pel; be.ref_w = J.ref_w + pel;
+            right_mv = search_block( be, J, P, tab, bx, by, blk, right_mv );
+            // warm L1 for the next block of this row: 32 rows x 32 columns of the four phase planes around its
+            // position displaced by this block's MV (a miss inside a candidate round costs an L2 round trip on the
+            // serial critical path; second ncu capture: 6 % sector misses ~ one per round)
+            if( bx > 0 )
+            {
+                const int cx = ( bx - 1 ) * 8 + ( (int)(int16_t)( right_mv & 0xffff ) >> 2 ) - 12, cy = by * 8 + ( ( right_mv >> 16 ) >> 2 ) - 12 + lane;
+                const int y = min( max( cy, -X264CU_PAD ), P.lh + X264CU_PAD - 1 ), x = min( max( cx, -X264CU_PAD ), P.lw + X264CU_PAD - 33 );
+                const uint8_t *p = J.ref + (int64_t)y * P.stride + x;
+#pragma unroll
+                for( int k = 0; k < 4; k++ )
+                {
+                    asm volatile( "prefetch.global.L1 [%0];" :: "l"( p + k * P.plane_size ) );
+                    asm volatile( "prefetch.global.L1 [%0];" :: "l"( p + k * P.plane_size + 31 ) );
+                }
+            }
+        }
+        else
+        {   // never evaluated (slicetype.c:823-828): the field keeps frame_new's zero MV; publish it for the row above
+            right_mv = 0;
+            if( lane == 0 ) __stcg( (int *)J.mv_out + blk, 0 );
+        }
+    }
+}
+
+// returns the number of launches
+int launch_search_serial( const SearchJob *d_jobs, int njobs, const LaParams &P, int *d_err, int max_resident_ctas, cudaStream_t st )
+{
+    // every warp of a launch should be resident: split the fields over several launches if one would not fit
+    const int warps_per_job = P.mbh, ctas_per_job = ( warps_per_job + SERIAL_WARPS - 1 ) / SERIAL_WARPS;
+    int jobs_per_launch = max( 1, max_resident_ctas / max( ctas_per_job, 1 ) ), n = 0;
+    for( int j0 = 0; j0 < njobs; j0 += jobs_per_launch, n++ )
+    {
+        const int nj = min( jobs_per_launch, njobs - j0 );
+        const int ctas = ( nj * warps_per_job + SERIAL_WARPS - 1 ) / SERIAL_WARPS;
+        search_kernel_serial<<<ctas, SERIAL_WARPS*32, 0, st>>>( d_jobs, P, j0, nj, d_err );
+    }
+    return n;
+}
+
+int search_serial_max_ctas_per_sm()
+{
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &n, search_kernel_serial, SERIAL_WARPS*32, 0 );
+    return n;
 }
 
 void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
