@@ -361,15 +361,35 @@ struct WarpBE
         }
         return v;
     }
+    // sum over the 8 lanes of this lane's subgroup: xor-shuffles (REDUX with four different 8-lane masks per warp
+    // measured 60 % slower, profiles/r01/tuning.md)
+    __device__ __forceinline__ int rsum8( int v ) const { return red8( v, g ); }
+    // x264_pixel_satd_8x8 with the rows across the subgroup's lanes
+    __device__ __forceinline__ int satd8( uint2 a, uint2 b ) const
+    {
+        u32 d[4], h0, h1, h2, h3;
+        diff_row8( a, b, d );
+        HADAMARD4( h0, h1, h2, h3, d[0], d[1], d[2], d[3] );
+#define VSTAGE( v, bit ) { u32 o_ = __shfl_xor_sync( 0xffffffffu, v, bit ); v = ( g.r & bit ) ? o_ - v : v + o_; }
+        VSTAGE( h0, 1 ) VSTAGE( h1, 1 ) VSTAGE( h2, 1 ) VSTAGE( h3, 1 )
+        VSTAGE( h0, 2 ) VSTAGE( h1, 2 ) VSTAGE( h2, 2 ) VSTAGE( h3, 2 )
+#undef VSTAGE
+        const u32 s = abs2( h0 ) + abs2( h1 ) + abs2( h2 ) + abs2( h3 );
+        // each 8x4 half: ((sum & 0xffff) + (sum >> 16)) >> 1 over its 4 lanes (pixel.c:300-306)
+        u32 t = s + __shfl_xor_sync( 0xffffffffu, s, 1 );
+        t += __shfl_xor_sync( 0xffffffffu, t, 2 );
+        const int v = (int)( ( ( t & 0xffff ) + ( t >> 16 ) ) >> 1 );
+        return v + __shfl_xor_sync( 0xffffffffu, v, 4 );
+    }
+    __device__ __forceinline__ int cmp8( uint2 a, uint2 b ) const { return P->b_satd ? satd8( a, b ) : rsum8( (int)sad8( a, b ) ); }
     __device__ __forceinline__ bool leader() const { return ( threadIdx.x & 31 ) == 0; }
     __device__ __forceinline__ bool satd() const { return P->b_satd != 0; }
-    __device__ __forceinline__ int zero_cmp() const { return cmp_rows( fenc, load8u( ref0 ), g, P->b_satd ); }
+    __device__ __forceinline__ int zero_cmp() const { return cmp8( fenc, load8u( ref0 ) ); }
     // slot s scores candidate k0 + s; `c` is this subgroup's full cost (identical in its 8 lanes)
     __device__ __forceinline__ void take_min4( int c, bool valid, int k0, int &bcost, int &best ) const
     {
         u32 key = valid ? ( (u32)c << 2 ) | (u32)sub : 0xffffffffu;
-        key = min( key, __shfl_xor_sync( 0xffffffffu, key, 8 ) );
-        key = min( key, __shfl_xor_sync( 0xffffffffu, key, 16 ) );
+        key = __reduce_min_sync( 0xffffffffu, key );                 // REDUX over the whole warp: one instruction, 7 % faster than two shuffle stages
         if( key != 0xffffffffu && (int)( key >> 2 ) < bcost ) { bcost = (int)( key >> 2 ); best = k0 + (int)( key & 3 ); }
     }
     template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
@@ -378,7 +398,7 @@ struct WarpBE
         {
             int x, y;
             xy( min( k0 + sub, n-1 ), x, y );
-            const int c = red8( (int)sad8( fenc, load8u( ref_w + (int64_t)y * P->stride + x ) ), g ) + mvcost( tab, m, x*4, y*4 );
+            const int c = rsum8( (int)sad8( fenc, load8u( ref_w + (int64_t)y * P->stride + x ) ) ) + mvcost( tab, m, x*4, y*4 );
             take_min4( c, k0 + sub < n, k0, bcost, best );
         }
     }
@@ -388,7 +408,7 @@ struct WarpBE
         {
             int x, y;
             xy( min( k0 + sub, n-1 ), x, y );
-            const int c = red8( (int)sad8( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ) ), g ) + mvcost( tab, m, x, y );
+            const int c = rsum8( (int)sad8( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ) ) ) + mvcost( tab, m, x, y );
             take_min4( c, k0 + sub < n, k0, bcost, best );
         }
     }
@@ -399,7 +419,7 @@ struct WarpBE
         {
             int x, y;
             xy( min( k0 + sub, n-1 ), x, y );
-            const int c = red8( (int)sad8( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ) ), g ) + mvcost( tab, m, x, y );
+            const int c = rsum8( (int)sad8( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ) ) ) + mvcost( tab, m, x, y );
             if( k0 == 0 ) cost0 = __shfl_sync( 0xffffffffu, c, 0 );
             take_min4( c, k0 + sub < n, k0, bcost, best );
         }
@@ -409,18 +429,18 @@ struct WarpBE
     {
         int x, y;
         xy( sub, x, y );
-        const int c = satd_rows( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ), g ) + mvcost( tab, m, x, y );
+        const int c = satd8( fenc, qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ) ) + mvcost( tab, m, x, y );
         take_min4( c, !( ( skip >> sub ) & 1 ), 0, bcost, best );
     }
     __device__ __forceinline__ void hex6( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
     { fpel_best( 6, [&]( int k, int &x, int &y ) { x = ox + hex2x( k+1 ); y = oy + hex2y( k+1 ); }, tab, m, bcost, best ); }
     __device__ __forceinline__ void square8( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
     { fpel_best( 8, [&]( int k, int &x, int &y ) { x = ox + c_sq1[k+1][0]; y = oy + c_sq1[k+1][1]; }, tab, m, bcost, best ); }
-    __device__ __forceinline__ int fpel1( int mx, int my ) const { return red8( (int)sad8( fenc, load8u( ref_w + (int64_t)my * P->stride + mx ) ), g ); }
+    __device__ __forceinline__ int fpel1( int mx, int my ) const { return rsum8( (int)sad8( fenc, load8u( ref_w + (int64_t)my * P->stride + mx ) ) ); }
     __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const
-    { return red8( (int)sad8( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ), g ); }
+    { return rsum8( (int)sad8( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ) ); }
     __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const
-    { return satd_rows( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ), g ); }
+    { return satd8( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ); }
 };
 
 // ---- 1 thread per block ---------------------------------------------------------------------------

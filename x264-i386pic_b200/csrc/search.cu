@@ -367,7 +367,12 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJ
 // lower-numbered warp, which the hardware dispatched earlier: no deadlock; a bounded spin turns a violated assumption
 // into an error flag instead of a hang.
 #define X264CU_MV_NOT_READY 0x7F7F7F7F
-#define SERIAL_WARPS 4
+#ifndef X264CU_SERIAL_PREFETCH
+#define X264CU_SERIAL_PREFETCH 2
+#endif
+#ifndef SERIAL_WARPS
+#define SERIAL_WARPS 2
+#endif
 __global__ void __launch_bounds__(SERIAL_WARPS*32) search_kernel_serial( const SearchJob *__restrict__ jobs, LaParams P, int first_job, int njobs,
                                                                           int *__restrict__ err )
 {
@@ -396,11 +401,21 @@ __global__ void __launch_bounds__(SERIAL_WARPS*32) search_kernel_serial( const S
                 const int cx = ( bx - 1 ) * 8 + ( (int)(int16_t)( right_mv & 0xffff ) >> 2 ) - 12, cy = by * 8 + ( ( right_mv >> 16 ) >> 2 ) - 12 + lane;
                 const int y = min( max( cy, -X264CU_PAD ), P.lh + X264CU_PAD - 1 ), x = min( max( cx, -X264CU_PAD ), P.lw + X264CU_PAD - 33 );
                 const uint8_t *p = J.ref + (int64_t)y * P.stride + x;
+                (void)p;
 #pragma unroll
                 for( int k = 0; k < 4; k++ )
                 {
+#if X264CU_SERIAL_PREFETCH == 2
+                    // plain loads whose results are never read: the warp does not wait for them (prefetch.global.L1 measured
+                    // 16 % slower than no prefetch at all, these 3 % faster; profiles/r01/tuning.md)
+                    u32 d0, d1;
+                    asm volatile( "ld.global.nc.u8 %0, [%1];" : "=r"( d0 ) : "l"( p + k * P.plane_size ) );
+                    asm volatile( "ld.global.nc.u8 %0, [%1];" : "=r"( d1 ) : "l"( p + k * P.plane_size + 31 ) );
+                    (void)d0; (void)d1;
+#elif X264CU_SERIAL_PREFETCH == 1
                     asm volatile( "prefetch.global.L1 [%0];" :: "l"( p + k * P.plane_size ) );
                     asm volatile( "prefetch.global.L1 [%0];" :: "l"( p + k * P.plane_size + 31 ) );
+#endif
                 }
             }
         }
