@@ -123,9 +123,13 @@ int x264cu_frame_upload_aq( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *lum
 /* the same with DEVICE pointers (no PCIe copy); results stay on the device */
 int x264cu_frame_upload_aq_device( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint8_t *d_chroma_nv12,
                                    int cstride, const x264cu_aq_cfg *aq, const float *d_quant_offsets );
+/* For callers that keep x264_adaptive_quant_frame on the host (the unmodified encoder, encoder.c:3417): the frame's
+ * i_pixel_sum[0] / i_pixel_ssd[0] (after the mean removal, ratecontrol.c:406-414), which is all that
+ * x264cu_weights_analyse needs besides the planes.  Call it after x264cu_frame_upload. */
+int x264cu_frame_set_pixel_stats( x264cu_ctx *ctx, x264cu_frame *f, uint64_t pixel_sum, uint64_t pixel_ssd );
 /* x264_weights_analyse( h, fenc, fref, b_lookahead = 1 ) (slicetype.c:284-501): luma weight of `fenc` against `fref`
  * (dist = frame distance, 1..bframes+1) from the frames' pixel statistics, the intra costs and -- when the list-0 field
- * has already been searched -- the motion-compensated reference.  Both frames must come from x264cu_frame_upload_aq.
+ * has already been searched -- the motion-compensated reference.  Both frames need their pixel statistics (x264cu_frame_upload_aq, or x264cu_frame_set_pixel_stats).
  * The result stays in device memory for a following evaluation with weight.enabled == X264CU_WEIGHT_DEVICE and is
  * copied to `out` (host, may be NULL) when x264cu_flush returns.  numslices: weight_slice_header_cost (:170-189). */
 int x264cu_weights_analyse( x264cu_ctx *ctx, x264cu_frame *fenc, x264cu_frame *fref, int dist, int numslices, x264cu_weight *out );

@@ -138,3 +138,19 @@ def test_device_weight_requires_analysis():
     with pytest.raises(RuntimeError, match="weights_analyse"):
         gpu.frame_cost(0, 1, 1, weight="device")
     gpu.close()
+
+
+def test_weights_analyse_with_host_side_aq_statistics():
+    """the unmodified encoder keeps x264_adaptive_quant_frame on the host: plain upload + x264cu_frame_set_pixel_stats"""
+    W, H, n = 320, 192, 3
+    frames = _fade(synth_frames(W, H, n, seed=6, pan=(0, 0), noise=1), 0.09)
+    chroma = synth_chroma(W, H, n)
+    gpu, orc = _pair(W, H, bframes=3)
+    for i in range(n):
+        orc.put_frame_yuv(i, frames[i], chroma[i])
+        _, inv, sums = orc.get_aq(i)
+        gpu.put_frame(i, frames[i], inv)
+        gpu.ctx.set_pixel_stats(gpu.frames[i], sums[0], sums[1])
+    for b, r in [(1, 0), (2, 0), (2, 1)]:
+        assert gpu.weights_analyse(b, r) == orc.weights_analyse(b, r)
+    gpu.close(); orc.close()

@@ -634,6 +634,24 @@ extern "C" int x264cu_frame_upload_aq_device( x264cu_ctx *c, x264cu_frame *f, co
     return end_batch( c );
 }
 
+// for callers that ran x264_adaptive_quant_frame on the host (the unmodified encoder does, encoder.c:3417): hand the
+// luma statistics x264cu_weights_analyse needs to the device.  sum / ssd are i_pixel_sum[0] / i_pixel_ssd[0] AFTER the
+// mean removal (ratecontrol.c:406-414); the raw sum of squares is recovered exactly.
+extern "C" int x264cu_frame_set_pixel_stats( x264cu_ctx *c, x264cu_frame *f, uint64_t sum, uint64_t ssd )
+{
+    if( !c || !f ) FAIL( "x264cu_frame_set_pixel_stats: null argument" );
+    CU( cudaSetDevice( c->device ) );
+    if( begin_batch( c ) ) return -1;
+    const uint64_t wh = (uint64_t)( 16 * c->P.mbw ) * ( 16 * c->P.mbh );
+    uint64_t *p = (uint64_t *)pin_alloc_sync( c, 64 );
+    if( !p ) return -1;
+    memset( p, 0, 64 );
+    p[0] = sum; p[1] = ssd + ( sum * sum + wh / 2 ) / wh;
+    CU( cudaMemcpyAsync( f->pixstats, p, 64, cudaMemcpyHostToDevice, c->st ) );
+    f->have_aq = true;
+    return end_batch( c );
+}
+
 // x264_weights_analyse( h, fenc, fref, 1 ) (slicetype.c:284-501), SURVEY.md section 8f row 2
 extern "C" int x264cu_weights_analyse( x264cu_ctx *c, x264cu_frame *fenc, x264cu_frame *fref, int dist, int numslices, x264cu_weight *out )
 {
@@ -1014,7 +1032,12 @@ extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_fr
         fenc->searched[list][dist-1] = 1;
         std::vector<SearchTask> tasks( 1 );
         tasks[0] = { fenc, fref, list, dist, { 0, 0, 0, 0 } };
-        if( list == 0 && w && w->enabled ) tasks[0].w = *w;
+        if( list == 0 && w && w->enabled )
+        {
+            if( w->enabled == X264CU_WEIGHT_DEVICE && !fenc->wanalysed[dist-1] )
+                FAIL( "x264cu_motionsearch: X264CU_WEIGHT_DEVICE without a preceding x264cu_weights_analyse for distance %d", dist );
+            tasks[0].w = *w;
+        }
         if( run_searches( c, tasks ) ) return -1;
         CU( cudaGetLastError() );
     }

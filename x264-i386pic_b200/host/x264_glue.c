@@ -101,6 +101,13 @@ int x264_opencl_lowres_init( x264_t *h, x264_frame_t *fenc, int lambda )
     if( x264cu_frame_upload( CU_CTX( h ), CU_FRAME( fenc ), fenc->plane[0], fenc->i_stride[0],
                              h->param.rc.i_aq_mode ? fenc->i_inv_qscale_factor : NULL ) )
         return cu_fail( h, "x264cu_frame_upload" );
+#ifdef X264CU_GLUE_DEVICE_WEIGHTS
+    /* x264_adaptive_quant_frame ran on the host (encoder.c:3417): give its luma statistics to the device so that
+     * x264cu_weights_analyse can replace x264_weights_analyse without a host round trip */
+    if( h->param.analyse.i_weighted_pred &&
+        x264cu_frame_set_pixel_stats( CU_CTX( h ), CU_FRAME( fenc ), fenc->i_pixel_sum[0], fenc->i_pixel_ssd[0] ) )
+        return cu_fail( h, "x264cu_frame_set_pixel_stats" );
+#endif
     fenc->b_intra_calculated = 1;                        /* set eagerly, as slicetype-cl.c:84-86 does */
     return 0;
 }
@@ -174,13 +181,30 @@ void x264_opencl_slicetype_prep( x264_t *h, x264_frame_t **frames, int num_frame
                 if( p0 >= 0 && frames[b]->lowres_mvs[0][b-p0-1][0][0] == 0x7FFF )
                 {
                     const x264_weight_t *w = x264_weight_none;
+#ifdef X264CU_GLUE_DEVICE_WEIGHTS
+                    if( h->param.analyse.i_weighted_pred )
+                    {   /* analysis, weighted plane and search all on the device; the weight reaches frames[b]->weight[0]
+                         * with the flush at the end of this function (slicetype.c:284-501 without the host sync) */
+                        x264cu_weight dev = { X264CU_WEIGHT_DEVICE, 0, 0, 0 };
+                        frames[b]->lowres_mvs[0][b-p0-1][0][0] = 0;
+                        if( x264cu_weights_analyse( CU_CTX( h ), CU_FRAME( frames[b] ), CU_FRAME( frames[p0] ), b-p0,
+                                                    h->param.i_slice_count ? h->param.i_slice_count : 1, NULL ) ||
+                            x264cu_motionsearch( CU_CTX( h ), CU_FRAME( frames[b] ), CU_FRAME( frames[p0] ), 0, b-p0, &dev,
+                                                 (int16_t *)frames[b]->lowres_mvs[0][b-p0-1], frames[b]->lowres_mv_costs[0][b-p0-1] ) )
+                            cu_fail( h, "x264cu_weights_analyse" );
+                    }
+                    else
+#else
                     if( h->param.analyse.i_weighted_pred )
                     {
                         x264_weights_analyse( h, frames[b], frames[p0], 1 );
                         w = frames[b]->weight[0];
                     }
+#endif
+                    {
                     frames[b]->lowres_mvs[0][b-p0-1][0][0] = 0;
                     x264_opencl_motionsearch( h, frames, b, p0, 0, lambda, w );
+                    }
                 }
                 if( p1 <= num_frames && frames[b]->lowres_mvs[1][p1-b-1][0][0] == 0x7FFF )
                 {

@@ -74,6 +74,7 @@ def load():
     L.x264cu_frame_upload_device.argtypes = [vp, vp, vp, C.c_int, vp]
     L.x264cu_frame_upload_aq.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(AqCfg), vp, C.POINTER(AqOut)]
     L.x264cu_frame_upload_aq_device.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(AqCfg), vp]
+    L.x264cu_frame_set_pixel_stats.argtypes = [vp, vp, C.c_uint64, C.c_uint64]
     L.x264cu_weights_analyse.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(Weight)]
     L.x264cu_frame_cost.argtypes = [vp, C.POINTER(Job)]
     L.x264cu_frame_cost_batch.argtypes = [vp, C.POINTER(Job), C.c_int]
@@ -229,6 +230,9 @@ class Context:
         check(self.L.x264cu_frame_upload_aq(self.ctx, f, luma.ctypes.data, self.W, chroma.ctypes.data, self.W, C.byref(cfg),
                                             _ptr(qo), C.byref(out)), "x264cu_frame_upload_aq")
         return res
+
+    def set_pixel_stats(self, f, pixel_sum, pixel_ssd):
+        check(self.L.x264cu_frame_set_pixel_stats(self.ctx, f, int(pixel_sum), int(pixel_ssd)), "x264cu_frame_set_pixel_stats")
 
     def weights_analyse(self, fenc, fref, dist, numslices=1):
         """x264cu_weights_analyse; returns a Weight that is filled at flush (and stays on the device for
