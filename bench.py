@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(p)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.1)
 
     def summary(self):
         self.stop_flag = True
@@ -88,6 +88,30 @@ class ClockSampler(threading.Thread):
         reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
                 "reasons": reasons, "samples": len(self.samples)}
+
+
+def bind_to_gpu_numa_node(index):
+    """pin this rank's threads (and therefore its page-locked staging memory, first-touch) to the NUMA node of its
+    GPU: the end-to-end path moves 5.7 MB per step over PCIe, and on a two-socket host transfers of GPUs on the far
+    socket would otherwise all cross the inter-socket link.  Best effort; returns a description for the JSON line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus            # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:      # no sysfs / no permission: run unbound
+        return "unbound (%s)" % type(e).__name__
 
 
 def dist_setup(n_gpus):
@@ -109,13 +133,13 @@ def barrier_sync(dist, local):
         torch.cuda.synchronize(local)
 
 
-def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=None, dev=None, profile=False, dist=None, local=0):
+def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=None, dev=None, profile=False, dist=None, local=0, arrays=True):
     """ramp (untimed) -> warmup -> timed steps; returns (ms, evals per step, launches, kernel times, bytes).
     ctxs: one context for all streams (they then share its in-order CUDA stream), or one context per encode stream
     (--contexts: kernels of different streams overlap on the device; this is how concurrent encoders would run)."""
     L = ctxs[0].L
     cx = [ctxs[s % len(ctxs)] for s in range(streams_n)]
-    wins = [L.x264cu_stream_open(cx[s].ctx, BFRAMES, 1 if e2e else 0) for s in range(streams_n)]
+    wins = [L.x264cu_stream_open(cx[s].ctx, BFRAMES, 1 if e2e and arrays else 0) for s in range(streams_n)]
     assert all(wins), x264cu.last_error()
     pos = [0] * streams_n
 
@@ -171,7 +195,7 @@ def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=No
         for k, v in c.kernel_times().items():
             kt[k] = (kt.get(k, (0.0, 0))[0] + v[0], kt.get(k, (0.0, 0))[1] + v[1])
     launches = sum(c.launches() for c in ctxs) - l0
-    res_bytes = int(L.x264cu_stream_result_bytes(wins[0])) if e2e else 0
+    res_bytes = int(L.x264cu_stream_result_bytes(wins[0])) if e2e and arrays else 0
     # a result the caller would read: the P cost of the newest frame against its predecessor
     st = (x264cu.C.c_int32 * 4)()
     L.x264cu_stream_cost(wins[(warmup + steps - 1) % streams_n], 1, 0, st)
@@ -295,6 +319,8 @@ def main():
     ap.add_argument("--value-only", action="store_true", help="profiling aid: skip the end-to-end pass")
     ap.add_argument("--contexts", type=int, default=0, help="contexts per GPU; 0 (default): one context (own CUDA streams) per encode stream, "
                     "as concurrent encoders would run; 1: all streams share one in-order context")
+    ap.add_argument("--e2e-scalars-only", action="store_true", help="diagnostic: the end-to-end pass uploads host luma but reads back only "
+                    "the cost scalars (isolates the D2H share of the PCIe traffic)")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k", "64streams"],
                     help="1080p: BASELINE.json configs[2] (the headline); 4k: configs[3] (3840x2160, 62 live frames per window); "
                          "64streams: configs[4] (8 independent 1080p encode streams per GPU)")
@@ -335,6 +361,8 @@ def main():
         return 0
 
     import x264cu
+    local_early = int(os.environ.get("LOCAL_RANK", 0))
+    config["cpu_binding"] = bind_to_gpu_numa_node(local_early) if int(os.environ.get("WORLD_SIZE", 1)) > 1 else "unbound (single rank)"
     rank, world, local, dist = dist_setup(args.gpus)
     S = args.streams
     per_stream = RAMP + (warmup + args.steps + S - 1) // S + 1
@@ -363,8 +391,9 @@ def main():
         pinned.append([hp + i * fbytes for i in range(per_stream)])
         dev.append([dp + i * fbytes for i in range(per_stream)])
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local)          # rank 0 reports; the other ranks do not spawn nvidia-smi during the timed region
+    if rank == 0:
+        sampler.start()
     # device-resident pass ("value"): inputs already in HBM, only the cost scalars come back
     # (kernel timing pass first: ONE context, so that the per-kernel CUDA events do not span kernels of other streams)
     psteps = min(args.steps, 16)
@@ -374,8 +403,9 @@ def main():
     if args.value_only:
         ms_e, wall_e, res_bytes, chk_e = ms_v, wall_v, 0, chk_v
     else:
-        ms_e, wall_e, _, _, _, res_bytes, chk_e = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, True, pinned=pinned, dist=dist, local=local)
-    clocks = sampler.summary()
+        ms_e, wall_e, _, _, _, res_bytes, chk_e = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, True, pinned=pinned, dist=dist, local=local,
+                                                                 arrays=not args.e2e_scalars_only)
+    clocks = sampler.summary() if rank == 0 else {}
     assert chk_v > 0 and chk_e > 0
 
     t_v, t_e = ms_v, ms_e
