@@ -35,30 +35,33 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
             bmy = omy + ( best == 0 ? -2 : best == 1 ? 2 : 0 );
         }
     }
-    if( be.satd() )   // mbcmp != fpelcmp: re-measure the winner with SATD (me.c:925-929)
-        bcost = be.qsatd( m, bmx, bmy ) + mvcost( tab, m, bmx, bmy );
-    int bdir = -1;
-    for( int i = qpel_iters; i > 0; i-- )
-    {   // me.c:947-963
-        if( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx ) break;
-        const int odir = bdir, omx = bmx, omy = bmy;
-        if constexpr( BE::PAR4 )
-        {   // the four quarter-pel neighbours in one round
+    if constexpr( BE::PAR4 )
+    {
+        if( be.satd() )   // mbcmp != fpelcmp: re-measure the winner with SATD (me.c:925-929)
+            bcost = be.qsatd( m, bmx, bmy ) + mvcost( tab, m, bmx, bmy );
+        if( qpel_iters && !( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx ) )
+        {   // the four quarter-pel neighbours in one round (me.c:947-963, one iteration at la subme 4)
+            const int omx = bmx, omy = bmy;
             int best = -1;
             be.qsatd_best4( [&]( int k, int &x, int &y ) { x = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ); y = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 ); },
-                            odir >= 0 ? 1 << ( odir ^ 1 ) : 0, tab, m, bcost, best );
-            if( best >= 0 ) { bmx = omx + ( best == 2 ? -1 : best == 3 ? 1 : 0 ); bmy = omy + ( best == 0 ? -1 : best == 1 ? 1 : 0 ); bdir = best; }
+                            0, tab, m, bcost, best );
+            if( best >= 0 ) { bmx = omx + ( best == 2 ? -1 : best == 3 ? 1 : 0 ); bmy = omy + ( best == 0 ? -1 : best == 1 ? 1 : 0 ); }
         }
-        else
+    }
+    else
+    {   // the SATD re-measurement of the winner (me.c:925-929, k = -1) and the quarter-pel diamond (me.c:947-963, k = 0..3;
+        // the lookahead runs one iteration, so no direction is excluded) share ONE call site: the SATD body is ~600
+        // instructions and the kernel is instruction-cache sensitive (ncu: 16 % no-instruction stalls)
+        const int omx = bmx, omy = bmy;
+        const bool diamond = qpel_iters && !( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx );
 #pragma unroll 1
-        for( int k = 0; k < 4; k++ )
-            if( ( k ^ 1 ) != odir )
-            {
-                int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
-                int cost = be.qsatd( m, mx, my ) + mvcost( tab, m, mx, my );
-                if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; bdir = k; }
-            }
-        if( bmx == omx && bmy == omy ) break;
+        for( int k = be.satd() ? -1 : 0; k < ( diamond ? 4 : 0 ); k++ )
+        {
+            const int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
+            const int cost = be.qsatd( m, mx, my ) + mvcost( tab, m, mx, my );
+            if( k < 0 ) bcost = cost;
+            else if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
+        }
     }
 }
 
@@ -93,15 +96,19 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
         }
         else
         {
-        bpred_cost = be.qsad1( m, bpred_mx, bpred_my ) + mvcost( tab, m, bpred_mx, bpred_my );
-        pmv_cost = bpred_cost;
+        // the predictor itself (i = -1, me.c:219-222) and its candidates (me.c:230-246) through one call site
+        pmv_cost = 0;
 #pragma unroll 1
-        for( int i = 0; i < i_mvc; i++ )
+        for( int i = -1; i < i_mvc; i++ )
         {   // x264_predictor_clip (common.h:790-805): drop zero and == pmv, clip the rest
-            int mx = mvc[i][0], my = mvc[i][1];
-            if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
-            mx = iclip3( mx, 4*m.fminx, 4*m.fmaxx ); my = iclip3( my, 4*m.fminy, 4*m.fmaxy );
-            int cost = be.qsad1( m, mx, my ) + mvcost( tab, m, mx, my );
+            int mx = i < 0 ? pmvx : mvc[i][0], my = i < 0 ? pmvy : mvc[i][1];
+            if( i >= 0 )
+            {
+                if( ( !mx && !my ) || ( mx == pmvx && my == pmvy ) ) continue;
+                mx = iclip3( mx, 4*m.fminx, 4*m.fmaxx ); my = iclip3( my, 4*m.fminy, 4*m.fmaxy );
+            }
+            const int cost = be.qsad1( m, mx, my ) + mvcost( tab, m, mx, my );
+            if( i < 0 ) pmv_cost = cost;
             if( cost < bpred_cost ) { bpred_cost = cost; bpred_mx = mx; bpred_my = my; }
         }
         }
