@@ -111,6 +111,35 @@ def test_both_lane_mappings(monkeypatch, lanes, W, H, subme, mbtree, aq):
         gpu.close()
 
 
+@pytest.mark.parametrize("W,H,subme,passes", [(352, 288, 7, 2), (360, 270, 1, 2), (1920, 1080, 7, 2), (352, 288, 7, 0)])
+def test_runtime_pitch_kernels(monkeypatch, W, H, subme, passes):
+    """frames wider than 4K run the instantiations with a run-time plane pitch (the compile-time-pitch ones cover
+    pitch 1024 / 2048); X264CU_RUNTIME_PITCH forces that path at small sizes.  Weighted search included."""
+    monkeypatch.setenv("X264CU_RUNTIME_PITCH", "1")
+    monkeypatch.setenv("X264CU_LANES", "1")
+    x264cu = _cu()
+    frames = synth_frames(W, H, 4, seed=23, pan=(2, 1))
+    mvr = x264cu.default_mv_range(W, H)
+    cpu = Lookahead(OracleLib(), "oracle", W, H, bframes=3, subme=subme, mv_range=mvr, passes=passes)
+    gpu = x264cu.CudaLookahead(W, H, bframes=3, subme=subme, mv_range=mvr, passes=passes)
+    try:
+        assert gpu.ctx.stride not in (1024, 2048)
+        for i, f in enumerate(frames):
+            cpu.put_frame(i, f)
+            gpu.put_frame(i, f)
+        w = (1, 60, 6, -3)
+        assert gpu.frame_cost(0, 1, 1, weight=w[1:]) == cpu.frame_cost(0, 1, 1, weight=w)
+        compare_eval(gpu, cpu, 0, 1, 1, "runtime pitch weighted (0,1,1)")
+        triples = [(0, 3, 3), (0, 3, 1), (0, 3, 2), (1, 3, 2)]
+        sg = gpu.frame_cost_many(triples)
+        for (p0, p1, b), sgpu in zip(triples, sg):
+            assert cpu.frame_cost(p0, p1, b) == sgpu
+            compare_eval(gpu, cpu, p0, p1, b, f"runtime pitch ({p0},{p1},{b})")
+    finally:
+        cpu.close()
+        gpu.close()
+
+
 def test_batch_equals_sequential():
     """x264cu_frame_cost_batch == the same evaluations issued one by one (array order semantics)."""
     x264cu = _cu()
