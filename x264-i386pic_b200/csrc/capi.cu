@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 
 static thread_local char g_err[512] = "";
 #define FAIL( ... ) do { snprintf( g_err, sizeof(g_err), __VA_ARGS__ ); return -1; } while( 0 )
@@ -59,6 +60,7 @@ struct x264cu_ctx
     uint16_t *d_cost_mv;
     float *d_log2_lut;
     uint8_t *d_exp2_lut;
+    uint32_t *d_tiles;
     bool exact_waves; int serial_ctas_per_sm; int serial_error;      // exact raster-serial mode (search_passes == 0)
     uint8_t *d_chroma[2]; int chroma_pitch;      // NV12 chroma staging, paired with d_luma[]
     int stat_pitch;
@@ -101,6 +103,32 @@ static int ctx_sync( x264cu_ctx *c );
 
 static inline size_t align_up( size_t v, size_t a ) { return ( v + a - 1 ) / a * a; }
 
+// Warp tiles of the thread-per-block kernels.  The frame is cut into strips of `strip_h` block rows; inside a strip,
+// columns are covered left to right by chunks of `tile_w` columns, each chunk by warp tiles of tile_w x (32/tile_w)
+// blocks stacked vertically (consecutive table entries = one CTA tile of tile_w x strip_h blocks, as before).  The
+// columns left over at the right edge are decomposed into narrower power-of-two widths whose tiles are taller, so that
+// every warp still owns 32 real blocks: at 1080p (120 columns) the 32-wide search tiles leave 24 = 16 + 8 columns, which
+// become 16x2 and 8x4 tiles instead of a quarter-empty 32x1 tile per row (6 % of all lanes).
+static std::vector<uint32_t> build_warp_tiles( int mbw, int mbh, int tile_w, int strip_h )
+{
+    std::vector<uint32_t> t;
+    auto lg = []( int v ) { int l = 0; while( ( 1 << l ) < v ) l++; return l; };
+    for( int y0 = 0; y0 < mbh; y0 += strip_h )
+    {
+        const int rows = std::min( strip_h, mbh - y0 );
+        int x = 0;
+        while( x < mbw )
+        {
+            int w = tile_w;
+            while( w > 1 && x + w > mbw && 32 / ( w / 2 ) <= strip_h ) w /= 2;      // shrink at the right edge while the taller tile still fits the strip
+            const int h = 32 / w;
+            for( int y = 0; y < rows; y += h ) t.push_back( (uint32_t)x | ( (uint32_t)( y0 + y ) << 12 ) | ( (uint32_t)lg( w ) << 24 ) );
+            x += w;
+        }
+    }
+    return t;
+}
+
 extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
 {
     if( !cfg || cfg->width < 16 || cfg->height < 16 || cfg->bframes < 0 || cfg->bframes > X264CU_BFRAME_MAX || cfg->mv_range < 32 )
@@ -141,6 +169,15 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
     {   // tuning/test knob: force one of the two lane mappings (default: chosen per launch)
         const char *e = getenv( "X264CU_LANES" );
         P.lanes_per_block = e ? atoi( e ) : 0;
+    }
+    {
+        const std::vector<uint32_t> ts = build_warp_tiles( P.mbw, P.mbh, 32, 4 ), tf = build_warp_tiles( P.mbw, P.mbh, 16, 8 );
+        uint32_t *d = NULL;
+        CUP( cudaMalloc( &d, ( ts.size() + tf.size() ) * 4 ) );
+        CUP( cudaMemcpy( d, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice ) );
+        CUP( cudaMemcpy( d + ts.size(), tf.data(), tf.size() * 4, cudaMemcpyHostToDevice ) );
+        c->d_tiles = d;
+        P.tiles_s = d; P.ntiles_s = (int)ts.size(); P.tiles_f = d + ts.size(); P.ntiles_f = (int)tf.size();
     }
     c->plane_alloc = 4 * (size_t)P.plane_size + 256;
     c->stat_pitch = (int)align_up( P.mbh + 4, 4 );
@@ -245,7 +282,7 @@ extern "C" void x264cu_close( x264cu_ctx *c )
     while( !c->frames.empty() ) x264cu_frame_free( c, c->frames.back() );
     for( cudaEvent_t e : c->ev_pool ) cudaEventDestroy( e );
     for( int i = 0; i < 2; i++ ) { cudaFree( c->d_luma[i] ); cudaEventDestroy( c->luma_free[i] ); }
-    cudaFree( c->d_exp2_lut ); cudaFree( c->d_chroma[0] ); cudaFree( c->d_chroma[1] );
+    cudaFree( c->d_exp2_lut ); cudaFree( c->d_tiles ); cudaFree( c->d_chroma[0] ); cudaFree( c->d_chroma[1] );
     cudaFree( c->d_cost_mv ); cudaFree( c->d_log2_lut ); cudaFree( c->d_jobs ); cudaFree( c->arena );
     cudaFreeHost( c->pin ); cudaFreeHost( c->h_jobs );
     cudaEventDestroy( c->tm_a ); cudaEventDestroy( c->tm_b );

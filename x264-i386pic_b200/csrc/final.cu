@@ -109,13 +109,13 @@ __global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *_
 template<bool SATD, int PITCH>
 __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_kernel_t( const FinalJob *__restrict__ jobs, int njobs, LaParams P )
 {
-    const int bx = blockIdx.x * F_TILE_W + threadIdx.x % F_TILE_W, by = blockIdx.y * F_TILE_H + threadIdx.x / F_TILE_W;
-    if( bx >= P.mbw || by >= P.mbh ) return;
+    int bx, by;
+    if( !warp_tile_block( P.tiles_f, P.ntiles_f, P, bx, by ) ) return;
     const int blk = by * P.mbw + bx;
     ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> be; be.P = &P;
     const int pel = ( by*8 ) * be.pitch() + bx*8;
 #pragma unroll 1
-    for( int z = blockIdx.z * F_JOBS; z < min( njobs, ( blockIdx.z + 1 ) * F_JOBS ); z++ )
+    for( int z = blockIdx.y * F_JOBS; z < min( njobs, ( blockIdx.y + 1 ) * F_JOBS ); z++ )
     {
         const FinalJob J = jobs[z];
         if( skipped_border( P, bx, by ) ) { if( !J.b_intra_only ) J.lowres_costs[blk] = 0; continue; }
@@ -134,7 +134,8 @@ void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStr
 {
     if( use_thread_mapping( P, njobs ) )
     {
-        dim3 grid( ( P.mbw + F_TILE_W - 1 ) / F_TILE_W, ( P.mbh + F_TILE_H - 1 ) / F_TILE_H, ( njobs + F_JOBS - 1 ) / F_JOBS );
+        const int warps_per_cta = F_TILE_W * F_TILE_H / 32;
+        dim3 grid( ( P.ntiles_f + warps_per_cta - 1 ) / warps_per_cta, ( njobs + F_JOBS - 1 ) / F_JOBS );
 #define FINAL_T( PITCH ) { if( P.b_satd ) final_kernel_t<true, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, njobs, P ); \
                            else           final_kernel_t<false, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, njobs, P ); }
         if( P.stride == 1024 )      FINAL_T( 1024 )

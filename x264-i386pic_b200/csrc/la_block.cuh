@@ -702,6 +702,18 @@ __device__ __forceinline__ bool skipped_border( const LaParams &P, int bx, int b
     return border && !P.do_edges && P.mbw > 2 && P.mbh > 2;
 }
 
+// block owned by this lane under the warp-tile table; false: idle lane
+__device__ __forceinline__ bool warp_tile_block( const uint32_t *__restrict__ tiles, int ntiles, const LaParams &P, int &bx, int &by )
+{
+    const int wt = blockIdx.x * ( blockDim.x >> 5 ) + ( threadIdx.x >> 5 ), lane = threadIdx.x & 31;
+    if( wt >= ntiles ) return false;
+    const uint32_t d = __ldg( tiles + wt );
+    const int lw = d >> 24;
+    bx = (int)( d & 0xfff ) + ( lane & ( ( 1 << lw ) - 1 ) );
+    by = (int)( ( d >> 12 ) & 0xfff ) + ( lane >> lw );
+    return bx < P.mbw && by < P.mbh;
+}
+
 static inline bool use_thread_mapping( const LaParams &P, int njobs )
 {
     if( P.lanes_per_block == 1 ) return true;

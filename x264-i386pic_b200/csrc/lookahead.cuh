@@ -19,6 +19,11 @@ struct LaParams
     int lanes_per_block;        // tuning: 0 auto, 1 thread-per-block kernels, 8 eight-lanes-per-block kernels
     int cost_mv_n;              // table covers |d| <= cost_mv_n
     const uint16_t *cost_mv;    // device table indexed by |mvd| in qpel
+    // warp tiles of the thread-per-block kernels (capi.cu build_warp_tiles): entry = x0 | y0 << 12 | log2(width) << 24;
+    // a warp covers width x (32/width) blocks.  Frame widths that are not a multiple of the tile width are packed with
+    // narrower, taller tiles instead of leaving lanes idle (1080p: 120 block columns = 3 x 32 + 16 + 8)
+    const uint32_t *tiles_s; int ntiles_s;      // search kernels: CTA = 4 consecutive tiles
+    const uint32_t *tiles_f; int ntiles_f;      // decision kernels
 };
 
 // One motion-search pass over one (fenc, ref, list) field: x264_me_search for every block.

@@ -328,10 +328,10 @@ template<bool SATD, bool WEIGHTED, int PITCH>
 __global__ void __launch_bounds__(S_TILE_W*S_TILE_H, X264CU_MINB_SEARCH) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
 {
     const CostTab tab = stage_cost_tab( P );
-    SearchJob J = jobs[blockIdx.z];
+    SearchJob J = jobs[blockIdx.y];
     resolve_device_weight( J );
-    const int bx = blockIdx.x * S_TILE_W + threadIdx.x % S_TILE_W, by = blockIdx.y * S_TILE_H + threadIdx.x / S_TILE_W;
-    if( bx >= P.mbw || by >= P.mbh ) return;
+    int bx, by;
+    if( !warp_tile_block( P.tiles_s, P.ntiles_s, P, bx, by ) ) return;
     const int blk = by * P.mbw + bx;
     if( skipped_border( P, bx, by ) ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; return; }
     ThreadBE<SATD, WEIGHTED, PITCH, X264CU_SEARCH_LD64 != 0, X264CU_SEARCH_PTXPRED != 0> be; be.P = &P;
@@ -467,7 +467,7 @@ void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P,
 template<int PITCH>
 static void launch_search_t( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
 {
-    dim3 grid( ( P.mbw + S_TILE_W - 1 ) / S_TILE_W, ( P.mbh + S_TILE_H - 1 ) / S_TILE_H, njobs );
+    dim3 grid( ( P.ntiles_s + S_TILE_H - 1 ) / S_TILE_H, njobs );       // S_TILE_H warp tiles per CTA
     if( P.b_satd )
     {
         if( any_weighted ) search_kernel_t<true, true, PITCH><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
