@@ -4,7 +4,10 @@
  * hook site in slicetype.c / encoder.c / frame.c stays as it is.
  *
  * This file is compiled INSIDE an x264 tree (it includes x264's private headers); it is not part of
- * libx264cuda.so.  oracle/Makefile's `glue-check` target type-checks it against /root/reference.
+ * libx264cuda.so.  oracle/Makefile's `glue-check` target type-checks it against /root/reference, and its `cli`
+ * target links it with the reference's unmodified encoder + CLI sources into oracle/_ref/x264cu_cli, which
+ * tests/test_gpu_x264_cli.py runs on a B200: `x264 --opencl` then encodes through this backend, and in the exact
+ * search mode the slices it writes are byte-identical to the CPU-only run.
  *
  * State: the reference embeds x264_opencl_t in x264_t by value and copies x264_t into the lookahead
  * thread (encoder/lookahead.c:153-154), so everything mutable lives behind ONE heap pointer that we
@@ -21,7 +24,26 @@ void x264_weights_analyse( x264_t *h, x264_frame_t *fenc, x264_frame_t *ref, int
 
 #if HAVE_OPENCL   /* the reference's own gate (configure:1425-1428): 8-bit builds only */
 
-#define CU_CTX(h)   ((x264cu_ctx *)(h)->opencl.context)
+/* The scalar results of an evaluation (i_cost_est & co.) are ints scattered over x264_frame_t; the device delivers
+ * them into a staging slot when the queue is flushed, and the flush copies them to their fields -- the same
+ * deferred-copy protocol as the reference's (slicetype-cl.c:58-70). */
+typedef struct
+{
+    x264_frame_t *f;
+    int d0, d1;                 /* b-p0, p1-b; 0,0: the intra results of x264_opencl_lowres_init */
+    int32_t st[8];              /* x264cu_out.stats (4) + intra_stats (2) */
+} cu_pending;
+
+#define CU_MAX_PENDING 1024     /* the reference's own bound on queued copies (opencl.h:715) */
+typedef struct
+{
+    x264cu_ctx *c;
+    int n_pend;
+    cu_pending pend[CU_MAX_PENDING];
+} cu_state;
+
+#define CU_STATE(h) ((cu_state *)(h)->opencl.context)
+#define CU_CTX(h)   (CU_STATE(h)->c)
 #define CU_FRAME(f) ((x264cu_frame *)(f)->opencl.luma_hpel)
 
 static int cu_fail( x264_t *h, const char *what )
@@ -30,6 +52,17 @@ static int cu_fail( x264_t *h, const char *what )
     h->param.b_opencl = 0;
     h->opencl.b_fatal_error = 1;
     return -1;
+}
+
+static cu_pending *cu_pend( x264_t *h, x264_frame_t *f, int d0, int d1 )
+{
+    cu_state *s = CU_STATE( h );
+    if( s->n_pend == CU_MAX_PENDING )
+        x264_opencl_flush( h );                          /* slots are handed to the device by address */
+    cu_pending *p = &s->pend[s->n_pend++];
+    memset( p, 0, sizeof(*p) );
+    p->f = f; p->d0 = d0; p->d1 = d1;
+    return p;
 }
 
 /* opencl.h:796-799.  There is no library to dlopen; hand back a non-NULL token. */
@@ -56,16 +89,23 @@ int x264_opencl_lookahead_init( x264_t *h )
     cfg.aq = h->param.rc.i_aq_mode != 0;
     cfg.weighted_bipred = h->param.analyse.b_weighted_bipred;
     cfg.bframe_bias = h->param.i_bframe_bias;
-    cfg.search_passes = 2;
+    /* 2: the dependency-free schedule; 0: the reference's own raster-serial order, whose
+     * costs, MVs and therefore decisions and bitstream equal the CPU path's */
+    const char *e = getenv( "X264CU_SEARCH_PASSES" );
+    cfg.search_passes = e ? atoi( e ) : 2;
     cfg.max_frames = h->param.rc.i_lookahead + h->param.i_bframe + 3;
     cfg.cost_mv = h->cost_mv[X264_LOOKAHEAD_QP];          /* the encoder's own table (analyse.c:143-157) */
-    x264cu_ctx *c = x264cu_open( h->param.i_opencl_device, &cfg );
-    if( !c )
+    cu_state *s = calloc( 1, sizeof(*s) );
+    if( !s )
+        return -1;
+    s->c = x264cu_open( h->param.i_opencl_device, &cfg );
+    if( !s->c )
     {
         x264_log( h, X264_LOG_ERROR, "x264cu: %s\n", x264cu_last_error() );
+        free( s );
         return -1;
     }
-    h->opencl.context = (cl_context)c;
+    h->opencl.context = (cl_context)s;
     h->opencl.b_fatal_error = 0;
     return 0;
 }
@@ -73,7 +113,11 @@ int x264_opencl_lookahead_init( x264_t *h )
 /* opencl.h:803-804, called from encoder.c:4207-4209,4574-4576 */
 void x264_opencl_lookahead_delete( x264_t *h )
 {
-    x264cu_close( CU_CTX( h ) );
+    cu_state *s = CU_STATE( h );
+    if( !s )
+        return;
+    x264cu_close( s->c );
+    free( s );
     h->opencl.context = NULL;
 }
 
@@ -85,7 +129,9 @@ void x264_opencl_frame_delete( x264_frame_t *frame )
     frame->opencl.luma_hpel = NULL;
 }
 
-/* slicetype-cl.h:29-30: x264_frame_init_lowres on the device + intra costs, once per frame */
+/* slicetype-cl.h:29-30: x264_frame_init_lowres on the device + intra costs, once per frame; the intra results
+ * (i_intra_cost, i_row_satds[0][0], i_cost_est[0][0], i_cost_est_aq[0][0]) reach the frame with the next flush,
+ * as in the reference (slicetype-cl.c:254-280) */
 int x264_opencl_lowres_init( x264_t *h, x264_frame_t *fenc, int lambda )
 {
     (void)lambda;                                        /* lambda == 1 at X264_LOOKAHEAD_QP */
@@ -108,6 +154,15 @@ int x264_opencl_lowres_init( x264_t *h, x264_frame_t *fenc, int lambda )
         x264cu_frame_set_pixel_stats( CU_CTX( h ), CU_FRAME( fenc ), fenc->i_pixel_sum[0], fenc->i_pixel_ssd[0] ) )
         return cu_fail( h, "x264cu_frame_set_pixel_stats" );
 #endif
+    cu_pending *p = cu_pend( h, fenc, 0, 0 );
+    x264cu_job j;
+    memset( &j, 0, sizeof(j) );
+    j.fenc = j.fref0 = j.fref1 = CU_FRAME( fenc );
+    j.out.intra_costs = fenc->i_intra_cost;
+    j.out.intra_row_satds = fenc->i_row_satds[0][0];
+    j.out.intra_stats = p->st + 4;
+    if( x264cu_frame_cost( CU_CTX( h ), &j ) )
+        return cu_fail( h, "x264cu_frame_cost" );
     fenc->b_intra_calculated = 1;                        /* set eagerly, as slicetype-cl.c:84-86 does */
     return 0;
 }
@@ -131,24 +186,16 @@ int x264_opencl_finalize_cost( x264_t *h, int lambda, x264_frame_t **frames, int
 {
     (void)lambda; (void)dist_scale_factor;               /* recomputed from (b-p0, p1-b), slicetype.c:869-870 */
     x264_frame_t *fenc = frames[b];
+    cu_pending *p = cu_pend( h, fenc, b - p0, p1 - b );
     x264cu_job j;
     memset( &j, 0, sizeof(j) );
     j.fenc = CU_FRAME( fenc ); j.fref0 = CU_FRAME( frames[p0] ); j.fref1 = CU_FRAME( frames[p1] );
     j.d0 = b - p0; j.d1 = p1 - b;
     j.out.lowres_costs = fenc->lowres_costs[b-p0][p1-b];
     j.out.row_satds = fenc->i_row_satds[b-p0][p1-b];
-    j.out.intra_row_satds = fenc->i_row_satds[0][0];
-    /* i_cost_est / i_cost_est_aq / i_intra_mbs are ints scattered in the frame struct: stage them */
-    int32_t *st = (int32_t *)h->scratch_buffer2;         /* lookahead-thread private (macroblock.c:398-401) */
-    j.out.stats = st;
-    j.out.intra_stats = st + 4;
-    if( x264cu_frame_cost( CU_CTX( h ), &j ) || x264cu_flush( CU_CTX( h ) ) )
+    j.out.stats = p->st;
+    if( x264cu_frame_cost( CU_CTX( h ), &j ) )
         return cu_fail( h, "x264cu_frame_cost" );
-    fenc->i_cost_est[b-p0][p1-b] = st[0];
-    fenc->i_cost_est_aq[b-p0][p1-b] = st[1];
-    if( b == p1 ) fenc->i_intra_mbs[b-p0] = st[2];
-    fenc->i_cost_est[0][0] = st[4];
-    fenc->i_cost_est_aq[0][0] = st[5];
     return 0;
 }
 
@@ -159,11 +206,32 @@ int x264_opencl_precalculate_frame_cost( x264_t *h, x264_frame_t **frames, int l
     return 0;
 }
 
-/* slicetype-cl.h:37-38 */
+/* slicetype-cl.h:37-38: wait for the device, then finish the scalar results (slicetype-cl.c:58-70) */
 void x264_opencl_flush( x264_t *h )
 {
-    if( x264cu_flush( CU_CTX( h ) ) )
+    cu_state *s = CU_STATE( h );
+    if( x264cu_flush( s->c ) )
+    {
         cu_fail( h, "x264cu_flush" );
+        s->n_pend = 0;
+        return;
+    }
+    for( int i = 0; i < s->n_pend; i++ )
+    {
+        cu_pending *p = &s->pend[i];
+        if( !( p->d0 | p->d1 ) )
+        {   /* slicetype.c:949-953: the intra sums are the I cost */
+            p->f->i_cost_est[0][0] = p->st[4];
+            p->f->i_cost_est_aq[0][0] = p->st[5];
+        }
+        else
+        {   /* slicetype.c:965-989 */
+            p->f->i_cost_est[p->d0][p->d1] = p->st[0];
+            p->f->i_cost_est_aq[p->d0][p->d1] = p->st[1];
+            if( !p->d1 ) p->f->i_intra_mbs[p->d0] = p->st[2];
+        }
+    }
+    s->n_pend = 0;
 }
 
 /* slicetype-cl.h:39-40: intra for all frames, then (trellis) every (b, b+-j) search, one flush each */
