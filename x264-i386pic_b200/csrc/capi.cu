@@ -171,7 +171,7 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
         P.lanes_per_block = e ? atoi( e ) : 0;
     }
     {
-        const std::vector<uint32_t> ts = build_warp_tiles( P.mbw, P.mbh, 32, 4 ), tf = build_warp_tiles( P.mbw, P.mbh, 16, 8 );
+        const std::vector<uint32_t> ts = build_warp_tiles( P.mbw, P.mbh, X264CU_S_TILE_W, X264CU_S_TILE_H ), tf = build_warp_tiles( P.mbw, P.mbh, X264CU_F_TILE_W, X264CU_F_TILE_H );
         uint32_t *d = NULL;
         CUP( cudaMalloc( &d, ( ts.size() + tf.size() ) * 4 ) );
         CUP( cudaMemcpy( d, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice ) );

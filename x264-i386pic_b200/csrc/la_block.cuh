@@ -9,16 +9,12 @@
 // ---- tuning knobs, all measured on B200 (profiles/r01/tuning.md).  The thread-per-block kernels are sensitive to
 // ptxas's choices under register pressure (if-conversion of the second-plane fetch, rematerialised row addresses), so
 // the knobs are per kernel family and each family is its own translation unit.
-// CTA tiles in blocks: one block row per warp for the search kernels; 16x8 for the decision kernels (squarer tile =
-// less halo in the L2->L1 fill traffic that bounds them)
-#ifndef S_TILE_W
-#define S_TILE_W 32
-#define S_TILE_H 4
-#endif
-#ifndef F_TILE_W
-#define F_TILE_W 16
-#define F_TILE_H 8
-#endif
+// CTA tiles in blocks (lookahead.cuh: X264CU_S_TILE_* / X264CU_F_TILE_*): one block row per warp for the search kernels,
+// 16x8 for the decision kernels (squarer tile = less halo in the L2->L1 fill traffic that bounds them)
+#define S_TILE_W X264CU_S_TILE_W
+#define S_TILE_H X264CU_S_TILE_H
+#define F_TILE_W X264CU_F_TILE_W
+#define F_TILE_H X264CU_F_TILE_H
 // row loads as two aligned 64-bit words (1) or three 32-bit words (0)
 #ifndef X264CU_SEARCH_LD64
 #define X264CU_SEARCH_LD64 1

@@ -2,6 +2,17 @@
 #pragma once
 #include "common.cuh"
 
+// CTA tiles of the thread-per-block kernels in blocks; shared by the kernels (la_block.cuh) and the host-side warp-tile
+// table (capi.cu build_warp_tiles).  A CTA is TILE_W * TILE_H threads; a warp covers TILE_W x (32 / TILE_W) blocks.
+#ifndef X264CU_S_TILE_W
+#define X264CU_S_TILE_W 32
+#define X264CU_S_TILE_H 4
+#endif
+#ifndef X264CU_F_TILE_W
+#define X264CU_F_TILE_W 16
+#define X264CU_F_TILE_H 8
+#endif
+
 // Geometry and policy of one context; passed by value to every kernel.
 struct LaParams
 {

@@ -467,7 +467,8 @@ void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P,
 template<int PITCH>
 static void launch_search_t( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
 {
-    dim3 grid( ( P.ntiles_s + S_TILE_H - 1 ) / S_TILE_H, njobs );       // S_TILE_H warp tiles per CTA
+    const int warps_per_cta = S_TILE_W * S_TILE_H / 32;
+    dim3 grid( ( P.ntiles_s + warps_per_cta - 1 ) / warps_per_cta, njobs );
     if( P.b_satd )
     {
         if( any_weighted ) search_kernel_t<true, true, PITCH><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
