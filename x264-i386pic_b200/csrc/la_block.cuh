@@ -30,6 +30,10 @@
 #define X264CU_FINAL_PTXPRED 0
 #endif
 // __launch_bounds__ minimum CTAs per SM: 3 leaves ptxas at ~115 registers (4 resident CTAs of 128 threads)
+// dedicated half-pel diamond for even centres in the thread-per-block search (1) or the generic qpel fetch only (0)
+#ifndef X264CU_HPEL_EVEN
+#define X264CU_HPEL_EVEN 1
+#endif
 #ifndef X264CU_MINB_SEARCH
 #define X264CU_MINB_SEARCH 3
 #endif
@@ -222,6 +226,19 @@ struct RowSrc
         const u32 w0 = __ldg( q + w4 ), w1 = __ldg( q + w4 + 1 ), w2 = __ldg( q + w4 + 2 );
         return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
     }
+    // 9+ pixels of a row as three words (bytes 0..11 of the window; only byte 8 of the third word is guaranteed)
+    __device__ __forceinline__ void row12( int w4, u32 &t0, u32 &t1, u32 &t2 ) const
+    {
+        if( LD64 )
+        {
+            const uint2 A = __ldg( (const uint2 *)( q + w4 ) ), B = __ldg( (const uint2 *)( q + w4 ) + 1 );
+            const u32 a = k ? A.y : A.x, b = k ? B.x : A.y, c = k ? B.y : B.x, d = k ? B.y : B.y;
+            t0 = __funnelshift_r( a, b, sh ); t1 = __funnelshift_r( b, c, sh ); t2 = __funnelshift_r( c, d, sh );
+            return;
+        }
+        const u32 w0 = __ldg( q + w4 ), w1 = __ldg( q + w4 + 1 ), w2 = __ldg( q + w4 + 2 ), w3 = __ldg( q + w4 + 3 );
+        t0 = __funnelshift_r( w0, w1, sh ); t1 = __funnelshift_r( w1, w2, sh ); t2 = __funnelshift_r( w2, w3, sh );
+    }
     // The same fetch under a per-thread predicate, written in PTX so that it stays predicated: get_ref reads a second
     // plane only at quarter-pel positions, and whether the compiler turns `if( avg )` into predication or into two
     // specialised copies of the 8-row body flips with unrelated edits (r01: the branchy form runs 13 % slower, because
@@ -253,7 +270,7 @@ static __constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {
 // ---- 8 lanes per block -------------------------------------------------------------------------------
 struct GroupBE
 {
-    static constexpr bool PAR4 = false;
+    static constexpr bool PAR4 = false, HPEL_EVEN = false;
     Grp g;
     uint2 fenc;              // this lane's row of the block
     const uint8_t *ref0;     // this lane's row of reference 0's F plane at mv 0
@@ -336,7 +353,7 @@ struct GroupBE
 // "strict <, earlier candidate wins ties" rule.  Single evaluations are computed redundantly by the four subgroups.
 struct WarpBE
 {
-    static constexpr bool PAR4 = true;
+    static constexpr bool PAR4 = true, HPEL_EVEN = false;
     Grp g;                   // mask: the whole warp; r: pixel row
     int sub;                 // candidate slot of this lane
     uint2 fenc;
@@ -536,7 +553,7 @@ struct QpelRows
 template<bool SATD, bool WEIGHTED, int PITCH, bool LD64, bool PTXPRED>
 struct ThreadBE
 {
-    static constexpr bool PAR4 = false;
+    static constexpr bool PAR4 = false, HPEL_EVEN = true;
     uint2 fenc[8];
     const uint8_t *ref0, *ref1, *ref_w;      // block origins (8-byte aligned)
     const LaParams *P;
@@ -579,6 +596,44 @@ struct ThreadBE
             int x, y;
             xy( k, x, y );
             int c = qsad1( m, x, y ) + mvcost( tab, m, x, y );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
+    }
+    // The half-pel diamond (me.c:898-921) around a centre whose components are both even (full- or half-pel): the four
+    // candidates are single-plane fetches (no averaging), up/down read the same plane one row apart and left/right
+    // the same plane one pixel apart, so 9 + 8 row fetches serve all four.  Order and ties as qsad_best: up, down, left, right.
+    __device__ __forceinline__ void hpel4_even( int omx, int omy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        const int s4 = pitch() >> 2, psz = (int)P->plane_size;
+        u32 acc[4] = {0, 0, 0, 0};
+        {   // up (omx, omy-2) is row 0..7, down (omx, omy+2) row 1..8 of the same plane
+            const int y = omy - 2, pl = ( ( omx & 2 ) >> 1 ) | ( y & 2 );
+            const RowSrc<LD64> src( ref0, ( y >> 2 ) * pitch() + ( omx >> 2 ) + pl * psz );
+#pragma unroll
+            for( int r = 0; r < 9; r++ )
+            {
+                const uint2 v = src.row( r*s4 );
+                if( r < 8 ) acc[0] = __vsadu4( fenc[r].x, v.x ) + __vsadu4( fenc[r].y, v.y ) + acc[0];
+                if( r > 0 ) acc[1] = __vsadu4( fenc[r-1].x, v.x ) + __vsadu4( fenc[r-1].y, v.y ) + acc[1];
+            }
+        }
+        {   // left (omx-2, omy) starts at byte 0, right (omx+2, omy) at byte 1 of the same rows
+            const int x = omx - 2, pl = ( ( x & 2 ) >> 1 ) | ( omy & 2 );
+            const RowSrc<LD64> src( ref0, ( omy >> 2 ) * pitch() + ( x >> 2 ) + pl * psz );
+#pragma unroll
+            for( int r = 0; r < 8; r++ )
+            {
+                u32 t0, t1, t2;
+                src.row12( r*s4, t0, t1, t2 );
+                acc[2] = __vsadu4( fenc[r].x, t0 ) + __vsadu4( fenc[r].y, t1 ) + acc[2];
+                acc[3] = __vsadu4( fenc[r].x, __funnelshift_r( t0, t1, 8 ) ) + __vsadu4( fenc[r].y, __funnelshift_r( t1, t2, 8 ) ) + acc[3];
+            }
+        }
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            const int x = omx + ( k == 2 ? -2 : k == 3 ? 2 : 0 ), y = omy + ( k == 0 ? -2 : k == 1 ? 2 : 0 );
+            const int c = (int)acc[k] + mvcost( tab, m, x, y );
             if( c < bcost ) { bcost = c; best = k; }
         }
     }

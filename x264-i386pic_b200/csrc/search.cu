@@ -28,6 +28,15 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
         {   // me.c:898-921, tie order: up, down, left, right
             const int omx = bmx, omy = bmy;
             int best = -1;
+#if X264CU_HPEL_EVEN
+            if constexpr( BE::HPEL_EVEN )
+            {
+                if( !( ( omx | omy ) & 1 ) && m.wdenom < 0 ) be.hpel4_even( omx, omy, tab, m, bcost, best );
+                else be.qsad_best( 4, [&]( int k, int &x, int &y ) { x = omx + ( k == 2 ? -2 : k == 3 ? 2 : 0 ); y = omy + ( k == 0 ? -2 : k == 1 ? 2 : 0 ); },
+                                   tab, m, bcost, best );
+            }
+            else
+#endif
             be.qsad_best( 4, [&]( int k, int &x, int &y ) { x = omx + ( k == 2 ? -2 : k == 3 ? 2 : 0 ); y = omy + ( k == 0 ? -2 : k == 1 ? 2 : 0 ); },
                           tab, m, bcost, best );
             if( best < 0 ) break;
