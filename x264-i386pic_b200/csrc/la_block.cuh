@@ -346,11 +346,16 @@ struct GroupBE
     }
 };
 
+#ifndef X264CU_SPIN_NS0
+#define X264CU_SPIN_NS0 20
+#define X264CU_SPIN_NS1 640
+#endif
 // ---- 32 lanes per block: 4 candidates x 8 pixel rows ---------------------------------------------------
 // The latency-oriented mapping of the exact raster-serial mode (search_kernel_serial): every candidate round of
 // x264_me_search scores up to FOUR candidates at once, one per 8-lane subgroup (lane & 7 = pixel row, lane >> 3 =
 // candidate slot); the winner is the minimum of (cost << 2 | slot) over the subgroups, which is the reference's
 // "strict <, earlier candidate wins ties" rule.  Single evaluations are computed redundantly by the four subgroups.
+template<bool SATD>
 struct WarpBE
 {
     static constexpr bool PAR4 = true, HPEL_EVEN = false;
@@ -365,12 +370,16 @@ struct WarpBE
     __device__ __forceinline__ int wait_mv( const int *p ) const
     {
         int v;
+        unsigned ns = X264CU_SPIN_NS0;
         for( int spins = 1; ; spins++ )
         {
             asm volatile( "ld.volatile.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
             if( v != 0x7F7F7F7F ) break;
             if( ( spins & 1023 ) == 0 && ( *(volatile int *)err || spins > ( 1 << 22 ) ) ) { *(volatile int *)err = 1; v = 0; break; }
-            __nanosleep( 20 );
+            // exponential back-off: rows near the top of the frame wait for milliseconds before their first block, and a
+            // warp that polls every few cycles takes issue slots from the launches of other encode streams
+            __nanosleep( ns );
+            ns = min( ns * 2, (unsigned)X264CU_SPIN_NS1 );
         }
         return v;
     }
@@ -394,9 +403,9 @@ struct WarpBE
         const int v = (int)( ( ( t & 0xffff ) + ( t >> 16 ) ) >> 1 );
         return v + __shfl_xor_sync( 0xffffffffu, v, 4 );
     }
-    __device__ __forceinline__ int cmp8( uint2 a, uint2 b ) const { return P->b_satd ? satd8( a, b ) : rsum8( (int)sad8( a, b ) ); }
+    __device__ __forceinline__ int cmp8( uint2 a, uint2 b ) const { return SATD ? satd8( a, b ) : rsum8( (int)sad8( a, b ) ); }
     __device__ __forceinline__ bool leader() const { return ( threadIdx.x & 31 ) == 0; }
-    __device__ __forceinline__ bool satd() const { return P->b_satd != 0; }
+    __device__ __forceinline__ bool satd() const { return SATD; }
     __device__ __forceinline__ int zero_cmp() const { return cmp8( fenc, load8u( ref0 ) ); }
     // slot s scores candidate k0 + s; `c` is this subgroup's full cost (identical in its 8 lanes)
     __device__ __forceinline__ void take_min4( int c, bool valid, int k0, int &bcost, int &best ) const

@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJ
 #ifndef SERIAL_WARPS
 #define SERIAL_WARPS 2
 #endif
+template<bool SATD>
 __global__ void __launch_bounds__(SERIAL_WARPS*32) search_kernel_serial( const SearchJob *__restrict__ jobs, LaParams P, int first_job, int njobs,
                                                                           int *__restrict__ err )
 {
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(SERIAL_WARPS*32) search_kernel_serial( const S
     const int ji = first_job + worker / P.mbh, by = P.mbh - 1 - worker % P.mbh;      // bottom rows first
     SearchJob J = jobs[ji];
     resolve_device_weight( J );
-    WarpBE be; be.g.r = lane & 7; be.g.mask = 0xffffffffu; be.sub = lane >> 3; be.P = &P; be.ref1 = NULL; be.err = err;
+    WarpBE<SATD> be; be.g.r = lane & 7; be.g.mask = 0xffffffffu; be.sub = lane >> 3; be.P = &P; be.ref1 = NULL; be.err = err;
     int right_mv = 0;
     for( int i = 0; i < P.mbw; i++ )
     {
@@ -453,7 +454,8 @@ int launch_search_serial( const SearchJob *d_jobs, int njobs, const LaParams &P,
     {
         const int nj = min( jobs_per_launch, njobs - j0 );
         const int ctas = ( nj * warps_per_job + SERIAL_WARPS - 1 ) / SERIAL_WARPS;
-        search_kernel_serial<<<ctas, SERIAL_WARPS*32, 0, st>>>( d_jobs, P, j0, nj, d_err );
+        if( P.b_satd ) search_kernel_serial<true><<<ctas, SERIAL_WARPS*32, 0, st>>>( d_jobs, P, j0, nj, d_err );
+        else           search_kernel_serial<false><<<ctas, SERIAL_WARPS*32, 0, st>>>( d_jobs, P, j0, nj, d_err );
     }
     return n;
 }
@@ -461,7 +463,7 @@ int launch_search_serial( const SearchJob *d_jobs, int njobs, const LaParams &P,
 int search_serial_max_ctas_per_sm()
 {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &n, search_kernel_serial, SERIAL_WARPS*32, 0 );
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &n, search_kernel_serial<true>, SERIAL_WARPS*32, 0 );
     return n;
 }
 
