@@ -319,6 +319,7 @@ def main():
     ap.add_argument("--value-only", action="store_true", help="profiling aid: skip the end-to-end pass")
     ap.add_argument("--contexts", type=int, default=0, help="contexts per GPU; 0 (default): one context (own CUDA streams) per encode stream, "
                     "as concurrent encoders would run; 1: all streams share one in-order context")
+    ap.add_argument("--subme", type=int, default=7, help="analyse.i_subpel_refine of the encoder: > 1 selects the SATD/HEX/subme-4 lookahead (default), <= 1 the SAD/DIA/subme-2 one")
     ap.add_argument("--e2e-scalars-only", action="store_true", help="diagnostic: the end-to-end pass uploads host luma but reads back only "
                     "the cost scalars (isolates the D2H share of the PCIe traffic)")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k", "64streams"],
@@ -337,7 +338,7 @@ def main():
           "4k": "4K (3840x2160) lookahead cost-matrix increment per frame, bframes=16 (BASELINE.json configs[3]); streams sharded across GPUs",
           "64streams": "64 concurrent 1080p encode streams' lookahead, 8 per GPU (BASELINE.json configs[4])"}[args.workload]
     config = {"workload": wl,
-              "width": W, "height": H, "bframes": BFRAMES, "search_passes": args.search_passes, "subme": 7, "mbtree_edges": 1, "aq": 1,
+              "width": W, "height": H, "bframes": BFRAMES, "search_passes": args.search_passes, "subme": args.subme, "mbtree_edges": 1, "aq": 1,
               "evals_per_step": 154, "new_search_fields_per_step": 33, "streams_per_gpu": args.streams,
               "sharding": "independent encode streams per GPU, no collective", "host_pipeline_depth": "one outstanding step per stream",
               "l2": "inputs larger than L2: %d windows x 18 frames x ~10 MB of planes+cost arrays per GPU" % args.streams}
@@ -367,7 +368,7 @@ def main():
     S = args.streams
     per_stream = RAMP + (warmup + args.steps + S - 1) // S + 1
     n_ctx = S if args.contexts == 0 else max(1, min(args.contexts, S))
-    ctxs = [x264cu.Context(W, H, bframes=BFRAMES, subme=7, do_edges=1, aq=1, passes=args.search_passes, device=local) for _ in range(n_ctx)]
+    ctxs = [x264cu.Context(W, H, bframes=BFRAMES, subme=args.subme, do_edges=1, aq=1, passes=args.search_passes, device=local) for _ in range(n_ctx)]
     ctx = ctxs[0]
     config["contexts_per_gpu"] = n_ctx
     peaks = {}

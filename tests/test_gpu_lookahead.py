@@ -140,6 +140,41 @@ def test_runtime_pitch_kernels(monkeypatch, W, H, subme, passes):
         gpu.close()
 
 
+@pytest.mark.parametrize("W,H,bframes,subme,passes,pan", [
+    (208, 160, 16, 7, 2, (5, -2)),     # the bench's bframes with long distances: MVs far from zero, temporal direct at every distance
+    (208, 160, 16, 7, 0, (5, -2)),     # the same in the exact raster-serial mode
+    (176, 144, 0, 7, 2, (2, 1)),       # no B frames at all
+    (176, 144, 1, 1, 2, (-3, 2)),      # one B frame, SAD flavour
+    (528, 80, 7, 7, 2, (9, 0)),        # wide and flat: 66 x 10 blocks, warp tiles 32+32+2
+])
+def test_bframe_depths_and_shapes(W, H, bframes, subme, passes, pan):
+    """every (p0, p1, b) with p1 - p0 <= bframes + 1 that contains the newest frame, as the lookahead window issues them"""
+    x264cu = _cu()
+    n = min(bframes + 2, 8) if bframes < 16 else 18
+    frames = synth_frames(W, H, n, seed=41, pan=pan)
+    mvr = x264cu.default_mv_range(W, H)
+    cpu = Lookahead(OracleLib(), "oracle", W, H, bframes=bframes, subme=subme, passes=passes, mv_range=mvr)
+    gpu = x264cu.CudaLookahead(W, H, bframes=bframes, subme=subme, passes=passes, mv_range=mvr)
+    try:
+        for i, f in enumerate(frames):
+            cpu.put_frame(i, f)
+            gpu.put_frame(i, f)
+        last = n - 1
+        triples = [(last, last, last)]
+        for p0 in range(last - 1, max(last - (bframes + 1), 0) - 1, -1):
+            triples.append((p0, last, last))
+            triples += [(p0, last, b) for b in range(p0 + 1, last)]
+        if bframes == 16:
+            triples = triples[:1] + triples[1::3]          # keep the run short: every third evaluation, all distances
+        sg = gpu.frame_cost_many(triples)
+        for (p0, p1, b), s_gpu in zip(triples, sg):
+            assert cpu.frame_cost(p0, p1, b) == s_gpu, (p0, p1, b)
+            compare_eval(gpu, cpu, p0, p1, b, f"bframes={bframes} ({p0},{p1},{b})")
+    finally:
+        cpu.close()
+        gpu.close()
+
+
 def test_batch_equals_sequential():
     """x264cu_frame_cost_batch == the same evaluations issued one by one (array order semantics)."""
     x264cu = _cu()
