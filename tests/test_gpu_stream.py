@@ -126,3 +126,49 @@ def test_4k_maximum_size():
         assert sb > 0 and ((G.results[(1, 1, 1)]["lowres_costs"] >> 14) != 0).all()
     finally:
         G.close()
+
+
+def test_concurrent_contexts_from_host_threads():
+    """64 concurrent encode streams = many contexts driven by many host threads (one lookahead thread per encoder,
+    encoder/lookahead.c:223-252).  Four threads, one context each, both schedules: results must equal the oracle's."""
+    import threading
+    import x264cu
+    W, H, n = 208, 160, 5
+    mvr = x264cu.default_mv_range(W, H)
+    triples = [(0, 0, 0), (0, 1, 1), (0, 4, 4), (0, 4, 2), (1, 4, 2), (2, 4, 3), (3, 4, 4)]
+    jobs = [(seed, passes) for seed in (3, 4) for passes in (2, 0)]
+    expect = {}
+    for seed, passes in jobs:
+        frames = synth_frames(W, H, n, seed=seed)
+        cpu = Lookahead(OracleLib(), "oracle", W, H, bframes=3, mv_range=mvr, passes=passes)
+        for i, f in enumerate(frames):
+            cpu.put_frame(i, f)
+        expect[(seed, passes)] = ([cpu.frame_cost(*t) for t in triples],
+                                  [cpu.get(t[2], GET_LOWRES_COSTS, t[2] - t[0], t[1] - t[2]).copy() for t in triples if t[0] != t[1]])
+        cpu.close()
+    got, errors = {}, []
+
+    def worker(seed, passes):
+        try:
+            frames = synth_frames(W, H, n, seed=seed)
+            gpu = x264cu.CudaLookahead(W, H, bframes=3, mv_range=mvr, passes=passes)
+            for rep in range(3):                       # keep the contexts busy at the same time
+                for i, f in enumerate(frames):
+                    gpu.put_frame(i, f)
+                costs = gpu.frame_cost_many(triples)
+            arrays = [gpu.results[(t[2], t[2] - t[0], t[1] - t[2])]["lowres_costs"].copy() for t in triples if t[0] != t[1]]
+            got[(seed, passes)] = (costs, arrays)
+            gpu.close()
+        except Exception as e:                         # surfaced in the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for j in jobs:
+        assert got[j][0] == expect[j][0], j
+        for a, b in zip(got[j][1], expect[j][1]):
+            assert (a == b).all(), j
