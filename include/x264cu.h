@@ -144,6 +144,18 @@ int x264cu_frame_cost( x264cu_ctx *ctx, const x264cu_job *job );
  * list 0 only; mvs / mv_costs are optional host destinations (i16x2 / i32 per block). */
 int x264cu_motionsearch( x264cu_ctx *ctx, x264cu_frame *fenc, x264cu_frame *fref, int list, int dist,
                          const x264cu_weight *w, int16_t *mvs, int32_t *mv_costs );
+/* Several searches as ONE batch of wide launches (what x264_opencl_slicetype_prep does with its loop of
+ * x264_opencl_motionsearch calls, slicetype-cl.c:676-704); cached fields are skipped.  No host outputs. */
+typedef struct { x264cu_frame *fenc, *fref; int list, dist; x264cu_weight weight; } x264cu_search_job;
+int x264cu_search_batch( x264cu_ctx *ctx, const x264cu_search_job *jobs, int n_jobs );
+/* One-stream sharding across GPUs (BASELINE.json configs[3]): a searched MV field is the one
+ * piece of data an evaluation on another GPU needs (fref1->lowres_mvs[0] for the temporal-direct candidate,
+ * slicetype.c:629; lowres_mvs / lowres_mv_costs of list 0 for later B evaluations).  x264cu_field_device returns the
+ * DEVICE addresses of a field's MVs (i16 x 2 x mb_count) and MV costs (i32 x mb_count) so that the caller can move
+ * them between contexts with NCCL / peer copies; x264cu_field_set_searched marks a field that was filled that way
+ * (the 0x7FFF sentinel protocol of slicetype.c:855-867). */
+int x264cu_field_device( x264cu_ctx *ctx, x264cu_frame *f, int list, int dist, void **d_mvs, void **d_mv_costs );
+int x264cu_field_set_searched( x264cu_ctx *ctx, x264cu_frame *f, int list, int dist );
 /* x264_opencl_slicetype_prep (slicetype-cl.c:653-712): many evaluations, semantically in array
  * order, executed as a few wide launches (all searches of a pass together, all decisions together). */
 int x264cu_frame_cost_batch( x264cu_ctx *ctx, const x264cu_job *jobs, int n_jobs );
@@ -174,6 +186,16 @@ x264cu_stream *x264cu_stream_open( x264cu_ctx *ctx, int bframes, int want_arrays
 void     x264cu_stream_close( x264cu_stream *s );
 /* returns the number of evaluations enqueued (asynchronously) or -1; on_device: device pointers */
 int      x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int stride, const uint16_t *inv_qscale, int on_device );
+/* The same push split over `world` GPUs that all hold the window of ONE encode stream (every rank pushes every frame).
+ * phase 0: upload frame n and enqueue this rank's share of the new searches -- list-0 field (n -> p0) where
+ * p0 % world == rank, list-1 field (b -> n) where b % world == rank.  The caller then exchanges the list-0 fields of
+ * frame n between the ranks (x264cu_stream_frame + x264cu_field_device + x264cu_field_set_searched).
+ * phase 1: enqueue this rank's share of the evaluations -- P (p0, n, n) where p0 % world == rank, B (p0, n, b) where
+ * b % world == rank, I where n % world == rank.  Results of other ranks' evaluations read as -1 in x264cu_stream_cost. */
+int      x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, int stride, const uint16_t *inv_qscale, int on_device,
+                                   int rank, int world, int phase );
+/* frame pushed `age` pushes ago (0 = the newest; during phase 0/1 of a sharded push the frame being pushed) */
+x264cu_frame *x264cu_stream_frame( x264cu_stream *s, int age );
 int      x264cu_stream_sync( x264cu_stream *s );
 /* after sync: stats of slicetype_frame_cost(p0, n, b) of the newest frame n, d0 = b-p0, d1 = n-b */
 int      x264cu_stream_cost( x264cu_stream *s, int d0, int d1, int32_t *out4 );
@@ -281,6 +303,7 @@ void *x264cu_host_alloc( x264cu_ctx *ctx, size_t bytes );
 void  x264cu_host_free( x264cu_ctx *ctx, void *p );
 int   x264cu_memcpy_h2d( x264cu_ctx *ctx, void *dst, const void *src, size_t bytes );
 int   x264cu_memcpy_d2h( x264cu_ctx *ctx, void *dst, const void *src, size_t bytes );
+int   x264cu_memcpy_d2d( x264cu_ctx *ctx, void *dst, const void *src, size_t bytes );      /* on the context's compute stream */
 /* bracket device work with CUDA events on the context's stream: returns elapsed ms of [begin,end) */
 int   x264cu_timer_begin( x264cu_ctx *ctx );
 float x264cu_timer_end( x264cu_ctx *ctx );

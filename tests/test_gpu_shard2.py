@@ -1,0 +1,86 @@
+"""BASELINE.json configs[3] / SURVEY.md section 8e: ONE encode stream's lookahead split over two GPUs (search fields and
+evaluations by step_units(), the list-0 MV fields of the newest frame all-gathered over NCCL) must give exactly the
+costs of the single-GPU window, step by step.  Needs two GPUs (skipped otherwise): gpurun --gpus 2."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "x264-i386pic_b200"))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, W, H, B, nframes, passes, q):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import shard
+    import x264cu
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from checkers import synth_frames
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    frames = [np.ascontiguousarray(f) for f in synth_frames(W, H, nframes, seed=51, pan=(3, 1))]
+    ctx = x264cu.Context(W, H, bframes=B, passes=passes, device=rank)
+    win = shard.ShardedWindow(x264cu, ctx, B, rank, world, dist=dist, device=torch.device("cuda", rank))
+    mine = []
+    for f in frames:
+        win.push(f.ctypes.data, W, False)
+        win.sync()
+        mine.append(win.costs())
+    win.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    if rank == 0:
+        # the same stream on one GPU
+        L = ctx.L
+        ref = L.x264cu_stream_open(ctx.ctx, B, 0)
+        single = []
+        st = (C.c_int32 * 4)()
+        for f in frames:
+            assert L.x264cu_stream_push(ref, f.ctypes.data, W, None, 0) >= 0
+            x264cu.check(L.x264cu_stream_sync(ref), "sync")
+            d = {}
+            for d0 in range(B + 2):
+                for d1 in range(B + 2 - d0):
+                    L.x264cu_stream_cost(ref, d0, d1, st)
+                    if st[0] >= 0:
+                        d[(d0, d1)] = list(st)
+            single.append(d)
+        L.x264cu_stream_close(ref)
+        q.put((gathered, single))
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("passes", [2, 0])
+def test_one_stream_on_two_gpus_equals_one_gpu(passes):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    W, H, B, n = 320, 192, 5, 14
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300 + passes
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, W, H, B, n, passes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, single = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for step in range(n):
+        merged = {}
+        for r in range(2):
+            for k, v in gathered[r][step].items():
+                assert k not in merged, (step, k)          # every evaluation on exactly one rank
+                merged[k] = v
+        assert merged == single[step], step
+    # both ranks had work
+    assert all(sum(len(gathered[r][s]) for s in range(n)) > 0 for r in range(2))

@@ -55,3 +55,26 @@ def test_field_sharding_covers_everything():
         assert sorted(flat) == sorted(fields)
         sizes = [len(parts[r]) for r in range(world)]
         assert max(sizes) - min(sizes) <= len(fields) // world // 2 + 2
+
+
+def test_one_stream_step_units_are_a_disjoint_cover():
+    """BASELINE.json configs[3]: the step that frame n opens, split over `world` GPUs, covers every search field and every
+    evaluation of the single-GPU step exactly once."""
+    import shard
+    B = 16
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 5, 17, 40):
+            lo = max(0, n - (B + 1))
+            want_l0 = sorted(range(lo, n))
+            want_l1 = sorted(range(lo + 1, n))
+            want_ev = sorted([(n, n, n)] + [(p0, n, n) for p0 in range(lo, n)] + [(p0, n, b) for p0 in range(lo, n) for b in range(p0 + 1, n)])
+            l0, l1, ev = [], [], []
+            for rank in range(world):
+                a, b_, c = shard.step_units(n, B, rank, world)
+                l0 += a; l1 += b_; ev += c
+                # a B evaluation lives where its frame's list-1 search lives, a P evaluation where its list-0 search does
+                assert all((p1 == b and (p0 == b or p0 % world == rank)) or (b % world == rank) for (p0, p1, b) in c)
+            assert sorted(l0) == want_l0 and sorted(l1) == want_l1 and sorted(ev) == want_ev, (world, n)
+            if n >= B + 1 and world <= 8:
+                sizes = [len(shard.step_units(n, B, r, world)[2]) for r in range(world)]
+                assert max(sizes) - min(sizes) <= 2 * (B + 1) // world + 2 + (B + 1)

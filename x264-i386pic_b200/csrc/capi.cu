@@ -1084,6 +1084,49 @@ extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_fr
     return end_batch( c );
 }
 
+extern "C" int x264cu_search_batch( x264cu_ctx *c, const x264cu_search_job *jobs, int n )
+{
+    if( !c || ( n > 0 && !jobs ) ) FAIL( "x264cu_search_batch: null argument" );
+    CU( cudaSetDevice( c->device ) );
+    if( begin_batch( c ) ) return -1;
+    std::vector<SearchTask> tasks;
+    for( int i = 0; i < n; i++ )
+    {
+        const x264cu_search_job &j = jobs[i];
+        if( !j.fenc || !j.fref || j.list < 0 || j.list > 1 || j.dist < 1 || j.dist > c->cfg.bframes + 1 ) FAIL( "x264cu_search_batch: bad job %d", i );
+        if( !j.fenc->uploaded || !j.fref->uploaded ) FAIL( "x264cu_search_batch: frame not uploaded" );
+        if( j.fenc->searched[j.list][j.dist-1] ) continue;
+        j.fenc->searched[j.list][j.dist-1] = 1;
+        SearchTask t = { j.fenc, j.fref, j.list, j.dist, { 0, 0, 0, 0 } };
+        if( j.list == 0 && j.weight.enabled )
+        {
+            if( j.weight.enabled == X264CU_WEIGHT_DEVICE && !j.fenc->wanalysed[j.dist-1] )
+                FAIL( "x264cu_search_batch: X264CU_WEIGHT_DEVICE without a preceding x264cu_weights_analyse for distance %d", j.dist );
+            t.w = j.weight;
+        }
+        tasks.push_back( t );
+    }
+    if( run_searches( c, tasks ) ) return -1;
+    CU( cudaGetLastError() );
+    return end_batch( c );
+}
+
+extern "C" int x264cu_field_device( x264cu_ctx *c, x264cu_frame *f, int list, int dist, void **d_mvs, void **d_mv_costs )
+{
+    if( !c || !f || list < 0 || list > 1 || dist < 1 || dist > c->cfg.bframes + 1 ) FAIL( "x264cu_field_device: bad argument" );
+    const int fi = field_index( c, list, dist );
+    if( d_mvs ) *d_mvs = f->mvs + (size_t)fi * c->P.nmb * 2;
+    if( d_mv_costs ) *d_mv_costs = f->mvcosts + (size_t)fi * c->P.nmb;
+    return 0;
+}
+
+extern "C" int x264cu_field_set_searched( x264cu_ctx *c, x264cu_frame *f, int list, int dist )
+{
+    if( !c || !f || list < 0 || list > 1 || dist < 1 || dist > c->cfg.bframes + 1 ) FAIL( "x264cu_field_set_searched: bad argument" );
+    f->searched[list][dist-1] = 1;
+    return 0;
+}
+
 // sequence number of the most recently enqueued batch / wait for everything up to a sequence number:
 // lets a caller keep NSLOT-1 batches in flight and still pick up results in order (x264cu_stream_sync)
 extern "C" uint64_t x264cu_last_batch( x264cu_ctx *c ) { return c ? c->seq : 0; }
@@ -1195,6 +1238,13 @@ extern "C" int x264cu_memcpy_h2d( x264cu_ctx *c, void *dst, const void *src, siz
     CU( cudaSetDevice( c->device ) );
     CU( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyHostToDevice, c->st ) );
     CU( cudaStreamSynchronize( c->st ) );
+    return 0;
+}
+extern "C" int x264cu_memcpy_d2d( x264cu_ctx *c, void *dst, const void *src, size_t bytes )
+{
+    if( !c ) FAIL( "null context" );
+    CU( cudaSetDevice( c->device ) );
+    CU( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyDeviceToDevice, c->st ) );
     return 0;
 }
 extern "C" int x264cu_memcpy_d2h( x264cu_ctx *c, void *dst, const void *src, size_t bytes )

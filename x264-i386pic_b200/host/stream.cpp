@@ -28,6 +28,7 @@ struct x264cu_stream
     // optional array destinations (pinned when possible)
     uint8_t *arr; size_t arr_bytes; bool arr_pinned;
     std::vector<x264cu_job> jobs;
+    bool shard_open;                    // between phase 0 and phase 1 of a sharded push
 };
 
 extern "C" void *x264cu_host_alloc( x264cu_ctx *ctx, size_t bytes );
@@ -41,7 +42,7 @@ extern "C" x264cu_stream *x264cu_stream_open( x264cu_ctx *ctx, int bframes, int 
     s->ctx = ctx; s->bframes = bframes; s->depth = bframes + 2;
     s->mbw = info[0]; s->mbh = info[1]; s->nmb = info[0] * info[1];
     s->want_arrays = want_arrays;
-    s->n_pushed = 0; s->last_seq = 0;
+    s->n_pushed = 0; s->last_seq = 0; s->shard_open = false;
     s->stats.assign( (size_t)( bframes+2 ) * ( bframes+2 ) * 4, -1 );
     s->intra_stats.assign( 2, -1 );
     s->arr = NULL; s->arr_bytes = 0; s->arr_pinned = false;
@@ -121,6 +122,82 @@ extern "C" int x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int st
     if( x264cu_frame_cost_batch( s->ctx, s->jobs.data(), (int)s->jobs.size() ) ) return -1;
     s->last_seq = x264cu_last_batch( s->ctx );
     s->n_pushed++;
+    return (int)s->jobs.size();
+}
+
+// ---- one stream over several GPUs (BASELINE.json configs[3]) -------------------------------------
+// Every rank holds the whole window (it uploads every frame; lowres + intra are replicated, they are 5 % of a step) and
+// owns a share of the step's units: the list-0 search (n -> p0) and the P evaluation (p0, n, n) belong to rank p0 % world,
+// the list-1 search (b -> n) and the B evaluations (p0, n, b) to rank b % world, the I evaluation to rank n % world.
+// The only data another rank needs are the list-0 fields of the newest frame (temporal-direct source of this step's B
+// evaluations, list-0 side of later ones): the caller all-gathers them between phase 0 and phase 1.
+extern "C" x264cu_frame *x264cu_stream_frame( x264cu_stream *s, int age )
+{
+    if( !s || age < 0 || age >= s->depth ) return NULL;
+    const int64_t n = s->n_pushed + ( s->shard_open ? 0 : -1 ) - age;
+    return n < 0 ? NULL : s->ring[n % s->depth];
+}
+
+extern "C" int x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, int stride, const uint16_t *inv_qscale, int on_device,
+                                         int rank, int world, int phase )
+{
+    if( !s || world < 1 || rank < 0 || rank >= world ) return -1;
+    const int B = s->bframes, D = s->depth;
+    const int64_t n = s->n_pushed;
+    x264cu_frame *fn = s->ring[n % D];
+    const int64_t lo = n - ( B + 1 ) < 0 ? 0 : n - ( B + 1 );
+    if( phase == 0 )
+    {
+        if( !luma || s->shard_open ) return -1;
+        int r = on_device ? x264cu_frame_upload_device( s->ctx, fn, luma, stride, inv_qscale )
+                          : x264cu_frame_upload( s->ctx, fn, luma, stride, inv_qscale );
+        if( r ) return -1;
+        std::vector<x264cu_search_job> sj;
+        for( int64_t p0 = n - 1; p0 >= lo; p0-- )
+            if( p0 % world == rank )
+            {
+                x264cu_search_job j; memset( &j, 0, sizeof(j) );
+                j.fenc = fn; j.fref = s->ring[p0 % D]; j.list = 0; j.dist = (int)( n - p0 );
+                sj.push_back( j );
+            }
+        for( int64_t b = lo + 1; b < n; b++ )
+            if( b % world == rank )
+            {
+                x264cu_search_job j; memset( &j, 0, sizeof(j) );
+                j.fenc = s->ring[b % D]; j.fref = fn; j.list = 1; j.dist = (int)( n - b );
+                sj.push_back( j );
+            }
+        if( x264cu_search_batch( s->ctx, sj.data(), (int)sj.size() ) ) return -1;
+        s->last_seq = x264cu_last_batch( s->ctx );
+        s->shard_open = true;
+        return (int)sj.size();
+    }
+    if( !s->shard_open ) return -1;
+    s->jobs.clear();
+    std::fill( s->stats.begin(), s->stats.end(), -1 );
+    if( n % world == rank )
+    {
+        x264cu_job j; memset( &j, 0, sizeof(j) );
+        j.fenc = j.fref0 = j.fref1 = fn;
+        j.out.stats = &s->stats[0];
+        j.out.intra_stats = s->intra_stats.data();
+        s->jobs.push_back( j );
+    }
+    for( int64_t p0 = n - 1; p0 >= lo; p0-- )
+        for( int k = 0; k < (int)( n - p0 ); k++ )
+        {
+            const int64_t b = k == 0 ? n : p0 + k;
+            if( ( k == 0 ? p0 : b ) % world != rank ) continue;
+            x264cu_job j; memset( &j, 0, sizeof(j) );
+            j.fenc = s->ring[b % D]; j.fref0 = s->ring[p0 % D]; j.fref1 = fn;
+            j.d0 = (int)( b - p0 ); j.d1 = (int)( n - b );
+            j.out.stats = &s->stats[( (size_t)j.d0 * ( B+2 ) + j.d1 ) * 4];
+            s->jobs.push_back( j );
+        }
+    if( x264cu_frame_cost_batch( s->ctx, s->jobs.data(), (int)s->jobs.size() ) ) return -1;
+    s->last_seq = x264cu_last_batch( s->ctx );
+    s->n_pushed++;
+    s->shard_open = false;
     return (int)s->jobs.size();
 }
 

@@ -20,3 +20,98 @@ def assign_fields(fields, world):
 def stream_seed(global_stream_id):
     """synthetic content seed of a stream; depends on the global id only, so any world size sees the same streams."""
     return 7 * global_stream_id + 1
+
+
+# ---- one encode stream over several GPUs (BASELINE.json configs[3]: 4K, frame-pair sharding) --------------------------
+def step_units(n, bframes, rank, world):
+    """This rank's share of the step that frame n opens (host/stream.cpp x264cu_stream_push_shard uses the same rule):
+    list-0 search (n -> p0) and P evaluation (p0, n, n): rank p0 % world; list-1 search (b -> n) and B evaluations
+    (p0, n, b): rank b % world; I evaluation: rank n % world.  Returns (l0_searches [p0], l1_searches [b], evals [(p0, n, b)])."""
+    lo = max(0, n - (bframes + 1))
+    l0 = [p0 for p0 in range(n - 1, lo - 1, -1) if p0 % world == rank]
+    l1 = [b for b in range(lo + 1, n) if b % world == rank]
+    ev = [(n, n, n)] if n % world == rank else []
+    for p0 in range(n - 1, lo - 1, -1):
+        if p0 % world == rank:
+            ev.append((p0, n, n))
+        ev += [(p0, n, b) for b in range(p0 + 1, n) if b % world == rank]
+    return l0, l1, ev
+
+
+class ShardedWindow:
+    """One lookahead window held by `world` ranks (one GPU each).  Every rank pushes every frame; a step's searches and
+    evaluations are split by step_units(); the list-0 MV fields (+ costs) of the newest frame are the one exchange step
+    of the path: an NCCL all-gather between the two phases of x264cu_stream_push_shard."""
+
+    def __init__(self, x264cu, ctx, bframes, rank, world, dist=None, device=None):
+        import ctypes as C
+        self.x, self.ctx, self.B, self.rank, self.world, self.dist = x264cu, ctx, bframes, rank, world, dist
+        self.L = ctx.L
+        self.win = self.L.x264cu_stream_open(ctx.ctx, bframes, 0)
+        assert self.win, x264cu.last_error()
+        self.n = 0
+        self.fb = ctx.nmb * 4                                   # bytes of an MV field; the cost field has the same size
+        self.slots = (bframes + 1 + world - 1) // world
+        self.send = self.recv = None
+        if world > 1:
+            import torch
+            self.torch = torch
+            self.send = torch.zeros(self.slots * 2 * self.fb, dtype=torch.uint8, device=device)
+            self.recv = torch.zeros(world * self.slots * 2 * self.fb, dtype=torch.uint8, device=device)
+        self._C = C
+
+    def _field(self, frame, dist_):
+        mv, mc = self._C.c_void_p(), self._C.c_void_p()
+        self.x.check(self.L.x264cu_field_device(self.ctx.ctx, frame, 0, dist_, self._C.byref(mv), self._C.byref(mc)), "field_device")
+        return mv.value, mc.value
+
+    def push(self, luma, stride, on_device):
+        L, n = self.L, self.n
+        r = L.x264cu_stream_push_shard(self.win, luma, stride, None, int(on_device), self.rank, self.world, 0)
+        if r < 0:
+            raise RuntimeError("x264cu_stream_push_shard(0): " + self.x.last_error())
+        if self.world > 1 and n > 0:
+            fn = L.x264cu_stream_frame(self.win, 0)
+            lo = max(0, n - (self.B + 1))
+            owner_fields = [[p0 for p0 in range(n - 1, lo - 1, -1) if p0 % self.world == r2] for r2 in range(self.world)]
+            for k, p0 in enumerate(owner_fields[self.rank]):
+                mv, mc = self._field(fn, n - p0)
+                base = self.send.data_ptr() + k * 2 * self.fb
+                self.x.check(L.x264cu_memcpy_d2d(self.ctx.ctx, base, mv, self.fb), "d2d")
+                self.x.check(L.x264cu_memcpy_d2d(self.ctx.ctx, base + self.fb, mc, self.fb), "d2d")
+            # the searches and the packing ran on the context's stream; NCCL runs on torch's: order them through the host
+            self.x.check(L.x264cu_wait(self.ctx.ctx, L.x264cu_last_batch(self.ctx.ctx)), "wait")
+            self.x.check(L.x264cu_flush(self.ctx.ctx), "flush")
+            self.dist.all_gather_into_tensor(self.recv, self.send)
+            self.torch.cuda.current_stream().synchronize()
+            for r2 in range(self.world):
+                if r2 == self.rank:
+                    continue
+                for k, p0 in enumerate(owner_fields[r2]):
+                    mv, mc = self._field(fn, n - p0)
+                    base = self.recv.data_ptr() + (r2 * self.slots + k) * 2 * self.fb
+                    self.x.check(L.x264cu_memcpy_d2d(self.ctx.ctx, mv, base, self.fb), "d2d")
+                    self.x.check(L.x264cu_memcpy_d2d(self.ctx.ctx, mc, base + self.fb, self.fb), "d2d")
+                    self.x.check(L.x264cu_field_set_searched(self.ctx.ctx, fn, 0, n - p0), "set_searched")
+        r = L.x264cu_stream_push_shard(self.win, None, 0, None, 0, self.rank, self.world, 1)
+        if r < 0:
+            raise RuntimeError("x264cu_stream_push_shard(1): " + self.x.last_error())
+        self.n += 1
+        return r
+
+    def sync(self):
+        self.x.check(self.L.x264cu_stream_sync(self.win), "sync")
+
+    def costs(self):
+        """this rank's stats of the newest step: {(d0, d1): [cost_est, cost_est_aq, intra_mbs, raw]} (others absent)"""
+        out = {}
+        st = (self._C.c_int32 * 4)()
+        for d0 in range(self.B + 2):
+            for d1 in range(self.B + 2 - d0):
+                self.L.x264cu_stream_cost(self.win, d0, d1, st)
+                if st[0] >= 0:
+                    out[(d0, d1)] = list(st)
+        return out
+
+    def close(self):
+        self.L.x264cu_stream_close(self.win)

@@ -37,6 +37,10 @@ class Job(C.Structure):
                 ("weight", Weight), ("out", Out)]
 
 
+class SearchJob(C.Structure):
+    _fields_ = [("fenc", vp), ("fref", vp), ("list", C.c_int), ("dist", C.c_int), ("weight", Weight)]
+
+
 class AqCfg(C.Structure):
     _fields_ = [("mode", C.c_int), ("strength", C.c_float)]
 
@@ -104,6 +108,13 @@ def load():
     L.x264cu_stream_open.argtypes = [vp, C.c_int, C.c_int]
     L.x264cu_stream_close.argtypes = [vp]
     L.x264cu_stream_push.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.x264cu_stream_push_shard.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.x264cu_stream_frame.restype = vp
+    L.x264cu_stream_frame.argtypes = [vp, C.c_int]
+    L.x264cu_search_batch.argtypes = [vp, C.POINTER(SearchJob), C.c_int]
+    L.x264cu_field_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+    L.x264cu_field_set_searched.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.x264cu_memcpy_d2d.argtypes = [vp, vp, vp, C.c_size_t]
     L.x264cu_stream_sync.argtypes = [vp]
     L.x264cu_stream_cost.argtypes = [vp, C.c_int, C.c_int, vp]
     L.x264cu_stream_frames.argtypes = [vp]
