@@ -308,6 +308,81 @@ def cpu_reference_run(frames, warmup, steps, threads, ramp=RAMP):
     return dt, evals, kind, threads
 
 
+def run_one_stream(args):
+    """BASELINE.json configs[3]: one encode stream, its units sharded over the ranks (shard.ShardedWindow).  Every rank
+    pushes every frame (device-resident luma for `value`, pinned host luma for `e2e`); a step is complete when every
+    rank's share of the 154 evaluations is back on its host."""
+    import x264cu
+    import shard
+    warmup = max(args.warmup, 3)
+    rank, world, local, dist = dist_setup(args.gpus)
+    ctx = x264cu.Context(W, H, bframes=BFRAMES, subme=args.subme, do_edges=1, aq=1, passes=args.search_passes, device=local)
+    n = RAMP + warmup + args.steps
+    frames = make_stream_frames(shard.stream_seed(0), n)
+    fbytes = W * H
+    hp = ctx.host_alloc(fbytes * n)
+    dp = ctx.malloc(fbytes * n + 256)
+    for i, f in enumerate(frames):
+        x264cu.C.memmove(hp + i * fbytes, f.ctypes.data, fbytes)
+    x264cu.check(ctx.L.x264cu_memcpy_h2d(ctx.ctx, dp, hp, fbytes * n))
+    dev_t = None
+    if dist is not None:
+        import torch
+        dev_t = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    times = []
+    for e2e in (False, True):
+        win = shard.ShardedWindow(x264cu, ctx, BFRAMES, rank, world, dist=dist, device=dev_t)
+        src = hp if e2e else dp
+        for i in range(RAMP + warmup):
+            win.push(src + i * fbytes, W, not e2e)
+        win.sync()
+        nxt = lambda i: src + (i + 1) * fbytes if i + 1 < n else None
+        l0 = ctx.launches()
+        barrier_sync(dist, local)
+        ctx.timer_begin()
+        for i in range(RAMP + warmup, n):
+            win.push(src + i * fbytes, W, not e2e, next_luma=nxt(i))      # the next frame's searches overlap this step's exchange
+        win.sync()
+        ms = ctx.timer_end()
+        barrier_sync(dist, local)
+        launches = ctx.launches() - l0
+        got = win.costs()
+        assert world > 1 or got[(1, 0)][0] > 0
+        win.close()
+        times.append(ms)
+    clocks = sampler.summary() if rank == 0 else {}
+    t_v, t_e = times
+    if dist is not None:
+        import torch
+        t = torch.tensor(times, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_v, t_e = float(t[0]), float(t[1])
+    if rank == 0:
+        res = "4K" if W == 3840 else "1080p"
+        print(json.dumps({
+            "metric": "lookahead frames/s at %s (bframes=16 cost-matrix increment per frame), one encode stream" % res,
+            "value": round(args.steps / (t_v / 1e3), 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": round(t_v / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "ONE %s encode stream, search fields and evaluations sharded over the GPUs by frame "
+                                   "(BASELINE.json configs[3]); exchange: NCCL all-gather of the newest frame's list-0 MV fields "
+                                   "and costs, %d bytes per rank and frame" % (res, ((BFRAMES + 1 + world - 1) // world) * 8 * ctx.nmb),
+                       "width": W, "height": H, "bframes": BFRAMES, "search_passes": args.search_passes, "subme": args.subme,
+                       "evals_per_step": 154, "new_search_fields_per_step": 33,
+                       "l2": "inputs larger than L2 at 4K (18 frames x 40 MB); at 1080p the window (18 x 10 MB) is about L2-sized"},
+            "clocks": clocks,
+            "e2e": {"value": round(args.steps / (t_e / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": fbytes * world,
+                    "d2h_bytes_per_step": 154 * 32, "ms_per_step": round(t_e / args.steps, 4)},
+            "gpu_launches": int(launches)}))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -324,11 +399,17 @@ def main():
     ap.add_argument("--subme", type=int, default=7, help="analyse.i_subpel_refine of the encoder: > 1 selects the SATD/HEX/subme-4 lookahead (default), <= 1 the SAD/DIA/subme-2 one")
     ap.add_argument("--e2e-scalars-only", action="store_true", help="diagnostic: the end-to-end pass uploads host luma but reads back only "
                     "the cost scalars (isolates the D2H share of the PCIe traffic)")
-    ap.add_argument("--workload", default="1080p", choices=["1080p", "4k", "64streams"],
-                    help="1080p: BASELINE.json configs[2] (the headline); 4k: configs[3] (3840x2160, 62 live frames per window); "
-                         "64streams: configs[4] (8 independent 1080p encode streams per GPU)")
+    ap.add_argument("--workload", default="1080p", choices=["1080p", "4k", "64streams", "4k-one-stream", "1080p-one-stream"],
+                    help="1080p: BASELINE.json configs[2] (the headline); 4k: configs[3] with independent streams per GPU; "
+                         "64streams: configs[4] (8 independent 1080p encode streams per GPU); 4k-one-stream / 1080p-one-stream: "
+                         "configs[3] as written -- ONE encode stream whose search fields and evaluations are split over all GPUs "
+                         "(strong scaling, one NCCL all-gather of MV fields per frame)")
     args = ap.parse_args()
     global W, H
+    if args.workload.endswith("one-stream"):
+        if args.workload.startswith("4k"):
+            W, H = 3840, 2160
+        return run_one_stream(args)
     if args.workload == "4k":
         W, H = 3840, 2160
         args.streams = min(args.streams, 2)

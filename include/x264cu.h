@@ -165,6 +165,8 @@ int x264cu_flush( x264cu_ctx *ctx );
  * be enqueued before the host has to wait for the oldest one.  x264cu_wait completes (device work + host copies)
  * every batch up to `seq` only -- the tail keeps running -- whereas x264cu_flush completes everything. */
 uint64_t x264cu_last_batch( x264cu_ctx *ctx );
+/* an empty batch: its sequence number completes when everything enqueued so far (kernels and x264cu_memcpy_* copies) has */
+uint64_t x264cu_fence( x264cu_ctx *ctx );
 int x264cu_wait( x264cu_ctx *ctx, uint64_t seq );
 /* number of kernels launched by this context so far */
 int64_t x264cu_launch_count( x264cu_ctx *ctx );
@@ -194,8 +196,9 @@ int      x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int stride, 
  * b % world == rank, I where n % world == rank.  Results of other ranks' evaluations read as -1 in x264cu_stream_cost. */
 int      x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, int stride, const uint16_t *inv_qscale, int on_device,
                                    int rank, int world, int phase );
-/* frame pushed `age` pushes ago (0 = the newest; during phase 0/1 of a sharded push the frame being pushed) */
-x264cu_frame *x264cu_stream_frame( x264cu_stream *s, int age );
+/* phase 0 of frame n+1 may be issued before phase 1 of frame n, so that the exchange of one step overlaps the searches
+ * of the next.  x264cu_stream_frame: the handle of frame number `index` (0 = first frame pushed) while it is in the window. */
+x264cu_frame *x264cu_stream_frame( x264cu_stream *s, int64_t index );
 int      x264cu_stream_sync( x264cu_stream *s );
 /* after sync: stats of slicetype_frame_cost(p0, n, b) of the newest frame n, d0 = b-p0, d1 = n-b */
 int      x264cu_stream_cost( x264cu_stream *s, int d0, int d1, int32_t *out4 );

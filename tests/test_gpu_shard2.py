@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "x264-i386pic_b200"))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, W, H, B, nframes, passes, q):
+def _worker(rank, world, port, W, H, B, nframes, passes, pipelined, q):
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -28,8 +28,9 @@ def _worker(rank, world, port, W, H, B, nframes, passes, q):
     ctx = x264cu.Context(W, H, bframes=B, passes=passes, device=rank)
     win = shard.ShardedWindow(x264cu, ctx, B, rank, world, dist=dist, device=torch.device("cuda", rank))
     mine = []
-    for f in frames:
-        win.push(f.ctypes.data, W, False)
+    for i, f in enumerate(frames):
+        nxt = frames[i + 1].ctypes.data if pipelined and i + 1 < len(frames) else None
+        win.push(f.ctypes.data, W, False, next_luma=nxt)      # pipelined: frame i+1 is uploaded and searched ahead
         win.sync()
         mine.append(win.costs())
     win.close()
@@ -58,8 +59,8 @@ def _worker(rank, world, port, W, H, B, nframes, passes, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("passes", [2, 0])
-def test_one_stream_on_two_gpus_equals_one_gpu(passes):
+@pytest.mark.parametrize("passes,pipelined", [(2, False), (0, False), (2, True)])
+def test_one_stream_on_two_gpus_equals_one_gpu(passes, pipelined):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -67,8 +68,8 @@ def test_one_stream_on_two_gpus_equals_one_gpu(passes):
     W, H, B, n = 320, 192, 5, 14
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300 + passes
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, W, H, B, n, passes, q)) for r in range(2)]
+    port = 29600 + os.getpid() % 300 + passes + 5 * pipelined
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, W, H, B, n, passes, pipelined, q)) for r in range(2)]
     for p in procs:
         p.start()
     gathered, single = q.get(timeout=600)

@@ -1130,6 +1130,11 @@ extern "C" int x264cu_field_set_searched( x264cu_ctx *c, x264cu_frame *f, int li
 // sequence number of the most recently enqueued batch / wait for everything up to a sequence number:
 // lets a caller keep NSLOT-1 batches in flight and still pick up results in order (x264cu_stream_sync)
 extern "C" uint64_t x264cu_last_batch( x264cu_ctx *c ) { return c ? c->seq : 0; }
+extern "C" uint64_t x264cu_fence( x264cu_ctx *c )
+{
+    if( !c || cudaSetDevice( c->device ) != cudaSuccess || begin_batch( c ) || end_batch( c ) ) return 0;
+    return c->seq;
+}
 extern "C" int x264cu_wait( x264cu_ctx *c, uint64_t seq )
 {
     if( !c ) FAIL( "null context" );

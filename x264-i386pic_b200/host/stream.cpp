@@ -16,7 +16,7 @@
 struct x264cu_stream
 {
     x264cu_ctx *ctx;
-    int bframes, depth;                 // depth = bframes + 2 frames alive
+    int bframes, depth;                 // depth = bframes + 3 frame handles: the window (bframes + 2) + one frame uploaded ahead
     int mbw, mbh, nmb;
     int want_arrays;                    // also bring lowres_costs / row_satds / MVs back (the full hook protocol)
     std::vector<x264cu_frame *> ring;   // frame n lives in ring[n % depth]
@@ -28,7 +28,7 @@ struct x264cu_stream
     // optional array destinations (pinned when possible)
     uint8_t *arr; size_t arr_bytes; bool arr_pinned;
     std::vector<x264cu_job> jobs;
-    bool shard_open;                    // between phase 0 and phase 1 of a sharded push
+    int shard_ahead;                    // sharded pushes whose phase 0 ran but whose phase 1 did not yet (0..2)
 };
 
 extern "C" void *x264cu_host_alloc( x264cu_ctx *ctx, size_t bytes );
@@ -39,10 +39,10 @@ extern "C" x264cu_stream *x264cu_stream_open( x264cu_ctx *ctx, int bframes, int 
     int info[6];
     if( !ctx || bframes < 0 || bframes > X264CU_BFRAME_MAX || x264cu_info( ctx, info ) ) return NULL;
     x264cu_stream *s = new x264cu_stream();
-    s->ctx = ctx; s->bframes = bframes; s->depth = bframes + 2;
+    s->ctx = ctx; s->bframes = bframes; s->depth = bframes + 3;
     s->mbw = info[0]; s->mbh = info[1]; s->nmb = info[0] * info[1];
     s->want_arrays = want_arrays;
-    s->n_pushed = 0; s->last_seq = 0; s->shard_open = false;
+    s->n_pushed = 0; s->last_seq = 0; s->shard_ahead = 0;
     s->stats.assign( (size_t)( bframes+2 ) * ( bframes+2 ) * 4, -1 );
     s->intra_stats.assign( 2, -1 );
     s->arr = NULL; s->arr_bytes = 0; s->arr_pinned = false;
@@ -131,11 +131,10 @@ extern "C" int x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int st
 // the list-1 search (b -> n) and the B evaluations (p0, n, b) to rank b % world, the I evaluation to rank n % world.
 // The only data another rank needs are the list-0 fields of the newest frame (temporal-direct source of this step's B
 // evaluations, list-0 side of later ones): the caller all-gathers them between phase 0 and phase 1.
-extern "C" x264cu_frame *x264cu_stream_frame( x264cu_stream *s, int age )
-{
-    if( !s || age < 0 || age >= s->depth ) return NULL;
-    const int64_t n = s->n_pushed + ( s->shard_open ? 0 : -1 ) - age;
-    return n < 0 ? NULL : s->ring[n % s->depth];
+extern "C" x264cu_frame *x264cu_stream_frame( x264cu_stream *s, int64_t index )
+{   // frame number `index` (0 = the first frame pushed); valid for the frames of the current window and the one uploaded ahead
+    if( !s || index < 0 || index > s->n_pushed + 1 || index < s->n_pushed - ( s->bframes + 1 ) ) return NULL;
+    return s->ring[index % s->depth];
 }
 
 extern "C" int x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, int stride, const uint16_t *inv_qscale, int on_device,
@@ -143,12 +142,13 @@ extern "C" int x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, 
 {
     if( !s || world < 1 || rank < 0 || rank >= world ) return -1;
     const int B = s->bframes, D = s->depth;
-    const int64_t n = s->n_pushed;
+    // phase 0 may run one frame ahead of phase 1 (the caller overlaps the exchange of step n with the searches of step n+1)
+    const int64_t n = phase == 0 ? s->n_pushed + s->shard_ahead : s->n_pushed;
     x264cu_frame *fn = s->ring[n % D];
     const int64_t lo = n - ( B + 1 ) < 0 ? 0 : n - ( B + 1 );
     if( phase == 0 )
     {
-        if( !luma || s->shard_open ) return -1;
+        if( !luma || s->shard_ahead >= 2 ) return -1;
         int r = on_device ? x264cu_frame_upload_device( s->ctx, fn, luma, stride, inv_qscale )
                           : x264cu_frame_upload( s->ctx, fn, luma, stride, inv_qscale );
         if( r ) return -1;
@@ -168,11 +168,10 @@ extern "C" int x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, 
                 sj.push_back( j );
             }
         if( x264cu_search_batch( s->ctx, sj.data(), (int)sj.size() ) ) return -1;
-        s->last_seq = x264cu_last_batch( s->ctx );
-        s->shard_open = true;
+        s->shard_ahead++;
         return (int)sj.size();
     }
-    if( !s->shard_open ) return -1;
+    if( s->shard_ahead < 1 ) return -1;
     s->jobs.clear();
     std::fill( s->stats.begin(), s->stats.end(), -1 );
     if( n % world == rank )
@@ -197,7 +196,7 @@ extern "C" int x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, 
     if( x264cu_frame_cost_batch( s->ctx, s->jobs.data(), (int)s->jobs.size() ) ) return -1;
     s->last_seq = x264cu_last_batch( s->ctx );
     s->n_pushed++;
-    s->shard_open = false;
+    s->shard_ahead--;
     return (int)s->jobs.size();
 }
 

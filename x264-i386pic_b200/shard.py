@@ -53,11 +53,14 @@ class ShardedWindow:
         self.fb = ctx.nmb * 4                                   # bytes of an MV field; the cost field has the same size
         self.slots = (bframes + 1 + world - 1) // world
         self.send = self.recv = None
+        self.ahead, self.fence = 0, [0, 0]
         if world > 1:
             import torch
             self.torch = torch
-            self.send = torch.zeros(self.slots * 2 * self.fb, dtype=torch.uint8, device=device)
-            self.recv = torch.zeros(world * self.slots * 2 * self.fb, dtype=torch.uint8, device=device)
+            # double-buffered: step n+1 packs while step n is being gathered, step n's imports may still be pending
+            # on the context's stream when step n+1 is gathered
+            self.send = [torch.zeros(self.slots * 2 * self.fb, dtype=torch.uint8, device=device) for _ in range(2)]
+            self.recv = [torch.zeros(world * self.slots * 2 * self.fb, dtype=torch.uint8, device=device) for _ in range(2)]
         self._C = C
 
     def _field(self, frame, dist_):
@@ -65,31 +68,48 @@ class ShardedWindow:
         self.x.check(self.L.x264cu_field_device(self.ctx.ctx, frame, 0, dist_, self._C.byref(mv), self._C.byref(mc)), "field_device")
         return mv.value, mc.value
 
-    def push(self, luma, stride, on_device):
-        L, n = self.L, self.n
+    def _phase0(self, n, luma, stride, on_device):
+        """upload frame n, enqueue this rank's searches, pack its list-0 fields of frame n for the all-gather"""
+        L = self.L
         r = L.x264cu_stream_push_shard(self.win, luma, stride, None, int(on_device), self.rank, self.world, 0)
         if r < 0:
             raise RuntimeError("x264cu_stream_push_shard(0): " + self.x.last_error())
         if self.world > 1 and n > 0:
-            fn = L.x264cu_stream_frame(self.win, 0)
+            fn = L.x264cu_stream_frame(self.win, n)
             lo = max(0, n - (self.B + 1))
-            owner_fields = [[p0 for p0 in range(n - 1, lo - 1, -1) if p0 % self.world == r2] for r2 in range(self.world)]
-            for k, p0 in enumerate(owner_fields[self.rank]):
+            send = self.send[n & 1]
+            for k, p0 in enumerate(p0 for p0 in range(n - 1, lo - 1, -1) if p0 % self.world == self.rank):
                 mv, mc = self._field(fn, n - p0)
-                base = self.send.data_ptr() + k * 2 * self.fb
+                base = send.data_ptr() + k * 2 * self.fb
                 self.x.check(L.x264cu_memcpy_d2d(self.ctx.ctx, base, mv, self.fb), "d2d")
                 self.x.check(L.x264cu_memcpy_d2d(self.ctx.ctx, base + self.fb, mc, self.fb), "d2d")
-            # the searches and the packing ran on the context's stream; NCCL runs on torch's: order them through the host
-            self.x.check(L.x264cu_wait(self.ctx.ctx, L.x264cu_last_batch(self.ctx.ctx)), "wait")
-            self.x.check(L.x264cu_flush(self.ctx.ctx), "flush")
-            self.dist.all_gather_into_tensor(self.recv, self.send)
+        self.fence[n & 1] = L.x264cu_fence(self.ctx.ctx)
+
+    def push(self, luma, stride, on_device, next_luma=None):
+        """frame n = number of frames pushed so far.  next_luma: the frame after it, if the caller already has it (an
+        encoder's lookahead queue does): its upload and searches are enqueued BEFORE this step's exchange, so the GPU
+        works on them while the host waits for this step's fields and runs the all-gather."""
+        L, n = self.L, self.n
+        if self.ahead == 0:
+            self._phase0(n, luma, stride, on_device)
+            self.ahead = 1
+        if next_luma is not None:
+            self._phase0(n + 1, next_luma, stride, on_device)
+            self.ahead = 2
+        if self.world > 1 and n > 0:
+            fn = L.x264cu_stream_frame(self.win, n)
+            lo = max(0, n - (self.B + 1))
+            # the searches and the packing ran on the context's stream, NCCL runs on torch's: order them through the host
+            self.x.check(L.x264cu_wait(self.ctx.ctx, self.fence[n & 1]), "wait")
+            send, recv = self.send[n & 1], self.recv[n & 1]
+            self.dist.all_gather_into_tensor(recv, send)
             self.torch.cuda.current_stream().synchronize()
             for r2 in range(self.world):
                 if r2 == self.rank:
                     continue
-                for k, p0 in enumerate(owner_fields[r2]):
+                for k, p0 in enumerate(p0 for p0 in range(n - 1, lo - 1, -1) if p0 % self.world == r2):
                     mv, mc = self._field(fn, n - p0)
-                    base = self.recv.data_ptr() + (r2 * self.slots + k) * 2 * self.fb
+                    base = recv.data_ptr() + (r2 * self.slots + k) * 2 * self.fb
                     self.x.check(L.x264cu_memcpy_d2d(self.ctx.ctx, mv, base, self.fb), "d2d")
                     self.x.check(L.x264cu_memcpy_d2d(self.ctx.ctx, mc, base + self.fb, self.fb), "d2d")
                     self.x.check(L.x264cu_field_set_searched(self.ctx.ctx, fn, 0, n - p0), "set_searched")
@@ -97,10 +117,11 @@ class ShardedWindow:
         if r < 0:
             raise RuntimeError("x264cu_stream_push_shard(1): " + self.x.last_error())
         self.n += 1
+        self.ahead -= 1
         return r
 
     def sync(self):
-        self.x.check(self.L.x264cu_stream_sync(self.win), "sync")
+        self.x.check(self.L.x264cu_flush(self.ctx.ctx), "flush")
 
     def costs(self):
         """this rank's stats of the newest step: {(d0, d1): [cost_est, cost_est_aq, intra_mbs, raw]} (others absent)"""

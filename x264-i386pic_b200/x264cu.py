@@ -110,7 +110,9 @@ def load():
     L.x264cu_stream_push.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.x264cu_stream_push_shard.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.x264cu_stream_frame.restype = vp
-    L.x264cu_stream_frame.argtypes = [vp, C.c_int]
+    L.x264cu_stream_frame.argtypes = [vp, C.c_int64]
+    L.x264cu_fence.argtypes = [vp]
+    L.x264cu_fence.restype = C.c_uint64
     L.x264cu_search_batch.argtypes = [vp, C.POINTER(SearchJob), C.c_int]
     L.x264cu_field_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     L.x264cu_field_set_searched.argtypes = [vp, vp, C.c_int, C.c_int]
