@@ -333,8 +333,11 @@ def run_one_stream(args):
     if rank == 0:
         sampler.start()
     times = []
+    peer = None
+    if dist is not None and args.exchange == "p2p":
+        peer = shard.PeerExchange(x264cu, ctx, BFRAMES, rank, world, dist)
     for e2e in (False, True):
-        win = shard.ShardedWindow(x264cu, ctx, BFRAMES, rank, world, dist=dist, device=dev_t)
+        win = shard.ShardedWindow(x264cu, ctx, BFRAMES, rank, world, dist=dist, device=dev_t, peer=peer)
         src = hp if e2e else dp
         for i in range(RAMP + warmup):
             win.push(src + i * fbytes, W, not e2e)
@@ -368,8 +371,11 @@ def run_one_stream(args):
             "ms_per_step": round(t_v / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "ONE %s encode stream, search fields and evaluations sharded over the GPUs by frame "
-                                   "(BASELINE.json configs[3]); exchange: NCCL all-gather of the newest frame's list-0 MV fields "
-                                   "and costs, %d bytes per rank and frame" % (res, ((BFRAMES + 1 + world - 1) // world) * 8 * ctx.nmb),
+                                   "(BASELINE.json configs[3]); exchange of the newest frame's list-0 MV fields and costs (%d bytes "
+                                   "per rank and frame): %s" % (res, ((BFRAMES + 1 + world - 1) // world) * 8 * ctx.nmb,
+                                   "none (1 GPU)" if world == 1 else "kernel stores into the peers' HBM over NVLink, flags polled on the device "
+                                   "(x264cu_peer_*)" if peer is not None else "NCCL all-gather ordered through the host"),
+                       "exchange": args.exchange if world > 1 else None,
                        "width": W, "height": H, "bframes": BFRAMES, "search_passes": args.search_passes, "subme": args.subme,
                        "evals_per_step": 154, "new_search_fields_per_step": 33,
                        "l2": "inputs larger than L2 at 4K (18 frames x 40 MB); at 1080p the window (18 x 10 MB) is about L2-sized"},
@@ -377,6 +383,8 @@ def run_one_stream(args):
             "e2e": {"value": round(args.steps / (t_e / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": fbytes * world,
                     "d2h_bytes_per_step": 154 * 32, "ms_per_step": round(t_e / args.steps, 4)},
             "gpu_launches": int(launches)}))
+    if peer is not None:
+        peer.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -391,6 +399,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--streams", type=int, default=4, help="independent encode streams per GPU (round-robin)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="one-stream workloads: how the ranks exchange MV fields")
     ap.add_argument("--search-passes", type=int, default=2, help="K of the dependency-free schedule; 0 = exact raster-serial wavefront mode")
     ap.add_argument("--no-primitives", action="store_true", help="skip the SATD/SAD primitive roofline section")
     ap.add_argument("--value-only", action="store_true", help="profiling aid: skip the end-to-end pass")

@@ -300,6 +300,21 @@ int x264cu_lowres_core( x264cu_ctx *ctx, const uint8_t *src, int src_stride, uin
 /* device memory helpers for callers that keep data resident (bench, tests) */
 void *x264cu_malloc( x264cu_ctx *ctx, size_t bytes );
 void  x264cu_free( x264cu_ctx *ctx, void *p );
+/* ---- peer exchange: one encode stream sharded over the GPUs of one box ----
+ * The one exchange step of the path: a B evaluation needs fref1->lowres_mvs[0][p1-p0-1] (slicetype.c:629-631), which
+ * another rank searched.  Every rank owns a mailbox in its HBM (exported with CUDA IPC); x264cu_peer_push stores this
+ * rank's fields straight into all peers' mailboxes over NVLink from one kernel and publishes the step with a
+ * release-store of a flag; x264cu_peer_import waits for the flag ON THE DEVICE and copies mailbox -> frame fields.
+ * Neither call synchronises with the host.  All ranks must issue the same sequence of push / import calls.
+ * handle_out / offset_out of every rank are exchanged by the caller (any host channel) and passed to connect. */
+typedef struct x264cu_peer x264cu_peer;
+x264cu_peer *x264cu_peer_create( x264cu_ctx *ctx, int rank, int world, int items_per_rank, uint8_t handle_out[64], uint64_t *offset_out );
+int  x264cu_peer_connect( x264cu_peer *p, const uint8_t *handles /* world x 64 */, const uint64_t *offsets /* world */ );
+int  x264cu_peer_push( x264cu_peer *p, const void *const *src, const int *slot, int n );
+int  x264cu_peer_import( x264cu_peer *p, void *const *dst, const int *from, const int *slot, int n );
+int  x264cu_peer_error( x264cu_peer *p );
+void x264cu_peer_destroy( x264cu_peer *p );
+
 /* page-locked host memory (the reference's CL_MEM_ALLOC_HOST_PTR buffer, opencl.c:380-392): uploads
  * from it and results into it skip the internal staging copy */
 void *x264cu_host_alloc( x264cu_ctx *ctx, size_t bytes );

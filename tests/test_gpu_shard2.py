@@ -1,6 +1,7 @@
 """BASELINE.json configs[3] / SURVEY.md section 8e: ONE encode stream's lookahead split over two GPUs (search fields and
-evaluations by step_units(), the list-0 MV fields of the newest frame all-gathered over NCCL) must give exactly the
-costs of the single-GPU window, step by step.  Needs two GPUs (skipped otherwise): gpurun --gpus 2."""
+evaluations by step_units(); the list-0 MV fields of the newest frame exchanged either through the peer mailboxes --
+kernels storing into the other GPU's HBM, flags polled on the device -- or through an NCCL all-gather) must give exactly
+the costs of the single-GPU window, step by step.  Needs two GPUs (skipped otherwise): gpurun --gpus 2."""
 import os
 import sys
 
@@ -12,7 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "x264-i386pic_b200"))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, W, H, B, nframes, passes, pipelined, q):
+def _worker(rank, world, port, W, H, B, nframes, passes, pipelined, exchange, sync_every, q):
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -26,14 +27,26 @@ def _worker(rank, world, port, W, H, B, nframes, passes, pipelined, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     frames = [np.ascontiguousarray(f) for f in synth_frames(W, H, nframes, seed=51, pan=(3, 1))]
     ctx = x264cu.Context(W, H, bframes=B, passes=passes, device=rank)
-    win = shard.ShardedWindow(x264cu, ctx, B, rank, world, dist=dist, device=torch.device("cuda", rank))
+    peer = shard.PeerExchange(x264cu, ctx, B, rank, world, dist) if exchange == "p2p" else None
+    win = shard.ShardedWindow(x264cu, ctx, B, rank, world, dist=dist, device=torch.device("cuda", rank), peer=peer)
     mine = []
     for i, f in enumerate(frames):
         nxt = frames[i + 1].ctypes.data if pipelined and i + 1 < len(frames) else None
         win.push(f.ctypes.data, W, False, next_luma=nxt)      # pipelined: frame i+1 is uploaded and searched ahead
-        win.sync()
-        mine.append(win.costs())
+        if sync_every or i == len(frames) - 1:
+            win.sync()
+            got = win.costs()
+            if not sync_every:
+                # the window's host-side stats are per (d0, d1): without a sync per step, results of older steps that
+                # this rank does not own in the newest step are still there -- keep the newest step's own units
+                own = {(b - p0, i - b) for (p0, _, b) in shard.step_units(i, B, rank, world)[2]}
+                got = {k: v for k, v in got.items() if k in own}
+            mine.append(got)
+        else:
+            mine.append(None)                                 # free-running: only the device-side flags order the ranks
     win.close()
+    if peer is not None:
+        peer.close()
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     if rank == 0:
@@ -59,24 +72,35 @@ def _worker(rank, world, port, W, H, B, nframes, passes, pipelined, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("passes,pipelined", [(2, False), (0, False), (2, True)])
-def test_one_stream_on_two_gpus_equals_one_gpu(passes, pipelined):
+@pytest.mark.parametrize("passes,pipelined,exchange,sync_every,n", [
+    (2, False, "nccl", True, 14), (0, False, "nccl", True, 14), (2, True, "nccl", True, 14),
+    (2, False, "p2p", True, 14), (0, True, "p2p", True, 14),
+    (2, True, "p2p", False, 45),         # free-running: the 4-deep mailboxes and the frame ring wrap several times
+])
+def test_one_stream_on_two_gpus_equals_one_gpu(passes, pipelined, exchange, sync_every, n):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    W, H, B, n = 320, 192, 5, 14
+    W, H, B = 320, 192, 5
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300 + passes + 5 * pipelined
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, W, H, B, n, passes, pipelined, q)) for r in range(2)]
+    port = 29600 + os.getpid() % 300 + passes + 5 * pipelined + 11 * (exchange == "p2p") + n
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, W, H, B, n, passes, pipelined, exchange, sync_every, q)) for r in range(2)]
     for p in procs:
         p.start()
-    gathered, single = q.get(timeout=600)
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        gathered, single = q.get(timeout=300)
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     for step in range(n):
+        if gathered[0][step] is None:
+            continue
         merged = {}
         for r in range(2):
             for k, v in gathered[r][step].items():
@@ -84,4 +108,4 @@ def test_one_stream_on_two_gpus_equals_one_gpu(passes, pipelined):
                 merged[k] = v
         assert merged == single[step], step
     # both ranks had work
-    assert all(sum(len(gathered[r][s]) for s in range(n)) > 0 for r in range(2))
+    assert all(sum(len(gathered[r][s] or ()) for s in range(n)) > 0 for r in range(2))

@@ -1506,3 +1506,226 @@ extern "C" int x264cu_lowres_core( x264cu_ctx *c, const uint8_t *src, int src_st
     for( int i = 0; i < 4; i++ ) if( t.down( h[i], d[i], db ) ) FAIL( "x264cu_lowres_core: copy back failed" );
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Peer exchange for one encode stream sharded over several GPUs (the MV field a B evaluation
+// needs from the rank that searched it).  Every rank owns a mailbox in its own HBM, exported with CUDA IPC; the
+// owner of a field stores it straight into every peer's mailbox over NVLink from ONE kernel (no copy-engine launches,
+// no collective, no host synchronisation) and then raises a flag in the peer's mailbox header; the consumer's import
+// kernel waits for the flag on the device and copies mailbox -> frame fields.  Mailboxes are PEER_DEPTH deep: a rank's
+// push of step m+4 follows (in its stream) its import of step m+2, which waited for this rank's push of step m+2,
+// which follows this rank's import of step m -- so a slot is never overwritten before it was read.
+// ------------------------------------------------------------------------------------------------
+enum { PEER_DEPTH = 4, PEER_MAX_ITEMS = 64, PEER_MAX_WORLD = 16, PEER_HEADER = 256 };
+
+struct PeerItems
+{
+    const uint32_t *src[PEER_MAX_ITEMS];    // push: local field; import: unused
+    uint32_t *dst[PEER_MAX_ITEMS];          // import: local field
+    short from[PEER_MAX_ITEMS], slot[PEER_MAX_ITEMS];
+    int n, words;
+};
+struct PeerTargets { uint8_t *box[PEER_MAX_WORLD]; int world, rank; };
+
+struct x264cu_peer
+{
+    x264cu_ctx *c;
+    int rank, world, items_per_rank;
+    size_t slot_stride, bytes;
+    uint8_t *box;                           // local mailbox: header (flags[world], error) + [PEER_DEPTH][world][items_per_rank][slot_stride]
+    uint8_t *remote[PEER_MAX_WORLD];        // peers' mailboxes as mapped here (remote[rank] = box)
+    void *remote_base[PEER_MAX_WORLD];
+    unsigned *d_done;                       // blocks of all push launches that finished their stores
+    unsigned long long done_expected;
+    uint32_t push_epoch, pull_epoch;
+    int *h_err;
+};
+
+static __device__ __forceinline__ void st_release_sys( uint32_t *p, uint32_t v ) { asm volatile( "st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory" ); }
+static __device__ __forceinline__ uint32_t ld_acquire_sys( const uint32_t *p )
+{ uint32_t v; asm volatile( "ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory" ); return v; }
+
+static __device__ __forceinline__ size_t peer_slot_offset( int depth_slot, int world, int items_per_rank, size_t slot_stride, int from, int slot )
+{ return PEER_HEADER + ( ( (size_t)depth_slot * world + from ) * items_per_rank + slot ) * slot_stride; }
+
+// grid (chunks, max(items,1)): every block stores its chunk of one field into all peers' mailboxes; the last block to
+// finish (device-wide counter) publishes the step to every peer
+static __global__ void __launch_bounds__( 256 ) peer_push_kernel( const __grid_constant__ PeerItems it, const __grid_constant__ PeerTargets tg,
+                                                                  int items_per_rank, size_t slot_stride, uint32_t epoch,
+                                                                  unsigned *done, unsigned done_expected )
+{
+    const int item = blockIdx.y;
+    if( item < it.n )
+    {
+        const uint32_t *src = it.src[item];
+        const size_t off = peer_slot_offset( epoch % PEER_DEPTH, tg.world, items_per_rank, slot_stride, tg.rank, it.slot[item] );
+        for( int w = blockIdx.x * blockDim.x + threadIdx.x; w < it.words; w += gridDim.x * blockDim.x )
+        {
+            const uint32_t v = src[w];
+            for( int p = 0; p < tg.world; p++ )
+                if( p != tg.rank ) ( (uint32_t *)( tg.box[p] + off ) )[w] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if( threadIdx.x == 0 && atomicAdd( done, 1u ) + 1 == done_expected )
+    {
+        __threadfence_system();
+        for( int p = 0; p < tg.world; p++ )
+            if( p != tg.rank ) st_release_sys( (uint32_t *)tg.box[p] + tg.rank, epoch + 1 );
+    }
+}
+
+// grid (chunks, max(items,1)): wait until the source rank has published the step, then mailbox -> frame field.
+// Block (0,0) also waits for every other peer, so that the mailbox re-use argument above holds for ranks that own nothing.
+static __global__ void __launch_bounds__( 256 ) peer_import_kernel( const __grid_constant__ PeerItems it, uint8_t *box, int world, int rank,
+                                                                    int items_per_rank, size_t slot_stride, uint32_t epoch )
+{
+    const int item = blockIdx.y;
+    uint32_t *flags = (uint32_t *)box;
+    __shared__ int ok;
+    if( threadIdx.x == 0 )
+    {
+        ok = 1;
+        const bool all = blockIdx.x == 0 && blockIdx.y == 0;
+        for( int p = 0; p < world; p++ )
+        {
+            if( p == rank || ( !all && ( item >= it.n || p != it.from[item] ) ) ) continue;
+            unsigned ns = 64;
+            long long t0 = clock64();
+            while( (int32_t)( ld_acquire_sys( flags + p ) - ( epoch + 1 ) ) < 0 )
+            {
+                __nanosleep( ns ); if( ns < 2048 ) ns *= 2;
+                if( clock64() - t0 > 20000000000ll ) { flags[PEER_MAX_WORLD] = 1; ok = 0; break; }     // ~10 s: a peer died
+            }
+        }
+    }
+    __syncthreads();
+    if( !ok || item >= it.n ) return;
+    const uint32_t *src = (const uint32_t *)( box + peer_slot_offset( epoch % PEER_DEPTH, world, items_per_rank, slot_stride, it.from[item], it.slot[item] ) );
+    uint32_t *dst = it.dst[item];
+    for( int w = blockIdx.x * blockDim.x + threadIdx.x; w < it.words; w += gridDim.x * blockDim.x )
+        dst[w] = __ldcg( src + w );
+}
+
+extern "C" x264cu_peer *x264cu_peer_create( x264cu_ctx *c, int rank, int world, int items_per_rank, uint8_t handle_out[64], uint64_t *offset_out )
+{
+    if( !c || world < 2 || world > PEER_MAX_WORLD || rank < 0 || rank >= world || items_per_rank < 1 || items_per_rank > PEER_MAX_ITEMS || !handle_out || !offset_out )
+    { snprintf( g_err, sizeof(g_err), "x264cu_peer_create: bad argument" ); return NULL; }
+    CUP( cudaSetDevice( c->device ) );
+    x264cu_peer *p = new x264cu_peer();
+    memset( p, 0, sizeof(*p) );
+    p->c = c; p->rank = rank; p->world = world; p->items_per_rank = items_per_rank;
+    p->slot_stride = ( (size_t)c->P.nmb * 4 + 255 ) & ~(size_t)255;
+    p->bytes = PEER_HEADER + (size_t)PEER_DEPTH * world * items_per_rank * p->slot_stride;
+    if( p->bytes < ( 4u << 20 ) ) p->bytes = 4u << 20;      // its own allocation block, not a sub-allocation
+    cudaIpcMemHandle_t h;
+    if( cudaMalloc( &p->box, p->bytes ) != cudaSuccess || cudaMemset( p->box, 0, PEER_HEADER ) != cudaSuccess ||
+        cudaMalloc( &p->d_done, 4 ) != cudaSuccess || cudaMemset( p->d_done, 0, 4 ) != cudaSuccess ||
+        cudaIpcGetMemHandle( &h, p->box ) != cudaSuccess )
+    {
+        snprintf( g_err, sizeof(g_err), "x264cu_peer_create: %s", cudaGetErrorString( cudaGetLastError() ) );
+        cudaFree( p->box ); cudaFree( p->d_done ); delete p; return NULL;
+    }
+    // offset of the mailbox inside the allocation the handle names (0 unless the allocator sub-allocated)
+    uint64_t off = 0;
+    {
+        typedef int (*range_fn)( unsigned long long *, size_t *, unsigned long long );
+        void *fn = NULL; cudaDriverEntryPointQueryResult qr;
+        if( cudaGetDriverEntryPoint( "cuMemGetAddressRange", &fn, cudaEnableDefault, &qr ) == cudaSuccess && fn )
+        {
+            unsigned long long base = 0; size_t sz = 0;
+            if( ( (range_fn)fn )( &base, &sz, (unsigned long long)(uintptr_t)p->box ) == 0 ) off = (uint64_t)(uintptr_t)p->box - base;
+        }
+    }
+    static_assert( sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes" );
+    memcpy( handle_out, &h, 64 ); *offset_out = off;
+    p->remote[rank] = p->box;
+    return p;
+}
+
+extern "C" int x264cu_peer_connect( x264cu_peer *p, const uint8_t *handles, const uint64_t *offsets )
+{
+    if( !p || !handles || !offsets ) FAIL( "x264cu_peer_connect: null argument" );
+    CU( cudaSetDevice( p->c->device ) );
+    for( int r = 0; r < p->world; r++ )
+    {
+        if( r == p->rank ) continue;
+        cudaIpcMemHandle_t h; memcpy( &h, handles + (size_t)r * 64, 64 );
+        CU( cudaIpcOpenMemHandle( &p->remote_base[r], h, cudaIpcMemLazyEnablePeerAccess ) );
+        p->remote[r] = (uint8_t *)p->remote_base[r] + offsets[r];
+    }
+    return 0;
+}
+
+static int peer_fill( x264cu_peer *p, PeerItems &it, const void *const *ptrs, const int *from, const int *slot, int n, bool push )
+{
+    if( n < 0 || n > PEER_MAX_ITEMS ) return -1;
+    memset( &it, 0, sizeof(it) );
+    it.n = n; it.words = p->c->P.nmb;
+    for( int i = 0; i < n; i++ )
+    {
+        if( slot[i] < 0 || slot[i] >= p->items_per_rank || ( !push && ( from[i] < 0 || from[i] >= p->world || from[i] == p->rank ) ) ) return -1;
+        if( push ) it.src[i] = (const uint32_t *)ptrs[i]; else it.dst[i] = (uint32_t *)ptrs[i];
+        it.from[i] = (short)( push ? p->rank : from[i] ); it.slot[i] = (short)slot[i];
+    }
+    return 0;
+}
+
+// enqueue on the context's stream: fields src[i] (nmb 32-bit words each) -> slot[i] of this rank's row in every peer's mailbox
+extern "C" int x264cu_peer_push( x264cu_peer *p, const void *const *src, const int *slot, int n )
+{
+    if( !p ) FAIL( "x264cu_peer_push: null argument" );
+    x264cu_ctx *c = p->c;
+    CU( cudaSetDevice( c->device ) );
+    PeerItems it;
+    if( peer_fill( p, it, src, NULL, slot, n, true ) ) FAIL( "x264cu_peer_push: bad item list" );
+    PeerTargets tg; memset( &tg, 0, sizeof(tg) );
+    tg.world = p->world; tg.rank = p->rank;
+    for( int r = 0; r < p->world; r++ ) { tg.box[r] = p->remote[r]; if( !tg.box[r] ) FAIL( "x264cu_peer_push: not connected" ); }
+    int chunks = ( it.words + 2047 ) / 2048; if( chunks < 1 ) chunks = 1;
+    dim3 grid( chunks, n > 0 ? n : 1 );
+    p->done_expected += (unsigned long long)grid.x * grid.y;
+    peer_push_kernel<<<grid, 256, 0, c->st>>>( it, tg, p->items_per_rank, p->slot_stride, p->push_epoch, p->d_done, (unsigned)p->done_expected );
+    CU( cudaGetLastError() );
+    c->launches++;
+    p->push_epoch++;
+    return 0;
+}
+
+// enqueue on the context's stream: wait (on the device) for the peers' push of the same step, then slot[i] of rank from[i] -> dst[i]
+extern "C" int x264cu_peer_import( x264cu_peer *p, void *const *dst, const int *from, const int *slot, int n )
+{
+    if( !p ) FAIL( "x264cu_peer_import: null argument" );
+    x264cu_ctx *c = p->c;
+    CU( cudaSetDevice( c->device ) );
+    PeerItems it;
+    if( peer_fill( p, it, (const void *const *)dst, from, slot, n, false ) ) FAIL( "x264cu_peer_import: bad item list" );
+    int chunks = ( it.words + 2047 ) / 2048; if( chunks < 1 ) chunks = 1;
+    dim3 grid( chunks, n > 0 ? n : 1 );
+    peer_import_kernel<<<grid, 256, 0, c->st>>>( it, p->box, p->world, p->rank, p->items_per_rank, p->slot_stride, p->pull_epoch );
+    CU( cudaGetLastError() );
+    c->launches++;
+    p->pull_epoch++;
+    return 0;
+}
+
+// after a flush: 1 when an import gave up waiting for a peer
+extern "C" int x264cu_peer_error( x264cu_peer *p )
+{
+    if( !p ) return -1;
+    uint32_t e = 0;
+    if( cudaSetDevice( p->c->device ) != cudaSuccess ||
+        cudaMemcpy( &e, (uint32_t *)p->box + PEER_MAX_WORLD, 4, cudaMemcpyDeviceToHost ) != cudaSuccess ) return -1;
+    return (int)e;
+}
+
+extern "C" void x264cu_peer_destroy( x264cu_peer *p )
+{
+    if( !p ) return;
+    cudaSetDevice( p->c->device );
+    cudaStreamSynchronize( p->c->st );
+    for( int r = 0; r < p->world; r++ ) if( r != p->rank && p->remote_base[r] ) cudaIpcCloseMemHandle( p->remote_base[r] );
+    cudaFree( p->box ); cudaFree( p->d_done );
+    delete p;
+}

@@ -38,12 +38,59 @@ def step_units(n, bframes, rank, world):
     return l0, l1, ev
 
 
+class PeerExchange:
+    """The ranks' mailboxes (x264cu_peer_*): created once per context, shared by every ShardedWindow opened on it.
+    The IPC handles travel through torch.distributed's object all-gather (host side, once); after that the exchange is
+    kernels storing into peer HBM over NVLink and flags polled on the device -- no collective, no host synchronisation."""
+
+    def __init__(self, x264cu, ctx, bframes, rank, world, dist):
+        import ctypes as C
+        self.x, self.ctx, self.L, self.rank, self.world, self._C = x264cu, ctx, ctx.L, rank, world, C
+        self.items = 2 * ((bframes + 1 + world - 1) // world)          # MV field + cost field per owned list-0 search
+        handle, off = (C.c_uint8 * 64)(), C.c_uint64()
+        self.p = self.L.x264cu_peer_create(ctx.ctx, rank, world, self.items, handle, C.byref(off))
+        if not self.p:
+            raise RuntimeError("x264cu_peer_create: " + x264cu.last_error())
+        mine = (bytes(handle), int(off.value))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        hs = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(h for h, _ in everyone))
+        offs = (C.c_uint64 * world)(*[o for _, o in everyone])
+        x264cu.check(self.L.x264cu_peer_connect(self.p, hs, offs), "peer_connect")
+        dist.barrier()                                                  # nobody pushes before everybody has mapped
+
+    def push(self, ptrs):
+        C, n = self._C, len(ptrs)
+        a = (C.c_void_p * max(n, 1))(*ptrs)
+        sl = (C.c_int * max(n, 1))(*range(n))
+        self.x.check(self.L.x264cu_peer_push(self.p, a, sl, n), "peer_push")
+
+    def imports(self, items):
+        """items: [(dst pointer, from rank, slot)]"""
+        C, n = self._C, len(items)
+        a = (C.c_void_p * max(n, 1))(*[i[0] for i in items])
+        fr = (C.c_int * max(n, 1))(*[i[1] for i in items])
+        sl = (C.c_int * max(n, 1))(*[i[2] for i in items])
+        self.x.check(self.L.x264cu_peer_import(self.p, a, fr, sl, n), "peer_import")
+
+    def check(self):
+        if self.L.x264cu_peer_error(self.p) != 0:
+            raise RuntimeError("peer exchange: an import gave up waiting for a peer's fields")
+
+    def close(self):
+        if self.p:
+            self.L.x264cu_peer_destroy(self.p)
+            self.p = None
+
+
 class ShardedWindow:
     """One lookahead window held by `world` ranks (one GPU each).  Every rank pushes every frame; a step's searches and
     evaluations are split by step_units(); the list-0 MV fields (+ costs) of the newest frame are the one exchange step
-    of the path: an NCCL all-gather between the two phases of x264cu_stream_push_shard."""
+    of the path, between the two phases of x264cu_stream_push_shard: with `peer` (a PeerExchange) the owners store them
+    straight into the peers' mailboxes and nothing waits on the host; without it, an NCCL all-gather ordered through
+    the host (kept as the plain-collective arm to compare with)."""
 
-    def __init__(self, x264cu, ctx, bframes, rank, world, dist=None, device=None):
+    def __init__(self, x264cu, ctx, bframes, rank, world, dist=None, device=None, peer=None):
         import ctypes as C
         self.x, self.ctx, self.B, self.rank, self.world, self.dist = x264cu, ctx, bframes, rank, world, dist
         self.L = ctx.L
@@ -54,7 +101,8 @@ class ShardedWindow:
         self.slots = (bframes + 1 + world - 1) // world
         self.send = self.recv = None
         self.ahead, self.fence = 0, [0, 0]
-        if world > 1:
+        self.peer = peer
+        if world > 1 and peer is None:
             import torch
             self.torch = torch
             # double-buffered: step n+1 packs while step n is being gathered, step n's imports may still be pending
@@ -74,6 +122,14 @@ class ShardedWindow:
         r = L.x264cu_stream_push_shard(self.win, luma, stride, None, int(on_device), self.rank, self.world, 0)
         if r < 0:
             raise RuntimeError("x264cu_stream_push_shard(0): " + self.x.last_error())
+        if self.peer is not None:
+            ptrs = []
+            if n > 0:
+                fn = L.x264cu_stream_frame(self.win, n)
+                for p0 in (p0 for p0 in range(n - 1, max(0, n - (self.B + 1)) - 1, -1) if p0 % self.world == self.rank):
+                    ptrs += list(self._field(fn, n - p0))
+            self.peer.push(ptrs)                 # every step, also with nothing to send: the peers wait for the step's flag
+            return
         if self.world > 1 and n > 0:
             fn = L.x264cu_stream_frame(self.win, n)
             lo = max(0, n - (self.B + 1))
@@ -96,7 +152,18 @@ class ShardedWindow:
         if next_luma is not None:
             self._phase0(n + 1, next_luma, stride, on_device)
             self.ahead = 2
-        if self.world > 1 and n > 0:
+        if self.peer is not None:
+            items = []
+            if n > 0:
+                fn = L.x264cu_stream_frame(self.win, n)
+                lo = max(0, n - (self.B + 1))
+                for r2 in (r2 for r2 in range(self.world) if r2 != self.rank):
+                    for k, p0 in enumerate(p0 for p0 in range(n - 1, lo - 1, -1) if p0 % self.world == r2):
+                        mv, mc = self._field(fn, n - p0)
+                        items += [(mv, r2, 2 * k), (mc, r2, 2 * k + 1)]
+                        self.x.check(L.x264cu_field_set_searched(self.ctx.ctx, fn, 0, n - p0), "set_searched")
+            self.peer.imports(items)
+        elif self.world > 1 and n > 0:
             fn = L.x264cu_stream_frame(self.win, n)
             lo = max(0, n - (self.B + 1))
             # the searches and the packing ran on the context's stream, NCCL runs on torch's: order them through the host
@@ -122,6 +189,8 @@ class ShardedWindow:
 
     def sync(self):
         self.x.check(self.L.x264cu_flush(self.ctx.ctx), "flush")
+        if self.peer is not None:
+            self.peer.check()
 
     def costs(self):
         """this rank's stats of the newest step: {(d0, d1): [cost_est, cost_est_aq, intra_mbs, raw]} (others absent)"""

@@ -113,6 +113,13 @@ def load():
     L.x264cu_stream_frame.argtypes = [vp, C.c_int64]
     L.x264cu_fence.argtypes = [vp]
     L.x264cu_fence.restype = C.c_uint64
+    L.x264cu_peer_create.restype = vp
+    L.x264cu_peer_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_uint64)]
+    L.x264cu_peer_connect.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.x264cu_peer_push.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.x264cu_peer_import.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+    L.x264cu_peer_error.argtypes = [vp]
+    L.x264cu_peer_destroy.argtypes = [vp]
     L.x264cu_search_batch.argtypes = [vp, C.POINTER(SearchJob), C.c_int]
     L.x264cu_field_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     L.x264cu_field_set_searched.argtypes = [vp, vp, C.c_int, C.c_int]
