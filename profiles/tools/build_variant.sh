@@ -1,12 +1,15 @@
 #!/bin/bash
-# usage: build_variant.sh NAME search|final "-DX264CU_MINB_SEARCH=6 ..."  -> x264-i386pic_b200/build/var/lib_NAME.so
-# (tuning builds only: one kernel file recompiled with extra defines, the rest taken from the in-tree build)
+# usage: build_variant.sh NAME search|final|final,capi "-DX264CU_MINB_SEARCH=6 ..."  -> x264-i386pic_b200/build/var/lib_NAME.so
+# (tuning builds only: the named kernel files recompiled with extra defines, the rest taken from the in-tree build)
 set -e
 cd "$(dirname "$0")/../../x264-i386pic_b200"
 mkdir -p build/var
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --split-compile=0 $3 -c csrc/$2.cu -o build/var/$2_$1.o
+FILES=$(echo $2 | tr ',' ' ')
+for f in $FILES; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --split-compile=0 $3 -c csrc/$f.cu -o build/var/${f}_$1.o
+done
 OBJS=""
 for o in lookahead search final aq_weights mbtree primitives capi stream slicetype mbtree_host; do
-  if [ $o = $2 ]; then OBJS="$OBJS build/var/$2_$1.o"; else OBJS="$OBJS build/$o.o"; fi
+  if echo " $FILES " | grep -q " $o "; then OBJS="$OBJS build/var/${o}_$1.o"; else OBJS="$OBJS build/$o.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/var/lib_$1.so $OBJS -cudart static

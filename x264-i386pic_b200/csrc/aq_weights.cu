@@ -260,8 +260,8 @@ void launch_weights_analyse( const uint8_t *fencF, const uint8_t *refF, const in
     dim3 grid( ( P.mbw + 31 ) / 32, ( P.mbh + 3 ) / 4 );
 #define WCOST( PITCH ) { if( P.b_satd ) weight_cost_kernel<true, PITCH><<<grid, 128, 0, st>>>( fencF, refF, mvs, intra, wres, P ); \
                          else           weight_cost_kernel<false, PITCH><<<grid, 128, 0, st>>>( fencF, refF, mvs, intra, wres, P ); }
-    if( P.stride == 1024 )      WCOST( 1024 )
-    else if( P.stride == 2048 ) WCOST( 2048 )
+    if( P.stride == X264CU_PITCH_A )      WCOST( X264CU_PITCH_A )
+    else if( P.stride == X264CU_PITCH_B ) WCOST( X264CU_PITCH_B )
     else                        WCOST( 0 )
 #undef WCOST
     weights_decide_kernel<<<1, 32, 0, st>>>( wres, numslices );

@@ -154,8 +154,8 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
     {
         const int padded = P.lw + 2*X264CU_PAD;
         const char *e = getenv( "X264CU_RUNTIME_PITCH" );      // testing aid: forces the run-time-pitch kernels
-        P.stride = ( e && atoi( e ) ) || padded > 2048 ? (int)align_up( padded, 128 ) + ( e && atoi( e ) && ( padded == 1024 || padded == 2048 ) ? 128 : 0 )
-                 : padded <= 1024 ? 1024 : 2048;
+        P.stride = ( e && atoi( e ) ) || padded > X264CU_PITCH_B ? (int)align_up( padded, 128 ) + ( e && atoi( e ) && ( padded == X264CU_PITCH_A || padded == X264CU_PITCH_B ) ? 128 : 0 )
+                 : padded <= X264CU_PITCH_A ? X264CU_PITCH_A : X264CU_PITCH_B;
     }
     P.plane_size = (int64_t)P.stride * ( P.lh + 2*X264CU_PAD );
     P.mv_range2 = 2 * cfg->mv_range;
@@ -981,8 +981,6 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
     {
         const x264cu_job &j = jobs[i];
         if( !j.out.stats ) continue;
-        int ti = tri_index( c, j.d0, j.d1 );
-        const int32_t *st = j.fenc->stats + (size_t)ti * c->stat_pitch;
         sts.push_back( { j.out.stats, offS, 32, ( j.d0 + j.d1 == 0 ) ? 0 : ( j.d1 > 0 ? 2 : 1 ) } );
         offS += 32;
     }

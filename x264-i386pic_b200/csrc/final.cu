@@ -138,8 +138,8 @@ void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStr
         dim3 grid( ( P.ntiles_f + warps_per_cta - 1 ) / warps_per_cta, ( njobs + F_JOBS - 1 ) / F_JOBS );
 #define FINAL_T( PITCH ) { if( P.b_satd ) final_kernel_t<true, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, njobs, P ); \
                            else           final_kernel_t<false, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, njobs, P ); }
-        if( P.stride == 1024 )      FINAL_T( 1024 )
-        else if( P.stride == 2048 ) FINAL_T( 2048 )
+        if( P.stride == X264CU_PITCH_A )      FINAL_T( X264CU_PITCH_A )
+        else if( P.stride == X264CU_PITCH_B ) FINAL_T( X264CU_PITCH_B )
         else                        FINAL_T( 0 )
 #undef FINAL_T
     }

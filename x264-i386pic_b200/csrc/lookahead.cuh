@@ -8,6 +8,11 @@
 #define X264CU_S_TILE_W 32
 #define X264CU_S_TILE_H 4
 #endif
+// the two compile-time plane pitches of the search / decision kernels (capi.cu picks the smaller one that fits)
+#ifndef X264CU_PITCH_A
+#define X264CU_PITCH_A 1024
+#define X264CU_PITCH_B 2048
+#endif
 #ifndef X264CU_F_TILE_W
 #define X264CU_F_TILE_W 16
 #define X264CU_F_TILE_H 8

@@ -497,8 +497,8 @@ void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const
     if( use_thread_mapping( P, njobs ) )
     {   // the context picks the pitch from {1024, 2048} whenever the padded width fits (capi.cu), anything wider runs the
         // run-time-pitch instantiation
-        if( P.stride == 1024 )      launch_search_t<1024>( d_jobs, njobs, any_weighted, P, st );
-        else if( P.stride == 2048 ) launch_search_t<2048>( d_jobs, njobs, any_weighted, P, st );
+        if( P.stride == X264CU_PITCH_A )      launch_search_t<X264CU_PITCH_A>( d_jobs, njobs, any_weighted, P, st );
+        else if( P.stride == X264CU_PITCH_B ) launch_search_t<X264CU_PITCH_B>( d_jobs, njobs, any_weighted, P, st );
         else                        launch_search_t<0>( d_jobs, njobs, any_weighted, P, st );
     }
     else
