@@ -531,14 +531,14 @@ def main():
         avg_ms = s_ms / s_n
         ach = alg / avg_ms / 1e6
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch from the committed
-        # `ncu --set full` capture (profiles/r01/ncu_summary_v7.md: 40.67 MB + 0.50 MB); below the algorithmic bytes
+        # `ncu --set full` capture (profiles/r01/ncu_summary_v11.md: 40.66 MB + 0.74 MB); below the algorithmic bytes
         # because the 18 frames of a window are shared by the 33 fields of a launch and stay in L2
         out["roofline"] = {"kernel": "search_kernel_t<SATD,unweighted>", "bound": "hbm", "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
-                           "frac": round(ach / peak_gbs, 4), "traffic": 41.17e6, "peak_source": peak_src,
+                           "frac": round(ach / peak_gbs, 4), "traffic": 41.40e6, "peak_source": peak_src,
                            "avg_launch_ms": round(avg_ms, 4), "launches_timed": s_n, "algorithmic_bytes_per_launch": alg,
                            "timed": "CUDA events around every launch in a separate %d-step pass on one context (no overlap with other streams' kernels)" % psteps,
-                           "integer_pipe": {"alu_pipe_pct": 63.3, "issue_active_pct": 53.6, "l1tex_wavefronts_pct": 58.3,
-                                            "source": "ncu --set full, profiles/r01/ncu_summary_v7.md (not measured in this run)"},
+                           "integer_pipe": {"alu_pipe_pct": 61.5, "issue_active_pct": 52.1, "l1tex_wavefronts_pct": 62.0,
+                                            "source": "ncu --set full, profiles/r01/ncu_summary_v11.md (not measured in this run)"},
                            "note": "compulsory bytes are tiny: the kernel is bound by integer issue (6 SATD 8x8 + ~35 SAD 8x8 per block and pass) "
                                    "and L1 wavefronts, not by HBM; the HBM-streaming kernels of the path are in `primitives`"}
         out["kernel_ms_per_step"] = {k: round(v[0] / psteps, 4) for k, v in kt.items()}
