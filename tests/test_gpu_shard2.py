@@ -72,21 +72,24 @@ def _worker(rank, world, port, W, H, B, nframes, passes, pipelined, exchange, sy
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("passes,pipelined,exchange,sync_every,n", [
-    (2, False, "nccl", True, 14), (0, False, "nccl", True, 14), (2, True, "nccl", True, 14),
-    (2, False, "p2p", True, 14), (0, True, "p2p", True, 14),
-    (2, True, "p2p", False, 45),         # free-running: the 4-deep mailboxes and the frame ring wrap several times
+@pytest.mark.parametrize("passes,pipelined,exchange,sync_every,n,world", [
+    (2, False, "nccl", True, 14, 2), (0, False, "nccl", True, 14, 2), (2, True, "nccl", True, 14, 2),
+    (2, False, "p2p", True, 14, 2), (0, True, "p2p", True, 14, 2),
+    (2, True, "p2p", False, 45, 2),      # free-running: the 4-deep mailboxes and the frame ring wrap several times
+    (2, True, "p2p", True, 14, 3),       # uneven shares: 6 list-0 fields over 3 ranks, ranks that own nothing in early steps
+    (2, True, "p2p", False, 45, 4),
+    (0, True, "nccl", True, 10, 4),
 ])
-def test_one_stream_on_two_gpus_equals_one_gpu(passes, pipelined, exchange, sync_every, n):
+def test_one_stream_on_two_gpus_equals_one_gpu(passes, pipelined, exchange, sync_every, n, world):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     W, H, B = 320, 192, 5
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300 + passes + 5 * pipelined + 11 * (exchange == "p2p") + n
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, W, H, B, n, passes, pipelined, exchange, sync_every, q)) for r in range(2)]
+    port = 29600 + os.getpid() % 300 + passes + 5 * pipelined + 11 * (exchange == "p2p") + n + 50 * world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, W, H, B, n, passes, pipelined, exchange, sync_every, q)) for r in range(world)]
     for p in procs:
         p.start()
     try:
@@ -102,10 +105,10 @@ def test_one_stream_on_two_gpus_equals_one_gpu(passes, pipelined, exchange, sync
         if gathered[0][step] is None:
             continue
         merged = {}
-        for r in range(2):
+        for r in range(world):
             for k, v in gathered[r][step].items():
                 assert k not in merged, (step, k)          # every evaluation on exactly one rank
                 merged[k] = v
         assert merged == single[step], step
     # both ranks had work
-    assert all(sum(len(gathered[r][s] or ()) for s in range(n)) > 0 for r in range(2))
+    assert all(sum(len(gathered[r][s] or ()) for s in range(n)) > 0 for r in range(world))
