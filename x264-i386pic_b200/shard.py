@@ -1,6 +1,7 @@
-"""Work partitioning across the GPUs of one box.  The path shards by independent
-units -- encode streams, or within one stream the (b, ref) search fields -- so there is no data-path
-collective: every rank computes its own units and returns per-frame cost/MV arrays to the host."""
+"""Work partitioning across the GPUs of one box.  Encode streams shard with no data-path
+collective: every rank computes its own streams and returns per-frame cost/MV arrays to its host.  ONE stream sharded
+over the GPUs (its search fields and evaluations) has one exchange step, the newest frame's list-0 MV fields, done by
+the product's own kernels over peer memory (PeerExchange / x264cu_peer_*); an NCCL all-gather arm is kept to compare."""
 
 
 def assign_streams(n_streams, world, rank):
