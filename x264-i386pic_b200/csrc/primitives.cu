@@ -73,7 +73,11 @@ __device__ __forceinline__ int satd_4x4( u32 a[4], u32 b[4] )   // one word (4 p
     return (int)( sum >> 1 );
 }
 
-// pixel.c:334-366
+// pixel.c:334-366.  The sum of |coef| over all 64 coefficients does not depend on the order of the butterfly stages,
+// so the rows are packed as in satd_8x4 (column k with column k+4, one PRMT-based expansion per row), the packed
+// words go through the 4-point horizontal and the 8-point vertical transform, and the remaining horizontal stage --
+// the butterfly BETWEEN the two halves of each word -- is folded into the absolute sum:
+// |lo+hi| + |lo-hi| == 2*max(|lo|,|hi|).  Fields stay below 2^15 (8 * 4 * 255 = 8160).
 template<class LD1, class LD2>
 __device__ __forceinline__ int sa8d_8x8_raw( const uint8_t *p1, int s1, const uint8_t *p2, int s2, LD1 ld1, LD2 ld2 )
 {
@@ -81,28 +85,27 @@ __device__ __forceinline__ int sa8d_8x8_raw( const uint8_t *p1, int s1, const ui
 #pragma unroll
     for( int i = 0; i < 8; i++ )
     {
-        uint2 a = ld1( p1 + (size_t)i*s1 ), b = ld2( p2 + (size_t)i*s2 );
-        u32 d[8];
-#pragma unroll
-        for( int k = 0; k < 4; k++ ) { d[k] = byte_of( a.x, k ) - byte_of( b.x, k ); d[4+k] = byte_of( a.y, k ) - byte_of( b.y, k ); }
-        u32 b0 = ( d[0] + d[1] ) + ( ( d[0] - d[1] ) << 16 ), b1 = ( d[2] + d[3] ) + ( ( d[2] - d[3] ) << 16 );
-        u32 b2 = ( d[4] + d[5] ) + ( ( d[4] - d[5] ) << 16 ), b3 = ( d[6] + d[7] ) + ( ( d[6] - d[7] ) << 16 );
-        HADAMARD4( t[i][0], t[i][1], t[i][2], t[i][3], b0, b1, b2, b3 );
+        u32 d[4];
+        diff_row8( ld1( p1 + (size_t)i*s1 ), ld2( p2 + (size_t)i*s2 ), d );
+        HADAMARD4( t[i][0], t[i][1], t[i][2], t[i][3], d[0], d[1], d[2], d[3] );
     }
     u32 sum = 0;
 #pragma unroll
-    for( int i = 0; i < 4; i++ )
+    for( int c = 0; c < 4; c++ )
     {
-        u32 a0, a1, a2, a3, a4, a5, a6, a7;
-        HADAMARD4( a0, a1, a2, a3, t[0][i], t[1][i], t[2][i], t[3][i] );
-        HADAMARD4( a4, a5, a6, a7, t[4][i], t[5][i], t[6][i], t[7][i] );
-        u32 b0 = abs2( a0 + a4 ) + abs2( a0 - a4 );
-        b0 += abs2( a1 + a5 ) + abs2( a1 - a5 );
-        b0 += abs2( a2 + a6 ) + abs2( a2 - a6 );
-        b0 += abs2( a3 + a7 ) + abs2( a3 - a7 );
-        sum += ( b0 & 0xffff ) + ( b0 >> 16 );
+        u32 a[8];
+        HADAMARD4( a[0], a[1], a[2], a[3], t[0][c], t[1][c], t[2][c], t[3][c] );
+        HADAMARD4( a[4], a[5], a[6], a[7], t[4][c], t[5][c], t[6][c], t[7][c] );
+        u32 col = 0;      // low half: sum of 8 maxima <= 8 * 8160 < 2^16; the high half is not used
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            const u32 u = abs2( a[k] + a[k+4] ), v = abs2( a[k] - a[k+4] );
+            col += __vmaxu2( u, u >> 16 ) + __vmaxu2( v, v >> 16 );
+        }
+        sum += col & 0xffff;
     }
-    return (int)sum;
+    return (int)( 2 * sum );
 }
 
 // pixel.c:383-418: returns (sum8<<32)+sum4 of one 8x8
