@@ -74,10 +74,17 @@ __device__ __forceinline__ int satd_4x4( u32 a[4], u32 b[4] )   // one word (4 p
 }
 
 // pixel.c:334-366.  The sum of |coef| over all 64 coefficients does not depend on the order of the butterfly stages,
-// so the rows are packed as in satd_8x4 (column k with column k+4, one PRMT-based expansion per row), the packed
-// words go through the 4-point horizontal and the 8-point vertical transform, and the remaining horizontal stage --
-// the butterfly BETWEEN the two halves of each word -- is folded into the absolute sum:
+// so neighbouring columns are packed into one word (p[2k] | p[2k+1] << 16: two PRMTs per input word), the packed
+// words go through the other two horizontal stages and the 8-point vertical transform, and the remaining horizontal
+// stage -- the butterfly BETWEEN the two halves of each word -- is folded into the absolute sum:
 // |lo+hi| + |lo-hi| == 2*max(|lo|,|hi|).  Fields stay below 2^15 (8 * 4 * 255 = 8160).
+__device__ __forceinline__ void diff_row8_pairs( uint2 a, uint2 b, u32 d[4] )
+{
+    d[0] = __byte_perm( a.x, 0, 0x4140 ) - __byte_perm( b.x, 0, 0x4140 );
+    d[1] = __byte_perm( a.x, 0, 0x4342 ) - __byte_perm( b.x, 0, 0x4342 );
+    d[2] = __byte_perm( a.y, 0, 0x4140 ) - __byte_perm( b.y, 0, 0x4140 );
+    d[3] = __byte_perm( a.y, 0, 0x4342 ) - __byte_perm( b.y, 0, 0x4342 );
+}
 template<class LD1, class LD2>
 __device__ __forceinline__ int sa8d_8x8_raw( const uint8_t *p1, int s1, const uint8_t *p2, int s2, LD1 ld1, LD2 ld2 )
 {
@@ -86,7 +93,7 @@ __device__ __forceinline__ int sa8d_8x8_raw( const uint8_t *p1, int s1, const ui
     for( int i = 0; i < 8; i++ )
     {
         u32 d[4];
-        diff_row8( ld1( p1 + (size_t)i*s1 ), ld2( p2 + (size_t)i*s2 ), d );
+        diff_row8_pairs( ld1( p1 + (size_t)i*s1 ), ld2( p2 + (size_t)i*s2 ), d );
         HADAMARD4( t[i][0], t[i][1], t[i][2], t[i][3], d[0], d[1], d[2], d[3] );
     }
     u32 sum = 0;
@@ -96,14 +103,15 @@ __device__ __forceinline__ int sa8d_8x8_raw( const uint8_t *p1, int s1, const ui
         u32 a[8];
         HADAMARD4( a[0], a[1], a[2], a[3], t[0][c], t[1][c], t[2][c], t[3][c] );
         HADAMARD4( a[4], a[5], a[6], a[7], t[4][c], t[5][c], t[6][c], t[7][c] );
-        u32 col = 0;      // low half: sum of 8 maxima <= 8 * 8160 < 2^16; the high half is not used
+        u32 col = 0;      // per half: 4 maxima <= 4 * 8160 < 2^15
 #pragma unroll
         for( int k = 0; k < 4; k++ )
         {
             const u32 u = abs2( a[k] + a[k+4] ), v = abs2( a[k] - a[k+4] );
-            col += __vmaxu2( u, u >> 16 ) + __vmaxu2( v, v >> 16 );
+            // (lo_u, lo_v) against (hi_u, hi_v): both maxima from one packed max
+            col += __vmaxu2( __byte_perm( u, v, 0x5410 ), __byte_perm( u, v, 0x7632 ) );
         }
-        sum += col & 0xffff;
+        sum += ( col & 0xffff ) + ( col >> 16 );
     }
     return (int)( 2 * sum );
 }
