@@ -232,6 +232,35 @@ def bench_satd(x264cu, ctx, peak_gbs):
         gbs = (2 * W * hh + (W // bw) * (hh // bh) * 4) / ms / 1e6
         out[name] = {"gpix_s": round(gpix, 1), "gb_s": round(gbs, 1), "hbm_frac": round(gbs / peak_gbs, 4), "ms": round(ms, 4)}
         ctx.free(dout)
+    # the other streaming primitives of SURVEY.md section 8(a)/(d) on the same stacks, device-resident in and out
+    def timed(name, call, alg_bytes, reps=10):
+        for _ in range(3):
+            x264cu.check(call(), name)
+        ctx.timer_begin()
+        for _ in range(reps):
+            call()
+        ms = ctx.timer_end() / reps
+        out[name] = {"gb_s": round(alg_bytes / ms / 1e6, 1), "hbm_frac": round(alg_bytes / ms / 1e6 / peak_gbs, 4), "ms": round(ms, 4)}
+
+    dac = ctx.malloc((W // 16) * (hh // 16) * 8)
+    timed("hadamard_ac_16x16", lambda: L.x264cu_hadamard_ac_grid(ctx.ctx, 0, d1, W, W, hh, dac, 1), W * hh + (W // 16) * (hh // 16) * 8)
+    ctx.free(dac)
+    dco = ctx.malloc(W * hh * 2)
+    timed("sub8x8_dct", lambda: L.x264cu_sub_dct_grid(ctx.ctx, 8, d1, W, d2, W, W, hh, dco, 1), 2 * W * hh + 2 * W * hh)
+    mf = np.full(16, 13107, dtype=np.uint16)
+    bias = np.full(16, 21845, dtype=np.uint16)
+    dmf, dbias = ctx.to_device(mf), ctx.to_device(bias)
+    nblk = W * hh // 16
+    dnz = ctx.malloc(nblk * 4)
+    timed("quant_4x4", lambda: L.x264cu_quant(ctx.ctx, 0, dco, nblk, dmf, dbias, dnz, 1), 2 * 2 * W * hh + nblk * 4)
+    for p in (dco, dmf, dbias, dnz):
+        ctx.free(p)
+    lw, lh = W // 2 - 8, hh // 4 - 1          # half of the stack (64 frames: 133 MB in, 133 MB out)
+    dl = [ctx.malloc((W // 2) * (hh // 4) + 256) for _ in range(4)]
+    timed("frame_init_lowres_core", lambda: L.x264cu_lowres_core(ctx.ctx, d1, W, dl[0], dl[1], dl[2], dl[3], W // 2, lw, lh, 1),
+          (2 * lw + 1) * (2 * lh + 1) + 4 * lw * lh)
+    for p in dl:
+        ctx.free(p)
     ctx.free(d1)
     ctx.free(d2)
     return out

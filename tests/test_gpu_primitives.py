@@ -177,3 +177,16 @@ def test_full_size_properties(cu):
     # a flat plane has no AC energy
     flat = np.full((64, 256), 200, dtype=np.uint8)
     assert (cu.hadamard_ac_grid(0, flat) == 0).all()
+
+
+@pytest.mark.parametrize("sstride,dstride", [(208, 104), (211, 101), (216, 102)])
+@pytest.mark.parametrize("width,height", [(101, 9), (100, 4), (7, 3), (4, 1), (3, 5)])
+def test_lowres_core_ragged_and_unaligned(cu, orc, sstride, dstride, width, height):
+    """frame_init_lowres_core (mc.c:484-507) at widths that are not a multiple of the 4-pixel vector, row counts that are
+    not a multiple of the rows per thread, and strides that keep the kernel off its aligned path"""
+    rng = np.random.default_rng(width * 131 + height * 7 + sstride)
+    src = rng.integers(0, 256, sstride * (2 * height + 2), dtype=np.uint8)
+    want = orc.lowres_core(src, sstride, width, height, dstride)
+    got = cu.lowres_core(src, sstride, width, height, dstride)
+    for k in range(4):
+        np.testing.assert_array_equal(got[k], want[k], err_msg="plane %d" % k)

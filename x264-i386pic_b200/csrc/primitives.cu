@@ -508,18 +508,51 @@ int launch_quant( int b8x8, int16_t *coefs, int64_t nblocks, const uint16_t *mf,
 }
 
 // ---- frame_init_lowres_core with the reference's own signature (mc.c:484-507) ------------------------
-__global__ void __launch_bounds__(128) lowres_core_kernel( const uint8_t *__restrict__ src, int ss, uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc,
-                                                           int ds, int width, int height )
+// One thread = 4 output pixels of each of the four planes for LR_ROWS consecutive rows.  Aligned form: per input row two
+// aligned words + the ninth byte (the next thread's first byte, an L1 hit); the third input row of one output row is
+// the first of the next and stays in registers; vertical then horizontal byte averages on packed words (FILTER of
+// mc.c:494 is avg(avg(a,b), avg(c,d)) with rounding byte averages), one 32-bit store per plane and row.
+#define LR_ROWS 4
+template<bool ALIGNED>
+__global__ void __launch_bounds__(128) lowres_core_kernel( const uint8_t *__restrict__ src, int ss, uint8_t *__restrict__ d0, uint8_t *__restrict__ dh,
+                                                           uint8_t *__restrict__ dv, uint8_t *__restrict__ dc, int ds, int width, int height )
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if( x >= width ) return;
-    const uint8_t *r0 = src + (size_t)2*y*ss + 2*x, *r1 = r0 + ss, *r2 = r1 + ss;
+    const int x0 = ( blockIdx.x * blockDim.x + threadIdx.x ) * 4, y0 = blockIdx.y * LR_ROWS;
+    if( x0 >= width ) return;
+    if( ALIGNED && x0 + 4 <= width )
+    {
+        const uint8_t *r = src + (size_t)2*y0*ss + 2*x0;
+        uint2 a = __ldg( (const uint2 *)r ); u32 a8 = __ldg( r + 8 );
+#pragma unroll
+        for( int j = 0; j < LR_ROWS; j++ )
+        {
+            if( y0 + j >= height ) break;
+            const uint8_t *r1 = r + ss, *r2 = r1 + ss;
+            const uint2 b = __ldg( (const uint2 *)r1 ), d = __ldg( (const uint2 *)r2 );
+            const u32 b8 = __ldg( r1 + 8 ), d8 = __ldg( r2 + 8 );
+            const u32 v0 = avg4( a.x, b.x ), v1 = avg4( a.y, b.y ), v8 = ( a8 + b8 + 1 ) >> 1;   // rows 2y, 2y+1
+            const u32 w0 = avg4( b.x, d.x ), w1 = avg4( b.y, d.y ), w8 = ( b8 + d8 + 1 ) >> 1;   // rows 2y+1, 2y+2
+            const u32 ve = __byte_perm( v0, v1, 0x6420 ), vo = __byte_perm( v0, v1, 0x7531 ), ve2 = ( ve >> 8 ) | ( v8 << 24 );
+            const u32 we = __byte_perm( w0, w1, 0x6420 ), wo = __byte_perm( w0, w1, 0x7531 ), we2 = ( we >> 8 ) | ( w8 << 24 );
+            const size_t o = (size_t)( y0 + j ) * ds + x0;
+            *(u32 *)( d0 + o ) = avg4( ve, vo ); *(u32 *)( dh + o ) = avg4( vo, ve2 );
+            *(u32 *)( dv + o ) = avg4( we, wo ); *(u32 *)( dc + o ) = avg4( wo, we2 );
+            a = d; a8 = d8; r = r2;
+        }
+        return;
+    }
 #define FILT(a,b,c,d) ((((((a)+(b)+1)>>1)+(((c)+(d)+1)>>1)+1)>>1))
-    int a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b1 = r1[1], b2 = r1[2], c0 = r2[0], c1 = r2[1], c2 = r2[2];
-    d0[(size_t)y*ds + x] = FILT( a0, b0, a1, b1 );
-    dh[(size_t)y*ds + x] = FILT( a1, b1, a2, b2 );
-    dv[(size_t)y*ds + x] = FILT( b0, c0, b1, c1 );
-    dc[(size_t)y*ds + x] = FILT( b1, c1, b2, c2 );
+    for( int j = 0; j < LR_ROWS && y0 + j < height; j++ )
+        for( int k = 0; k < 4 && x0 + k < width; k++ )
+        {
+            const int x = x0 + k, y = y0 + j;
+            const uint8_t *r0 = src + (size_t)2*y*ss + 2*x, *r1 = r0 + ss, *r2 = r1 + ss;
+            int a0 = r0[0], a1 = r0[1], a2 = r0[2], b0 = r1[0], b1 = r1[1], b2 = r1[2], c0 = r2[0], c1 = r2[1], c2 = r2[2];
+            d0[(size_t)y*ds + x] = FILT( a0, b0, a1, b1 );
+            dh[(size_t)y*ds + x] = FILT( a1, b1, a2, b2 );
+            dv[(size_t)y*ds + x] = FILT( b0, c0, b1, c1 );
+            dc[(size_t)y*ds + x] = FILT( b1, c1, b2, c2 );
+        }
 #undef FILT
 }
 
@@ -527,7 +560,10 @@ int launch_lowres_core( const uint8_t *src, int sstride, uint8_t *d0, uint8_t *d
                         int width, int height, cudaStream_t st )
 {
     if( width <= 0 || height <= 0 ) return 0;
-    dim3 grid( ( width + 127 ) / 128, height );
-    lowres_core_kernel<<<grid, 128, 0, st>>>( src, sstride, d0, dh, dv, dc, dstride, width, height );
+    dim3 grid( ( ( width + 3 ) / 4 + 127 ) / 128, ( height + LR_ROWS - 1 ) / LR_ROWS );
+    const bool aligned = ( ( (uintptr_t)src | (uintptr_t)sstride ) & 7 ) == 0 &&
+                         ( ( (uintptr_t)d0 | (uintptr_t)dh | (uintptr_t)dv | (uintptr_t)dc | (uintptr_t)dstride ) & 3 ) == 0;
+    if( aligned ) lowres_core_kernel<true><<<grid, 128, 0, st>>>( src, sstride, d0, dh, dv, dc, dstride, width, height );
+    else          lowres_core_kernel<false><<<grid, 128, 0, st>>>( src, sstride, d0, dh, dv, dc, dstride, width, height );
     return 0;
 }
