@@ -512,7 +512,9 @@ int launch_quant( int b8x8, int16_t *coefs, int64_t nblocks, const uint16_t *mf,
 // aligned words + the ninth byte (the next thread's first byte, an L1 hit); the third input row of one output row is
 // the first of the next and stays in registers; vertical then horizontal byte averages on packed words (FILTER of
 // mc.c:494 is avg(avg(a,b), avg(c,d)) with rounding byte averages), one 32-bit store per plane and row.
+#ifndef LR_ROWS
 #define LR_ROWS 4
+#endif
 template<bool ALIGNED>
 __global__ void __launch_bounds__(128) lowres_core_kernel( const uint8_t *__restrict__ src, int ss, uint8_t *__restrict__ d0, uint8_t *__restrict__ dh,
                                                            uint8_t *__restrict__ dv, uint8_t *__restrict__ dc, int ds, int width, int height )
