@@ -179,7 +179,7 @@ def test_full_size_properties(cu):
     assert (cu.hadamard_ac_grid(0, flat) == 0).all()
 
 
-@pytest.mark.parametrize("sstride,dstride", [(208, 104), (211, 101), (216, 102)])
+@pytest.mark.parametrize("sstride,dstride", [(208, 104), (232, 116), (211, 101), (216, 102)])   # 16-byte, 8-byte, unaligned paths
 @pytest.mark.parametrize("width,height", [(101, 9), (100, 4), (7, 3), (4, 1), (3, 5)])
 def test_lowres_core_ragged_and_unaligned(cu, orc, sstride, dstride, width, height):
     """frame_init_lowres_core (mc.c:484-507) at widths that are not a multiple of the 4-pixel vector, row counts that are
