@@ -205,40 +205,11 @@ int      x264cu_stream_cost( x264cu_stream *s, int d0, int d1, int32_t *out4 );
 int64_t  x264cu_stream_frames( x264cu_stream *s );
 int64_t  x264cu_stream_result_bytes( x264cu_stream *s );
 
-/* ---- slicetype decision on the host (host/slicetype.cpp): the control logic of x264_slicetype_analyse
- *      (slicetype.c:1473-1743: scenecut, B-adapt none/fast/trellis, keyframe limit) over a frame-cost
- *      callback, so that the decisions come from the device cost matrix. ---- */
-typedef struct
-{
-    int bframes;              /* i_bframe */
-    int b_adapt;              /* i_bframe_adaptive: 0 none, 1 fast, 2 trellis */
-    int bframe_pyramid;       /* i_bframe_pyramid != 0 (slicetype.c:1310) */
-    int scenecut_threshold;   /* i_scenecut_threshold (40) */
-    int keyint_max, keyint_min;
-    int open_gop, intra_refresh;
-    int psy_mbtree;           /* (analyse.b_psy && rc.b_mb_tree) || vbv lookahead (slicetype.c:1511) */
-} x264cu_slicetype_cfg;
-
-typedef struct
-{
-    int frame_num;            /* x264_frame_t.i_frame */
-    int type;                 /* in: X264_TYPE_AUTO (0) or a forced type; out: the decision (x264.h:278-287 values) */
-    int forced_type;          /* i_forced_type */
-    int b_scenecut;           /* starts at 1 (frame.c:792) */
-    int analysed_type;        /* out: the analysis result before undecided frames are reset (slicetype.c:1736-1738) */
-} x264cu_slicetype_frame;
-
-/* slicetype_frame_cost(h, a, frames, p0, p1, b) -> i_cost_est; indices address `frames`; stats4 as x264cu_out.stats */
-typedef int (*x264cu_cost_fn)( void *user, int p0, int p1, int b, int32_t *stats4 );
-
-/* frames[0] = last non-B frame, frames[1..n_lookahead] = lookahead->next.  Returns reset_start (frames[1..reset_start-1]
- * are decided), 0 when nothing but frames[1] was typed (scenecut / no frames), -1 on bad arguments. */
-int x264cu_slicetype_analyse( const x264cu_slicetype_cfg *cfg, x264cu_slicetype_frame *frames, int n_lookahead,
-                              int i_last_keyframe, int intra_minigop, x264cu_cost_fn cost, void *user );
-
 /* ---- MB-tree (the consumer right after the path): macroblock_tree_propagate =
  *      mbtree_propagate_cost + mbtree_propagate_list (common/mc.c:511-598) and macroblock_tree_finish
- *      (encoder/slicetype.c:1029-1089) on the device, the frame walk of macroblock_tree (:1091-1188) on the host. ---- */
+ *      (encoder/slicetype.c:1029-1089) on the device.  The frame walk of macroblock_tree (:1091-1188) and the slicetype decision
+ *      logic (:1288-1743) are NOT part of this library: they stay the reference's own host C and
+ *      call these entry points / read the cost matrix. ---- */
 int x264cu_mbtree_reset( x264cu_ctx *ctx, x264cu_frame *f );                         /* i_propagate_cost = 0 */
 int x264cu_mbtree_swap( x264cu_ctx *ctx, x264cu_frame *a, x264cu_frame *b );         /* XCHG of the two i_propagate_cost arrays */
 /* frame b = fb evaluated as (d0 = b-p0, d1 = p1-b) propagates into fp0 / fp1; fps_factor as slicetype.c:1065 */
@@ -249,19 +220,6 @@ int x264cu_mbtree_propagate( x264cu_ctx *ctx, x264cu_frame *fb, x264cu_frame *fp
 int x264cu_mbtree_finish( x264cu_ctx *ctx, x264cu_frame *f, int fps_factor, float weightdelta, float strength,
                           const float *qp_offset_aq, float *qp_offset );
 int x264cu_mbtree_get_propagate( x264cu_ctx *ctx, x264cu_frame *f, uint16_t *out );   /* i_propagate_cost, host u16[mb_count] */
-
-typedef struct
-{
-    x264cu_frame *f;
-    int type;                                   /* decided X264_TYPE_* */
-    float duration;                             /* f_duration */
-    const float *qp_offset_aq;                  /* f_qp_offset_aq, host float[mb_count] */
-    float *qp_offset;                           /* f_qp_offset, host float[mb_count] (out) */
-    float weighted_cost_delta[X264CU_BFRAME_MAX+2];   /* f_weighted_cost_delta */
-} x264cu_mbtree_frame;
-typedef struct { int rc_lookahead, bframe_pyramid, vbv, vbv_lookahead; float qcompress; } x264cu_mbtree_cfg;
-/* macroblock_tree( h, a, frames, num_frames, b_intra ): frames[0..num_frames] */
-int x264cu_macroblock_tree( x264cu_ctx *ctx, const x264cu_mbtree_cfg *cfg, x264cu_mbtree_frame *frames, int num_frames, int b_intra );
 
 /* ---- batched pixel primitives (config "checkasm-style"): x264_pixel_function_t sad/satd/sa8d/
  *      hadamard_ac (pixel.h:82-103), x264_dct_function_t sub4x4/8x8/16x16_dct (dct.h:28-33),

@@ -3,7 +3,7 @@ macroblock_tree_propagate / _finish and the macroblock_tree frame walk (encoder/
 
 CPU: the oracle restatement against the reference's own mc table entries on checkasm-style random data
 (tools/checkasm.c:1760-1844) and against the reference's own macroblock_tree run on the same frames, costs and MVs.
-GPU: the device kernels + the C++ frame walk against the oracle, bit-exact including the float qp offsets."""
+GPU: the device kernels (driven by the same test-side frame walk) against the oracle, bit-exact including the float qp offsets."""
 import ctypes as C
 import os
 import sys
@@ -217,13 +217,38 @@ def test_walk_oracle_vs_reference():
         O.close()
 
 
-class MbFrame(C.Structure):
-    _fields_ = [("f", vp), ("type", C.c_int), ("duration", C.c_float), ("qp_offset_aq", vp), ("qp_offset", vp),
-                ("weighted_cost_delta", C.c_float * 18)]
+class CudaBackend:
+    """the same abstract backend over the C ABI: x264cu_frame_cost / x264cu_mbtree_reset / _propagate / _finish.  The frame
+    walk itself is host control logic and stays outside the product (the reference's own macroblock_tree runs it)."""
 
+    def __init__(self, G, qp_aq):
+        self.G, self.L = G, G.ctx.L
+        self.qp_aq = qp_aq
+        self.qp = [a.copy() for a in qp_aq]
+        L = self.L
+        L.x264cu_mbtree_reset.argtypes = [vp, vp]
+        L.x264cu_mbtree_propagate.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_int]
+        L.x264cu_mbtree_finish.argtypes = [vp, vp, C.c_int, C.c_float, C.c_float, vp, vp]
+        L.x264cu_mbtree_get_propagate.argtypes = [vp, vp, vp]
 
-class MbCfg(C.Structure):
-    _fields_ = [("rc_lookahead", C.c_int), ("bframe_pyramid", C.c_int), ("vbv", C.c_int), ("vbv_lookahead", C.c_int), ("qcompress", C.c_float)]
+    def cost(self, p0, p1, b):
+        self.G.frame_cost(p0, p1, b)
+
+    def reset(self, i):
+        assert self.L.x264cu_mbtree_reset(self.G.ctx.ctx, self.G.frames[i]) == 0
+
+    def propagate(self, p0, p1, b, fps, referenced):
+        F = self.G.frames
+        assert self.L.x264cu_mbtree_propagate(self.G.ctx.ctx, F[b], F[p0], F[p1], b - p0, p1 - b, float(fps), referenced) == 0
+
+    def finish(self, i, fps, wd, strength):
+        assert self.L.x264cu_mbtree_finish(self.G.ctx.ctx, self.G.frames[i], fps, float(wd), float(strength),
+                                           self.qp_aq[i].ctypes.data, self.qp[i].ctypes.data) == 0
+
+    def prop(self, i):
+        out = np.zeros(self.G.nmb, dtype=np.uint16)
+        assert self.L.x264cu_mbtree_get_propagate(self.G.ctx.ctx, self.G.frames[i], out.ctypes.data) == 0
+        return out
 
 
 @pytest.mark.gpu
@@ -245,22 +270,12 @@ def test_device_walk_vs_oracle(W, H):
             G.put_frame(i, f, invq[i])
         be = OracleBackend(O, qp_aq)
         walk(be, TYPES, durations, n - 1, 1, rc_lookahead=20)
-        L = G.ctx.L
-        L.x264cu_macroblock_tree.argtypes = [vp, vp, vp, C.c_int, C.c_int]
-        L.x264cu_mbtree_get_propagate.argtypes = [vp, vp, vp]
-        qp = [a.copy() for a in qp_aq]
-        arr = (MbFrame * n)()
+        gb = CudaBackend(G, qp_aq)
+        walk(gb, TYPES, durations, n - 1, 1, rc_lookahead=20)
         for i in range(n):
-            arr[i].f = G.frames[i]; arr[i].type = TYPES[i]; arr[i].duration = float(durations[i])
-            arr[i].qp_offset_aq = qp_aq[i].ctypes.data; arr[i].qp_offset = qp[i].ctypes.data
-        cfg = MbCfg(20, 1, 0, 0, 0.6)
-        assert L.x264cu_macroblock_tree(G.ctx.ctx, C.byref(cfg), arr, n - 1, 1) == 0, x264cu.last_error()
-        for i in range(n):
-            np.testing.assert_array_equal(qp[i], be.qp[i], err_msg=f"f_qp_offset of frame {i}")
+            np.testing.assert_array_equal(gb.qp[i], be.qp[i], err_msg=f"f_qp_offset of frame {i}")
         for i in (0, 3, 5, 6):
-            p = np.zeros(O.nmb, dtype=np.uint16)
-            assert L.x264cu_mbtree_get_propagate(G.ctx.ctx, G.frames[i], p.ctypes.data) == 0
-            np.testing.assert_array_equal(p, be.prop(i), err_msg=f"i_propagate_cost of frame {i}")
+            np.testing.assert_array_equal(gb.prop(i), be.prop(i), err_msg=f"i_propagate_cost of frame {i}")
     finally:
         O.close()
         G.close()
