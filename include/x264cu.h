@@ -202,6 +202,15 @@ x264cu_frame *x264cu_stream_frame( x264cu_stream *s, int64_t index );
 int      x264cu_stream_sync( x264cu_stream *s );
 /* after sync: stats of slicetype_frame_cost(p0, n, b) of the newest frame n, d0 = b-p0, d1 = n-b */
 int      x264cu_stream_cost( x264cu_stream *s, int d0, int d1, int32_t *out4 );
+/* want_arrays: where the eagerly copied arrays of evaluation (d0, d1) of the most recent push are (host pointers owned by
+ * the window, NULL members = not produced; every new MV field is delivered once, with the first evaluation that uses it) */
+int      x264cu_stream_arrays( x264cu_stream *s, int d0, int d1, x264cu_out *out );
+/* On-demand arrays of slicetype_frame_cost( p0 = b-d0, p1 = b+d1, b ) for frame number b (0 = first frame pushed) while
+ * b-d0 .. b+d1 are in the window: the per-evaluation arrays stay on the device and only what a consumer reads crosses
+ * PCIe (the decided path of a mini-GOP needs lowres_costs + MV fields of <= bframes+1 evaluations, slicetype.c:1056,
+ * 1078-1083, mvpred.c:553; slicetype-cl.c:254-280 copies them eagerly instead).  Computes the evaluation if it was never
+ * asked for.  Any subset of `out` may be set; complete after x264cu_stream_sync. */
+int      x264cu_stream_fetch( x264cu_stream *s, int64_t b, int d0, int d1, const x264cu_out *out );
 int64_t  x264cu_stream_frames( x264cu_stream *s );
 int64_t  x264cu_stream_result_bytes( x264cu_stream *s );
 

@@ -379,3 +379,58 @@ def synth_chroma(width, height, n, seed=11):
         c = c + rng.integers(-6, 7, c.shape)
         out.append(np.clip(c, 0, 255).astype(np.uint8).reshape(height // 2, width))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# one steady-state step of a lookahead window against the oracle (tests/test_gpu_bench_config.py, bench.py parity_check)
+# ------------------------------------------------------------------------------------------------
+def stream_step_evaluations(n, bframes, b_list=None):
+    """(p0, n, b) of one x264cu_stream_push of frame n in the window's own order (host/stream.cpp): the I cost, then per p0
+    from near to far the P evaluation and the B evaluations between p0 and n.  b_list restricts the B evaluations."""
+    out = [(n, n, n)]
+    for p0 in range(n - 1, max(n - (bframes + 1), 0) - 1, -1):
+        out.append((p0, n, n))
+        for b in range(p0 + 1, n):
+            if b_list is None or b in b_list:
+                out.append((p0, n, b))
+    return out
+
+
+def check_step_against_oracle(window_frames, get_stats, get_arrays=None, bframes=16, subme=7, passes=2, mv_range=512,
+                              b_list=None, aq=1):
+    """window_frames: the frames of the window, oldest first, newest last (index n = len - 1).
+    get_stats(d0, d1) -> 4 ints of the CUDA path (cost_est, cost_est_aq, intra_mbs, raw cost);
+    get_arrays(d0, d1) -> dict with any of lowres_costs / row_satds / mvs0 / mvs1 (None entries are skipped).
+    Runs the same evaluations through the CPU oracle (K-pass dependency-free schedule) and compares bit for bit.
+    Returns {"evaluations": ..., "arrays": ..., "mismatches": [...]}."""
+    H, W = window_frames[0].shape
+    n = len(window_frames) - 1
+    O = Lookahead(OracleLib(), "oracle", W, H, bframes=bframes, subme=subme, mbtree=1, aq=aq, passes=passes, mv_range=mv_range)
+    bad, narr = [], 0
+    try:
+        for i, f in enumerate(window_frames):
+            O.put_frame(i, f)
+        evs = stream_step_evaluations(n, bframes, b_list)
+        for (p0, p1, b) in evs:
+            d0, d1 = b - p0, p1 - b
+            sc = O.frame_cost(p0, p1, b)
+            st = O.get(b, GET_STATS, d0, d1)
+            g = get_stats(d0, d1)
+            if int(g[0]) != int(sc) or int(g[1]) != int(st[1]) or (d1 == 0 and d0 > 0 and int(g[2]) != int(st[2])):
+                bad.append(("stats", d0, d1, [int(x) for x in g], int(sc), [int(x) for x in st]))
+            if get_arrays is None:
+                continue
+            a = get_arrays(d0, d1) or {}
+            want = {"lowres_costs": lambda: O.get(b, GET_LOWRES_COSTS, d0, d1) if d0 + d1 else O.get(b, GET_INTRA),
+                    "intra_costs": lambda: O.get(b, GET_INTRA),
+                    "row_satds": lambda: O.get(b, GET_ROW_SATDS, d0, d1),
+                    "mvs0": lambda: O.get(b, GET_MVS, 0, d0 - 1), "mvs1": lambda: O.get(b, GET_MVS, 1, d1 - 1)}
+            for k, v in a.items():
+                if v is None:
+                    continue
+                narr += 1
+                if not np.array_equal(np.asarray(v).reshape(-1), want[k]().reshape(-1)):
+                    bad.append((k, d0, d1))
+    finally:
+        O.close()
+    return {"evaluations": len(evs), "arrays": narr, "mismatches": bad}

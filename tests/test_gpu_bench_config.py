@@ -1,0 +1,166 @@
+"""GPU parity of the configuration bench.py times (BASELINE.json configs[2]): 1920x1080, bframes=16, the default
+compile-time-pitch thread-per-block kernels, x264cu_stream_push(want_arrays=1), four concurrent contexts with one window
+each.  One steady-state step of a window (all 154 evaluations: scalars, lowres_costs, row SATDs, the 33 new MV fields)
+against the CPU oracle, then the on-demand x264cu_stream_fetch against the eager arrays; the exact schedule
+(search_passes=0) at the same size against the UNMODIFIED reference's raster-serial slicetype_frame_cost."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from checkers import (GET_LOWRES_COSTS, GET_MVS, GET_ROW_SATDS, GET_STATS, Lookahead, RefLib, check_step_against_oracle, have_ref)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "x264-i386pic_b200"))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+W, H, B = 1920, 1080, 16
+
+
+def eager_arrays(x264cu, L, win, nmb, mbh):
+    def get(d0, d1):
+        o = x264cu.Out()
+        assert L.x264cu_stream_arrays(win, d0, d1, C.byref(o)) == 0
+        def arr(p, n, dt):
+            return None if not p else np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=(n,)).copy()
+        if d0 + d1 == 0:
+            return {"intra_costs": arr(o.intra_costs, nmb, C.c_uint16)}
+        return {"lowres_costs": arr(o.lowres_costs, nmb, C.c_uint16), "row_satds": arr(o.row_satds, mbh, C.c_int32),
+                "mvs0": arr(o.mvs[0], 2 * nmb, C.c_int16), "mvs1": arr(o.mvs[1], 2 * nmb, C.c_int16)}
+    return get
+
+
+def test_benchmarked_configuration_matches_oracle():
+    import bench
+    import x264cu
+    S, n = 4, B + 1                       # window fill (frames 0..16) + one steady-state step (frame 17)
+    ctxs = [x264cu.Context(W, H, bframes=B, subme=7, do_edges=1, aq=1, passes=2) for _ in range(S)]
+    L = ctxs[0].L
+    assert ctxs[0].stride == 1024          # the compile-time-pitch instantiation
+    frames = [bench.make_stream_frames(300 + s, n + 1) for s in range(S)]
+    pinned = []
+    for s in range(S):
+        hp = ctxs[s].host_alloc(W * H * (n + 1))
+        for i, f in enumerate(frames[s]):
+            C.memmove(hp + i * W * H, f.ctypes.data, W * H)
+        pinned.append(hp)
+    wins = [L.x264cu_stream_open(ctxs[s].ctx, B, 1) for s in range(S)]
+    assert all(wins)
+    try:
+        l0 = sum(c.launches() for c in ctxs)
+        for k in range(n):                # the four windows fill side by side, one outstanding step each
+            for s in range(S):
+                assert L.x264cu_stream_push(wins[s], pinned[s] + k * W * H, W, None, 0) > 0, x264cu.last_error()
+            for s in range(S):
+                assert L.x264cu_stream_sync(wins[s]) == 0, x264cu.last_error()
+        for s in range(S):                # the steady-state step of all four, in flight together
+            assert L.x264cu_stream_push(wins[s], pinned[s] + n * W * H, W, None, 0) == 154, x264cu.last_error()
+        for s in range(S):
+            assert L.x264cu_stream_sync(wins[s]) == 0, x264cu.last_error()
+        assert sum(c.launches() for c in ctxs) > l0
+
+        def stats_of(win):
+            def get(d0, d1):
+                st = (C.c_int32 * 4)()
+                assert L.x264cu_stream_cost(win, d0, d1, st) == 0
+                return list(st)
+            return get
+        # window 0: every evaluation of the step with every array; window 3: scalars and arrays of the P evaluations and two b
+        r = check_step_against_oracle(frames[0], stats_of(wins[0]), eager_arrays(x264cu, L, wins[0], ctxs[0].nmb, ctxs[0].mbh), bframes=B)
+        assert r["evaluations"] == 154 and r["arrays"] >= 1 + 2 * 153 + 33 and not r["mismatches"], r["mismatches"][:5]
+        r = check_step_against_oracle(frames[3], stats_of(wins[3]), eager_arrays(x264cu, L, wins[3], ctxs[3].nmb, ctxs[3].mbh), bframes=B,
+                                      b_list=(n - 1, n - 9))
+        assert r["evaluations"] == 1 + 17 + 16 + 8 and not r["mismatches"], r["mismatches"][:5]
+
+        # on-demand arrays (x264cu_stream_fetch) == the eager ones, for evaluations of this step and of earlier steps
+        c0, w0 = ctxs[0], wins[0]
+        nmb, mbh = c0.nmb, c0.mbh
+        eg = eager_arrays(x264cu, L, w0, nmb, mbh)
+        fetched = []
+        launches_before = c0.launches()
+        for (b, d0, d1) in [(n, 1, 0), (n, 17, 0), (n - 1, 1, 1), (n - 1, 16, 1), (n - 9, 3, 9), (n - 16, 1, 16), (n - 4, 2, 3), (n - 4, 5, 0)]:
+            res = {"lowres_costs": np.zeros(nmb, np.uint16), "row_satds": np.zeros(mbh, np.int32),
+                   "mvs0": np.zeros(2 * nmb, np.int16), "mvs1": np.zeros(2 * nmb, np.int16), "stats": np.zeros(4, np.int32)}
+            o = x264cu.Out()
+            o.lowres_costs = res["lowres_costs"].ctypes.data; o.row_satds = res["row_satds"].ctypes.data
+            o.mvs[0] = res["mvs0"].ctypes.data
+            if d1:
+                o.mvs[1] = res["mvs1"].ctypes.data
+            o.stats = res["stats"].ctypes.data
+            assert L.x264cu_stream_fetch(w0, b, d0, d1, C.byref(o)) == 0, x264cu.last_error()
+            fetched.append((b, d0, d1, res))
+        assert L.x264cu_stream_sync(w0) == 0
+        assert c0.launches() - launches_before == len(fetched)      # cache hits: one gather launch each, nothing recomputed
+        from checkers import OracleLib
+        O = Lookahead(OracleLib(), "oracle", W, H, bframes=B, subme=7, mbtree=1, aq=1, passes=2, mv_range=512)
+        try:
+            for i, f in enumerate(frames[0]):
+                O.put_frame(i, f)
+            for (b, d0, d1, res) in fetched:
+                if b + d1 == n:           # an evaluation of the newest step: also delivered eagerly
+                    e = eg(d0, d1)
+                    np.testing.assert_array_equal(res["lowres_costs"], e["lowres_costs"])
+                    np.testing.assert_array_equal(res["row_satds"], e["row_satds"])
+                    st = (C.c_int32 * 4)()
+                    L.x264cu_stream_cost(w0, d0, d1, st)
+                    assert list(st) == res["stats"].tolist()
+                sc = O.frame_cost(b - d0, b + d1, b)
+                assert int(res["stats"][0]) == sc, (b, d0, d1)
+                np.testing.assert_array_equal(res["lowres_costs"], O.get(b, GET_LOWRES_COSTS, d0, d1))
+                np.testing.assert_array_equal(res["row_satds"], O.get(b, GET_ROW_SATDS, d0, d1))
+                np.testing.assert_array_equal(res["mvs0"].reshape(-1, 2), O.get(b, GET_MVS, 0, d0 - 1))
+                if d1:
+                    np.testing.assert_array_equal(res["mvs1"].reshape(-1, 2), O.get(b, GET_MVS, 1, d1 - 1))
+        finally:
+            O.close()
+    finally:
+        for w in wins:
+            L.x264cu_stream_close(w)
+        for s in range(S):
+            ctxs[s].host_free(pinned[s])
+            ctxs[s].close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libx264ref.so not built")
+def test_benchmarked_size_exact_mode_matches_unmodified_reference():
+    """search_passes=0 at 1080p / bframes=16 through the window API against the reference's own raster-serial
+    slicetype_frame_cost (one lookahead thread), every evaluation of the last of five pushes."""
+    import bench
+    import x264cu
+    n = 4
+    frames = bench.make_stream_frames(77, n + 1)
+    ctx = x264cu.Context(W, H, bframes=B, subme=7, do_edges=1, aq=1, passes=0)
+    L = ctx.L
+    win = L.x264cu_stream_open(ctx.ctx, B, 1)
+    R = Lookahead(RefLib(), "ref_serial", W, H, bframes=B, subme=7, mbtree=1, aq=1)
+    try:
+        for k in range(n + 1):
+            f = np.ascontiguousarray(frames[k])
+            R.put_frame(k, f)
+            assert L.x264cu_stream_push(win, f.ctypes.data, W, None, 0) > 0, x264cu.last_error()
+            assert L.x264cu_stream_sync(win) == 0, x264cu.last_error()
+            # the reference evaluates the same triples in the same order at every push (its caches fill the same way)
+            from checkers import stream_step_evaluations
+            for (p0, p1, b) in stream_step_evaluations(k, B):
+                sc = R.frame_cost(p0, p1, b)
+                if k < n:
+                    continue
+                d0, d1 = b - p0, p1 - b
+                st = (C.c_int32 * 4)()
+                assert L.x264cu_stream_cost(win, d0, d1, st) == 0
+                rst = R.get(b, GET_STATS, d0, d1)
+                assert st[0] == sc and st[1] == rst[1], (p0, p1, b, list(st), sc, list(rst))
+                if d0 + d1:
+                    e = eager_arrays(x264cu, L, win, ctx.nmb, ctx.mbh)(d0, d1)
+                    np.testing.assert_array_equal(e["lowres_costs"], R.get(b, GET_LOWRES_COSTS, d0, d1), err_msg=str((p0, p1, b)))
+                    np.testing.assert_array_equal(e["row_satds"], R.get(b, GET_ROW_SATDS, d0, d1))
+                    if e["mvs0"] is not None:
+                        np.testing.assert_array_equal(e["mvs0"].reshape(-1, 2), R.get(b, GET_MVS, 0, d0 - 1))
+                    if e["mvs1"] is not None:
+                        np.testing.assert_array_equal(e["mvs1"].reshape(-1, 2), R.get(b, GET_MVS, 1, d1 - 1))
+    finally:
+        L.x264cu_stream_close(win)
+        ctx.close()
+        R.close()

@@ -81,6 +81,7 @@ struct x264cu_ctx
     uint64_t seq; int slot; bool batch_out;      // batch_out: this batch ends on the D2H stream
     cudaEvent_t slot_done[NSLOT]; uint64_t slot_seq[NSLOT]; bool slot_pending[NSLOT];
     int64_t launches;
+    std::vector<uint8_t *> batch_flags;      // cache flags set by the batch being built (rolled back if it fails)
     // timing
     bool profiling;
     std::vector<TimedSpan> spans;
@@ -231,7 +232,8 @@ extern "C" x264cu_ctx *x264cu_open( int device, const x264cu_cfg *cfg )
         CUP( cudaEventCreateWithFlags( &c->luma_free[i], cudaEventDisableTiming ) );
     }
     c->pin_size = (size_t)64 << 20;            // cf. PAGE_LOCKED_BUF_SIZE 32 MiB (opencl.h:715)
-    while( c->pin_size < 4 * (size_t)c->luma_pitch * cfg->height ) c->pin_size <<= 1;
+    // one region (pin_size / NSLOT) holds everything one upload stages: luma + NV12 chroma + the per-MB tables
+    while( c->pin_size / NSLOT < (size_t)c->luma_pitch * cfg->height * 3 / 2 + (size_t)P.nmb * 8 + ( 1 << 20 ) ) c->pin_size <<= 1;
     CUP( cudaHostAlloc( &c->pin, c->pin_size, cudaHostAllocDefault ) );
     c->jobs_size = (size_t)1 << 20;
     CUP( cudaHostAlloc( &c->h_jobs, c->jobs_size, cudaHostAllocDefault ) );
@@ -437,12 +439,39 @@ static int ctx_sync( x264cu_ctx *c )
     return 0;
 }
 
+// Every enqueueing entry point runs inside one Batch.  A batch that is left without end() -- any `return -1` after
+// work was enqueued -- is closed on the failure path: the context is drained (so that the staging, job and workspace
+// regions it used are idle before they are handed out again) and the cache flags it set (searched / evaluated /
+// analysed: "this field exists on the device") are rolled back, because their launches may never have been enqueued.
+struct Batch
+{
+    x264cu_ctx *c; bool open, failed;
+    explicit Batch( x264cu_ctx *c_ ) : c( c_ ), open( false ), failed( false )
+    {
+        c->batch_flags.clear();
+        if( begin_batch( c ) ) failed = true; else open = true;
+    }
+    int end( cudaStream_t last = NULL ) { open = false; c->batch_flags.clear(); return end_batch( c, last ); }
+    ~Batch()
+    {
+        if( !open ) return;
+        char keep[sizeof(g_err)];
+        memcpy( keep, g_err, sizeof(keep) );
+        for( uint8_t *f : c->batch_flags ) *f = 0;
+        c->batch_flags.clear();
+        ctx_sync( c );
+        cudaGetLastError();
+        memcpy( g_err, keep, sizeof(keep) );
+    }
+};
+static inline void mark( x264cu_ctx *c, uint8_t &flag ) { if( !flag ) { flag = 1; c->batch_flags.push_back( &flag ); } }
+
 extern "C" int x264cu_flush( x264cu_ctx *c )
 {
     if( !c ) FAIL( "null context" );
     CU( cudaSetDevice( c->device ) );
     if( ctx_sync( c ) ) return -1;
-    if( c->serial_error ) FAIL( "exact-mode search kernel: a row waited too long for the row below (launch not fully resident?)" );
+    if( c->serial_error ) { c->serial_error = 0; FAIL( "exact-mode search kernel: a row waited too long for the row below (launch not fully resident?)" ); }
     CU( cudaGetLastError() );
     return 0;
 }
@@ -478,6 +507,9 @@ static uint8_t *pin_alloc( x264cu_ctx *c, size_t bytes )
     c->pin_used[c->slot] = a + bytes;
     return c->pin + c->slot * region + a;
 }
+// NOTE for callers: the retry path synchronises the context and hands out the region from offset 0 again, so everything
+// staged earlier in the same batch must already have been ENQUEUED (its copy is then complete) -- stage and enqueue one
+// array at a time, never stage two arrays and enqueue afterwards.
 static uint8_t *pin_alloc_sync( x264cu_ctx *c, size_t bytes )
 {
     uint8_t *p = pin_alloc( c, bytes );
@@ -544,7 +576,8 @@ extern "C" int x264cu_frame_upload( x264cu_ctx *c, x264cu_frame *f, const uint8_
 {
     if( !c || !f || !luma ) FAIL( "x264cu_frame_upload: null argument" );
     CU( cudaSetDevice( c->device ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     const LaParams &P = c->P;
     const int W = c->cfg.width, H = c->cfg.height;
     int sel = c->luma_sel; c->luma_sel ^= 1;
@@ -578,7 +611,7 @@ extern "C" int x264cu_frame_upload( x264cu_ctx *c, x264cu_frame *f, const uint8_
         launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );         // memset_int16 (downscale.cl:132)
     if( upload_common( c, f, c->d_luma[sel], c->luma_pitch ) ) return -1;
     CU( cudaEventRecord( c->luma_free[sel], c->st ) );
-    return end_batch( c );
+    return B.end();
 }
 
 // x264_adaptive_quant_frame + x264_frame_init_lowres (encoder.c:3417-3421), SURVEY.md section 8f row 3
@@ -594,9 +627,12 @@ extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uin
     const int W = c->cfg.width, H = c->cfg.height;
     for( int i = 0; i < 2; i++ )
         if( !c->d_chroma[i] ) CU( cudaMalloc( &c->d_chroma[i], (size_t)c->chroma_pitch * ( H / 2 ) + 256 ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     int sel = c->luma_sel; c->luma_sel ^= 1;
     const uint8_t *src = luma, *csrc = chroma; int spitch = stride, cpitch = cstride;
+    CU( cudaStreamWaitEvent( c->st_in, c->luma_free[sel], 0 ) );
+    // one plane at a time: stage, enqueue, then stage the next (see pin_alloc_sync)
     if( !is_pinned( luma ) )
     {
         uint8_t *p = pin_alloc_sync( c, (size_t)W * H );
@@ -604,6 +640,7 @@ extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uin
         for( int y = 0; y < H; y++ ) memcpy( p + (size_t)y*W, luma + (size_t)y*stride, W );
         src = p; spitch = W;
     }
+    CU( cudaMemcpy2DAsync( c->d_luma[sel], c->luma_pitch, src, spitch, W, H, cudaMemcpyHostToDevice, c->st_in ) );
     if( !is_pinned( chroma ) )
     {
         uint8_t *p = pin_alloc_sync( c, (size_t)W * ( H / 2 ) );
@@ -611,8 +648,6 @@ extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uin
         for( int y = 0; y < H / 2; y++ ) memcpy( p + (size_t)y*W, chroma + (size_t)y*cstride, W );
         csrc = p; cpitch = W;
     }
-    CU( cudaStreamWaitEvent( c->st_in, c->luma_free[sel], 0 ) );
-    CU( cudaMemcpy2DAsync( c->d_luma[sel], c->luma_pitch, src, spitch, W, H, cudaMemcpyHostToDevice, c->st_in ) );
     CU( cudaMemcpy2DAsync( c->d_chroma[sel], c->chroma_pitch, csrc, cpitch, W, H / 2, cudaMemcpyHostToDevice, c->st_in ) );
     CU( cudaEventRecord( c->ev_up[sel], c->st_in ) );
     CU( cudaStreamWaitEvent( c->st, c->ev_up[sel], 0 ) );
@@ -650,7 +685,7 @@ extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uin
             c->copies.push_back( { out->pixel_stats, p, 48, 3, P.mbw | ( P.mbh << 16 ), c->seq } );
         }
     }
-    return end_batch( c );
+    return B.end();
 }
 
 extern "C" int x264cu_frame_upload_aq_device( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint8_t *d_chroma, int cstride,
@@ -659,7 +694,8 @@ extern "C" int x264cu_frame_upload_aq_device( x264cu_ctx *c, x264cu_frame *f, co
     if( !c || !f || !d_luma || !d_chroma || !aq ) FAIL( "x264cu_frame_upload_aq_device: null argument" );
     if( aq->mode < 0 || aq->mode > 1 ) FAIL( "x264cu_frame_upload_aq_device: aq-mode %d goes through powf and is not computed on the device", aq->mode );
     CU( cudaSetDevice( c->device ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     const LaParams &P = c->P;
     CU( cudaMemsetAsync( f->pixstats, 0, 8 * sizeof(unsigned long long), c->st ) );
     launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );
@@ -668,7 +704,7 @@ extern "C" int x264cu_frame_upload_aq_device( x264cu_ctx *c, x264cu_frame *f, co
                aq->mode ? d_quant_offsets : NULL, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats, c->st );
     f->have_aq = true;
     if( upload_common( c, f, d_luma, stride ) ) return -1;
-    return end_batch( c );
+    return B.end();
 }
 
 // for callers that ran x264_adaptive_quant_frame on the host (the unmodified encoder does, encoder.c:3417): hand the
@@ -678,7 +714,8 @@ extern "C" int x264cu_frame_set_pixel_stats( x264cu_ctx *c, x264cu_frame *f, uin
 {
     if( !c || !f ) FAIL( "x264cu_frame_set_pixel_stats: null argument" );
     CU( cudaSetDevice( c->device ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     const uint64_t wh = (uint64_t)( 16 * c->P.mbw ) * ( 16 * c->P.mbh );
     uint64_t *p = (uint64_t *)pin_alloc_sync( c, 64 );
     if( !p ) return -1;
@@ -686,7 +723,7 @@ extern "C" int x264cu_frame_set_pixel_stats( x264cu_ctx *c, x264cu_frame *f, uin
     p[0] = sum; p[1] = ssd + ( sum * sum + wh / 2 ) / wh;
     CU( cudaMemcpyAsync( f->pixstats, p, 64, cudaMemcpyHostToDevice, c->st ) );
     f->have_aq = true;
-    return end_batch( c );
+    return B.end();
 }
 
 // x264_weights_analyse( h, fenc, fref, 1 ) (slicetype.c:284-501), SURVEY.md section 8f row 2
@@ -696,7 +733,8 @@ extern "C" int x264cu_weights_analyse( x264cu_ctx *c, x264cu_frame *fenc, x264cu
     if( !fenc->uploaded || !fref->uploaded || !fenc->have_aq || !fref->have_aq )
         FAIL( "x264cu_weights_analyse: both frames need the pixel statistics of x264cu_frame_upload_aq" );
     CU( cudaSetDevice( c->device ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     const LaParams &P = c->P;
     int *wres = fenc->wres + 8 * ( dist - 1 );
     // weight_cost_init_luma (:76-103): motion-compensate the reference when the list-0 field has been searched
@@ -704,26 +742,27 @@ extern "C" int x264cu_weights_analyse( x264cu_ctx *c, x264cu_frame *fenc, x264cu
     // the intra costs exist since upload; the reference computes them here if need be (:361-366), which also makes a
     // later I evaluation a cache hit
     fenc->any_eval = true;
-    fenc->wanalysed[dist-1] = 1;
+    mark( c, fenc->wanalysed[dist-1] );
     c->launches += 3;
     launch_weights_analyse( planeF( c, fenc ), planeF( c, fref ), mvs, fenc->costs, fenc->pixstats, fref->pixstats, wres,
                             numslices > 0 ? numslices : 1, P, c->st );
     CU( cudaGetLastError() );
     if( queue_d2h( c, out, wres, sizeof(x264cu_weight) ) ) return -1;
-    return end_batch( c );
+    return B.end();
 }
 
 extern "C" int x264cu_frame_upload_device( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int stride, const uint16_t *d_inv_qscale )
 {
     if( !c || !f || !d_luma ) FAIL( "x264cu_frame_upload_device: null argument" );
     CU( cudaSetDevice( c->device ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     if( d_inv_qscale )
         CU( cudaMemcpyAsync( f->inv_qscale, d_inv_qscale, (size_t)c->P.nmb * 2, cudaMemcpyDeviceToDevice, c->st ) );
     else
         launch_fill_u16( f->inv_qscale, 256, c->P.nmb, c->st );
     if( upload_common( c, f, d_luma, stride ) ) return -1;
-    return end_batch( c );
+    return B.end();
 }
 
 extern "C" int x264cu_frame_get_lowres( x264cu_ctx *c, x264cu_frame *f, int plane, uint8_t *out )
@@ -792,8 +831,11 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
         const size_t field_bytes = align_up( (size_t)P.nmb * 4, 256 ), plane_bytes = align_up( (size_t)P.plane_size, 256 );
         size_t need = tasks.size() * 2 * field_bytes;
         for( const SearchTask &t : tasks ) if( t.w.enabled ) need += plane_bytes;
-        uint8_t *ws = arena_alloc( c, need );
+        // ONE allocation per batch before anything is enqueued: a second one could recycle (or re-allocate) the region
+        // while the pointers handed out by the first are still waiting to be used
+        uint8_t *ws = arena_alloc( c, need + 256 );
         if( !ws ) return -1;
+        int *derr = (int *)ws; ws += 256;
         std::vector<uint8_t *> tmp0( tasks.size() ), tmp1( tasks.size() ), wpl( tasks.size(), NULL );
         for( size_t t = 0; t < tasks.size(); t++ )
         {
@@ -837,11 +879,10 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
             else
             {   // one persistent launch: every MV word of the field is its own "ready" flag (search_kernel_serial)
                 for( const SearchJob &S : sj ) CU( cudaMemsetAsync( S.mv_out, 0x7F, (size_t)P.nmb * 4, c->st ) );
-                int *derr = (int *)arena_alloc( c, 256 );
-                if( !derr ) return -1;
                 CU( cudaMemsetAsync( derr, 0, 4, c->st ) );
                 Span s( c, K_SEARCH, 0 );
                 int nl = launch_search_serial( d, (int)sj.size(), P, derr, c->sm_count * c->serial_ctas_per_sm, c->st );
+                if( nl < 0 ) FAIL( "exact-mode search kernel: cooperative launch refused (one field row per warp does not fit the device)" );
                 c->launches += nl; c->class_n[K_SEARCH] += nl;
                 uint8_t *p = pin_alloc_sync( c, 4 );
                 if( !p ) return -1;
@@ -894,7 +935,7 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
         if( j.d0 == 0 && j.d1 == 0 && j.fenc->any_eval ) j.fenc->evaluated[0][0] = 1;
         j.fenc->any_eval = true;
         if( j.fenc->evaluated[j.d0][j.d1] ) continue;                  // i_cost_est >= 0 (slicetype.c:848)
-        j.fenc->evaluated[j.d0][j.d1] = 1;
+        mark( c, j.fenc->evaluated[j.d0][j.d1] );
         FinalJob F;
         memset( &F, 0, sizeof(F) );
         F.fenc = planeF( c, j.fenc ); F.ref0 = planeF( c, j.fref0 ); F.ref1 = planeF( c, j.fref1 );
@@ -906,7 +947,7 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
             int fi = field_index( c, l, dist );
             if( !j.fenc->searched[l][dist-1] )
             {   // do_search[l] (slicetype.c:855-867)
-                j.fenc->searched[l][dist-1] = 1;
+                mark( c, j.fenc->searched[l][dist-1] );
                 SearchTask t = { j.fenc, l ? j.fref1 : j.fref0, l, dist, { 0, 0, 0, 0 } };
                 if( l == 0 && j.d1 == 0 && j.weight.enabled )                      // w only when b == p1 (:859-864)
                 {
@@ -1050,9 +1091,10 @@ extern "C" int x264cu_frame_cost_batch( x264cu_ctx *c, const x264cu_job *jobs, i
 {
     if( !c || ( !jobs && n ) ) FAIL( "x264cu_frame_cost_batch: null argument" );
     CU( cudaSetDevice( c->device ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     if( run_batch( c, jobs, n ) ) return -1;
-    return end_batch( c, c->batch_out ? c->st_out : c->st );
+    return B.end( c->batch_out ? c->st_out : c->st );
 }
 
 extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_frame *fref, int list, int dist,
@@ -1061,10 +1103,11 @@ extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_fr
     if( !c || !fenc || !fref || list < 0 || list > 1 || dist < 1 || dist > c->cfg.bframes + 1 ) FAIL( "x264cu_motionsearch: bad argument" );
     if( !fenc->uploaded || !fref->uploaded ) FAIL( "x264cu_motionsearch: frame not uploaded" );
     CU( cudaSetDevice( c->device ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     if( !fenc->searched[list][dist-1] )
     {
-        fenc->searched[list][dist-1] = 1;
+        mark( c, fenc->searched[list][dist-1] );
         std::vector<SearchTask> tasks( 1 );
         tasks[0] = { fenc, fref, list, dist, { 0, 0, 0, 0 } };
         if( list == 0 && w && w->enabled )
@@ -1079,14 +1122,15 @@ extern "C" int x264cu_motionsearch( x264cu_ctx *c, x264cu_frame *fenc, x264cu_fr
     int fi = field_index( c, list, dist );
     if( queue_d2h( c, mvs, fenc->mvs + (size_t)fi * c->P.nmb * 2, (size_t)c->P.nmb * 4 ) ) return -1;
     if( queue_d2h( c, mv_costs, fenc->mvcosts + (size_t)fi * c->P.nmb, (size_t)c->P.nmb * 4 ) ) return -1;
-    return end_batch( c );
+    return B.end();
 }
 
 extern "C" int x264cu_search_batch( x264cu_ctx *c, const x264cu_search_job *jobs, int n )
 {
     if( !c || ( n > 0 && !jobs ) ) FAIL( "x264cu_search_batch: null argument" );
     CU( cudaSetDevice( c->device ) );
-    if( begin_batch( c ) ) return -1;
+    Batch B( c );
+    if( B.failed ) return -1;
     std::vector<SearchTask> tasks;
     for( int i = 0; i < n; i++ )
     {
@@ -1094,7 +1138,7 @@ extern "C" int x264cu_search_batch( x264cu_ctx *c, const x264cu_search_job *jobs
         if( !j.fenc || !j.fref || j.list < 0 || j.list > 1 || j.dist < 1 || j.dist > c->cfg.bframes + 1 ) FAIL( "x264cu_search_batch: bad job %d", i );
         if( !j.fenc->uploaded || !j.fref->uploaded ) FAIL( "x264cu_search_batch: frame not uploaded" );
         if( j.fenc->searched[j.list][j.dist-1] ) continue;
-        j.fenc->searched[j.list][j.dist-1] = 1;
+        mark( c, j.fenc->searched[j.list][j.dist-1] );
         SearchTask t = { j.fenc, j.fref, j.list, j.dist, { 0, 0, 0, 0 } };
         if( j.list == 0 && j.weight.enabled )
         {
@@ -1106,7 +1150,7 @@ extern "C" int x264cu_search_batch( x264cu_ctx *c, const x264cu_search_job *jobs
     }
     if( run_searches( c, tasks ) ) return -1;
     CU( cudaGetLastError() );
-    return end_batch( c );
+    return B.end();
 }
 
 extern "C" int x264cu_field_device( x264cu_ctx *c, x264cu_frame *f, int list, int dist, void **d_mvs, void **d_mv_costs )
@@ -1130,7 +1174,9 @@ extern "C" int x264cu_field_set_searched( x264cu_ctx *c, x264cu_frame *f, int li
 extern "C" uint64_t x264cu_last_batch( x264cu_ctx *c ) { return c ? c->seq : 0; }
 extern "C" uint64_t x264cu_fence( x264cu_ctx *c )
 {
-    if( !c || cudaSetDevice( c->device ) != cudaSuccess || begin_batch( c ) || end_batch( c ) ) return 0;
+    if( !c || cudaSetDevice( c->device ) != cudaSuccess ) return 0;
+    Batch B( c );
+    if( B.failed || B.end() ) return 0;
     return c->seq;
 }
 extern "C" int x264cu_wait( x264cu_ctx *c, uint64_t seq )
@@ -1138,7 +1184,7 @@ extern "C" int x264cu_wait( x264cu_ctx *c, uint64_t seq )
     if( !c ) FAIL( "null context" );
     CU( cudaSetDevice( c->device ) );
     if( wait_upto( c, seq ) ) return -1;
-    if( c->serial_error ) FAIL( "exact-mode search kernel: a row waited too long for the row below (launch not fully resident?)" );
+    if( c->serial_error ) { c->serial_error = 0; FAIL( "exact-mode search kernel: a row waited too long for the row below (launch not fully resident?)" ); }
     return 0;
 }
 

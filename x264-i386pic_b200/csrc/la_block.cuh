@@ -381,7 +381,7 @@ struct WarpBE
             __nanosleep( ns );
             ns = min( ns * 2, (unsigned)X264CU_SPIN_NS1 );
         }
-        return v;
+        return __shfl_sync( 0xffffffffu, v, 0 );      // one decision per warp, also on the time-out path
     }
     // sum over the 8 lanes of this lane's subgroup: xor-shuffles (REDUX with four different 8-lane masks per warp
     // measured 60 % slower, profiles/r01/tuning.md)

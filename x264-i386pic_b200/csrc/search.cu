@@ -450,12 +450,25 @@ int launch_search_serial( const SearchJob *d_jobs, int njobs, const LaParams &P,
     // every warp of a launch should be resident: split the fields over several launches if one would not fit
     const int warps_per_job = P.mbh, ctas_per_job = ( warps_per_job + SERIAL_WARPS - 1 ) / SERIAL_WARPS;
     int jobs_per_launch = max( 1, max_resident_ctas / max( ctas_per_job, 1 ) ), n = 0;
-    for( int j0 = 0; j0 < njobs; j0 += jobs_per_launch, n++ )
+    for( int j0 = 0; j0 < njobs; n++ )
     {
-        const int nj = min( jobs_per_launch, njobs - j0 );
-        const int ctas = ( nj * warps_per_job + SERIAL_WARPS - 1 ) / SERIAL_WARPS;
-        if( P.b_satd ) search_kernel_serial<true><<<ctas, SERIAL_WARPS*32, 0, st>>>( d_jobs, P, j0, nj, d_err );
-        else           search_kernel_serial<false><<<ctas, SERIAL_WARPS*32, 0, st>>>( d_jobs, P, j0, nj, d_err );
+        // a COOPERATIVE launch: the rows of a launch wait for one another, so every CTA must be resident at the same
+        // time.  The runtime refuses a grid that cannot be (and schedules the grid as a whole when other contexts share
+        // the device) instead of letting a partly resident launch spin into its time-out.
+        int nj = min( jobs_per_launch, njobs - j0 );
+        for( ;; )
+        {
+            const int ctas = ( nj * warps_per_job + SERIAL_WARPS - 1 ) / SERIAL_WARPS;
+            int first = j0;
+            void *args[] = { (void *)&d_jobs, (void *)&P, (void *)&first, (void *)&nj, (void *)&d_err };
+            const void *fn = P.b_satd ? (const void *)search_kernel_serial<true> : (const void *)search_kernel_serial<false>;
+            const cudaError_t e = cudaLaunchCooperativeKernel( fn, dim3( ctas ), dim3( SERIAL_WARPS*32 ), args, 0, st );
+            if( e == cudaSuccess ) break;
+            cudaGetLastError();
+            if( e != cudaErrorCooperativeLaunchTooLarge || nj == 1 ) return -1;
+            nj = ( nj + 1 ) / 2;
+        }
+        j0 += nj;
     }
     return n;
 }

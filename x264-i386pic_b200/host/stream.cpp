@@ -22,12 +22,17 @@ struct x264cu_stream
     std::vector<x264cu_frame *> ring;   // frame n lives in ring[n % depth]
     int64_t n_pushed;
     uint64_t last_seq;                  // batch sequence number of the most recent push (x264cu_wait target)
-    // host results of the most recent push: stats[d0][d1][4] for p1 = newest
-    std::vector<int32_t> stats;         // (B+2)*(B+2)*4, indexed [d0*(B+2)+d1]
-    std::vector<int32_t> intra_stats;   // 2
+    // host results of the most recent pushes: stats[d0][d1][4] for p1 = newest.  One set per push, NSETS deep: the
+    // deferred copies of push n land when its batch is awaited, which may be after push n+1 was enqueued, so a push
+    // never writes into (or resets) the set of the one before it.  A context keeps at most 4 batches = 2 pushes in flight.
+    enum { NSETS = 4 };
+    std::vector<int32_t> stats_set[NSETS];      // (B+2)*(B+2)*4, indexed [d0*(B+2)+d1]
+    std::vector<int32_t> intra_stats;   // NSETS x 2
+    int32_t *stats_of( int64_t push ) { return stats_set[push % NSETS].data(); }
     // optional array destinations (pinned when possible)
     uint8_t *arr; size_t arr_bytes; bool arr_pinned;
     std::vector<x264cu_job> jobs;
+    std::vector<x264cu_out> eager;      // want_arrays: where the arrays of evaluation [d0*(B+2)+d1] of the most recent push landed
     int shard_ahead;                    // sharded pushes whose phase 0 ran but whose phase 1 did not yet (0..2)
 };
 
@@ -43,8 +48,8 @@ extern "C" x264cu_stream *x264cu_stream_open( x264cu_ctx *ctx, int bframes, int 
     s->mbw = info[0]; s->mbh = info[1]; s->nmb = info[0] * info[1];
     s->want_arrays = want_arrays;
     s->n_pushed = 0; s->last_seq = 0; s->shard_ahead = 0;
-    s->stats.assign( (size_t)( bframes+2 ) * ( bframes+2 ) * 4, -1 );
-    s->intra_stats.assign( 2, -1 );
+    for( auto &v : s->stats_set ) v.assign( (size_t)( bframes+2 ) * ( bframes+2 ) * 4, -1 );
+    s->intra_stats.assign( 2 * x264cu_stream::NSETS, -1 );
     s->arr = NULL; s->arr_bytes = 0; s->arr_pinned = false;
     for( int i = 0; i < s->depth; i++ )
     {
@@ -80,11 +85,15 @@ extern "C" int x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int st
     const int B = s->bframes, D = s->depth;
     const int64_t n = s->n_pushed;
     x264cu_frame *fn = s->ring[n % D];
+    // the eager result arrays of the previous push are copied straight into s->arr: finish it before re-using them
+    if( s->want_arrays && s->last_seq && x264cu_wait( s->ctx, s->last_seq ) ) return -1;
     int r = on_device ? x264cu_frame_upload_device( s->ctx, fn, luma, stride, inv_qscale )
                       : x264cu_frame_upload( s->ctx, fn, luma, stride, inv_qscale );
     if( r ) return -1;
     s->jobs.clear();
-    std::fill( s->stats.begin(), s->stats.end(), -1 );
+    int32_t *stats = s->stats_of( n );
+    std::fill( stats, stats + s->stats_set[0].size(), -1 );
+    s->eager.assign( (size_t)( B+2 ) * ( B+2 ), x264cu_out() );
     uint8_t *ap = s->arr;
     auto take = [&]( size_t bytes ) { uint8_t *p = ap; ap += ( bytes + 63 ) & ~(size_t)63; return p; };
     // the I cost of the new frame (scenecut needs icost, slicetype.c:1401)
@@ -92,9 +101,10 @@ extern "C" int x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int st
         x264cu_job j;
         memset( &j, 0, sizeof(j) );
         j.fenc = j.fref0 = j.fref1 = fn; j.d0 = j.d1 = 0;
-        j.out.stats = &s->stats[0];
-        j.out.intra_stats = s->intra_stats.data();
+        j.out.stats = &stats[0];
+        j.out.intra_stats = &s->intra_stats[2 * ( n % x264cu_stream::NSETS )];
         if( s->want_arrays ) j.out.intra_costs = (uint16_t *)take( (size_t)s->nmb * 2 );
+        s->eager[0] = j.out;
         s->jobs.push_back( j );
     }
     // P evaluations first (they provide fref1->lowres_mvs[0] for the temporal-direct candidate of the
@@ -108,7 +118,7 @@ extern "C" int x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int st
             memset( &j, 0, sizeof(j) );
             j.fenc = s->ring[b % D]; j.fref0 = s->ring[p0 % D]; j.fref1 = fn;
             j.d0 = (int)( b - p0 ); j.d1 = (int)( n - b );
-            j.out.stats = &s->stats[( (size_t)j.d0 * ( B+2 ) + j.d1 ) * 4];
+            j.out.stats = &stats[( (size_t)j.d0 * ( B+2 ) + j.d1 ) * 4];
             if( s->want_arrays )
             {
                 j.out.lowres_costs = (uint16_t *)take( (size_t)s->nmb * 2 );
@@ -117,6 +127,7 @@ extern "C" int x264cu_stream_push( x264cu_stream *s, const uint8_t *luma, int st
                 if( b == n ) j.out.mvs[0] = (int16_t *)take( (size_t)s->nmb * 4 );
                 else if( p0 == b - 1 ) j.out.mvs[1] = (int16_t *)take( (size_t)s->nmb * 4 );
             }
+            s->eager[(size_t)j.d0 * ( B+2 ) + j.d1] = j.out;
             s->jobs.push_back( j );
         }
     if( x264cu_frame_cost_batch( s->ctx, s->jobs.data(), (int)s->jobs.size() ) ) return -1;
@@ -173,13 +184,14 @@ extern "C" int x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, 
     }
     if( s->shard_ahead < 1 ) return -1;
     s->jobs.clear();
-    std::fill( s->stats.begin(), s->stats.end(), -1 );
+    int32_t *stats = s->stats_of( n );
+    std::fill( stats, stats + s->stats_set[0].size(), -1 );
     if( n % world == rank )
     {
         x264cu_job j; memset( &j, 0, sizeof(j) );
         j.fenc = j.fref0 = j.fref1 = fn;
-        j.out.stats = &s->stats[0];
-        j.out.intra_stats = s->intra_stats.data();
+        j.out.stats = &stats[0];
+        j.out.intra_stats = &s->intra_stats[2 * ( n % x264cu_stream::NSETS )];
         s->jobs.push_back( j );
     }
     for( int64_t p0 = n - 1; p0 >= lo; p0-- )
@@ -190,7 +202,7 @@ extern "C" int x264cu_stream_push_shard( x264cu_stream *s, const uint8_t *luma, 
             x264cu_job j; memset( &j, 0, sizeof(j) );
             j.fenc = s->ring[b % D]; j.fref0 = s->ring[p0 % D]; j.fref1 = fn;
             j.d0 = (int)( b - p0 ); j.d1 = (int)( n - b );
-            j.out.stats = &s->stats[( (size_t)j.d0 * ( B+2 ) + j.d1 ) * 4];
+            j.out.stats = &stats[( (size_t)j.d0 * ( B+2 ) + j.d1 ) * 4];
             s->jobs.push_back( j );
         }
     if( x264cu_frame_cost_batch( s->ctx, s->jobs.data(), (int)s->jobs.size() ) ) return -1;
@@ -208,7 +220,40 @@ extern "C" int x264cu_stream_sync( x264cu_stream *s ) { return s ? x264cu_wait( 
 extern "C" int x264cu_stream_cost( x264cu_stream *s, int d0, int d1, int32_t *out4 )
 {
     if( !s || d0 < 0 || d1 < 0 || d0 + d1 > s->bframes + 1 ) return -1;
-    memcpy( out4, &s->stats[( (size_t)d0 * ( s->bframes+2 ) + d1 ) * 4], 16 );
+    if( s->n_pushed < 1 ) { out4[0] = out4[1] = out4[2] = out4[3] = -1; return 0; }
+    memcpy( out4, &s->stats_of( s->n_pushed - 1 )[( (size_t)d0 * ( s->bframes+2 ) + d1 ) * 4], 16 );
+    return 0;
+}
+
+// want_arrays: host pointers of the eagerly copied arrays of evaluation (d0, d1) of the most recent push (NULL members:
+// not produced -- each new MV field is delivered once, with the first evaluation that uses it); valid after sync and
+// until the next push of this window
+extern "C" int x264cu_stream_arrays( x264cu_stream *s, int d0, int d1, x264cu_out *out )
+{
+    if( !s || !out || !s->want_arrays || d0 < 0 || d1 < 0 || d0 + d1 > s->bframes + 1 || s->eager.empty() ) return -1;
+    *out = s->eager[(size_t)d0 * ( s->bframes+2 ) + d1];
+    return 0;
+}
+
+// On-demand result arrays.  The per-evaluation arrays of every frame of the window stay in device memory (the frame's
+// cost-matrix storage); a consumer asks for the few it reads -- the decided path of a mini-GOP needs, per frame,
+// lowres_costs[b-p0][p1-b], the row SATDs and the MV fields towards its two references (slicetype.c:1056,1078-1083;
+// mvpred.c:553) -- instead of all 154 evaluations of every step crossing PCIe.  `b` is a frame number (0 = the first
+// frame pushed); b-d0 .. b+d1 must still be in the window.  The evaluation is computed first if it was never asked for
+// (slicetype_frame_cost semantics), otherwise this is a cache hit: one gather launch + one D2H transfer.  The arrays
+// are complete after x264cu_stream_sync (or x264cu_flush).
+extern "C" int x264cu_stream_fetch( x264cu_stream *s, int64_t b, int d0, int d1, const x264cu_out *out )
+{
+    if( !s || !out || d0 < 0 || d1 < 0 || d0 + d1 > s->bframes + 1 ) return -1;
+    const int64_t newest = s->n_pushed - 1, p0 = b - d0, p1 = b + d1;
+    if( newest < 0 || p1 > newest || p0 < 0 || p0 < newest - ( s->bframes + 1 ) ) return -1;
+    x264cu_job j;
+    memset( &j, 0, sizeof(j) );
+    j.fenc = s->ring[b % s->depth]; j.fref0 = s->ring[p0 % s->depth]; j.fref1 = s->ring[p1 % s->depth];
+    j.d0 = d0; j.d1 = d1;
+    j.out = *out;
+    if( x264cu_frame_cost_batch( s->ctx, &j, 1 ) ) return -1;
+    s->last_seq = x264cu_last_batch( s->ctx );
     return 0;
 }
 

@@ -126,6 +126,8 @@ def load():
     L.x264cu_memcpy_d2d.argtypes = [vp, vp, vp, C.c_size_t]
     L.x264cu_stream_sync.argtypes = [vp]
     L.x264cu_stream_cost.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.x264cu_stream_arrays.argtypes = [vp, C.c_int, C.c_int, C.POINTER(Out)]
+    L.x264cu_stream_fetch.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.POINTER(Out)]
     L.x264cu_stream_frames.argtypes = [vp]
     L.x264cu_stream_frames.restype = C.c_int64
     L.x264cu_stream_result_bytes.argtypes = [vp]
