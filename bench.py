@@ -31,6 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W, H = 1920, 1080
 BFRAMES = 16
 RAMP = BFRAMES + 1            # frames that fill a window
+SUBME, SEARCH_PASSES = 7, 2   # set from the command line
 METRIC = "lookahead frames/s at 1080p (bframes=16 cost-matrix increment per frame)"      # --workload 4k reports 4K frames/s
 
 
@@ -133,15 +134,48 @@ def barrier_sync(dist, local):
         torch.cuda.synchronize(local)
 
 
-def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=None, dev=None, profile=False, dist=None, local=0, arrays=True):
-    """ramp (untimed) -> warmup -> timed steps; returns (ms, evals per step, launches, kernel times, bytes).
+FETCH_BYTES = None
+
+
+def fetch_layout(nmb, mbh):
+    """one decided evaluation as a consumer reads it (slicetype.c:1056,1078-1083; mvpred.c:553): lowres_costs, row SATDs
+    and the MV fields towards both references, laid out like the device gather block (64-byte aligned)"""
+    a64 = lambda v: (v + 63) & ~63      # noqa: E731
+    off, o = {}, 0
+    for name, size in (("lowres_costs", nmb * 2), ("row_satds", mbh * 4), ("mvs0", nmb * 4), ("mvs1", nmb * 4)):
+        off[name] = (o, size)
+        o += a64(size)
+    return off, o
+
+
+def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=None, dev=None, profile=False, dist=None, local=0,
+                  arrays="fetch", parity=False):
+    """ramp (untimed) -> warmup -> timed steps; returns a dict (ms, evals per step, launches, kernel times, bytes, parity).
     ctxs: one context for all streams (they then share its in-order CUDA stream), or one context per encode stream
-    (--contexts: kernels of different streams overlap on the device; this is how concurrent encoders would run)."""
+    (--contexts: kernels of different streams overlap on the device; this is how concurrent encoders would run).
+    e2e: host luma in through x264cu_stream_push, all 154 cost scalars out, plus (arrays == "fetch") the arrays of ONE
+    decided evaluation per step through x264cu_stream_fetch -- what an encoder's decided frame needs -- or
+    (arrays == "eager") every array of every evaluation, the reference's OpenCL copy protocol (slicetype-cl.c:254-280)."""
     L = ctxs[0].L
+    C = x264cu.C
     cx = [ctxs[s % len(ctxs)] for s in range(streams_n)]
-    wins = [L.x264cu_stream_open(cx[s].ctx, BFRAMES, 1 if e2e and arrays else 0) for s in range(streams_n)]
+    eager = e2e and arrays == "eager"
+    wins = [L.x264cu_stream_open(cx[s].ctx, BFRAMES, 1 if eager else 0) for s in range(streams_n)]
     assert all(wins), x264cu.last_error()
     pos = [0] * streams_n
+    nmb, mbh = ctxs[0].nmb, ctxs[0].mbh
+    lay, fbytes = fetch_layout(nmb, mbh)
+    fetch_on = e2e and arrays == "fetch"
+    fbuf = [cx[s].host_alloc(fbytes) for s in range(streams_n)] if (fetch_on or parity) else None
+
+    def fetch(s):
+        """arrays of slicetype_frame_cost(n-2, n, n-1) of stream s: a B frame between its two neighbours"""
+        n = pos[s] - 1
+        o = x264cu.Out()
+        o.lowres_costs = fbuf[s] + lay["lowres_costs"][0]; o.row_satds = fbuf[s] + lay["row_satds"][0]
+        o.mvs[0] = fbuf[s] + lay["mvs0"][0]; o.mvs[1] = fbuf[s] + lay["mvs1"][0]
+        if L.x264cu_stream_fetch(wins[s], n - 1, 1, 1, C.byref(o)) != 0:
+            raise RuntimeError("x264cu_stream_fetch: " + x264cu.last_error())
 
     def push(s):
         i = pos[s]
@@ -159,6 +193,8 @@ def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=No
             push(s)
         x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")
     for k in range(warmup):
+        if fetch_on:
+            fetch(k % streams_n)
         push(k % streams_n)
         x264cu.check(L.x264cu_stream_sync(wins[k % streams_n]), "sync")
     for c in ctxs:
@@ -180,6 +216,8 @@ def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=No
         if s in pending:
             pending.remove(s)
             x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")
+        if fetch_on:
+            fetch(s)         # the decided frame of the step that just completed; lands with the next sync of this window
         evals += push(s)
         pending.append(s)
         while len(pending) >= depth:
@@ -195,14 +233,63 @@ def run_cuda_pass(x264cu, ctxs, frames, streams_n, warmup, steps, e2e, pinned=No
         for k, v in c.kernel_times().items():
             kt[k] = (kt.get(k, (0.0, 0))[0] + v[0], kt.get(k, (0.0, 0))[1] + v[1])
     launches = sum(c.launches() for c in ctxs) - l0
-    res_bytes = int(L.x264cu_stream_result_bytes(wins[0])) if e2e and arrays else 0
-    # a result the caller would read: the P cost of the newest frame against its predecessor
-    st = (x264cu.C.c_int32 * 4)()
-    L.x264cu_stream_cost(wins[(warmup + steps - 1) % streams_n], 1, 0, st)
-    assert st[0] > 0, list(st)
+    res_bytes = int(L.x264cu_stream_result_bytes(wins[0])) if eager else (fbytes if fetch_on else 0)
+    # outside the timed region: the last timed step of one window against the CPU oracle, bit for bit
+    pc = None
+    if parity:
+        pc = parity_check(x264cu, L, wins, frames, pos, (warmup + steps - 1) % streams_n, fetch, fbuf, lay, nmb, mbh)
     for w in wins:
         L.x264cu_stream_close(w)
-    return ms, wall_ms, evals / max(steps, 1), launches, kt, res_bytes, int(st[0])
+    if fbuf:
+        for s in range(streams_n):
+            cx[s].host_free(fbuf[s])
+    return {"ms": ms, "wall_ms": wall_ms, "evals": evals / max(steps, 1), "launches": launches, "kt": kt, "res_bytes": res_bytes, "parity": pc}
+
+
+def parity_check(x264cu, L, wins, frames, pos, s, fetch, fbuf, lay, nmb, mbh):
+    """the step that was timed last (window s, newest frame n): the cost scalars of the I evaluation, the 17 P evaluations
+    and the 24 B evaluations of frames n-1 and n-9, and the fetched arrays of (n-2, n, n-1), against oracle/libx264oracle.so
+    (test infrastructure, used here only as the checker)."""
+    from checkers import check_step_against_oracle
+    C = x264cu.C
+    n = pos[s] - 1
+    fetch(s)
+    x264cu.check(L.x264cu_stream_sync(wins[s]), "sync")
+
+    def stats(d0, d1):
+        st = (C.c_int32 * 4)()
+        L.x264cu_stream_cost(wins[s], d0, d1, st)
+        return list(st)
+
+    def arrays(d0, d1):
+        if (d0, d1) != (1, 1):
+            return None
+        out = {}
+        for name, dt in (("lowres_costs", np.uint16), ("row_satds", np.int32), ("mvs0", np.int16), ("mvs1", np.int16)):
+            o, size = lay[name]
+            out[name] = np.frombuffer((C.c_uint8 * size).from_address(fbuf[s] + o), dtype=dt).copy()
+        return out
+    t0 = time.perf_counter()
+    r = check_step_against_oracle(frames[s][n - RAMP:n + 1], stats, arrays, bframes=BFRAMES, b_list=(RAMP - 1, RAMP - 9),
+                                  subme=SUBME, passes=SEARCH_PASSES)
+    ok = not r["mismatches"] and r["arrays"] == 4
+    return {"ok": ok, "window": s, "newest_frame": n, "evaluations": r["evaluations"], "arrays": r["arrays"],
+            "mismatches": r["mismatches"][:4], "checker": "oracle/libx264oracle.so (CPU restatement, pinned against the reference build)",
+            "seconds": round(time.perf_counter() - t0, 1)}
+
+
+def load_ncu_counters(kernel):
+    """counters of one kernel from the tracked ncu summary of this round (profiles/tools/summarise.py --json)"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02", "ncu_counters.json")))
+        for k, v in d.get("kernels", {}).items():
+            if kernel in k:
+                v = dict(v)
+                v["source"] = "profiles/r02/ncu_counters.json (ncu --set full, build %s; not measured in this run)" % d.get("git", "?")
+                return v
+    except Exception:
+        pass
+    return None
 
 
 def bench_satd(x264cu, ctx, peak_gbs):
@@ -301,12 +388,31 @@ def bench_frame_prep(x264cu, ctx, peak_gbs):
                      "time is how an encoder feeds its lookahead, and the whole sequence is 6 % of a step"}
 
 
-def cpu_reference_run(frames, warmup, steps, threads, ramp=RAMP):
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    import shutil
+    return {"cpu_model": model, "nproc": os.cpu_count() or 1, "nasm": shutil.which("nasm"), "yasm": shutil.which("yasm")}
+
+
+REF_FLAGS = {"": "-O2 -fno-tree-vectorize (the parity build)",
+             "_fast": "-O3 -ffast-math -fno-tree-vectorize -fomit-frame-pointer (the reference's own configure:1354-1363 release flags; C only)",
+             "_simd": "-O3 -ffast-math -ftree-vectorize -mavx2 -mfma -mbmi2 (C sources auto-vectorised by gcc: stand-in for the x86 asm, which needs nasm)"}
+
+
+def cpu_reference_run(frames, warmup, steps, threads, ramp=RAMP, flavour=None):
     """the reference's own slicetype_frame_cost (raster-serial C path with lookahead slices,
     slicetype.c:836-995) on the same frames, same evaluations in the same order as a CUDA step."""
-    from checkers import Lookahead, OracleLib, RefLib, have_ref
+    from checkers import Lookahead, OracleLib, RefLib, have_ref, ref_flavours
     if have_ref():
-        la = Lookahead(RefLib(), "ref_serial", W, H, bframes=BFRAMES, subme=7, mbtree=1, aq=1, la_threads=threads)
+        fl = ref_flavours()
+        la = Lookahead(RefLib(fl.get(flavour)), "ref_serial", W, H, bframes=BFRAMES, subme=7, mbtree=1, aq=1, la_threads=threads)
         kind = "reference"
     else:
         la = Lookahead(OracleLib(), "oracle", W, H, bframes=BFRAMES, subme=7, mbtree=1, aq=1, passes=2, mv_range=512)
@@ -335,6 +441,46 @@ def cpu_reference_run(frames, warmup, steps, threads, ramp=RAMP):
     dt = time.perf_counter() - t0
     la.close()
     return dt, evals, kind, threads
+
+
+def cli_configs0(threads, frames_n=90):
+    """BASELINE.json configs[0] on this box's host cores: the reference's own CLI, `--preset medium --rc-lookahead 40 --b-adapt 2`,
+    synthetic 1920x1080 y4m, CPU lookahead, whole-encode frames/s as x264 prints it.  Bounded sample (frames_n frames instead
+    of 300); the fastest prebuilt C flavour of the unmodified sources (no nasm: no asm)."""
+    import re
+    from checkers import ref_flavours
+    out = {"frames": frames_n, "threads": threads, "asm": False}
+    clis = {suf: os.path.join(ROOT, "oracle", "_ref", "x264cu_cli%s" % suf) for suf in ref_flavours()}
+    clis = {k: v for k, v in clis.items() if os.path.exists(v)}
+    if not clis:
+        out["unavailable"] = "oracle/_ref/x264cu_cli* not built"
+        return out
+    src = "/tmp/x264cu_bench_configs0.y4m"
+    with open(src, "wb") as f:
+        f.write(b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C420jpeg\n" % (W, H))
+        c = np.full(W * H // 2, 128, np.uint8).tobytes()
+        for x in make_stream_frames(7, frames_n):
+            f.write(b"FRAME\n"); f.write(x.tobytes()); f.write(c)
+    res = {}
+    for suf, cli in clis.items():
+        if suf == "" and len(clis) > 1:
+            continue                     # the -O2 parity build is not a timing build
+        cmd = [cli, "--preset", "medium", "--rc-lookahead", "40", "--b-adapt", "2", "--threads", str(threads), "-o", "/tmp/x264cu_bench_configs0.264", src]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            m = re.search(r"encoded (\d+) frames, ([0-9.]+) fps", r.stderr)
+            res[REF_FLAGS[suf].split(" (")[0]] = float(m.group(2)) if (r.returncode == 0 and m) else None
+        except Exception as e:
+            res[REF_FLAGS[suf].split(" (")[0]] = "failed: %s" % type(e).__name__
+    for fn in (src, "/tmp/x264cu_bench_configs0.264"):
+        try:
+            os.remove(fn)
+        except OSError:
+            pass
+    vals = [v for v in res.values() if isinstance(v, float)]
+    out.update({"fps": max(vals) if vals else None, "fps_by_build": res,
+                "command": "x264 --preset medium --rc-lookahead 40 --b-adapt 2 --threads %d (whole encode; the lookahead is one part of it)" % threads})
+    return out
 
 
 def run_one_stream(args):
@@ -428,6 +574,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--streams", type=int, default=4, help="independent encode streams per GPU (round-robin)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the configs[0] CLI sample inside cpu_baseline")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="one-stream workloads: how the ranks exchange MV fields")
     ap.add_argument("--search-passes", type=int, default=2, help="K of the dependency-free schedule; 0 = exact raster-serial wavefront mode")
     ap.add_argument("--no-primitives", action="store_true", help="skip the SATD/SAD primitive roofline section")
@@ -435,15 +582,19 @@ def main():
     ap.add_argument("--contexts", type=int, default=0, help="contexts per GPU; 0 (default): one context (own CUDA streams) per encode stream, "
                     "as concurrent encoders would run; 1: all streams share one in-order context")
     ap.add_argument("--subme", type=int, default=7, help="analyse.i_subpel_refine of the encoder: > 1 selects the SATD/HEX/subme-4 lookahead (default), <= 1 the SAD/DIA/subme-2 one")
-    ap.add_argument("--e2e-scalars-only", action="store_true", help="diagnostic: the end-to-end pass uploads host luma but reads back only "
-                    "the cost scalars (isolates the D2H share of the PCIe traffic)")
+    ap.add_argument("--e2e-arrays", default="fetch", choices=["fetch", "eager", "none"],
+                    help="what the end-to-end pass brings back besides the 154 cost scalars of a step: fetch (default) = the arrays of "
+                         "one decided evaluation per step through x264cu_stream_fetch (lowres_costs, row SATDs, both MV fields: what "
+                         "the encoder reads for a decided frame); eager = every array of every evaluation, the reference's OpenCL "
+                         "copy protocol (3.65 MB per step); none = scalars only")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k", "64streams", "4k-one-stream", "1080p-one-stream"],
                     help="1080p: BASELINE.json configs[2] (the headline); 4k: configs[3] with independent streams per GPU; "
                          "64streams: configs[4] (8 independent 1080p encode streams per GPU); 4k-one-stream / 1080p-one-stream: "
                          "configs[3] as written -- ONE encode stream whose search fields and evaluations are split over all GPUs "
                          "(strong scaling, one NCCL all-gather of MV fields per frame)")
     args = ap.parse_args()
-    global W, H
+    global W, H, SUBME, SEARCH_PASSES
+    SUBME, SEARCH_PASSES = args.subme, args.search_passes
     if args.workload.endswith("one-stream"):
         if args.workload.startswith("4k"):
             W, H = 3840, 2160
@@ -468,30 +619,42 @@ def main():
         rank = int(os.environ.get("RANK", 0))
         if rank != 0:
             return 0
+        from checkers import ref_flavours
         threads = min(16, nproc)             # X264_LOOKAHEAD_THREAD_MAX (common/base.h)
         steps = args.steps
         frames = make_stream_frames(100, RAMP + warmup + steps)
-        dt, evals, kind, threads = cpu_reference_run(frames, warmup, steps, threads)
-        v = steps / dt
-        sample = ("%d steady-state steps of stream 0 after an untimed %d-frame window fill; reference C sources built "
-                  "without asm (no nasm in the image), %d lookahead slice threads" % (steps, RAMP, threads))
+        # every build flavour of the unmodified reference that travelled to this box; the line reports the FASTEST one
+        runs = {}
+        for suf in (ref_flavours() or {"": None}):
+            dt, evals, kind, thr = cpu_reference_run(frames, warmup, steps, threads, flavour=suf)
+            runs[suf] = (steps / dt, dt, kind, thr)
+        best = max(runs, key=lambda k: runs[k][0])
+        v, dt, kind, threads = runs[best]
+        info = cpu_info()
+        sample = ("%d steady-state steps of stream 0 after an untimed %d-frame window fill; unmodified reference C sources, %d lookahead "
+                  "slice threads; build: %s" % (steps, RAMP, threads, REF_FLAGS[best]))
+        cb = {"value": round(v, 4), "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample, "asm": False,
+              "asm_note": "the reference's x86 asm needs nasm >= 2.13 (configure:972-973); nasm/yasm on this box: %s / %s; "
+                          "/root/reference is not on the GPU box either, so only prebuilt C flavours can run here" % (info["nasm"], info["yasm"]),
+              "flags": REF_FLAGS[best], "cpu_model": info["cpu_model"], "nproc": info["nproc"],
+              "flavours_frames_per_s": {REF_FLAGS[k].split(" (")[0]: round(r[0], 3) for k, r in runs.items()}}
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "frames/s", "n_gpus": args.gpus,
                           "steps": steps, "warmup": warmup, "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": round(v, 4), "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
+                          "cpu_baseline": cb,
                           "e2e": {"value": round(v, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
     import x264cu
     local_early = int(os.environ.get("LOCAL_RANK", 0))
-    config["cpu_binding"] = bind_to_gpu_numa_node(local_early) if int(os.environ.get("WORLD_SIZE", 1)) > 1 else "unbound (single rank)"
+    run_info = {"cpu_binding": bind_to_gpu_numa_node(local_early) if int(os.environ.get("WORLD_SIZE", 1)) > 1 else "unbound (single rank)"}
     rank, world, local, dist = dist_setup(args.gpus)
     S = args.streams
     per_stream = RAMP + (warmup + args.steps + S - 1) // S + 1
     n_ctx = S if args.contexts == 0 else max(1, min(args.contexts, S))
     ctxs = [x264cu.Context(W, H, bframes=BFRAMES, subme=args.subme, do_edges=1, aq=1, passes=args.search_passes, device=local) for _ in range(n_ctx)]
     ctx = ctxs[0]
-    config["contexts_per_gpu"] = n_ctx
+    run_info["contexts_per_gpu"] = n_ctx
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -519,16 +682,21 @@ def main():
     # device-resident pass ("value"): inputs already in HBM, only the cost scalars come back
     # (kernel timing pass first: ONE context, so that the per-kernel CUDA events do not span kernels of other streams)
     psteps = min(args.steps, 16)
-    _, _, _, _, kt, _, _ = run_cuda_pass(x264cu, ctxs[:1], frames, S, warmup, psteps, False, dev=dev, profile=True, dist=dist, local=local)
-    ms_v, wall_v, evals, launches, _, _, chk_v = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, False, dev=dev, profile=False, dist=dist, local=local)
-    # end-to-end pass: pinned host luma in, every result array of the hook protocol out, per step
+    kt = run_cuda_pass(x264cu, ctxs[:1], frames, S, warmup, psteps, False, dev=dev, profile=True, dist=dist, local=local)["kt"]
+    rv = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, False, dev=dev, profile=False, dist=dist, local=local,
+                       parity=args.value_only and rank == 0)
+    ms_v, evals, launches = rv["ms"], rv["evals"], rv["launches"]
+    # end-to-end pass: pinned host luma in; all 154 cost scalars + the arrays of one decided evaluation out, per step
     if args.value_only:
-        ms_e, wall_e, res_bytes, chk_e = ms_v, wall_v, 0, chk_v
+        re_ = rv
     else:
-        ms_e, wall_e, _, _, _, res_bytes, chk_e = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, True, pinned=pinned, dist=dist, local=local,
-                                                                 arrays=not args.e2e_scalars_only)
+        re_ = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, True, pinned=pinned, dist=dist, local=local,
+                            arrays=args.e2e_arrays, parity=rank == 0)
+    ms_e, res_bytes, pc = re_["ms"], re_["res_bytes"], re_["parity"]
     clocks = sampler.summary() if rank == 0 else {}
-    assert chk_v > 0 and chk_e > 0
+    if rank == 0 and pc is not None and not pc["ok"]:
+        print(json.dumps({"parity_check": pc}))
+        raise SystemExit("bench.py: the timed step does NOT match the CPU oracle -- no number is reported")
 
     t_v, t_e = ms_v, ms_e
     if dist is not None:
@@ -542,10 +710,13 @@ def main():
     metric = METRIC if args.workload != "4k" else "lookahead frames/s at 4K (bframes=16 cost-matrix increment per frame)"
     out = {"metric": metric, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
            "ms_per_step": round(t_v / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "u8", "data": "synthetic", "config": config, "clocks": clocks,
+           "dtype": "u8", "data": "synthetic", "config": config, "run": run_info, "clocks": clocks,
            "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": fbytes, "d2h_bytes_per_step": res_bytes + 154 * 32,
-                   "ms_per_step": round(t_e / args.steps, 4)},
-           "gpu_launches": int(launches)}
+                   "ms_per_step": round(t_e / args.steps, 4),
+                   "returns": {"fetch": "154 x 32 B cost scalars + the arrays of one decided evaluation (x264cu_stream_fetch)",
+                               "eager": "154 x 32 B cost scalars + every array of every evaluation (the OpenCL backend's protocol)",
+                               "none": "154 x 32 B cost scalars"}[args.e2e_arrays]},
+           "gpu_launches": int(launches), "parity_check": pc}
     # roofline of the dominant kernel: the motion-search pass (2 launches per step, 33 fields each)
     nmb = ctx.nmb
     s_ms, s_n = kt["search"]
@@ -559,17 +730,19 @@ def main():
         alg = per_block * nmb * fields
         avg_ms = s_ms / s_n
         ach = alg / avg_ms / 1e6
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch from the committed
-        # `ncu --set full` capture (profiles/r01/ncu_summary_v11.md: 40.66 MB + 0.74 MB); below the algorithmic bytes
-        # because the 18 frames of a window are shared by the 33 fields of a launch and stay in L2
+        # traffic / integer-pipe counters: NOT measured in this run (a number taken under a profiler is never a bench value);
+        # they are read from the tracked ncu summary profiles/r02/ncu_counters.json (written by profiles/tools/summarise.py
+        # --json from an `ncu --set full` capture, with the git revision of the captured build), else null
+        cnt = load_ncu_counters("search_kernel_t")
         out["roofline"] = {"kernel": "search_kernel_t<SATD,unweighted>", "bound": "hbm", "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
-                           "frac": round(ach / peak_gbs, 4), "traffic": 41.40e6, "peak_source": peak_src,
+                           "frac": round(ach / peak_gbs, 4), "traffic": cnt.get("dram_bytes") if cnt else None, "peak_source": peak_src,
                            "avg_launch_ms": round(avg_ms, 4), "launches_timed": s_n, "algorithmic_bytes_per_launch": alg,
                            "timed": "CUDA events around every launch in a separate %d-step pass on one context (no overlap with other streams' kernels)" % psteps,
-                           "integer_pipe": {"alu_pipe_pct": 61.5, "issue_active_pct": 52.1, "l1tex_wavefronts_pct": 62.0,
-                                            "source": "ncu --set full, profiles/r01/ncu_summary_v11.md (not measured in this run)"},
+                           "integer_pipe": cnt,
                            "note": "compulsory bytes are tiny: the kernel is bound by integer issue (6 SATD 8x8 + ~35 SAD 8x8 per block and pass) "
                                    "and L1 wavefronts, not by HBM; the HBM-streaming kernels of the path are in `primitives`"}
+        out["kernel_ms_note"] = ("kernel_ms_per_step comes from the one-context timing pass; `value` runs %d contexts whose kernels overlap, "
+                                 "so the per-kernel times add up to more than ms_per_step" % n_ctx)
         out["kernel_ms_per_step"] = {k: round(v[0] / psteps, 4) for k, v in kt.items()}
         if args.search_passes == 0:
             out["roofline"]["kernel"] = "search_kernel_serial (exact raster-serial mode: latency-bound wavefront, one launch per step)"
@@ -578,12 +751,23 @@ def main():
             out["primitives"] = bench_satd(x264cu, ctx, peak_gbs)
             out["primitives"]["frame_prep_1080p"] = bench_frame_prep(x264cu, ctx, peak_gbs)
         if world == 1 and not args.no_cpu_baseline and args.workload == "1080p":
-            bsteps = 12         # bounded sample: ~1.3 s of host work on a 9 frames/s box, ~9 s on a 1.4 frames/s one (+ the untimed fill)
+            from checkers import ref_flavours
+            bsteps = 12         # bounded sample: ~1 s of host work on a 32-core box, ~9 s on an 8-core one (+ the untimed fill), per build flavour
             bframes_ = make_stream_frames(shard.stream_seed(my_streams[0]), RAMP + 1 + bsteps)
-            dt, ev, kind, thr = cpu_reference_run(bframes_, 1, bsteps, min(16, nproc))
-            out["cpu_baseline"] = {"value": round(bsteps / dt, 4), "unit": "frames/s", "cores": thr, "kind": kind,
+            runs = {}
+            for suf in (ref_flavours() or {"": None}):
+                dt, ev, kind, thr = cpu_reference_run(bframes_, 1, bsteps, min(16, nproc), flavour=suf)
+                runs[suf] = (bsteps / dt, kind, thr)
+            best = max(runs, key=lambda k: runs[k][0])
+            info = cpu_info()
+            out["cpu_baseline"] = {"value": round(runs[best][0], 4), "unit": "frames/s", "cores": runs[best][2], "kind": runs[best][1],
                                    "sample": "%d steady-state steps of stream 0 after an untimed 17-frame window fill and 1 warm-up step; "
-                                             "C-only build of the reference (no nasm)" % bsteps}
+                                             "unmodified reference C sources, build: %s" % (bsteps, REF_FLAGS[best]),
+                                   "asm": False, "flags": REF_FLAGS[best], "cpu_model": info["cpu_model"], "nproc": info["nproc"],
+                                   "nasm_on_box": info["nasm"] or info["yasm"],
+                                   "flavours_frames_per_s": {REF_FLAGS[k].split(" (")[0]: round(r[0], 3) for k, r in runs.items()}}
+            if not args.no_cli:
+                out["cpu_baseline"]["configs0_cli"] = cli_configs0(nproc)
         print(json.dumps(out))
     for c in ctxs:
         c.close()

@@ -146,9 +146,27 @@ class OracleLib(_Base):
         return dst
 
 
+def ref_flavours():
+    """the builds of the unmodified reference that oracle/Makefile produced: '' = parity (-O2), '_fast' = the
+    reference's release flags (-O3 -ffast-math -fno-tree-vectorize), '_simd' = the same auto-vectorised for AVX2."""
+    out = {}
+    for suf in ("", "_fast", "_simd"):
+        p = REF_SO.replace(".so", suf + ".so")
+        if os.path.exists(p):
+            out[suf] = p
+    if "_simd" in out:
+        try:
+            flags = open("/proc/cpuinfo").read()
+            if not all(f in flags for f in (" avx2", " fma", " bmi2")):
+                del out["_simd"]
+        except OSError:
+            del out["_simd"]
+    return out
+
+
 class RefLib(_Base):
-    def __init__(self):
-        super().__init__(REF_SO, "ref_")
+    def __init__(self, path=None):
+        super().__init__(path or REF_SO, "ref_")
         L = self.lib
         L.ref_la_open.restype = vp
         L.ref_la_open.argtypes = [C.c_int] * 11

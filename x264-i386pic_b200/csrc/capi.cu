@@ -917,6 +917,38 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
     return 0;
 }
 
+// Order the decision jobs of a batch so that B evaluations sharing (fenc, ref1, list-1 field) -- the family (., p1, b)
+// over all p0 -- are consecutive, and cut every family into chunks of <= X264CU_F_CHUNK jobs (final.cu final_kernel_c:
+// one thread keeps the source block and the list-1 prediction for a whole chunk).  Jobs are independent (integer
+// atomics, distinct outputs), so any order is legal.  Long chunks first: they should not be the tail of the launch.
+static void group_finals( std::vector<FinalJob> &finals, std::vector<int2> &chunks )
+{
+    std::stable_sort( finals.begin(), finals.end(), []( const FinalJob &a, const FinalJob &b )
+    {
+        if( a.b_bidir != b.b_bidir ) return a.b_bidir > b.b_bidir;
+        if( !a.b_bidir ) return false;                      // non-bidir jobs keep their order
+        if( a.fenc != b.fenc ) return a.fenc < b.fenc;
+        if( a.ref1 != b.ref1 ) return a.ref1 < b.ref1;
+        return a.mv[1] < b.mv[1];
+    } );
+    const int n = (int)finals.size();
+    for( int i = 0; i < n; )
+    {
+        int j = i + 1;
+        if( finals[i].b_bidir )
+            while( j < n && j - i < X264CU_F_CHUNK && finals[j].b_bidir && finals[j].fenc == finals[i].fenc && finals[j].ref1 == finals[i].ref1 && finals[j].mv[1] == finals[i].mv[1] ) j++;
+        else
+            while( j < n && j - i < X264CU_F_CHUNK && !finals[j].b_bidir ) j++;
+        chunks.push_back( make_int2( i, j - i ) );
+        i = j;
+    }
+    std::stable_sort( chunks.begin(), chunks.end(), [&]( const int2 &a, const int2 &b )
+    {   // bidir work dominates; among bidir chunks the longer one first
+        const int wa = finals[a.x].b_bidir ? a.y : 0, wb = finals[b.x].b_bidir ? b.y : 0;
+        return wa > wb;
+    } );
+}
+
 static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
 {
     const LaParams &P = c->P;
@@ -976,10 +1008,12 @@ static int run_batch( x264cu_ctx *c, const x264cu_job *jobs, int n )
     if( run_searches( c, tasks ) ) return -1;
     if( !finals.empty() )
     {
-        const FinalJob *d;
-        if( push_jobs( c, finals, &d ) ) return -1;
+        std::vector<int2> chunks;
+        group_finals( finals, chunks );
+        const FinalJob *d; const int2 *dch;
+        if( push_jobs( c, finals, &d ) || push_jobs( c, chunks, &dch ) ) return -1;
         Span s( c, K_FINAL, 1 );
-        launch_final( d, (int)finals.size(), P, c->st );
+        launch_final( d, (int)finals.size(), dch, (int)chunks.size(), P, c->st );
     }
     CU( cudaGetLastError() );
     // result copies (slicetype-cl.c:254-280,513-535,613-649): every requested array is gathered on the

@@ -99,45 +99,190 @@ __global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *_
     final_block( be, J, P, bx, by, blk );
 }
 
-// F_JOBS consecutive evaluations of the job table per CTA, same block tile.  The batch lists the evaluations of one p0
-// back to back, so consecutive jobs read the same two reference frames and the tile's windows could stay in L1 from
-// one job to the next -- measured on B200 it does not pay (F_JOBS 4 / 8 / 16: 0.247 / 0.289 / 0.266 ms against 0.225 for 1:
-// fewer, longer CTAs balance worse over the SMs), so the default is one evaluation per CTA.
-#ifndef F_JOBS
-#define F_JOBS 1
+// ---- thread-per-block decision kernel over CHUNKS of evaluations ---------------------------------------------------
+// The B evaluations (p0, p1, b) of one batch that share the frame b AND the future reference p1 -- at bframes = 16 the
+// 136 B evaluations of a lookahead step are 16 such families of 1..16 members -- also share the source block, the
+// list-1 MV field and therefore the whole list-1 prediction get_ref( p1, mv(b -> p1) ), and their temporal-direct
+// list-1 windows overlap (d1 = -mv(p1 -> p0) * (p1-b)/(p1-p0) is about the same motion for every p0).  The host sorts
+// such families together (capi.cu group_finals) and cuts them into chunks of <= X264CU_F_CHUNK members; ONE thread
+// handles one block for all members of a chunk: the source rows stay in registers, the list-1 prediction is built once
+// (kept in registers, F_HOIST 1, or in shared memory, F_HOIST 2) and the list-1 windows of the later members hit in L1.
+// Measured on B200 (profiles/r02/tuning.md): the per-evaluation kernel re-fetched every plane ~27x into L1 (ncu r01:
+// 139 M L1 sectors per launch, hit rate 65 %, L1 data-pipe wavefronts 85 % of peak).
+// Semantics per member are those of final_block (slicetype.c:616-652,703-712,758-790), bit for bit.
+#ifndef X264CU_F_HOIST
+#define X264CU_F_HOIST 2
 #endif
 template<bool SATD, int PITCH>
-__global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_kernel_t( const FinalJob *__restrict__ jobs, int njobs, LaParams P )
+__global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_kernel_c( const FinalJob *__restrict__ jobs, const int2 *__restrict__ chunks, LaParams P )
 {
+#if X264CU_F_HOIST == 2
+    __shared__ uint2 s_pred1[8][F_TILE_W*F_TILE_H];
+#endif
     int bx, by;
     if( !warp_tile_block( P.tiles_f, P.ntiles_f, P, bx, by ) ) return;
     const int blk = by * P.mbw + bx;
-    ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> be; be.P = &P;
-    const int pel = ( by*8 ) * be.pitch() + bx*8;
-#pragma unroll 1
-    for( int z = blockIdx.y * F_JOBS; z < min( njobs, ( blockIdx.y + 1 ) * F_JOBS ); z++ )
+    const int2 ch = __ldg( chunks + blockIdx.y );           // first job, number of jobs
+    typedef ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> BE;
+    BE be; be.P = &P;
+    const int pitch = be.pitch(), s4 = pitch >> 2, pel = ( by*8 ) * pitch + bx*8;
+    if( skipped_border( P, bx, by ) )
     {
-        const FinalJob J = jobs[z];
-        if( skipped_border( P, bx, by ) ) { if( !J.b_intra_only ) J.lowres_costs[blk] = 0; continue; }
-        const uint8_t *src = J.fenc + pel;
+        for( int z = ch.x; z < ch.x + ch.y; z++ ) { const FinalJob &J = jobs[z]; if( !J.b_intra_only ) J.lowres_costs[blk] = 0; }
+        return;
+    }
+    const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
+    const bool score = !border || P.mbw <= 2 || P.mbh <= 2;
+    // what every member of a bidir chunk shares
+    int mv1x = 0, mv1y = 0, mc1 = X264CU_COST_MAX;
+#if X264CU_F_HOIST == 1
+    uint2 pred1[8];
+#endif
+    const bool bidir = jobs[ch.x].b_bidir != 0;
+    if( bidir )
+    {
+        const FinalJob &J0 = jobs[ch.x];
+        const uint8_t *src = J0.fenc + pel;
+#pragma unroll
+        for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * pitch ) );
+        be.ref1 = J0.ref1 + pel;
+        const int v = __ldg( (const int *)J0.mv[1] + blk );
+        mv1x = (int16_t)( v & 0xffff ); mv1y = v >> 16;
+        mc1 = __ldg( J0.mvcost[1] + blk );
+#if X264CU_F_HOIST
+        {   // the list-1 half of the L0+L1 candidate (slicetype.c:582-597): get_ref at mv1, or the half-pel plane for subme <= 1
+            uint2 t[8];
+            if( SATD )
+            {
+                QpelRows<false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> r1( be.ref1, P, mv1x, mv1y, 0, -1, 0 );
+#pragma unroll
+                for( int r = 0; r < 8; r++ ) t[r] = r1( r );
+            }
+            else
+            {
+                const int i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
+                const RowSrc<X264CU_FINAL_LD64 != 0> q1( be.ref1, ( mv1x >> 2 ) + ( mv1y >> 2 ) * pitch + i1 * (int)P.plane_size );
+#pragma unroll
+                for( int r = 0; r < 8; r++ ) t[r] = q1.row( r*s4 );
+            }
+#pragma unroll
+            for( int r = 0; r < 8; r++ )
+            {
+#if X264CU_F_HOIST == 1
+                pred1[r] = t[r];
+#else
+                s_pred1[r][threadIdx.x] = t[r];
+#endif
+            }
+        }
+#endif
+    }
+#pragma unroll 1
+    for( int z = ch.x; z < ch.x + ch.y; z++ )
+    {
+        // the job's fields are read where they are used (uniform loads that hit in L1): a by-value copy of the 120-byte
+        // descriptor would sit in 30 registers across the SATD bodies
+        const FinalJob &J = jobs[z];
+        int bcost = X264CU_COST_MAX, list_used = 0;
         if( !J.b_intra_only )
         {
-#pragma unroll
-            for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * be.pitch() ) );
+            int mv0x, mv0y, mc0;
+            {
+                const int v = __ldg( (const int *)J.mv[0] + blk );
+                mv0x = (int16_t)( v & 0xffff ); mv0y = v >> 16;
+                mc0 = __ldg( J.mvcost[0] + blk );
+            }
+            if( bidir )
+            {
+                be.ref0 = J.ref0 + pel;
+                int d0x = 0, d0y = 0, d1x = 0, d1y = 0;
+                if( J.dmv_src )
+                {   // temporal direct (slicetype.c:629-639)
+                    MeGeo m;
+                    me_limits( m, P, bx, by );
+                    const int w = __ldg( (const int *)J.dmv_src + blk );
+                    const int mrx = (int16_t)( w & 0xffff ), mry = w >> 16;
+                    d0x = ( mrx * J.dist_scale_factor + 128 ) >> 8;
+                    d0y = ( mry * J.dist_scale_factor + 128 ) >> 8;
+                    d1x = d0x - mrx; d1y = d0y - mry;
+                    d0x = iclip3( d0x, m.sminx, m.smaxx ); d0y = iclip3( d0y, m.sminy, m.smaxy );
+                    d1x = iclip3( d1x, m.sminx, m.smaxx ); d1y = iclip3( d1y, m.sminy, m.smaxy );
+                    if( !SATD ) { d0x &= ~1; d0y &= ~1; d1x &= ~1; d1y &= ~1; }
+                }
+                // candidates in the reference's order, ties keep the earlier one: direct, zero (:644-652), L0, L1 (:708),
+                // L0+L1 with the 5*lambda penalty (:711-712)
+                {
+                    const int cost = be.bidir( d0x, d0y, d1x, d1y, J.bipred_weight );
+                    if( cost < bcost ) { bcost = cost; list_used = 3; }
+                }
+                if( d0x | d0y | d1x | d1y )
+                {
+                    const int cz = be.bidir_zero( J.bipred_weight );
+                    if( cz < bcost ) { bcost = cz; list_used = 3; }
+                }
+                if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
+                if( mc1 < bcost ) { bcost = mc1; list_used = 2; }
+                if( mv0x | mv0y | mv1x | mv1y )
+                {
+                    const int w = J.bipred_weight;
+                    int cost;
+#if X264CU_F_HOIST
+#if X264CU_F_HOIST == 1
+#define PRED1( r ) pred1[r]
+#else
+#define PRED1( r ) s_pred1[r][threadIdx.x]
+#endif
+                    if( SATD )
+                    {
+                        QpelRows<false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> r0( be.ref0, P, mv0x, mv0y, 0, -1, 0 );
+                        cost = satd8x8_t( be.fenc, [&]( int r ) { const uint2 a = r0( r ), b = PRED1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+                    }
+                    else
+                    {
+                        const int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 );
+                        const RowSrc<X264CU_FINAL_LD64 != 0> q0( be.ref0, ( mv0x >> 2 ) + ( mv0y >> 2 ) * pitch + i0 * (int)P.plane_size );
+                        cost = sad8x8_t( be.fenc, [&]( int r ) { const uint2 a = q0.row( r*s4 ), b = PRED1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+                    }
+#undef PRED1
+#else
+                    cost = be.bidir( mv0x, mv0y, mv1x, mv1y, w );
+#endif
+                    cost += 5;
+                    if( cost < bcost ) { bcost = cost; list_used = 3; }
+                }
+            }
+            else if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
         }
-        be.ref0 = J.ref0 + pel; be.ref1 = J.ref1 + pel; be.ref_w = be.ref0;
-        final_block( be, J, P, bx, by, blk );
+        bcost += 4;                                         // lowres_penalty (slicetype.c:758)
+        if( !J.b_bidir )
+        {   // slicetype.c:762-773
+            const int icost = J.intra[blk];
+            const int b_intra = icost < bcost;
+            if( b_intra ) { bcost = icost; list_used = 0; }
+            if( score && b_intra ) atomicAdd( &J.stats[2], 1 );
+        }
+        if( !J.b_intra_only )
+        {   // slicetype.c:776-788
+            const int bcost_aq = P.aq ? ( bcost * J.inv_qscale[blk] + 128 ) >> 8 : bcost;
+            atomicAdd( &J.row_satds[by], bcost_aq );
+            if( score )
+            {
+                atomicAdd( &J.stats[0], bcost );
+                atomicAdd( &J.stats[1], bcost_aq );
+            }
+        }
+        J.lowres_costs[blk] = (uint16_t)( min( bcost, 0x3FFF ) + ( list_used << 14 ) );     // slicetype.c:790
     }
 }
 
-void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st )
+void launch_final( const FinalJob *d_jobs, int njobs, const int2 *d_chunks, int nchunks, const LaParams &P, cudaStream_t st )
 {
     if( use_thread_mapping( P, njobs ) )
     {
         const int warps_per_cta = F_TILE_W * F_TILE_H / 32;
-        dim3 grid( ( P.ntiles_f + warps_per_cta - 1 ) / warps_per_cta, ( njobs + F_JOBS - 1 ) / F_JOBS );
-#define FINAL_T( PITCH ) { if( P.b_satd ) final_kernel_t<true, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, njobs, P ); \
-                           else           final_kernel_t<false, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, njobs, P ); }
+        dim3 grid( ( P.ntiles_f + warps_per_cta - 1 ) / warps_per_cta, nchunks );
+#define FINAL_T( PITCH ) { if( P.b_satd ) final_kernel_c<true, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, d_chunks, P ); \
+                           else           final_kernel_c<false, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, d_chunks, P ); }
         if( P.stride == X264CU_PITCH_A )      FINAL_T( X264CU_PITCH_A )
         else if( P.stride == X264CU_PITCH_B ) FINAL_T( X264CU_PITCH_B )
         else                        FINAL_T( 0 )

@@ -38,7 +38,7 @@
 #define X264CU_MINB_SEARCH 3
 #endif
 #ifndef X264CU_MINB_FINAL
-#define X264CU_MINB_FINAL 6
+#define X264CU_MINB_FINAL 5
 #endif
 
 #define GROUPS_PER_CTA 32

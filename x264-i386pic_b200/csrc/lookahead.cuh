@@ -82,7 +82,12 @@ void launch_weight_plane( const uint8_t *src, uint8_t *dst, int64_t bytes, int s
 void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *intra, int32_t *row_satds,
                    int32_t *stats, const LaParams &P, cudaStream_t st );
 void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st );
-void launch_final( const FinalJob *d_jobs, int njobs, const LaParams &P, cudaStream_t st );
+// d_chunks: (first job, count) per CTA row of the thread-per-block kernel; every chunk is homogeneous (all bidir with the
+// same fenc / ref1 / list-1 field, or all non-bidir), see capi.cu group_finals
+void launch_final( const FinalJob *d_jobs, int njobs, const int2 *d_chunks, int nchunks, const LaParams &P, cudaStream_t st );
+#ifndef X264CU_F_CHUNK
+#define X264CU_F_CHUNK 8
+#endif
 void launch_aq( const uint8_t *luma, int ls, const uint8_t *chroma, int cs, int W, int H, const LaParams &P, int mode, float strength,
                 const float *quant_offsets, const float *log2_lut, const uint8_t *exp2_lut, float *qp_offset, uint16_t *inv_qscale,
                 unsigned long long *pixstats, cudaStream_t st );
