@@ -264,6 +264,28 @@ int x264cu_quant( x264cu_ctx *ctx, int b8x8, int16_t *coefs, int64_t nblocks, co
 int x264cu_lowres_core( x264cu_ctx *ctx, const uint8_t *src, int src_stride, uint8_t *dst0, uint8_t *dsth,
                         uint8_t *dstv, uint8_t *dstc, int dst_stride, int width, int height, int on_device );
 
+/* ---- the checkasm surfaces of the fetch / prediction code (x264_mc_functions_t mc.h:267-340, pixel.h intra_mbcmp_x3_8x8c,
+ *      quant.h:33).  The lookahead kernels carry in-register forms of the same arithmetic; these expose it per function. ---- */
+/* mc_luma == get_ref (common/mc.c:198-249; checkasm.c:1234-1307): block i = w x h pixels at byte offset org[i] of the four
+ * phase planes buf + plane_off[0..3], displaced by the quarter-pel vector mv[2i], mv[2i+1]; weight == NULL or !enabled:
+ * x264_weight_none; denom == 0 is the opscale_noden form (mc.c:118).  out: n blocks of w*h bytes, packed. */
+int x264cu_mc_luma( x264cu_ctx *ctx, const uint8_t *buf, int64_t len, const int64_t plane_off[4], int stride, int64_t n,
+                    const int64_t *org, const int16_t *mv, int w, int h, const x264cu_weight *weight, uint8_t *out, int on_device );
+/* x264_mc_functions_t.avg[size] (mc.c:49-103; checkasm.c:1325-1353): size = PIXEL_16x16 .. PIXEL_2x2 (0..11), any weight
+ * (-63..127: the clip of mc.c:86 acts); 32 = plain rounding average.  out: n blocks of w*h bytes, packed. */
+int x264cu_pixel_avg( x264cu_ctx *ctx, int size, const uint8_t *pix1, int64_t len1, int stride1, const uint8_t *pix2, int64_t len2, int stride2,
+                      int64_t n, const int64_t *off1, const int64_t *off2, int weight, uint8_t *out, int on_device );
+/* mc_weight (mc.c:117-137; checkasm.c:1355-1429) over a width x height plane: the form x264_weight_scale_plane uses
+ * (frame.c:825-840); enabled is ignored, denom >= 0 */
+int x264cu_mc_weight( x264cu_ctx *ctx, const uint8_t *src, int src_stride, uint8_t *dst, int dst_stride, int width, int height,
+                      const x264cu_weight *weight, int on_device );
+/* intra_sad_x3_8x8c / intra_satd_x3_8x8c (pixel.c:542-556; checkasm.c:754): res[3i..3i+2] = { DC, H, V } of the 8x8 block at
+ * fenc + off1[i]; the predictors read the row above and the column left of fdec + off2[i] (predict.c:221-277) */
+int x264cu_intra_x3_8x8c( x264cu_ctx *ctx, int b_satd, const uint8_t *fenc, int64_t len1, int stride1, const uint8_t *fdec, int64_t len2, int stride2,
+                          int64_t n, const int64_t *off1, const int64_t *off2, int32_t *res, int on_device );
+/* quant_4x4x4 (quant.c:75-86): ngroups x 4 blocks of 16 coefficients in place; nz_mask[g] bit j = block j of group g is non-zero */
+int x264cu_quant_4x4x4( x264cu_ctx *ctx, int16_t *coefs, int64_t ngroups, const uint16_t *mf, const uint16_t *bias, int32_t *nz_mask, int on_device );
+
 /* device memory helpers for callers that keep data resident (bench, tests) */
 void *x264cu_malloc( x264cu_ctx *ctx, size_t bytes );
 void  x264cu_free( x264cu_ctx *ctx, void *p );
@@ -277,6 +299,8 @@ void  x264cu_free( x264cu_ctx *ctx, void *p );
 typedef struct x264cu_peer x264cu_peer;
 x264cu_peer *x264cu_peer_create( x264cu_ctx *ctx, int rank, int world, int items_per_rank, uint8_t handle_out[64], uint64_t *offset_out );
 int  x264cu_peer_connect( x264cu_peer *p, const uint8_t *handles /* world x 64 */, const uint64_t *offsets /* world */ );
+/* the same for ranks that live in one process (their contexts may share a device): all[r] = rank r's peer object */
+int  x264cu_peer_connect_local( x264cu_peer *p, x264cu_peer *const *all, int world );
 int  x264cu_peer_push( x264cu_peer *p, const void *const *src, const int *slot, int n );
 int  x264cu_peer_import( x264cu_peer *p, void *const *dst, const int *from, const int *slot, int n );
 int  x264cu_peer_error( x264cu_peer *p );

@@ -221,6 +221,59 @@ EXPORT int ref_cqm_tables( int b8x8, int cat, int qp, uint16_t *mf, uint16_t *bi
     return 0;
 }
 
+/* the six CQM configurations of check_quant (tools/checkasm.c:2098-2139: flat, JVT, custom 4x4, custom 8x8, random, all-ones)
+ * installed on the table-source encoder; ref_cqm_tables then returns their tables.  The custom lists are generated here
+ * from `seed` (any list exercises the custom path).  i_cqm < 0 restores the flat default. */
+static uint8_t g_cqm_buf[3][64];
+EXPORT int ref_cqm_select( int i_cqm, unsigned seed )
+{
+    ensure_tables();
+    x264_t *h = g_h;
+    x264_cqm_delete( h );
+    srand( seed );
+    for( int i = 0; i < 64; i++ )
+    {
+        g_cqm_buf[0][i] = 16 + 8 * ( ( ( i & 3 ) == 2 ) + ( ( ( i >> 2 ) & 3 ) == 2 ) ) + rand() % 4;   /* a mild custom 4x4 list */
+        g_cqm_buf[1][i] = 3 + ( ( i & 3 ) == 2 ) + ( ( ( i >> 3 ) & 3 ) == 2 ) + rand() % 2;            /* a steep custom 8x8 list */
+        g_cqm_buf[2][i] = i_cqm == 5 ? 1 : 10 + rand() % 246;                                          /* random / all-ones */
+    }
+    int preset = X264_CQM_CUSTOM;
+    for( int i = 0; i < 8; i++ )
+        switch( i_cqm )
+        {
+            case 1:  h->sps->scaling_list[i] = x264_cqm_jvt[i]; preset = X264_CQM_JVT; break;
+            case 2:  h->sps->scaling_list[i] = i < 4 ? g_cqm_buf[0] : x264_cqm_flat16; break;
+            case 3:  h->sps->scaling_list[i] = i < 4 ? x264_cqm_flat16 : g_cqm_buf[1]; break;
+            case 4: case 5: h->sps->scaling_list[i] = g_cqm_buf[2]; break;
+            default: h->sps->scaling_list[i] = x264_cqm_flat16; preset = X264_CQM_FLAT; break;
+        }
+    h->param.i_cqm_preset = h->sps->i_cqm_preset = preset;
+    h->param.rc.i_qp_min = 0;
+    h->param.rc.i_qp_max = QP_MAX_SPEC;
+    x264_cqm_init( h );                      /* like checkasm, the "impossible QP constraints" verdict is not of interest here */
+    x264_quant_init( h, 0, &g_qf );
+    return 0;
+}
+
+/* quant.c:75-86 */
+EXPORT int ref_quant_4x4x4_batch( int16_t *coefs, int64_t ngroups, uint16_t *mf, uint16_t *bias, int32_t *nza )
+{
+    ensure_tables();
+    for( int64_t i = 0; i < ngroups; i++ )
+        nza[i] = g_qf.quant_4x4x4( (dctcoef(*)[16])( coefs + i*64 ), mf, bias );
+    return 0;
+}
+
+/* x264_mc_functions_t.weight[widx] (mc.c:119-137, widths 4,8,12,16,20 = widx 1..5 as checkasm.c:1358 numbers them) */
+EXPORT void ref_mc_weight( uint8_t *dst, intptr_t ds, uint8_t *src, intptr_t ss, int widx, int height, int scale, int denom, int offset )
+{
+    ensure_tables();
+    x264_weight_t w;
+    memset( &w, 0, sizeof(w) );
+    w.i_scale = scale; w.i_denom = denom; w.i_offset = offset;
+    g_mc.weight[widx]( dst, ds, src, ss, &w, height );
+}
+
 EXPORT void ref_lowres_core( uint8_t *src, intptr_t src_stride, uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc,
                              intptr_t dst_stride, int width, int height )
 {

@@ -320,6 +320,14 @@ void xo_avg( uint8_t *dst, intptr_t ds, const uint8_t *a, intptr_t as, const uin
                         : clip_pixel( ( a[x+y*as]*weight + b[x+y*bs]*(64-weight) + 32 ) >> 6 );
 }
 
+/* mc.c:119-137 mc_weight over a width x height area */
+void xo_mc_weight( uint8_t *dst, intptr_t ds, const uint8_t *src, intptr_t ss, int width, int height, int scale, int denom, int offset )
+{
+    for( int y = 0; y < height; y++ )
+        for( int x = 0; x < width; x++ )
+            dst[x+y*ds] = weight_px( src[x+y*ss], scale, denom, offset );
+}
+
 /* analyse.c:153-157,186-188 with lambda = x264_lambda_tab[X264_LOOKAHEAD_QP] = 1 (tables.c:97) */
 void xo_cost_mv_table( uint16_t *centre, int n )
 {
@@ -510,6 +518,26 @@ static int intra_min_cost( const uint8_t *src, intptr_t st, int b_satd )
         pred8x8_hu( p, &e );  best = imin( best, cmp8x8( 1, src, st, p ) );
     }
     return best;
+}
+
+/* intra_sad_x3_8x8c / intra_satd_x3_8x8c, pixel.c:542-556: res = { DC, H, V }; the predictors read the row above and the
+ * column left of fdec (predict.c:221-277) */
+void xo_intra_x3_8x8c( int b_satd, const uint8_t *fenc, intptr_t sf, const uint8_t *fdec, intptr_t sd, int res[3] )
+{
+    uint8_t top[17] = {0}, left[9], p[64];
+    for( int i = 0; i < 8; i++ ) top[1+i] = fdec[i - sd];
+    top[0] = left[0] = fdec[-1 - sd];
+    for( int i = 0; i < 8; i++ ) left[1+i] = fdec[i*sd - 1];
+    pred8x8c_dc( p, top + 1, left + 1 ); res[0] = cmp8x8( b_satd, fenc, sf, p );
+    pred8x8c_h( p, left + 1 );           res[1] = cmp8x8( b_satd, fenc, sf, p );
+    pred8x8c_v( p, top + 1 );            res[2] = cmp8x8( b_satd, fenc, sf, p );
+}
+int xo_intra_x3_8x8c_batch( int b_satd, const uint8_t *p1, intptr_t s1, const uint8_t *p2, intptr_t s2, int64_t n,
+                            const int64_t *off1, const int64_t *off2, int32_t *res )
+{
+    for( int64_t i = 0; i < n; i++ )
+        xo_intra_x3_8x8c( b_satd, p1 + off1[i], s1, p2 + off2[i], s2, res + 3*i );
+    return 0;
 }
 
 int xo_intra_cost_8x8( const uint8_t *src, intptr_t stride, int b_satd )

@@ -37,6 +37,10 @@ void     xo_mc_luma( uint8_t *dst, intptr_t ds, const uint8_t *const planes[4], 
                      int mvx, int mvy, int w, int h, int scale, int denom, int offset );
 void     xo_avg( uint8_t *dst, intptr_t ds, const uint8_t *a, intptr_t as, const uint8_t *b, intptr_t bs,
                  int w, int h, int weight );
+void     xo_mc_weight( uint8_t *dst, intptr_t ds, const uint8_t *src, intptr_t ss, int width, int height, int scale, int denom, int offset );
+void     xo_intra_x3_8x8c( int b_satd, const uint8_t *fenc, intptr_t sf, const uint8_t *fdec, intptr_t sd, int res[3] );
+int      xo_intra_x3_8x8c_batch( int b_satd, const uint8_t *p1, intptr_t s1, const uint8_t *p2, intptr_t s2, int64_t n,
+                                 const int64_t *off1, const int64_t *off2, int32_t *res );
 /* intra cost of one 8x8 lowres block given its padded plane (slicetype.c:714-747, before AQ) */
 int      xo_intra_cost_8x8( const uint8_t *src, intptr_t stride, int b_satd_flavour );
 void     xo_cost_mv_table( uint16_t *centre, int n );   /* analyse.c:153-157,186-188 with lambda 1 */

@@ -9,7 +9,7 @@ for f in $FILES; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --split-compile=0 $3 -c csrc/$f.cu -o build/var/${f}_$1.o
 done
 OBJS=""
-for o in lookahead search final aq_weights mbtree primitives capi stream; do
+for o in lookahead search final aq_weights mbtree primitives primitives_mc capi stream; do
   if echo " $FILES " | grep -q " $o "; then OBJS="$OBJS build/var/${o}_$1.o"; else OBJS="$OBJS build/$o.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/var/lib_$1.so $OBJS -cudart shared -Xlinker -rpath,/usr/local/cuda/lib64

@@ -6,9 +6,5 @@ CMD="python bench.py --steps 4 --warmup 3 --streams 1 --no-cpu-baseline --no-pri
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_l_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:search_kernel_t -s 40 -c 1 -f -o gpurun_out/prof_search_$TAG $CMD > gpurun_out/ncu_s_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:final_kernel_t -s 20 -c 1 -f -o gpurun_out/prof_final_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:final_kernel_ -s 20 -c 1 -f -o gpurun_out/prof_final_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
 ls -la gpurun_out/*_$TAG*
-# the per-frame streaming kernels (adaptive quantisation, lowres, intra) run in the `primitives` section of a full bench
-CMD2="python bench.py --steps 4 --warmup 3 --streams 1 --no-cpu-baseline"
-ncu --set full --clock-control none --import-source on -k regex:"aq_kernel|lowres_kernel|intra_kernel" -s 40 -c 3 -f -o gpurun_out/prof_prep_$TAG $CMD2 > gpurun_out/ncu_p_$TAG.log 2>&1
-ls -la gpurun_out/prof_prep_$TAG.ncu-rep

@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""usage: summarise.py REPORT.ncu-rep [REPORT...]  -> markdown on stdout.
+"""usage: summarise.py [--json OUT.json] REPORT.ncu-rep [REPORT...]  -> markdown on stdout.
+--json additionally writes the counters bench.py quotes (DRAM bytes, pipe utilisation, L1/L2 figures, duration) per
+kernel of the first launch of every report, together with the git revision, to OUT.json (tracked under profiles/rNN/).
 Reads `ncu -i REPORT --page raw --csv` (selected metrics per launch) and `--page source --csv` (opcode mix and
 stall-sample shares per opcode), as recommended in /opt/skills/guides/B200_PROFILING.md."""
 import collections
@@ -30,12 +32,46 @@ def ncu(rep, page):
     return list(csv.reader(io.StringIO(out[start:])))
 
 
+JSON_OUT = {}
+
+
+def to_bytes(val, unit):
+    v = float(val.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
 def raw(rep):
     rows = ncu(rep, "raw")
     head, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(head)}
     name_col = idx.get("Kernel Name")
     launches = rows[2:]
+    for r in launches:
+        name = r[name_col] if name_col is not None else rep
+        if name in JSON_OUT:
+            continue
+
+        def num(m, scale=1.0):
+            try:
+                return round(float(r[idx[m]].replace(",", "")) * scale, 3)
+            except (KeyError, ValueError):
+                return None
+        try:
+            dram = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
+                   to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        except (KeyError, ValueError):
+            dram = None
+        JSON_OUT[name] = {
+            "report": rep.split("/")[-1], "dram_bytes": dram,
+            "duration_us_under_ncu": num("gpu__time_duration.sum"),
+            "alu_pipe_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            "fma_pipe_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "l1tex_wavefronts_pct": num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+            "l1_hit_pct": num("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": num("lts__t_sector_hit_rate.pct"),
+            "l1_sectors_global_ld": num("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"),
+            "dram_throughput_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "warp_instructions": num("smsp__inst_executed.sum"), "registers": num("launch__registers_per_thread")}
     print("| metric | unit | " + " | ".join("launch %d (%s)" % (i, (r[name_col].split("(")[0] if name_col is not None else "")[:40]) for i, r in enumerate(launches)) + " |")
     print("|---|---|" + "---|" * len(launches))
     for m in METRICS:
@@ -91,7 +127,21 @@ def source(rep):
     print(", ".join("%s %.3f/%.3f" % (op, v / te, s[op] / ts) for op, v in e.most_common(14)))
 
 
-for rep in sys.argv[1:]:
+args = sys.argv[1:]
+json_path = None
+if args and args[0] == "--json":
+    json_path, args = args[1], args[2:]
+for rep in args:
     print("\n## %s\n" % rep.split("/")[-1])
     raw(rep)
     source(rep)
+if json_path:
+    import json
+    import os
+    git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    prev = {}
+    if os.path.exists(json_path):
+        prev = json.load(open(json_path)).get("kernels", {})
+    prev.update(JSON_OUT)
+    json.dump({"git": git, "how": "ncu --set full --clock-control none, first captured launch of each report; profiles/tools/summarise.py --json",
+               "kernels": prev}, open(json_path, "w"), indent=1)

@@ -25,7 +25,9 @@ def _pair(W, H, **kw):
     return gpu, orc
 
 
-@pytest.mark.parametrize("W,H", [(320, 192), (200, 120), (1920, 1080), (3840, 2160)])
+# 5120x2880: luma + chroma of one pageable upload exceed a quarter of the 64 MiB staging buffer the context had in round 1
+# (the second staging allocation of a batch recycled the region under the first)
+@pytest.mark.parametrize("W,H", [(320, 192), (200, 120), (1920, 1080), (3840, 2160), (5120, 2880)])
 def test_device_aq_matches_oracle(W, H):
     n = 2
     luma = synth_frames(W, H, n, seed=3)
@@ -42,9 +44,28 @@ def test_device_aq_matches_oracle(W, H):
         assert (qg.view(np.uint32) == qo_.view(np.uint32)).all()
         assert (ig == io).all()
         assert (sg == so).all()
+    for pl in range(4):
+        assert (gpu.lowres(1, pl) == orc.lowres(1, pl)).all(), pl
     # the AQ output feeds the path: intra costs / frame costs with the device-computed inv_qscale
     assert gpu.frame_cost(0, 1, 1) == orc.frame_cost(0, 1, 1)
     assert (gpu.results[(1, 1, 0)]["lowres_costs"] == orc.get(1, GET_LOWRES_COSTS, 1, 0)).all()
+    gpu.close(); orc.close()
+
+
+def test_pageable_upload_whose_luma_fills_a_staging_region():
+    """4096x4096 from pageable memory with a host inv_qscale table: W*H equals a quarter of a 64 MiB staging buffer, so the
+    table's staging allocation used to land on the first bytes of the staged luma"""
+    W, H = 4096, 4096
+    rng = np.random.default_rng(12)
+    luma = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    gpu, orc = _pair(W, H, bframes=3)
+    q = rng.integers(128, 512, gpu.nmb).astype(np.uint16)
+    gpu.put_frame(0, luma, q)
+    orc.put_frame(0, luma, q)
+    for pl in range(4):
+        assert (gpu.lowres(0, pl) == orc.lowres(0, pl)).all(), pl
+    assert gpu.frame_cost(0, 0, 0) == orc.frame_cost(0, 0, 0)
+    assert (gpu.results[(0, 0, 0)]["intra_costs"] == orc.get(0, GET_INTRA)).all()
     gpu.close(); orc.close()
 
 

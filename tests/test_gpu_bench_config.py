@@ -106,6 +106,8 @@ def test_benchmarked_configuration_matches_oracle():
                     st = (C.c_int32 * 4)()
                     L.x264cu_stream_cost(w0, d0, d1, st)
                     assert list(st) == res["stats"].tolist()
+                if d1:                    # as in the window: the P evaluation (p0, p1, p1) came first, so the temporal-direct
+                    O.frame_cost(b - d0, b + d1, b + d1)      # candidate finds mv(p1 -> p0) (slicetype.c:629)
                 sc = O.frame_cost(b - d0, b + d1, b)
                 assert int(res["stats"][0]) == sc, (b, d0, d1)
                 np.testing.assert_array_equal(res["lowres_costs"], O.get(b, GET_LOWRES_COSTS, d0, d1))
@@ -155,7 +157,8 @@ def test_benchmarked_size_exact_mode_matches_unmodified_reference():
                 if d0 + d1:
                     e = eager_arrays(x264cu, L, win, ctx.nmb, ctx.mbh)(d0, d1)
                     np.testing.assert_array_equal(e["lowres_costs"], R.get(b, GET_LOWRES_COSTS, d0, d1), err_msg=str((p0, p1, b)))
-                    np.testing.assert_array_equal(e["row_satds"], R.get(b, GET_ROW_SATDS, d0, d1))
+                    # (row SATDs: the reference fills i_row_satds only under VBV, slicetype.c:848,976-981; the default-schedule
+                    # test above compares them with the oracle)
                     if e["mvs0"] is not None:
                         np.testing.assert_array_equal(e["mvs0"].reshape(-1, 2), R.get(b, GET_MVS, 0, d0 - 1))
                     if e["mvs1"] is not None:

@@ -112,3 +112,62 @@ def test_one_stream_on_two_gpus_equals_one_gpu(passes, pipelined, exchange, sync
         assert merged == single[step], step
     # both ranks had work
     assert all(sum(len(gathered[r][s] or ()) for s in range(n)) > 0 for r in range(world))
+
+
+@pytest.mark.parametrize("passes", [2, 0])
+def test_one_stream_two_ranks_on_one_gpu(passes):
+    """The same sharding with both ranks as contexts of this process on ONE device (x264cu_peer_connect_local), so that the
+    peer push / import kernels and the partition run on a single-GPU box as well.  Kernels that wait on one another must
+    not be run as separate launches on one GPU (B200_PROFILING.md), so the two phases are ordered through the host here:
+    every rank's searches + mailbox stores are complete before any rank's import is launched -- the import kernels find
+    their flags already published.  Costs must equal the one-context window's, step by step."""
+    import ctypes as C
+    import shard
+    import x264cu
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from checkers import synth_frames
+    W, H, B, n, world = 320, 192, 5, 12, 2
+    frames = [np.ascontiguousarray(f) for f in synth_frames(W, H, n, seed=51, pan=(3, 1))]
+    ctxs = [x264cu.Context(W, H, bframes=B, passes=passes) for _ in range(world)]
+    peers = shard.PeerExchange.local(x264cu, ctxs, B)
+    wins = [shard.ShardedWindow(x264cu, ctxs[r], B, r, world, peer=peers[r]) for r in range(world)]
+    ref_ctx = x264cu.Context(W, H, bframes=B, passes=passes)
+    L = ref_ctx.L
+    ref = L.x264cu_stream_open(ref_ctx.ctx, B, 0)
+    st = (C.c_int32 * 4)()
+    try:
+        launches0 = sum(c.launches() for c in ctxs)
+        for i, f in enumerate(frames):
+            for r in range(world):
+                wins[r]._phase0(i, f.ctypes.data, W, False)      # upload, this rank's searches, stores into the peer's mailbox
+                wins[r].ahead = 1
+            for r in range(world):
+                ctxs[r].flush()                                   # flags are published before any import kernel starts
+            merged = {}
+            for r in range(world):
+                wins[r].push(f.ctypes.data, W, False)             # import (no waiting) + this rank's evaluations
+                wins[r].sync()
+                own = {(b - p0, i - b) for (p0, _, b) in shard.step_units(i, B, r, world)[2]}
+                for k, v in wins[r].costs().items():
+                    if k in own:
+                        assert k not in merged
+                        merged[k] = v
+            assert L.x264cu_stream_push(ref, f.ctypes.data, W, None, 0) >= 0
+            x264cu.check(L.x264cu_stream_sync(ref), "sync")
+            single = {}
+            for d0 in range(B + 2):
+                for d1 in range(B + 2 - d0):
+                    L.x264cu_stream_cost(ref, d0, d1, st)
+                    if st[0] >= 0:
+                        single[(d0, d1)] = list(st)
+            assert merged == single, i
+        assert sum(c.launches() for c in ctxs) - launches0 >= 4 * n      # incl. one push and one import launch per rank and step
+    finally:
+        L.x264cu_stream_close(ref)
+        ref_ctx.close()
+        for w in wins:
+            w.close()
+        for p in peers:
+            p.close()
+        for c in ctxs:
+            c.close()

@@ -2,6 +2,7 @@
 tests/golden/make_golden.py produced from the unmodified reference build."""
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -133,3 +134,33 @@ def test_lookahead(look, orc, name):
                 np.testing.assert_array_equal(la.get(b, GET_MV_COSTS, 1, j - 1), look[f"{name}_{t}_mc1"])
     finally:
         la.close()
+
+
+# ---- the checkasm mc / intra / quant surfaces (tests/golden/mc_surfaces.npz, make_golden_mc.py) ----
+def _mc_golden():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_mc as G
+    return G, np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mc_surfaces.npz"))
+
+
+def test_oracle_mc_surfaces_match_golden():
+    import mc_cases as M
+    G, gold = _mc_golden()
+    O = OracleLib()
+    I = G.golden_inputs()
+    for (w, h), (org, mv) in I["mc"].items():
+        for k, wt in enumerate(G.GOLD_WEIGHTS):
+            np.testing.assert_array_equal(M.oracle_mc_luma(O, I["buf"], I["po"], I["stride"], org, mv, w, h, wt), gold["mc_%dx%d_%d" % (w, h, k)])
+    for size in range(12):
+        for weight in G.AVG_WEIGHTS:
+            np.testing.assert_array_equal(M.oracle_avg(O, I["a"], 64, I["b"], 48, I["off1"], I["off2"], size, weight), gold["avg_%d_%d" % (size, weight)])
+    for k, wt in enumerate(G.W_CASES):
+        np.testing.assert_array_equal(M.oracle_weight(O, I["wsrc"], 32, 20, 16, wt), gold["weight_%d" % k])
+    for b_satd in (0, 1):
+        np.testing.assert_array_equal(M.oracle_intra_x3(O, b_satd, I["p1"], I["s1"], I["p2"], I["s2"], I["io1"], I["io2"]), gold["intra_x3_%d" % b_satd])
+    k = 0
+    for i_cqm in range(6):
+        for qp in range(0, 52, 13):
+            q, mask = M.quant_4x4x4_expect(O.quant, gold["q444_in"], gold["cqm_mf4"][i_cqm, qp], gold["cqm_bias4"][i_cqm, qp])
+            np.testing.assert_array_equal(q, gold["q444_out"][k]); np.testing.assert_array_equal(mask, gold["q444_mask"][k])
+            k += 1

@@ -40,7 +40,8 @@ def cost_matrix(la, n, bframes):
     for (p0, p1, b) in all_triples(0, n, bframes):
         sc = la.frame_cost(p0, p1, b)
         st = la.results[(b, b - p0, p1 - b)]["stats"] if hasattr(la, "results") else la.get(b, GET_STATS, b - p0, p1 - b)
-        costs[(p0, p1, b)] = (int(sc), int(st[1]), int(st[2]))
+        # i_intra_mbs exists per P distance only (frame.h: i_intra_mbs[X264_BFRAME_MAX+2], written when b == p1)
+        costs[(p0, p1, b)] = (int(sc), int(st[1]), int(st[2]) if b == p1 else 0)
     return costs
 
 

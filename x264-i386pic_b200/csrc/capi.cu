@@ -917,17 +917,26 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
     return 0;
 }
 
-// Order the decision jobs of a batch so that B evaluations sharing (fenc, ref1, list-1 field) -- the family (., p1, b)
-// over all p0 -- are consecutive, and cut every family into chunks of <= X264CU_F_CHUNK jobs (final.cu final_kernel_c:
-// one thread keeps the source block and the list-1 prediction for a whole chunk).  Jobs are independent (integer
-// atomics, distinct outputs), so any order is legal.  Long chunks first: they should not be the tail of the launch.
+// Order the decision jobs of a batch so that evaluations of one frame that share their list-1 side -- the family
+// (., p1, b) over all p0 of the B evaluations, or the I / P evaluations of a frame -- are consecutive, and cut every
+// family into chunks of <= X264CU_F_CHUNK jobs (final.cu final_kernel_c: one thread keeps the source block and the
+// list-1 prediction for a whole chunk; intra cost and AQ factor are read once).  Jobs are independent (integer atomics,
+// distinct outputs), so any order is legal.  Long chunks first: they should not be the tail of the launch.
+static bool same_family( const FinalJob &a, const FinalJob &b )
+{
+    if( a.b_bidir != b.b_bidir || a.fenc != b.fenc || a.intra != b.intra || a.inv_qscale != b.inv_qscale ) return false;
+    return !a.b_bidir || ( a.ref1 == b.ref1 && a.mv[1] == b.mv[1] && a.mvcost[1] == b.mvcost[1] );
+}
+#ifndef X264CU_F_SORT
+#define X264CU_F_SORT 1          // 0: tuning builds only (jobs stay in the caller's order)
+#endif
 static void group_finals( std::vector<FinalJob> &finals, std::vector<int2> &chunks )
 {
-    std::stable_sort( finals.begin(), finals.end(), []( const FinalJob &a, const FinalJob &b )
+    if( X264CU_F_SORT ) std::stable_sort( finals.begin(), finals.end(), []( const FinalJob &a, const FinalJob &b )
     {
         if( a.b_bidir != b.b_bidir ) return a.b_bidir > b.b_bidir;
-        if( !a.b_bidir ) return false;                      // non-bidir jobs keep their order
         if( a.fenc != b.fenc ) return a.fenc < b.fenc;
+        if( !a.b_bidir ) return false;                      // the I / P evaluations of a frame keep their order
         if( a.ref1 != b.ref1 ) return a.ref1 < b.ref1;
         return a.mv[1] < b.mv[1];
     } );
@@ -935,14 +944,11 @@ static void group_finals( std::vector<FinalJob> &finals, std::vector<int2> &chun
     for( int i = 0; i < n; )
     {
         int j = i + 1;
-        if( finals[i].b_bidir )
-            while( j < n && j - i < X264CU_F_CHUNK && finals[j].b_bidir && finals[j].fenc == finals[i].fenc && finals[j].ref1 == finals[i].ref1 && finals[j].mv[1] == finals[i].mv[1] ) j++;
-        else
-            while( j < n && j - i < X264CU_F_CHUNK && !finals[j].b_bidir ) j++;
+        while( j < n && j - i < X264CU_F_CHUNK && same_family( finals[i], finals[j] ) ) j++;
         chunks.push_back( make_int2( i, j - i ) );
         i = j;
     }
-    std::stable_sort( chunks.begin(), chunks.end(), [&]( const int2 &a, const int2 &b )
+    if( X264CU_F_SORT ) std::stable_sort( chunks.begin(), chunks.end(), [&]( const int2 &a, const int2 &b )
     {   // bidir work dominates; among bidir chunks the longer one first
         const int wa = finals[a.x].b_bidir ? a.y : 0, wb = finals[b.x].b_bidir ? b.y : 0;
         return wa > wb;
@@ -1585,6 +1591,119 @@ extern "C" int x264cu_lowres_core( x264cu_ctx *c, const uint8_t *src, int src_st
     return 0;
 }
 
+// ---- checkasm surfaces of the fetch / prediction code (primitives_mc.cu) ----
+extern "C" int x264cu_mc_luma( x264cu_ctx *c, const uint8_t *buf, int64_t len, const int64_t plane_off[4], int stride, int64_t n,
+                               const int64_t *org, const int16_t *mv, int w, int h, const x264cu_weight *weight, uint8_t *out, int on_device )
+{
+    PRIM_ENTER( c );
+    if( !buf || !plane_off || ( n > 0 && ( !org || !mv || !out ) ) ) FAIL( "x264cu_mc_luma: null argument" );
+    const int ws = weight && weight->enabled ? weight->scale : 0, wd = weight && weight->enabled ? weight->denom : -1, wo = weight && weight->enabled ? weight->offset : 0;
+    if( on_device )
+    {
+        int r = launch_mc_luma( buf, plane_off, stride, n, org, mv, w, h, ws, wd, wo, out, c->st );
+        PRIM_CHECK( r, "x264cu_mc_luma" );
+        return 0;
+    }
+    DevTmp t( c );
+    uint8_t *d = (uint8_t *)t.up( buf, len );
+    int64_t *o = (int64_t *)t.up( org, n*8 );
+    int16_t *m = (int16_t *)t.up( mv, n*4 );
+    uint8_t *dout = (uint8_t *)t.up( NULL, (size_t)n * w * h );
+    if( !t.ok ) FAIL( "x264cu_mc_luma: device allocation/copy failed" );
+    int r = launch_mc_luma( d, plane_off, stride, n, o, m, w, h, ws, wd, wo, dout, c->st );
+    PRIM_CHECK( r, "x264cu_mc_luma" );
+    if( n > 0 && t.down( out, dout, (size_t)n * w * h ) ) FAIL( "x264cu_mc_luma: copy back failed" );
+    return 0;
+}
+
+static const int g_aw[12] = { 16, 16, 8, 8, 8, 4, 4, 4, 4, 2, 2, 2 };      // PIXEL_16x16 .. PIXEL_2x2 (pixel.h:52-68)
+static const int g_ah[12] = { 16, 8, 16, 8, 4, 8, 4, 16, 2, 8, 4, 2 };
+
+extern "C" int x264cu_pixel_avg( x264cu_ctx *c, int size, const uint8_t *pix1, int64_t len1, int stride1, const uint8_t *pix2, int64_t len2, int stride2,
+                                 int64_t n, const int64_t *off1, const int64_t *off2, int weight, uint8_t *out, int on_device )
+{
+    PRIM_ENTER( c );
+    if( size < 0 || size > 11 ) FAIL( "x264cu_pixel_avg: bad size" );
+    const int w = g_aw[size], h = g_ah[size];
+    if( on_device )
+    {
+        int r = launch_pixel_avg( pix1, stride1, pix2, stride2, n, off1, off2, w, h, weight, out, c->st );
+        PRIM_CHECK( r, "x264cu_pixel_avg" );
+        return 0;
+    }
+    DevTmp t( c );
+    uint8_t *d1 = (uint8_t *)t.up( pix1, len1 ), *d2 = (uint8_t *)t.up( pix2, len2 );
+    int64_t *o1 = (int64_t *)t.up( off1, n*8 ), *o2 = (int64_t *)t.up( off2, n*8 );
+    uint8_t *dout = (uint8_t *)t.up( NULL, (size_t)n * w * h );
+    if( !t.ok ) FAIL( "x264cu_pixel_avg: device allocation/copy failed" );
+    int r = launch_pixel_avg( d1, stride1, d2, stride2, n, o1, o2, w, h, weight, dout, c->st );
+    PRIM_CHECK( r, "x264cu_pixel_avg" );
+    if( n > 0 && t.down( out, dout, (size_t)n * w * h ) ) FAIL( "x264cu_pixel_avg: copy back failed" );
+    return 0;
+}
+
+extern "C" int x264cu_mc_weight( x264cu_ctx *c, const uint8_t *src, int src_stride, uint8_t *dst, int dst_stride, int width, int height,
+                                 const x264cu_weight *weight, int on_device )
+{
+    PRIM_ENTER( c );
+    if( !src || !dst || !weight || weight->denom < 0 ) FAIL( "x264cu_mc_weight: bad argument" );
+    if( on_device )
+    {
+        int r = launch_mc_weight( src, src_stride, dst, dst_stride, width, height, weight->scale, weight->denom, weight->offset, c->st );
+        PRIM_CHECK( r, "x264cu_mc_weight" );
+        return 0;
+    }
+    DevTmp t( c );
+    uint8_t *ds = (uint8_t *)t.up( src, (size_t)src_stride * height ), *dd = (uint8_t *)t.up( NULL, (size_t)width * height );
+    if( !t.ok ) FAIL( "x264cu_mc_weight: device allocation/copy failed" );
+    int r = launch_mc_weight( ds, src_stride, dd, width, width, height, weight->scale, weight->denom, weight->offset, c->st );
+    PRIM_CHECK( r, "x264cu_mc_weight" );
+    CU( cudaMemcpy2DAsync( dst, dst_stride, dd, width, width, height, cudaMemcpyDeviceToHost, c->st ) );
+    CU( cudaStreamSynchronize( c->st ) );
+    return 0;
+}
+
+extern "C" int x264cu_intra_x3_8x8c( x264cu_ctx *c, int b_satd, const uint8_t *fenc, int64_t len1, int stride1, const uint8_t *fdec, int64_t len2, int stride2,
+                                     int64_t n, const int64_t *off1, const int64_t *off2, int32_t *res, int on_device )
+{
+    PRIM_ENTER( c );
+    if( on_device )
+    {
+        int r = launch_intra_x3_8x8c( b_satd, fenc, stride1, fdec, stride2, n, off1, off2, res, c->st );
+        PRIM_CHECK( r, "x264cu_intra_x3_8x8c" );
+        return 0;
+    }
+    DevTmp t( c );
+    uint8_t *d1 = (uint8_t *)t.up( fenc, len1 ), *d2 = (uint8_t *)t.up( fdec, len2 );
+    int64_t *o1 = (int64_t *)t.up( off1, n*8 ), *o2 = (int64_t *)t.up( off2, n*8 );
+    int32_t *dres = (int32_t *)t.up( NULL, (size_t)n * 12 );
+    if( !t.ok ) FAIL( "x264cu_intra_x3_8x8c: device allocation/copy failed" );
+    int r = launch_intra_x3_8x8c( b_satd, d1, stride1, d2, stride2, n, o1, o2, dres, c->st );
+    PRIM_CHECK( r, "x264cu_intra_x3_8x8c" );
+    if( n > 0 && t.down( res, dres, (size_t)n * 12 ) ) FAIL( "x264cu_intra_x3_8x8c: copy back failed" );
+    return 0;
+}
+
+extern "C" int x264cu_quant_4x4x4( x264cu_ctx *c, int16_t *coefs, int64_t ngroups, const uint16_t *mf, const uint16_t *bias, int32_t *nz_mask, int on_device )
+{
+    PRIM_ENTER( c );
+    if( on_device )
+    {
+        int r = launch_quant_4x4x4( coefs, ngroups, mf, bias, nz_mask, c->st );
+        PRIM_CHECK( r, "x264cu_quant_4x4x4" );
+        return 0;
+    }
+    DevTmp t( c );
+    int16_t *d = (int16_t *)t.up( coefs, (size_t)ngroups * 64 * 2 );
+    uint16_t *dm = (uint16_t *)t.up( mf, 32 ), *db = (uint16_t *)t.up( bias, 32 );
+    int32_t *dz = (int32_t *)t.up( NULL, ngroups*4 );
+    if( !t.ok ) FAIL( "x264cu_quant_4x4x4: device allocation/copy failed" );
+    int r = launch_quant_4x4x4( d, ngroups, dm, db, dz, c->st );
+    PRIM_CHECK( r, "x264cu_quant_4x4x4" );
+    if( ngroups > 0 && ( t.down( coefs, d, (size_t)ngroups * 64 * 2 ) || t.down( nz_mask, dz, ngroups*4 ) ) ) FAIL( "x264cu_quant_4x4x4: copy back failed" );
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Peer exchange for one encode stream sharded over several GPUs (the MV field a B evaluation
 // needs from the rank that searched it).  Every rank owns a mailbox in its own HBM, exported with CUDA IPC; the
@@ -1732,6 +1851,34 @@ extern "C" int x264cu_peer_connect( x264cu_peer *p, const uint8_t *handles, cons
         cudaIpcMemHandle_t h; memcpy( &h, handles + (size_t)r * 64, 64 );
         CU( cudaIpcOpenMemHandle( &p->remote_base[r], h, cudaIpcMemLazyEnablePeerAccess ) );
         p->remote[r] = (uint8_t *)p->remote_base[r] + offsets[r];
+    }
+    return 0;
+}
+
+// ranks that live in ONE process (one encoder driving several GPUs from its lookahead thread, or several contexts on one
+// device): no IPC handle is needed -- or allowed: a handle cannot be opened by the process that exported it -- the peers'
+// mailboxes are mapped by enabling peer access between the devices
+extern "C" int x264cu_peer_connect_local( x264cu_peer *p, x264cu_peer *const *all, int world )
+{
+    if( !p || !all || world != p->world ) FAIL( "x264cu_peer_connect_local: bad argument" );
+    CU( cudaSetDevice( p->c->device ) );
+    for( int r = 0; r < world; r++ )
+    {
+        if( r == p->rank ) continue;
+        if( !all[r] || all[r]->rank != r || all[r]->world != world || all[r]->items_per_rank != p->items_per_rank || all[r]->slot_stride != p->slot_stride )
+            FAIL( "x264cu_peer_connect_local: peer %d does not match", r );
+        const int dev = all[r]->c->device;
+        if( dev != p->c->device )
+        {
+            int can = 0;
+            CU( cudaDeviceCanAccessPeer( &can, p->c->device, dev ) );
+            if( !can ) FAIL( "x264cu_peer_connect_local: device %d cannot access device %d", p->c->device, dev );
+            cudaError_t e = cudaDeviceEnablePeerAccess( dev, 0 );
+            if( e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled ) CU( e );
+            cudaGetLastError();
+        }
+        p->remote[r] = all[r]->box;
+        p->remote_base[r] = NULL;       // nothing to close
     }
     return 0;
 }

@@ -113,35 +113,56 @@ __global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *_
 #ifndef X264CU_F_HOIST
 #define X264CU_F_HOIST 2
 #endif
+// Which thread-per-block decision kernel launch_final() uses: 1 (default) = final_kernel_t, one CTA per (evaluation, tile),
+// jobs in family order; 0 = final_kernel_c, one CTA per (chunk of a family, tile).  Measured on B200 (profiles/r02/tuning.md):
+// the chunked kernel issues 27 % fewer L1 requests but keeps fewer warps resident (96 vs 80 registers) and runs in few long
+// CTAs, so the L1 data pipe that bounds both kernels is 60 % busy instead of 86 %: 0.285 ms against 0.217 ms per step.
+#ifndef X264CU_F_OLD
+#define X264CU_F_OLD 1
+#endif
+
 template<bool SATD, int PITCH>
 __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_kernel_c( const FinalJob *__restrict__ jobs, const int2 *__restrict__ chunks, LaParams P )
 {
 #if X264CU_F_HOIST == 2
     __shared__ uint2 s_pred1[8][F_TILE_W*F_TILE_H];
 #endif
+    // the chunk's job descriptors, staged once per CTA: every field a member needs is then one shared-memory broadcast
+    // away instead of a chain of dependent global loads (ncu r02a: 30 % of the stall samples sat on descriptor -> pointer
+    // -> value chains in this latency-bound kernel)
+    __shared__ __align__(16) FinalJob s_jobs[X264CU_F_CHUNK];
+    const int2 ch = __ldg( chunks + blockIdx.y );           // first job, number of jobs (<= X264CU_F_CHUNK)
+    {
+        const unsigned long long *src = (const unsigned long long *)( jobs + ch.x );
+        unsigned long long *dst = (unsigned long long *)s_jobs;
+        for( int i = threadIdx.x; i < ch.y * (int)( sizeof(FinalJob) / 8 ); i += blockDim.x ) dst[i] = __ldg( src + i );
+    }
+    __syncthreads();
     int bx, by;
     if( !warp_tile_block( P.tiles_f, P.ntiles_f, P, bx, by ) ) return;
     const int blk = by * P.mbw + bx;
-    const int2 ch = __ldg( chunks + blockIdx.y );           // first job, number of jobs
     typedef ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> BE;
     BE be; be.P = &P;
-    const int pitch = be.pitch(), s4 = pitch >> 2, pel = ( by*8 ) * pitch + bx*8;
+    const int pitch = be.pitch(), pel = ( by*8 ) * pitch + bx*8;
     if( skipped_border( P, bx, by ) )
     {
-        for( int z = ch.x; z < ch.x + ch.y; z++ ) { const FinalJob &J = jobs[z]; if( !J.b_intra_only ) J.lowres_costs[blk] = 0; }
+        for( int z = 0; z < ch.y; z++ ) if( !s_jobs[z].b_intra_only ) s_jobs[z].lowres_costs[blk] = 0;
         return;
     }
     const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
     const bool score = !border || P.mbw <= 2 || P.mbh <= 2;
-    // what every member of a bidir chunk shares
+    // what every member of the chunk shares: the frame (source block, intra cost, AQ factor) and, for B evaluations, the
+    // list-1 reference with its MV field
+    const bool bidir = s_jobs[0].b_bidir != 0;
+    const int icost = bidir ? 0 : (int)__ldg( s_jobs[0].intra + blk );
+    const int invq = P.aq ? (int)__ldg( s_jobs[0].inv_qscale + blk ) : 256;
     int mv1x = 0, mv1y = 0, mc1 = X264CU_COST_MAX;
 #if X264CU_F_HOIST == 1
     uint2 pred1[8];
 #endif
-    const bool bidir = jobs[ch.x].b_bidir != 0;
     if( bidir )
     {
-        const FinalJob &J0 = jobs[ch.x];
+        const FinalJob &J0 = s_jobs[0];
         const uint8_t *src = J0.fenc + pel;
 #pragma unroll
         for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * pitch ) );
@@ -163,7 +184,7 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
                 const int i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
                 const RowSrc<X264CU_FINAL_LD64 != 0> q1( be.ref1, ( mv1x >> 2 ) + ( mv1y >> 2 ) * pitch + i1 * (int)P.plane_size );
 #pragma unroll
-                for( int r = 0; r < 8; r++ ) t[r] = q1.row( r*s4 );
+                for( int r = 0; r < 8; r++ ) t[r] = q1.row( r * ( pitch >> 2 ) );
             }
 #pragma unroll
             for( int r = 0; r < 8; r++ )
@@ -177,33 +198,39 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
         }
 #endif
     }
-#pragma unroll 1
-    for( int z = ch.x; z < ch.x + ch.y; z++ )
+    // this block's scalars of member z: list-0 MV and cost, and the MV the temporal-direct candidate is derived from.
+    // They are fetched one member AHEAD, so that their latency hides behind the SATDs of the current member.
+    auto fetch = [&]( int z, int &mv0, int &mc0, int &dmv )
     {
-        // the job's fields are read where they are used (uniform loads that hit in L1): a by-value copy of the 120-byte
-        // descriptor would sit in 30 registers across the SATD bodies
-        const FinalJob &J = jobs[z];
+        const FinalJob &Jn = s_jobs[z];
+        mv0 = 0; mc0 = X264CU_COST_MAX; dmv = 0;
+        if( !Jn.b_intra_only ) { mv0 = __ldg( (const int *)Jn.mv[0] + blk ); mc0 = __ldg( Jn.mvcost[0] + blk ); }
+        if( Jn.dmv_src ) dmv = __ldg( (const int *)Jn.dmv_src + blk );
+    };
+    int n_mv0, n_mc0, n_dmv;
+    fetch( 0, n_mv0, n_mc0, n_dmv );
+#pragma unroll 1
+    for( int z = 0; z < ch.y; z++ )
+    {
+        const FinalJob &J = s_jobs[z];
+        const int mv0 = n_mv0, mc0 = n_mc0, dmv = n_dmv;
+        if( z + 1 < ch.y ) fetch( z + 1, n_mv0, n_mc0, n_dmv );
         int bcost = X264CU_COST_MAX, list_used = 0;
         if( !J.b_intra_only )
         {
-            int mv0x, mv0y, mc0;
-            {
-                const int v = __ldg( (const int *)J.mv[0] + blk );
-                mv0x = (int16_t)( v & 0xffff ); mv0y = v >> 16;
-                mc0 = __ldg( J.mvcost[0] + blk );
-            }
+            const int mv0x = (int16_t)( mv0 & 0xffff ), mv0y = mv0 >> 16;
             if( bidir )
             {
                 be.ref0 = J.ref0 + pel;
+                const int w = J.bipred_weight;
                 int d0x = 0, d0y = 0, d1x = 0, d1y = 0;
                 if( J.dmv_src )
                 {   // temporal direct (slicetype.c:629-639)
                     MeGeo m;
                     me_limits( m, P, bx, by );
-                    const int w = __ldg( (const int *)J.dmv_src + blk );
-                    const int mrx = (int16_t)( w & 0xffff ), mry = w >> 16;
-                    d0x = ( mrx * J.dist_scale_factor + 128 ) >> 8;
-                    d0y = ( mry * J.dist_scale_factor + 128 ) >> 8;
+                    const int mrx = (int16_t)( dmv & 0xffff ), mry = dmv >> 16, dsf = J.dist_scale_factor;
+                    d0x = ( mrx * dsf + 128 ) >> 8;
+                    d0y = ( mry * dsf + 128 ) >> 8;
                     d1x = d0x - mrx; d1y = d0y - mry;
                     d0x = iclip3( d0x, m.sminx, m.smaxx ); d0y = iclip3( d0y, m.sminy, m.smaxy );
                     d1x = iclip3( d1x, m.sminx, m.smaxx ); d1y = iclip3( d1y, m.sminy, m.smaxy );
@@ -212,19 +239,18 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
                 // candidates in the reference's order, ties keep the earlier one: direct, zero (:644-652), L0, L1 (:708),
                 // L0+L1 with the 5*lambda penalty (:711-712)
                 {
-                    const int cost = be.bidir( d0x, d0y, d1x, d1y, J.bipred_weight );
+                    const int cost = be.bidir( d0x, d0y, d1x, d1y, w );
                     if( cost < bcost ) { bcost = cost; list_used = 3; }
                 }
                 if( d0x | d0y | d1x | d1y )
                 {
-                    const int cz = be.bidir_zero( J.bipred_weight );
+                    const int cz = be.bidir_zero( w );
                     if( cz < bcost ) { bcost = cz; list_used = 3; }
                 }
                 if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
                 if( mc1 < bcost ) { bcost = mc1; list_used = 2; }
                 if( mv0x | mv0y | mv1x | mv1y )
                 {
-                    const int w = J.bipred_weight;
                     int cost;
 #if X264CU_F_HOIST
 #if X264CU_F_HOIST == 1
@@ -241,7 +267,7 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
                     {
                         const int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 );
                         const RowSrc<X264CU_FINAL_LD64 != 0> q0( be.ref0, ( mv0x >> 2 ) + ( mv0y >> 2 ) * pitch + i0 * (int)P.plane_size );
-                        cost = sad8x8_t( be.fenc, [&]( int r ) { const uint2 a = q0.row( r*s4 ), b = PRED1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+                        cost = sad8x8_t( be.fenc, [&]( int r ) { const uint2 a = q0.row( r * ( pitch >> 2 ) ), b = PRED1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
                     }
 #undef PRED1
 #else
@@ -254,16 +280,15 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
             else if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
         }
         bcost += 4;                                         // lowres_penalty (slicetype.c:758)
-        if( !J.b_bidir )
+        if( !bidir )
         {   // slicetype.c:762-773
-            const int icost = J.intra[blk];
             const int b_intra = icost < bcost;
             if( b_intra ) { bcost = icost; list_used = 0; }
             if( score && b_intra ) atomicAdd( &J.stats[2], 1 );
         }
         if( !J.b_intra_only )
         {   // slicetype.c:776-788
-            const int bcost_aq = P.aq ? ( bcost * J.inv_qscale[blk] + 128 ) >> 8 : bcost;
+            const int bcost_aq = P.aq ? ( bcost * invq + 128 ) >> 8 : bcost;
             atomicAdd( &J.row_satds[by], bcost_aq );
             if( score )
             {
@@ -275,14 +300,55 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
     }
 }
 
+#if X264CU_F_OLD
+// one CTA per (evaluation, block tile): many short CTAs keep the L1 data pipe, which bounds the decision kernels, busiest
+// F_JOBS consecutive evaluations of the job table per CTA, same block tile.  The batch lists the evaluations of one p0
+// back to back, so consecutive jobs read the same two reference frames and the tile's windows could stay in L1 from
+// one job to the next -- measured on B200 it does not pay (F_JOBS 4 / 8 / 16: 0.247 / 0.289 / 0.266 ms against 0.225 for 1:
+// fewer, longer CTAs balance worse over the SMs), so the default is one evaluation per CTA.
+#ifndef F_JOBS
+#define F_JOBS 1
+#endif
+template<bool SATD, int PITCH>
+__global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_kernel_t( const FinalJob *__restrict__ jobs, int njobs, LaParams P )
+{
+    int bx, by;
+    if( !warp_tile_block( P.tiles_f, P.ntiles_f, P, bx, by ) ) return;
+    const int blk = by * P.mbw + bx;
+    ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> be; be.P = &P;
+    const int pel = ( by*8 ) * be.pitch() + bx*8;
+#pragma unroll 1
+    for( int z = blockIdx.y * F_JOBS; z < min( njobs, ( blockIdx.y + 1 ) * F_JOBS ); z++ )
+    {
+        const FinalJob J = jobs[z];
+        if( skipped_border( P, bx, by ) ) { if( !J.b_intra_only ) J.lowres_costs[blk] = 0; continue; }
+        const uint8_t *src = J.fenc + pel;
+        if( !J.b_intra_only )
+        {
+#pragma unroll
+            for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * be.pitch() ) );
+        }
+        be.ref0 = J.ref0 + pel; be.ref1 = J.ref1 + pel; be.ref_w = be.ref0;
+        final_block( be, J, P, bx, by, blk );
+    }
+}
+
+#endif
+
 void launch_final( const FinalJob *d_jobs, int njobs, const int2 *d_chunks, int nchunks, const LaParams &P, cudaStream_t st )
 {
     if( use_thread_mapping( P, njobs ) )
     {
         const int warps_per_cta = F_TILE_W * F_TILE_H / 32;
         dim3 grid( ( P.ntiles_f + warps_per_cta - 1 ) / warps_per_cta, nchunks );
+#if X264CU_F_OLD
+        grid.y = njobs;
+#define FINAL_T( PITCH ) { if( P.b_satd ) final_kernel_t<true, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, njobs, P ); \
+                           else           final_kernel_t<false, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, njobs, P ); }
+#else
 #define FINAL_T( PITCH ) { if( P.b_satd ) final_kernel_c<true, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, d_chunks, P ); \
                            else           final_kernel_c<false, PITCH><<<grid, F_TILE_W*F_TILE_H, 0, st>>>( d_jobs, d_chunks, P ); }
+#endif
         if( P.stride == X264CU_PITCH_A )      FINAL_T( X264CU_PITCH_A )
         else if( P.stride == X264CU_PITCH_B ) FINAL_T( X264CU_PITCH_B )
         else                        FINAL_T( 0 )

@@ -38,7 +38,7 @@
 #define X264CU_MINB_SEARCH 3
 #endif
 #ifndef X264CU_MINB_FINAL
-#define X264CU_MINB_FINAL 5
+#define X264CU_MINB_FINAL 6
 #endif
 
 #define GROUPS_PER_CTA 32
@@ -549,6 +549,13 @@ struct QpelRows
             const uint2 w = s2.row_if( avg, r*s4, v );
             v.x = avg ? avg4( v.x, w.x ) : v.x; v.y = avg ? avg4( v.y, w.y ) : v.y;
         }
+#ifdef X264CU_QPEL_BOTH
+        else if( true )
+        {   // tuning: always fetch the second plane (its address is valid for every phase), select afterwards -- no branch, no predicate
+            const uint2 w = s2.row( r*s4 );
+            v.x = avg ? avg4( v.x, w.x ) : v.x; v.y = avg ? avg4( v.y, w.y ) : v.y;
+        }
+#endif
         else if( avg )
         {
             const uint2 w = s2.row( r*s4 );

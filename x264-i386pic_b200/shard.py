@@ -60,6 +60,27 @@ class PeerExchange:
         x264cu.check(self.L.x264cu_peer_connect(self.p, hs, offs), "peer_connect")
         dist.barrier()                                                  # nobody pushes before everybody has mapped
 
+    @classmethod
+    def local(cls, x264cu, ctxs, bframes):
+        """the ranks as contexts of THIS process (one per GPU, or several on one device): mailboxes are connected directly
+        (x264cu_peer_connect_local), no IPC handles and no torch.distributed.  Returns one PeerExchange per rank."""
+        import ctypes as C
+        world = len(ctxs)
+        out = []
+        for rank, ctx in enumerate(ctxs):
+            pe = cls.__new__(cls)
+            pe.x, pe.ctx, pe.L, pe.rank, pe.world, pe._C = x264cu, ctx, ctx.L, rank, world, C
+            pe.items = 2 * ((bframes + 1 + world - 1) // world)
+            handle, off = (C.c_uint8 * 64)(), C.c_uint64()
+            pe.p = pe.L.x264cu_peer_create(ctx.ctx, rank, world, pe.items, handle, C.byref(off))
+            if not pe.p:
+                raise RuntimeError("x264cu_peer_create: " + x264cu.last_error())
+            out.append(pe)
+        arr = (C.c_void_p * world)(*[pe.p for pe in out])
+        for pe in out:
+            x264cu.check(pe.L.x264cu_peer_connect_local(pe.p, arr, world), "peer_connect_local")
+        return out
+
     def push(self, ptrs):
         C, n = self._C, len(ptrs)
         a = (C.c_void_p * max(n, 1))(*ptrs)

@@ -103,6 +103,11 @@ def load():
                                  vp, vp, vp, C.c_int]
     L.x264cu_sub_dct_grid.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
     L.x264cu_quant.argtypes = [vp, C.c_int, vp, C.c_int64, vp, vp, vp, C.c_int]
+    L.x264cu_mc_luma.argtypes = [vp, vp, C.c_int64, vp, C.c_int, C.c_int64, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int]
+    L.x264cu_pixel_avg.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int, vp, C.c_int64, C.c_int, C.c_int64, vp, vp, C.c_int, vp, C.c_int]
+    L.x264cu_mc_weight.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+    L.x264cu_intra_x3_8x8c.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int, vp, C.c_int64, C.c_int, C.c_int64, vp, vp, vp, C.c_int]
+    L.x264cu_quant_4x4x4.argtypes = [vp, vp, C.c_int64, vp, vp, vp, C.c_int]
     L.x264cu_lowres_core.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.x264cu_stream_open.restype = vp
     L.x264cu_stream_open.argtypes = [vp, C.c_int, C.c_int]
@@ -116,6 +121,7 @@ def load():
     L.x264cu_peer_create.restype = vp
     L.x264cu_peer_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_uint64)]
     L.x264cu_peer_connect.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.x264cu_peer_connect_local.argtypes = [vp, C.POINTER(vp), C.c_int]
     L.x264cu_peer_push.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
     L.x264cu_peer_import.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
     L.x264cu_peer_error.argtypes = [vp]
