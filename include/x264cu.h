@@ -109,8 +109,9 @@ int x264cu_frame_upload_device( x264cu_ctx *ctx, x264cu_frame *f, const uint8_t 
  * encoder.c:3417-3421: upload luma and the interleaved NV12 chroma plane (width x height/2 bytes), compute on the
  * device the per-macroblock AC energy (luma 16x16 + both chroma 8x8), f_qp_offset / f_qp_offset_aq,
  * i_inv_qscale_factor and the frame's i_pixel_sum / i_pixel_ssd, then everything x264cu_frame_upload does.
- * aq_mode 0 (X264_AQ_NONE: sums only) and 1 (X264_AQ_VARIANCE) are computed bit-exactly; the auto-variance modes 2/3
- * go through powf and are refused (compute them on the host and use x264cu_frame_upload). */
+ * aq_mode 0 (X264_AQ_NONE: sums only), 1 (X264_AQ_VARIANCE), 2 (X264_AQ_AUTOVARIANCE) and 3 (X264_AQ_AUTOVARIANCE_BIASED)
+ * are all bit-exact with the reference, floats included.  Modes 2/3 reproduce the host libm's powf(x, 0.125f)
+ * (ratecontrol.c:361) through a rounded triple square root plus an exception table built from that libm on first use. */
 typedef struct { int mode; float strength; } x264cu_aq_cfg;                      /* rc.i_aq_mode, rc.f_aq_strength */
 typedef struct
 {

@@ -1393,13 +1393,16 @@ static uint32_t ac_energy_var( const uint8_t *p, int stride, int x0, int y0, int
     return sqr - (uint32_t)( ( (uint64_t)sum * sum ) >> shift );
 }
 
-/* x264_adaptive_quant_frame (ratecontrol.c:304-415) for a progressive 4:2:0 frame, aq-mode 0 or 1 (mode 2/3 go through
- * powf and are not restated), followed by x264_frame_init_lowres through xo_put_frame -- the order of encoder.c:3417-3421 */
+/* x264_adaptive_quant_frame (ratecontrol.c:304-415) for a progressive 4:2:0 frame, aq-mode 0..3 (the auto-variance modes 2
+ * and 3 call libm's powf exactly as the reference does, :361), followed by x264_frame_init_lowres through xo_put_frame --
+ * the order of encoder.c:3417-3421 */
 int xo_put_frame_aq( xo_ctx *c, int idx, const uint8_t *luma, int stride, const uint8_t *chroma, int cstride,
                      int aq_mode, float aq_strength, const float *quant_offsets )
 {
-    if( aq_mode < 0 || aq_mode > 1 ) return -1;
+    if( aq_mode < 0 || aq_mode > 3 ) return -1;
     const int W = c->cfg.width, H = c->cfg.height;
+    const int autovar = aq_mode >= 2 && aq_strength != 0;
+    float avg_adj = 0.f, avg_adj_pow2 = 0.f;
     uint64_t sum[3] = {0,0,0}, ssd[3] = {0,0,0};
     float *qp = calloc( c->nmb, sizeof(float) );
     uint16_t *inv = malloc( c->nmb * sizeof(uint16_t) );
@@ -1411,7 +1414,14 @@ int xo_put_frame_aq( xo_ctx *c, int idx, const uint8_t *luma, int stride, const 
             uint32_t energy = ac_energy_var( luma, stride, 16*mx, 16*my, 16, 1, W-1, H-1, 8, &sum[0], &ssd[0] );
             energy += ac_energy_var( chroma,   cstride, 8*mx, 8*my, 8, 2, W/2-1, H/2-1, 6, &sum[1], &ssd[1] );
             energy += ac_energy_var( chroma+1, cstride, 8*mx, 8*my, 8, 2, W/2-1, H/2-1, 6, &sum[2], &ssd[2] );
-            if( aq_mode == 1 && aq_strength != 0 )
+            if( autovar )
+            {   /* first pass of the auto-variance modes (ratecontrol.c:355-366) */
+                float qp_adj = powf( energy * 1.f + 1, 0.125f );
+                qp[mx + my*c->mbw] = qp_adj;
+                avg_adj += qp_adj;
+                avg_adj_pow2 += qp_adj * qp_adj;
+            }
+            else if( aq_mode == 1 && aq_strength != 0 )
             {   /* ratecontrol.c:388-399 */
                 float qp_adj = strength * ( xo_log2( energy > 1 ? energy : 1 ) - 14.427f );
                 if( quant_offsets ) qp_adj += quant_offsets[mx + my*c->mbw];
@@ -1424,6 +1434,23 @@ int xo_put_frame_aq( xo_ctx *c, int idx, const uint8_t *luma, int stride, const 
                 inv[mx + my*c->mbw] = xo_exp2fix8( quant_offsets[mx + my*c->mbw] );
             }
         }
+    if( autovar )
+    {   /* ratecontrol.c:367-396 */
+        avg_adj /= c->nmb;
+        avg_adj_pow2 /= c->nmb;
+        const float strength2 = aq_strength * avg_adj;
+        avg_adj = avg_adj - 0.5f * ( avg_adj_pow2 - 14.f ) / avg_adj;
+        const float bias_strength = aq_strength;
+        for( int i = 0; i < c->nmb; i++ )
+        {
+            float qp_adj = qp[i];
+            if( aq_mode == 3 ) qp_adj = strength2 * ( qp_adj - avg_adj ) + bias_strength * ( 1.f - 14.f / ( qp_adj * qp_adj ) );
+            else               qp_adj = strength2 * ( qp_adj - avg_adj );
+            if( quant_offsets ) qp_adj += quant_offsets[i];
+            qp[i] = qp_adj;
+            inv[i] = xo_exp2fix8( qp_adj );
+        }
+    }
     if( xo_put_frame( c, idx, luma, stride, aq_mode ? inv : NULL ) ) { free( qp ); free( inv ); return -1; }
     xo_frame *f = &c->fr[idx];
     for( int i = 0; i < 3; i++ )

@@ -44,6 +44,30 @@ def test_adaptive_quant_matches_reference(W, H):
     ref.close(); orc.close()
 
 
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("W,H", [(320, 192), (200, 120), (1920, 1080)])
+def test_auto_variance_modes_match_reference(W, H, mode):
+    """aq-mode 2 / 3 (ratecontrol.c:355-392): powf(energy + 1, 0.125), the frame averages accumulated in raster order, then
+    the offsets -- floats bit for bit"""
+    n = 2
+    luma = synth_frames(W, H, n, seed=13)
+    chroma = synth_chroma(W, H, n)
+    luma[1][: H // 3] = 17
+    luma[1][H // 3: H // 2, : W // 2] = 255
+    ref = Lookahead(RefLib(), "ref", W, H, bframes=3, weightp=2, aq=mode)
+    orc = Lookahead(OracleLib(), "oracle", W, H, bframes=3, mv_range=ref.mv_range, aq=mode)
+    qo = np.linspace(-2.5, 2.5, ref.nmb).astype(np.float32)
+    for i in range(n):
+        offs = qo if i else None
+        ref.put_frame_yuv(i, luma[i], chroma[i], quant_offsets=offs)
+        orc.put_frame_yuv(i, luma[i], chroma[i], aq_mode=mode, quant_offsets=offs)
+        (qr, ir, sr), (qo_, io, so) = ref.get_aq(i), orc.get_aq(i)
+        assert (qr.view(np.uint32) == qo_.view(np.uint32)).all()
+        assert (ir == io).all() and (sr == so).all()
+    assert len(np.unique(ir)) > 8
+    ref.close(); orc.close()
+
+
 def _fade(frames, k):
     out = []
     for i, f in enumerate(frames):

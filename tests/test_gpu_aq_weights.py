@@ -81,14 +81,52 @@ def test_device_aq_mode0_and_zero_strength():
     gpu.close(); orc.close()
 
 
-def test_device_aq_refuses_powf_modes():
-    import x264cu
-    ctx = x264cu.Context(320, 192, bframes=3)
-    f = ctx.frame_new()
-    luma, chroma = synth_frames(320, 192, 1)[0], synth_chroma(320, 192, 1)[0]
-    with pytest.raises(RuntimeError, match="powf"):
-        ctx.upload_aq(f, luma, chroma, aq_mode=2)
-    ctx.close()
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("W,H", [(320, 192), (200, 120), (1920, 1080)])
+def test_device_auto_variance_modes_match_oracle(W, H, mode):
+    """aq-mode 2 / 3 (ratecontrol.c:355-392) on the device: powf(energy + 1, 0.125f) reproduced bit for bit, the frame
+    averages accumulated in the reference's raster order, then the offsets; with and without quant_offsets, zero strength"""
+    n = 3
+    luma = synth_frames(W, H, n, seed=13)
+    chroma = synth_chroma(W, H, n)
+    luma[1][: H // 3] = 17
+    luma[1][H // 3: H // 2, : W // 2] = 255
+    gpu, orc = _pair(W, H, bframes=3, aq=mode)
+    qo = np.linspace(-2.5, 2.5, gpu.nmb).astype(np.float32)
+    for i in range(n):
+        offs = qo if i == 1 else None
+        strength = 0.0 if i == 2 else 1.3
+        gpu.put_frame_yuv(i, luma[i], chroma[i], aq_mode=mode, aq_strength=strength, quant_offsets=offs)
+        orc.put_frame_yuv(i, luma[i], chroma[i], aq_mode=mode, aq_strength=strength, quant_offsets=offs)
+        (qg, ig, sg), (qo_, io, so) = gpu.get_aq(i), orc.get_aq(i)
+        assert (qg.view(np.uint32) == qo_.view(np.uint32)).all(), i
+        assert (ig == io).all() and (sg == so).all(), i
+    assert gpu.frame_cost(0, 1, 1) == orc.frame_cost(0, 1, 1)
+    gpu.close(); orc.close()
+
+
+def test_device_powf_eighth_root_over_a_wide_energy_sweep():
+    """8160 macroblocks whose AC energies sweep 0 .. ~4e6 (random two-level blocks of random amplitude and density): thousands
+    of distinct arguments of powf(energy + 1, 0.125f), against the oracle, which calls libm's powf like the reference.
+    (The exception table itself is built from libm over the WHOLE domain 1 .. 2^24, capi.cu ensure_pow_table.)"""
+    W, H = 1920, 1088
+    rng = np.random.default_rng(21)
+    luma = np.zeros((H, W), dtype=np.uint8)
+    mbh, mbw = H // 16, W // 16
+    for my in range(mbh):                  # per macroblock: amplitude / pattern chosen so that energies cover 0 .. ~4e6 densely
+        for mx in range(mbw):
+            amp = int(rng.integers(0, 256))
+            frac = rng.random()
+            blk = (rng.random((16, 16)) < frac).astype(np.uint8) * amp + int(rng.integers(0, 256 - amp))
+            luma[16 * my:16 * my + 16, 16 * mx:16 * mx + 16] = blk
+    chroma = np.full((H // 2, W), 128, dtype=np.uint8)
+    gpu, orc = _pair(W, H, bframes=3, aq=2)
+    gpu.put_frame_yuv(0, luma, chroma, aq_mode=2, aq_strength=1.0)
+    orc.put_frame_yuv(0, luma, chroma, aq_mode=2, aq_strength=1.0)
+    (qg, ig, sg), (qo_, io, so) = gpu.get_aq(0), orc.get_aq(0)
+    assert (qg.view(np.uint32) == qo_.view(np.uint32)).all() and (ig == io).all()
+    assert len(np.unique(qg)) > 5000
+    gpu.close(); orc.close()
 
 
 @pytest.mark.parametrize("subme", [7, 1])

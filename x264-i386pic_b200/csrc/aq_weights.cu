@@ -1,6 +1,6 @@
 // aq_weights.cu -- the two producers right before the lookahead cost path, sm_100a.
 //
-//   aq_kernel               x264_adaptive_quant_frame for aq-mode 0/1 (ratecontrol.c:226-415): per macroblock the AC
+//   aq_kernel               x264_adaptive_quant_frame for aq-mode 0..3 (ratecontrol.c:226-415): per macroblock the AC
 //                           energy of luma 16x16 + both chroma 8x8 (ac_energy_mb :262-294, pixel_var pixel.c:158-175),
 //                           qp_adj = strength * (x264_log2(energy) - 14.427) (:388-399), i_inv_qscale_factor =
 //                           x264_exp2fix8(qp_adj) (base.h:216-224), and the frame's i_pixel_sum / i_pixel_ssd
@@ -31,6 +31,22 @@ __device__ __forceinline__ int x264_exp2fix8_dev( float x, const uint8_t *lut )
     return ( ( lut[i & 63] + 256 ) << ( i >> 6 ) ) >> 8;
 }
 
+// powf( x, 0.125f ) of ratecontrol.c:361 for x = energy + 1 (an integer below 2^24, exact in float), bit-identical with the
+// host libm the reference links: the candidate sqrt(sqrt(sqrt((double)x))) rounded to float (three correctly rounded
+// IEEE square roots: the same bits on host and device) differs from glibc's powf -- which is accurate to ~0.5 ulp but not
+// correctly rounded -- on ~0.07 % of the inputs; capi.cu finds exactly those inputs by running the host's powf over the
+// whole domain once and hands them over as a sorted exception table (pow_x: float bits of x, pow_v: powf's result).
+struct PowTab { const u32 *x; const float *v; int n; };
+__device__ __forceinline__ float pow_eighth_dev( u32 energy, const PowTab &t )
+{
+    const float x = __fadd_rn( __fmul_rn( __uint2float_rn( energy ), 1.f ), 1.f );      // energy * bit_depth_correction + 1
+    const u32 key = __float_as_uint( x );
+    int lo = 0, hi = t.n;
+    while( lo < hi ) { const int mid = ( lo + hi ) >> 1; if( __ldg( t.x + mid ) < key ) lo = mid + 1; else hi = mid; }
+    if( lo < t.n && __ldg( t.x + lo ) == key ) return __ldg( t.v + lo );
+    return __double2float_rn( sqrt( sqrt( sqrt( (double)x ) ) ) );
+}
+
 // One warp per macroblock: lanes 0-15 own the 16 luma rows, lanes 16-23 the 8 rows of interleaved NV12 chroma.
 // Pixels beyond the picture replicate the last row / column / chroma pair (x264_frame_expand_border_mod16).
 __global__ void __launch_bounds__(256) aq_kernel( const uint8_t *__restrict__ luma, int ls, const uint8_t *__restrict__ chroma, int cs,
@@ -38,7 +54,7 @@ __global__ void __launch_bounds__(256) aq_kernel( const uint8_t *__restrict__ lu
                                                   const float *__restrict__ quant_offsets, const float *__restrict__ log2_lut,
                                                   const uint8_t *__restrict__ exp2_lut,
                                                   float *__restrict__ qp_offset, uint16_t *__restrict__ inv_qscale,
-                                                  unsigned long long *__restrict__ pixstats )
+                                                  unsigned long long *__restrict__ pixstats, PowTab pw )
 {
     __shared__ unsigned long long s_acc[6];
     __shared__ float s_lut[128];
@@ -114,7 +130,9 @@ __global__ void __launch_bounds__(256) aq_kernel( const uint8_t *__restrict__ lu
             u32 energy = v[1] - (u32)( ( (unsigned long long)v[0] * v[0] ) >> 8 );
             energy += v[3] - (u32)( ( (unsigned long long)v[2] * v[2] ) >> 6 );
             energy += v[5] - (u32)( ( (unsigned long long)v[4] * v[4] ) >> 6 );
-            if( mode == 1 )
+            if( mode >= 2 && strength != 0.f )
+                qp_offset[mb] = pow_eighth_dev( energy, pw );        // first pass of the auto-variance modes (ratecontrol.c:355-366)
+            else if( mode >= 1 )
             {
                 float qp_adj;
                 if( strength != 0.f )
@@ -137,12 +155,60 @@ __global__ void __launch_bounds__(256) aq_kernel( const uint8_t *__restrict__ lu
     if( threadIdx.x < 6 && s_acc[threadIdx.x] ) atomicAdd( &pixstats[threadIdx.x], s_acc[threadIdx.x] );
 }
 
-void launch_aq( const uint8_t *luma, int ls, const uint8_t *chroma, int cs, int W, int H, const LaParams &P, int mode, float strength,
-                const float *quant_offsets, const float *log2_lut, const uint8_t *exp2_lut, float *qp_offset, uint16_t *inv_qscale,
-                unsigned long long *pixstats, cudaStream_t st )
+// aq-mode 2 / 3, second and third step (ratecontrol.c:363-398).  The frame averages are float sums accumulated in raster
+// order by the reference, so ONE thread adds the nmb values in that order (8160 dependent adds at 1080p, ~25 us; the
+// auto-variance modes are not x264's default and this keeps them bit-exact), then every macroblock gets its offset.
+__global__ void aq_auto_reduce_kernel( const float *__restrict__ qp, int nmb, float strength, float *__restrict__ out3 )
 {
+    if( threadIdx.x | blockIdx.x ) return;
+    float a = 0.f, p = 0.f;
+    int i = 0;
+    for( ; i + 4 <= nmb && ( ( (uintptr_t)qp & 15 ) == 0 ); i += 4 )
+    {
+        const float4 q = __ldg( (const float4 *)( qp + i ) );
+        a = __fadd_rn( a, q.x ); p = __fadd_rn( p, __fmul_rn( q.x, q.x ) );
+        a = __fadd_rn( a, q.y ); p = __fadd_rn( p, __fmul_rn( q.y, q.y ) );
+        a = __fadd_rn( a, q.z ); p = __fadd_rn( p, __fmul_rn( q.z, q.z ) );
+        a = __fadd_rn( a, q.w ); p = __fadd_rn( p, __fmul_rn( q.w, q.w ) );
+    }
+    for( ; i < nmb; i++ ) { const float q = qp[i]; a = __fadd_rn( a, q ); p = __fadd_rn( p, __fmul_rn( q, q ) ); }
+    a = __fdiv_rn( a, (float)nmb );
+    p = __fdiv_rn( p, (float)nmb );
+    out3[0] = __fmul_rn( strength, a );                                                              // strength = f_aq_strength * avg_adj
+    out3[1] = __fsub_rn( a, __fdiv_rn( __fmul_rn( 0.5f, __fsub_rn( p, 14.f ) ), a ) );               // avg_adj - 0.5f * (avg_adj_pow2 - 14.f) / avg_adj
+    out3[2] = strength;                                                                              // bias_strength
+}
+
+__global__ void __launch_bounds__(256) aq_auto_apply_kernel( int mode, int nmb, const float *__restrict__ red3, const float *__restrict__ quant_offsets,
+                                                             const uint8_t *__restrict__ exp2_lut, float *__restrict__ qp_offset, uint16_t *__restrict__ inv_qscale )
+{
+    __shared__ uint8_t s_exp[64];
+    if( threadIdx.x < 64 ) s_exp[threadIdx.x] = exp2_lut[threadIdx.x];
+    __syncthreads();
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if( mb >= nmb ) return;
+    const float strength = red3[0], avg_adj = red3[1], bias_strength = red3[2];
+    float q = qp_offset[mb];
+    float r = __fmul_rn( strength, __fsub_rn( q, avg_adj ) );
+    if( mode == 3 )      // + bias_strength * (1.f - 14.f / (qp_adj * qp_adj))
+        r = __fadd_rn( r, __fmul_rn( bias_strength, __fsub_rn( 1.f, __fdiv_rn( 14.f, __fmul_rn( q, q ) ) ) ) );
+    if( quant_offsets ) r = __fadd_rn( r, quant_offsets[mb] );
+    qp_offset[mb] = r;
+    inv_qscale[mb] = (uint16_t)x264_exp2fix8_dev( r, s_exp );
+}
+
+// strength: f_aq_strength * 1.0397f for mode 1 (ratecontrol.c:371), f_aq_strength itself for modes 2 / 3
+int launch_aq( const uint8_t *luma, int ls, const uint8_t *chroma, int cs, int W, int H, const LaParams &P, int mode, float strength,
+               const float *quant_offsets, const float *log2_lut, const uint8_t *exp2_lut, float *qp_offset, uint16_t *inv_qscale,
+               unsigned long long *pixstats, const u32 *pow_x, const float *pow_v, int pow_n, float *red3, cudaStream_t st )
+{
+    PowTab pw = { pow_x, pow_v, pow_n };
     aq_kernel<<<( P.nmb + 7 ) / 8, 256, 0, st>>>( luma, ls, chroma, cs, W, H, P.mbw, P.nmb, mode, strength, quant_offsets, log2_lut, exp2_lut,
-                                                  qp_offset, inv_qscale, pixstats );
+                                                  qp_offset, inv_qscale, pixstats, pw );
+    if( mode < 2 || strength == 0.f ) return 1;
+    aq_auto_reduce_kernel<<<1, 32, 0, st>>>( qp_offset, P.nmb, strength, red3 );
+    aq_auto_apply_kernel<<<( P.nmb + 255 ) / 256, 256, 0, st>>>( mode, P.nmb, red3, quant_offsets, exp2_lut, qp_offset, inv_qscale );
+    return 3;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -60,6 +60,7 @@ struct x264cu_ctx
     uint16_t *d_cost_mv;
     float *d_log2_lut;
     uint8_t *d_exp2_lut;
+    uint32_t *d_pow_x; float *d_pow_v; int pow_n;      // aq-mode 2 / 3: inputs on which libm's powf(x, 0.125f) is not the rounded triple square root
     uint32_t *d_tiles;
     bool exact_waves; int serial_ctas_per_sm; int serial_error;      // exact raster-serial mode (search_passes == 0)
     uint8_t *d_chroma[2]; int chroma_pitch;      // NV12 chroma staging, paired with d_luma[]
@@ -284,6 +285,7 @@ extern "C" void x264cu_close( x264cu_ctx *c )
     while( !c->frames.empty() ) x264cu_frame_free( c, c->frames.back() );
     for( cudaEvent_t e : c->ev_pool ) cudaEventDestroy( e );
     for( int i = 0; i < 2; i++ ) { cudaFree( c->d_luma[i] ); cudaEventDestroy( c->luma_free[i] ); }
+    cudaFree( c->d_pow_x ); cudaFree( c->d_pow_v );
     cudaFree( c->d_exp2_lut ); cudaFree( c->d_tiles ); cudaFree( c->d_chroma[0] ); cudaFree( c->d_chroma[1] );
     cudaFree( c->d_cost_mv ); cudaFree( c->d_log2_lut ); cudaFree( c->d_jobs ); cudaFree( c->arena );
     cudaFreeHost( c->pin ); cudaFreeHost( c->h_jobs );
@@ -540,6 +542,38 @@ static inline uint8_t *planeF( x264cu_ctx *c, x264cu_frame *f ) { return f->plan
 static inline int tri_index( x264cu_ctx *c, int d0, int d1 ) { return d0 * ( c->cfg.bframes + 2 ) + d1; }
 static inline int field_index( x264cu_ctx *c, int list, int dist ) { return list * ( c->cfg.bframes + 1 ) + dist - 1; }
 
+// aq-mode 2 / 3 call powf( energy + 1, 0.125f ) (ratecontrol.c:361).  energy < 2^24, so the argument is an exact integer in
+// float; the device computes sqrt(sqrt(sqrt((double)x))) rounded to float, and this table lists every x of the domain where the
+// HOST's libm -- the one the reference encoder links -- returns something else (glibc 2.39: 0.07 % of the inputs; powf is
+// not correctly rounded).  Built once per process by running powf over the whole domain (~0.5 s), on first use of those modes.
+static int ensure_pow_table( x264cu_ctx *c )
+{
+    if( c->d_pow_x ) return 0;
+    static std::vector<uint32_t> hx;
+    static std::vector<float> hv;
+    static bool built = false;
+    if( !built )
+    {
+        for( uint32_t e = 0; e < ( 1u << 24 ); e++ )
+        {
+            volatile float x = (float)e * 1.f + 1;
+            const float a = powf( x, 0.125f );
+            const float b = (float)sqrt( sqrt( sqrt( (double)x ) ) );
+            if( a != b ) { float xv = x; uint32_t bits; memcpy( &bits, &xv, 4 ); hx.push_back( bits ); hv.push_back( a ); }
+        }
+        built = true;       // positive floats: bit patterns ascend with the value, so hx is sorted
+    }
+    c->pow_n = (int)hx.size();
+    CU( cudaMalloc( &c->d_pow_x, ( hx.size() + 1 ) * 4 ) );
+    CU( cudaMalloc( &c->d_pow_v, ( hv.size() + 1 ) * 4 ) );
+    if( c->pow_n )
+    {
+        CU( cudaMemcpy( c->d_pow_x, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice ) );
+        CU( cudaMemcpy( c->d_pow_v, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice ) );
+    }
+    return 0;
+}
+
 // h->param.rc.f_aq_strength * 1.0397f as one single-precision product (ratecontrol.c:371)
 static float aq_strength_f32( float s ) { volatile float r = s * 1.0397f; return r; }
 
@@ -619,8 +653,7 @@ extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uin
                                        const x264cu_aq_cfg *aq, const float *quant_offsets, const x264cu_aq_out *out )
 {
     if( !c || !f || !luma || !chroma || !aq ) FAIL( "x264cu_frame_upload_aq: null argument" );
-    if( aq->mode < 0 || aq->mode > 1 )
-        FAIL( "x264cu_frame_upload_aq: aq-mode %d goes through powf and is not computed on the device (use x264cu_frame_upload with host inv_qscale)", aq->mode );
+    if( aq->mode < 0 || aq->mode > 3 ) FAIL( "x264cu_frame_upload_aq: aq-mode %d", aq->mode );
     if( ( c->cfg.width | c->cfg.height ) & 1 ) FAIL( "x264cu_frame_upload_aq: 4:2:0 needs even dimensions" );
     CU( cudaSetDevice( c->device ) );
     const LaParams &P = c->P;
@@ -667,9 +700,13 @@ extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uin
     }
     CU( cudaMemsetAsync( f->pixstats, 0, 8 * sizeof(unsigned long long), c->st ) );
     launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );
-    c->launches += 2;
-    launch_aq( c->d_luma[sel], c->luma_pitch, c->d_chroma[sel], c->chroma_pitch, W, H, P, aq->mode, aq_strength_f32( aq->strength ),
-               d_qo, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats, c->st );
+    c->launches += 1;
+    if( aq->mode >= 2 && ensure_pow_table( c ) ) return -1;
+    // pixstats[6..7] (unused by the sums) are the three floats the auto-variance reduction hands to the apply kernel
+    c->launches += launch_aq( c->d_luma[sel], c->luma_pitch, c->d_chroma[sel], c->chroma_pitch, W, H, P, aq->mode,
+                              aq->mode == 1 ? aq_strength_f32( aq->strength ) : aq->strength,
+                              d_qo, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats, c->d_pow_x, c->d_pow_v, c->pow_n,
+                              (float *)( f->pixstats + 6 ), c->st );
     f->have_aq = true;
     if( upload_common( c, f, c->d_luma[sel], c->luma_pitch ) ) return -1;
     CU( cudaEventRecord( c->luma_free[sel], c->st ) );
@@ -692,16 +729,19 @@ extern "C" int x264cu_frame_upload_aq_device( x264cu_ctx *c, x264cu_frame *f, co
                                               const x264cu_aq_cfg *aq, const float *d_quant_offsets )
 {
     if( !c || !f || !d_luma || !d_chroma || !aq ) FAIL( "x264cu_frame_upload_aq_device: null argument" );
-    if( aq->mode < 0 || aq->mode > 1 ) FAIL( "x264cu_frame_upload_aq_device: aq-mode %d goes through powf and is not computed on the device", aq->mode );
+    if( aq->mode < 0 || aq->mode > 3 ) FAIL( "x264cu_frame_upload_aq_device: aq-mode %d", aq->mode );
     CU( cudaSetDevice( c->device ) );
     Batch B( c );
     if( B.failed ) return -1;
     const LaParams &P = c->P;
     CU( cudaMemsetAsync( f->pixstats, 0, 8 * sizeof(unsigned long long), c->st ) );
     launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );
-    c->launches += 2;
-    launch_aq( d_luma, stride, d_chroma, cstride, c->cfg.width, c->cfg.height, P, aq->mode, aq_strength_f32( aq->strength ),
-               aq->mode ? d_quant_offsets : NULL, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats, c->st );
+    c->launches += 1;
+    if( aq->mode >= 2 && ensure_pow_table( c ) ) return -1;
+    c->launches += launch_aq( d_luma, stride, d_chroma, cstride, c->cfg.width, c->cfg.height, P, aq->mode,
+                              aq->mode == 1 ? aq_strength_f32( aq->strength ) : aq->strength,
+                              aq->mode ? d_quant_offsets : NULL, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats,
+                              c->d_pow_x, c->d_pow_v, c->pow_n, (float *)( f->pixstats + 6 ), c->st );
     f->have_aq = true;
     if( upload_common( c, f, d_luma, stride ) ) return -1;
     return B.end();

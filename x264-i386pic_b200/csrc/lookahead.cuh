@@ -88,9 +88,10 @@ void launch_final( const FinalJob *d_jobs, int njobs, const int2 *d_chunks, int 
 #ifndef X264CU_F_CHUNK
 #define X264CU_F_CHUNK 8
 #endif
-void launch_aq( const uint8_t *luma, int ls, const uint8_t *chroma, int cs, int W, int H, const LaParams &P, int mode, float strength,
+// returns the number of launches; pow_x / pow_v / pow_n: the powf exception table of aq-mode 2 / 3 (aq_weights.cu), red3: 3 floats of scratch
+int  launch_aq( const uint8_t *luma, int ls, const uint8_t *chroma, int cs, int W, int H, const LaParams &P, int mode, float strength,
                 const float *quant_offsets, const float *log2_lut, const uint8_t *exp2_lut, float *qp_offset, uint16_t *inv_qscale,
-                unsigned long long *pixstats, cudaStream_t st );
+                unsigned long long *pixstats, const u32 *pow_x, const float *pow_v, int pow_n, float *red3, cudaStream_t st );
 void launch_weights_analyse( const uint8_t *fencF, const uint8_t *refF, const int16_t *mvs, const uint16_t *intra,
                              const unsigned long long *st_fenc, const unsigned long long *st_ref, int *wres, int numslices,
                              const LaParams &P, cudaStream_t st );
