@@ -319,6 +319,27 @@ def bench_satd(x264cu, ctx, peak_gbs):
         gbs = (2 * W * hh + (W // bw) * (hh // bh) * 4) / ms / 1e6
         out[name] = {"gpix_s": round(gpix, 1), "gb_s": round(gbs, 1), "hbm_frac": round(gbs / peak_gbs, 4), "ms": round(ms, 4)}
         ctx.free(dout)
+    # SURVEY.md section 8d config 2 as written: every block against the reference at sub-offsets 1..63 (checkasm's pbuf2+j,
+    # tools/checkasm.c:393-397): the second plane is then read through the unaligned row path (three words + two funnel shifts
+    # per 8 pixels).  The compared region is 64 pixels narrower so that every offset stays inside the row.
+    wu = W - 64
+    for name, metric, size, bw, bh in (("satd_8x8", 1, 3, 8, 8), ("sad_16x16", 0, 0, 16, 16), ("satd_16x16", 1, 0, 16, 16), ("sa8d_8x8", 2, 3, 8, 8)):
+        dout = ctx.malloc((wu // bw) * (hh // bh) * 4)
+        worst = None
+        for dx in (1, 4, 7, 33, 63):
+            for _ in range(2):
+                x264cu.check(L.x264cu_pixel_cmp_grid(ctx.ctx, metric, size, d1, W, d2, W, wu, hh - 8, dx, 1, dout, 1), name)
+            reps = 5
+            ctx.timer_begin()
+            for _ in range(reps):
+                L.x264cu_pixel_cmp_grid(ctx.ctx, metric, size, d1, W, d2, W, wu, hh - 8, dx, 1, dout, 1)
+            ms = ctx.timer_end() / reps
+            gbs = (2 * wu * (hh - 8) + (wu // bw) * ((hh - 8) // bh) * 4) / ms / 1e6
+            if worst is None or gbs < worst[1]:
+                worst = (dx, gbs, ms)
+        out[name + "_unaligned"] = {"offsets_timed": [1, 4, 7, 33, 63], "slowest_offset": worst[0], "gb_s": round(worst[1], 1),
+                                    "hbm_frac": round(worst[1] / peak_gbs, 4), "ms": round(worst[2], 4)}
+        ctx.free(dout)
     # the other streaming primitives of SURVEY.md section 8(a)/(d) on the same stacks, device-resident in and out
     def timed(name, call, alg_bytes, reps=10):
         for _ in range(3):
@@ -383,9 +404,10 @@ def bench_frame_prep(x264cu, ctx, peak_gbs):
     ctx.free(dl)
     ctx.free(dc)
     return {"ms_per_frame": round(ms, 4), "gb_s": round(alg / ms / 1e6, 1), "hbm_frac": round(alg / ms / 1e6 / peak_gbs, 4),
-            "kernels": "memset + fill + aq + lowres + intra (5 launches per frame)", "algorithmic_bytes": alg,
-            "bound": "launch latency: five dependent launches of 2-14 us each move 8.3 MB (1.3 us of HBM time); one frame at a "
-                     "time is how an encoder feeds its lookahead, and the whole sequence is 6 % of a step"}
+            "kernels": "lowres (with the per-frame resets) + aq + intra: 3 dependent launches per frame", "algorithmic_bytes": alg,
+            "bound": "latency: three dependent launches of 3-14 us each move 8.3 MB (1.3 us of HBM time); every kernel is a single "
+                     "wave of one frame's 8160 macroblocks -- one frame at a time is how an encoder feeds its lookahead -- and the "
+                     "whole sequence is 5 % of a step"}
 
 
 def cpu_info():

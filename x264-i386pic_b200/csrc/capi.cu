@@ -306,7 +306,7 @@ extern "C" x264cu_frame *x264cu_frame_new( x264cu_ctx *c )
     memset( f, 0, sizeof(*f) );
     size_t ntri = (size_t)( B+2 ) * ( B+2 ), nfield = 2 * (size_t)( B+1 );
     if( cudaMalloc( &f->planes, c->plane_alloc ) != cudaSuccess ||
-        cudaMalloc( &f->inv_qscale, (size_t)P.nmb * 2 ) != cudaSuccess ||
+        cudaMalloc( &f->inv_qscale, (size_t)P.nmb * 2 + 4 ) != cudaSuccess ||
         cudaMalloc( &f->costs, ntri * P.nmb * 2 ) != cudaSuccess ||
         cudaMalloc( &f->mvs, nfield * P.nmb * 4 ) != cudaSuccess ||
         cudaMalloc( &f->mvcosts, nfield * P.nmb * 4 ) != cudaSuccess ||
@@ -585,16 +585,30 @@ static void reset_caches( x264cu_frame *f )
     f->any_eval = false;
 }
 
-static int upload_common( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int pitch )
+// adaptive quantisation between the downscale and the intra costs (x264cu_frame_upload_aq*)
+struct AqRun { const uint8_t *luma; int ls; const uint8_t *chroma; int cs; int mode; float strength; const float *quant_offsets; };
+
+// downscale (+ the per-frame resets), [adaptive quantisation], intra costs: 2 launches per frame, 3-5 with AQ
+static int upload_common( x264cu_ctx *c, x264cu_frame *f, const uint8_t *d_luma, int pitch, bool fill_inv_qscale, const AqRun *aq = NULL )
 {
     const LaParams &P = c->P;
     const int B = c->cfg.bframes;
     reset_caches( f );
-    size_t ntri = (size_t)( B+2 ) * ( B+2 );
-    CU( cudaMemsetAsync( f->stats, 0, ntri * c->stat_pitch * 4, c->st ) );
+    const int ntri = ( B+2 ) * ( B+2 );
     {
         Span s( c, K_LOWRES, 1 );
-        launch_lowres( d_luma, pitch, c->cfg.width, c->cfg.height, f->planes, P, c->st );
+        launch_lowres( d_luma, pitch, c->cfg.width, c->cfg.height, f->planes, P, f->stats, ntri * c->stat_pitch,
+                       fill_inv_qscale ? f->inv_qscale : NULL, aq ? f->pixstats : NULL, c->st );
+    }
+    if( aq )
+    {
+        if( aq->mode >= 2 && ensure_pow_table( c ) ) return -1;
+        // pixstats[6..7] (unused by the sums) are the three floats the auto-variance reduction hands to its apply kernel
+        c->launches += launch_aq( aq->luma, aq->ls, aq->chroma, aq->cs, c->cfg.width, c->cfg.height, P, aq->mode,
+                                  aq->mode == 1 ? aq_strength_f32( aq->strength ) : aq->strength, aq->quant_offsets,
+                                  c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats, c->d_pow_x, c->d_pow_v, c->pow_n,
+                                  (float *)( f->pixstats + 6 ), c->st );
+        f->have_aq = true;
     }
     {
         Span s( c, K_INTRA, 1 );
@@ -641,9 +655,7 @@ extern "C" int x264cu_frame_upload( x264cu_ctx *c, x264cu_frame *f, const uint8_
         }
         CU( cudaMemcpyAsync( f->inv_qscale, q, (size_t)P.nmb * 2, cudaMemcpyHostToDevice, c->st ) );
     }
-    else
-        launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );         // memset_int16 (downscale.cl:132)
-    if( upload_common( c, f, c->d_luma[sel], c->luma_pitch ) ) return -1;
+    if( upload_common( c, f, c->d_luma[sel], c->luma_pitch, inv_qscale == NULL ) ) return -1;
     CU( cudaEventRecord( c->luma_free[sel], c->st ) );
     return B.end();
 }
@@ -698,17 +710,8 @@ extern "C" int x264cu_frame_upload_aq( x264cu_ctx *c, x264cu_frame *f, const uin
         CU( cudaMemcpyAsync( f->qp, q, (size_t)P.nmb * 4, cudaMemcpyHostToDevice, c->st ) );
         d_qo = f->qp;
     }
-    CU( cudaMemsetAsync( f->pixstats, 0, 8 * sizeof(unsigned long long), c->st ) );
-    launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );
-    c->launches += 1;
-    if( aq->mode >= 2 && ensure_pow_table( c ) ) return -1;
-    // pixstats[6..7] (unused by the sums) are the three floats the auto-variance reduction hands to the apply kernel
-    c->launches += launch_aq( c->d_luma[sel], c->luma_pitch, c->d_chroma[sel], c->chroma_pitch, W, H, P, aq->mode,
-                              aq->mode == 1 ? aq_strength_f32( aq->strength ) : aq->strength,
-                              d_qo, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats, c->d_pow_x, c->d_pow_v, c->pow_n,
-                              (float *)( f->pixstats + 6 ), c->st );
-    f->have_aq = true;
-    if( upload_common( c, f, c->d_luma[sel], c->luma_pitch ) ) return -1;
+    const AqRun run = { c->d_luma[sel], c->luma_pitch, c->d_chroma[sel], c->chroma_pitch, aq->mode, aq->strength, d_qo };
+    if( upload_common( c, f, c->d_luma[sel], c->luma_pitch, true, &run ) ) return -1;
     CU( cudaEventRecord( c->luma_free[sel], c->st ) );
     if( out )
     {
@@ -734,16 +737,8 @@ extern "C" int x264cu_frame_upload_aq_device( x264cu_ctx *c, x264cu_frame *f, co
     Batch B( c );
     if( B.failed ) return -1;
     const LaParams &P = c->P;
-    CU( cudaMemsetAsync( f->pixstats, 0, 8 * sizeof(unsigned long long), c->st ) );
-    launch_fill_u16( f->inv_qscale, 256, P.nmb, c->st );
-    c->launches += 1;
-    if( aq->mode >= 2 && ensure_pow_table( c ) ) return -1;
-    c->launches += launch_aq( d_luma, stride, d_chroma, cstride, c->cfg.width, c->cfg.height, P, aq->mode,
-                              aq->mode == 1 ? aq_strength_f32( aq->strength ) : aq->strength,
-                              aq->mode ? d_quant_offsets : NULL, c->d_log2_lut, c->d_exp2_lut, f->qp_aq, f->inv_qscale, f->pixstats,
-                              c->d_pow_x, c->d_pow_v, c->pow_n, (float *)( f->pixstats + 6 ), c->st );
-    f->have_aq = true;
-    if( upload_common( c, f, d_luma, stride ) ) return -1;
+    const AqRun run = { d_luma, stride, d_chroma, cstride, aq->mode, aq->strength, aq->mode ? d_quant_offsets : NULL };
+    if( upload_common( c, f, d_luma, stride, true, &run ) ) return -1;
     return B.end();
 }
 
@@ -799,9 +794,7 @@ extern "C" int x264cu_frame_upload_device( x264cu_ctx *c, x264cu_frame *f, const
     if( B.failed ) return -1;
     if( d_inv_qscale )
         CU( cudaMemcpyAsync( f->inv_qscale, d_inv_qscale, (size_t)c->P.nmb * 2, cudaMemcpyDeviceToDevice, c->st ) );
-    else
-        launch_fill_u16( f->inv_qscale, 256, c->P.nmb, c->st );
-    if( upload_common( c, f, d_luma, stride ) ) return -1;
+    if( upload_common( c, f, d_luma, stride, d_inv_qscale == NULL ) ) return -1;
     return B.end();
 }
 

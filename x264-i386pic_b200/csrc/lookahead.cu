@@ -17,12 +17,23 @@ __device__ __forceinline__ int lum( const uint8_t *luma, int ls, int W, int H, i
 }
 #define FILT(a,b,c,d) ((((((a)+(b)+1)>>1)+(((c)+(d)+1)>>1)+1)>>1))
 
+// The per-frame resets ride along: the evaluation statistics (x264_frame_init_lowres resets i_cost_est / i_row_satds,
+// mc.c:473-481; ours are accumulated with atomics and must start at zero), the raw pixel sums of the AQ kernel and the
+// default i_inv_qscale_factor of 256 (memset_int16, downscale.cl:132) -- three tiny launches in round 1.
+struct FrameClear { u32 *stats; int nstats; u32 *invq2; int ninvq2; unsigned long long *pix; };
+
 __global__ void __launch_bounds__(128) lowres_kernel( const uint8_t *__restrict__ luma, int ls, int W, int H,
-                                                      uint8_t *__restrict__ planes, LaParams P )
+                                                      uint8_t *__restrict__ planes, LaParams P, FrameClear fc )
 {
     const int pw4 = ( P.lw + 2*X264CU_PAD ) >> 2;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int py = blockIdx.y;
+    {
+        const int t = ( blockIdx.y * gridDim.x + blockIdx.x ) * blockDim.x + threadIdx.x, nt = gridDim.x * gridDim.y * blockDim.x;
+        for( int i = t; i < fc.nstats; i += nt ) fc.stats[i] = 0;
+        for( int i = t; i < fc.ninvq2; i += nt ) fc.invq2[i] = 0x01000100u;
+        if( fc.pix && t < 8 ) fc.pix[t] = 0;
+    }
     if( g >= pw4 ) return;
     const int y = min( max( py - X264CU_PAD, 0 ), P.lh - 1 );
     const int x0 = g*4 - X264CU_PAD;
@@ -64,11 +75,15 @@ __global__ void __launch_bounds__(128) lowres_kernel( const uint8_t *__restrict_
         *(u32 *)( planes + k*P.plane_size + off ) = o[k];
 }
 
-void launch_lowres( const uint8_t *luma, int stride, int width, int height, uint8_t *planes, const LaParams &P, cudaStream_t st )
+// stats / nstats: 32-bit words to zero; inv_qscale != NULL: fill nmb entries (rounded up to a pair; the array has slack) with 256;
+// pixstats != NULL: zero its 8 words
+void launch_lowres( const uint8_t *luma, int stride, int width, int height, uint8_t *planes, const LaParams &P,
+                    int32_t *stats, int nstats, uint16_t *inv_qscale, unsigned long long *pixstats, cudaStream_t st )
 {
     int pw4 = ( P.lw + 2*X264CU_PAD ) >> 2;
     dim3 grid( ( pw4 + 127 ) / 128, P.lh + 2*X264CU_PAD );
-    lowres_kernel<<<grid, 128, 0, st>>>( luma, stride, width, height, planes, P );
+    FrameClear fc = { (u32 *)stats, stats ? nstats : 0, (u32 *)inv_qscale, inv_qscale ? ( P.nmb + 1 ) / 2 : 0, pixstats };
+    lowres_kernel<<<grid, 128, 0, st>>>( luma, stride, width, height, planes, P, fc );
 }
 
 __global__ void weight_kernel( const u32 *__restrict__ src, u32 *__restrict__ dst, int64_t nwords, int scale, int denom, int offset )

@@ -76,8 +76,8 @@ struct FinalJob
 struct GatherSeg { const uint8_t *src; unsigned long long dst_off; unsigned bytes; };
 void launch_gather( const GatherSeg *d_segs, int nsegs, uint8_t *dst_base, cudaStream_t st );
 
-void launch_lowres( const uint8_t *luma, int stride, int width, int height, uint8_t *planes,
-                    const LaParams &P, cudaStream_t st );
+void launch_lowres( const uint8_t *luma, int stride, int width, int height, uint8_t *planes, const LaParams &P,
+                    int32_t *stats, int nstats, uint16_t *inv_qscale, unsigned long long *pixstats, cudaStream_t st );
 void launch_weight_plane( const uint8_t *src, uint8_t *dst, int64_t bytes, int scale, int denom, int offset, cudaStream_t st );
 void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *intra, int32_t *row_satds,
                    int32_t *stats, const LaParams &P, cudaStream_t st );

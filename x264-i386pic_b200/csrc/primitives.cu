@@ -116,44 +116,45 @@ __device__ __forceinline__ int sa8d_8x8_raw( const uint8_t *p1, int s1, const ui
     return (int)( 2 * sum );
 }
 
-// pixel.c:383-418: returns (sum8<<32)+sum4 of one 8x8
+// pixel.c:383-418: returns (sum8<<32)+sum4 of one 8x8.  sum4 / sum8 are the sums of |coefficient| of the four 4x4 and of the
+// 8x8 Hadamard transform of the SOURCE block (minus DC), and a sum of absolute values does not depend on the order of the
+// butterfly stages.  Columns k and k+4 share a word (expand_row8, the layout of x264_pixel_satd_8x4), so one HADAMARD4 per row
+// is the 4-point horizontal transform of the left (low halves) and right (high halves) 4x4 blocks at once and one per column
+// word the vertical one of the top / bottom blocks: sum4 is the packed abs-sum of those 32 words.  For sum8 the butterfly
+// between top and bottom is explicit and the one between the halves of a word is folded into the absolute sum,
+// |lo+hi| + |lo-hi| == 2*max(|lo|,|hi|), two words per packed max.  Every 16-bit field stays in range for 8-bit pixels:
+// |coefficient| <= 64*255, a packed accumulator half <= 65280.  ~500 integer instructions per 8x8 (was ~600 byte by byte).
 template<class LD>
 __device__ __forceinline__ uint64_t hadamard_ac_8x8( const uint8_t *p, int st, LD ld )
 {
-    u32 tmp[32];
+    u32 v[8][4];
 #pragma unroll
     for( int i = 0; i < 8; i++ )
     {
-        uint2 r = ld( p + (size_t)i*st );
-        u32 px[8];
-#pragma unroll
-        for( int k = 0; k < 4; k++ ) { px[k] = byte_of( r.x, k ); px[4+k] = byte_of( r.y, k ); }
-        const int o = ( i & 3 ) + ( i & 4 ) * 4;
-        u32 a0 = ( px[0] + px[1] ) + ( ( px[0] - px[1] ) << 16 ), a1 = ( px[2] + px[3] ) + ( ( px[2] - px[3] ) << 16 );
-        tmp[o] = a0 + a1; tmp[o+4] = a0 - a1;
-        u32 a2 = ( px[4] + px[5] ) + ( ( px[4] - px[5] ) << 16 ), a3 = ( px[6] + px[7] ) + ( ( px[6] - px[7] ) << 16 );
-        tmp[o+8] = a2 + a3; tmp[o+12] = a2 - a3;
+        u32 e[4];
+        expand_row8( ld( p + (size_t)i*st ), e );
+        HADAMARD4( v[i][0], v[i][1], v[i][2], v[i][3], e[0], e[1], e[2], e[3] );
     }
-    u32 sum4 = 0, sum8 = 0;
+    u32 sum4 = 0, acc8 = 0, dc = 0;
 #pragma unroll
-    for( int i = 0; i < 8; i++ )
+    for( int c = 0; c < 4; c++ )
     {
-        u32 a0, a1, a2, a3;
-        HADAMARD4( a0, a1, a2, a3, tmp[i*4+0], tmp[i*4+1], tmp[i*4+2], tmp[i*4+3] );
-        tmp[i*4+0] = a0; tmp[i*4+1] = a1; tmp[i*4+2] = a2; tmp[i*4+3] = a3;
-        sum4 += abs2( a0 ) + abs2( a1 ) + abs2( a2 ) + abs2( a3 );
-    }
+        u32 t[4], b[4];
+        HADAMARD4( t[0], t[1], t[2], t[3], v[0][c], v[1][c], v[2][c], v[3][c] );
+        HADAMARD4( b[0], b[1], b[2], b[3], v[4][c], v[5][c], v[6][c], v[7][c] );
+        if( c == 0 ) dc = t[0] + b[0];                      // the four 4x4 DC terms, two per word
 #pragma unroll
-    for( int i = 0; i < 8; i++ )
-    {
-        u32 a0, a1, a2, a3;
-        HADAMARD4( a0, a1, a2, a3, tmp[i], tmp[8+i], tmp[16+i], tmp[24+i] );
-        sum8 += abs2( a0 ) + abs2( a1 ) + abs2( a2 ) + abs2( a3 );
+        for( int j = 0; j < 4; j++ )
+        {
+            sum4 += abs2( t[j] ) + abs2( b[j] );
+            const u32 u = abs2( t[j] + b[j] ), d = abs2( t[j] - b[j] );
+            acc8 += __vmaxu2( __byte_perm( u, d, 0x5410 ), __byte_perm( u, d, 0x7632 ) );
+        }
     }
-    u32 dc = ( tmp[0] + tmp[8] + tmp[16] + tmp[24] ) & 0xffff;
-    sum4 = ( sum4 & 0xffff ) + ( sum4 >> 16 ) - dc;
-    sum8 = ( sum8 & 0xffff ) + ( sum8 >> 16 ) - dc;
-    return ( (uint64_t)sum8 << 32 ) + sum4;
+    dc = ( dc & 0xffff ) + ( dc >> 16 );
+    const u32 s4 = ( sum4 & 0xffff ) + ( sum4 >> 16 ) - dc;
+    const u32 s8 = 2 * ( ( acc8 & 0xffff ) + ( acc8 >> 16 ) ) - dc;
+    return ( (uint64_t)s8 << 32 ) + s4;
 }
 
 // dct.c:157-189: one 4x4, rows as words; writes 16 coefficients
