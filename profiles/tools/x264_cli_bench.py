@@ -16,7 +16,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from bench import make_stream_frames
 
-CLI = os.path.join(ROOT, "oracle", "_ref", "x264cu_cli")
+# the fastest prebuilt flavour of the unmodified sources (oracle/Makefile: _simd = -O3 -ffast-math + AVX2 auto-vectorisation,
+# _fast = the reference's release flags, "" = the -O2 parity build)
+CLI = next(p for p in (os.path.join(ROOT, "oracle", "_ref", "x264cu_cli" + suf) for suf in ("_simd", "_fast", "")) if os.path.exists(p))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 threads = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 1)
 preset = sys.argv[3] if len(sys.argv) > 3 else "medium"        # a faster preset makes the lookahead the bottleneck
@@ -30,7 +32,7 @@ with open(src, "wb") as f:
         f.write(b"FRAME\n"); f.write(x.tobytes()); f.write(c)
 base = [CLI, "--preset", preset, "--rc-lookahead", "40", "--b-adapt", "2", "--bframes", "3", "--threads", str(threads), "-o", "/tmp/x264cu_bench.264", src]
 for name, extra, env in (("cpu lookahead (%d lookahead threads auto)" % threads, [], {}),
-                         ("b200 lookahead, default schedule", ["--opencl"], {}),
+                         ("b200 lookahead, default schedule", ["--opencl"], {"X264CU_SEARCH_PASSES": "2"}),
                          ("b200 lookahead, exact mode", ["--opencl"], {"X264CU_SEARCH_PASSES": "0"})):
     e = dict(os.environ); e.update(env)
     t0 = time.time()
@@ -38,6 +40,6 @@ for name, extra, env in (("cpu lookahead (%d lookahead threads auto)" % threads,
     dt = time.time() - t0
     m = re.search(r"encoded (\d+) frames, ([0-9.]+) fps, ([0-9.]+) kb/s", r.stderr)
     ok = r.returncode == 0 and m and "failed to load OpenCL" not in r.stderr and "x264cu:" not in r.stderr
-    print(json.dumps({"preset": preset, "run": name, "ok": bool(ok), "frames": int(m.group(1)) if m else None, "fps": float(m.group(2)) if m else None,
+    print(json.dumps({"cli": os.path.basename(CLI), "preset": preset, "run": name, "ok": bool(ok), "frames": int(m.group(1)) if m else None, "fps": float(m.group(2)) if m else None,
                       "kbps": float(m.group(3)) if m else None, "wall_s": round(dt, 2), "threads": threads,
                       "bytes": os.path.getsize("/tmp/x264cu_bench.264") if os.path.exists("/tmp/x264cu_bench.264") else None}))

@@ -68,7 +68,10 @@ def test_x264_cli_exact_mode_is_bit_identical_to_cpu(tmp_path, W, H, n, extra):
     src = str(tmp_path / "in.y4m")
     _y4m(src, W, H, n, seed=31, scene_cut_at=n // 2, fade_at=4)
     cpu, _ = _encode(str(tmp_path), "cpu.264", src, extra + ["--lookahead-threads", "1"])
-    gpu, log = _encode(str(tmp_path), "gpu.264", src, extra + ["--opencl"], {"X264CU_SEARCH_PASSES": "0"})
+    # the glue selects the exact mode from the encoder's own parameters (one lookahead thread + deterministic encode);
+    # the environment override is exercised by the other two cases
+    env = {} if extra == ["--preset", "medium"] else {"X264CU_SEARCH_PASSES": "0"}
+    gpu, log = _encode(str(tmp_path), "gpu.264", src, extra + ["--opencl"], env)
     assert "failed to load OpenCL" not in log and "x264cu:" not in log, log[-1500:]
     a = [(t, hashlib.md5(p).hexdigest()) for t, p in _nals(cpu) if t in (1, 5, 7, 8)]      # slices, SPS, PPS
     b = [(t, hashlib.md5(p).hexdigest()) for t, p in _nals(gpu) if t in (1, 5, 7, 8)]
@@ -81,7 +84,7 @@ def test_x264_cli_default_schedule_encodes(tmp_path):
     src = str(tmp_path / "in.y4m")
     _y4m(src, W, H, n, seed=32, scene_cut_at=20)
     cpu, _ = _encode(str(tmp_path), "cpu.264", src, ["--preset", "medium", "--lookahead-threads", "1"])
-    gpu, log = _encode(str(tmp_path), "gpu.264", src, ["--preset", "medium", "--opencl"])
+    gpu, log = _encode(str(tmp_path), "gpu.264", src, ["--preset", "medium", "--opencl"], {"X264CU_SEARCH_PASSES": "2"})
     assert "failed to load OpenCL" not in log and "x264cu:" not in log, log[-1500:]
     a, b = _nals(cpu), _nals(gpu)
     assert sum(t in (1, 5) for t, _ in a) == sum(t in (1, 5) for t, _ in b) == n

@@ -90,9 +90,13 @@ int x264_opencl_lookahead_init( x264_t *h )
     cfg.weighted_bipred = h->param.analyse.b_weighted_bipred;
     cfg.bframe_bias = h->param.i_bframe_bias;
     /* 2: the dependency-free schedule; 0: the reference's own raster-serial order, whose
-     * costs, MVs and therefore decisions and bitstream equal the CPU path's */
+     * costs, MVs and therefore decisions and bitstream equal the CPU path's.  Selected by the encoder's own parameters:
+     * with ONE lookahead thread (--lookahead-threads 1, or --threads 1) the CPU lookahead is a single raster-serial pass
+     * over the frame (slicetype.c:901-944 runs no slices), and a deterministic encode (b_deterministic, the default) is
+     * then reproduced bit for bit by the exact mode; with several lookahead threads the CPU path cuts the frame into
+     * slices of its own and the throughput-oriented schedule is used.  X264CU_SEARCH_PASSES overrides (tests, tuning). */
     const char *e = getenv( "X264CU_SEARCH_PASSES" );
-    cfg.search_passes = e ? atoi( e ) : 2;
+    cfg.search_passes = e ? atoi( e ) : ( h->param.i_lookahead_threads == 1 && h->param.b_deterministic ) ? 0 : 2;
     cfg.max_frames = h->param.rc.i_lookahead + h->param.i_bframe + 3;
     cfg.cost_mv = h->cost_mv[X264_LOOKAHEAD_QP];          /* the encoder's own table (analyse.c:143-157) */
     cu_state *s = calloc( 1, sizeof(*s) );
