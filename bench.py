@@ -601,6 +601,7 @@ def main():
     ap.add_argument("--search-passes", type=int, default=2, help="K of the dependency-free schedule; 0 = exact raster-serial wavefront mode")
     ap.add_argument("--no-primitives", action="store_true", help="skip the SATD/SAD primitive roofline section")
     ap.add_argument("--value-only", action="store_true", help="profiling aid: skip the end-to-end pass")
+    ap.add_argument("--no-parity", action="store_true", help="tuning aid for timing-only builds whose results are wrong on purpose: skip the parity check (the line says so)")
     ap.add_argument("--contexts", type=int, default=0, help="contexts per GPU; 0 (default): one context (own CUDA streams) per encode stream, "
                     "as concurrent encoders would run; 1: all streams share one in-order context")
     ap.add_argument("--subme", type=int, default=7, help="analyse.i_subpel_refine of the encoder: > 1 selects the SATD/HEX/subme-4 lookahead (default), <= 1 the SAD/DIA/subme-2 one")
@@ -706,14 +707,14 @@ def main():
     psteps = min(args.steps, 16)
     kt = run_cuda_pass(x264cu, ctxs[:1], frames, S, warmup, psteps, False, dev=dev, profile=True, dist=dist, local=local)["kt"]
     rv = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, False, dev=dev, profile=False, dist=dist, local=local,
-                       parity=args.value_only and rank == 0)
+                       parity=args.value_only and rank == 0 and not args.no_parity)
     ms_v, evals, launches = rv["ms"], rv["evals"], rv["launches"]
     # end-to-end pass: pinned host luma in; all 154 cost scalars + the arrays of one decided evaluation out, per step
     if args.value_only:
         re_ = rv
     else:
         re_ = run_cuda_pass(x264cu, ctxs, frames, S, warmup, args.steps, True, pinned=pinned, dist=dist, local=local,
-                            arrays=args.e2e_arrays, parity=rank == 0)
+                            arrays=args.e2e_arrays, parity=rank == 0 and not args.no_parity)
     ms_e, res_bytes, pc = re_["ms"], re_["res_bytes"], re_["parity"]
     clocks = sampler.summary() if rank == 0 else {}
     if rank == 0 and pc is not None and not pc["ok"]:
