@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
     int bx, by;
     if( !warp_tile_block( P.tiles_f, P.ntiles_f, P, bx, by ) ) return;
     const int blk = by * P.mbw + bx;
-    typedef ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> BE;
+    typedef ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64, X264CU_FINAL_PTXPRED != 0> BE;
     BE be; be.P = &P;
     const int pitch = be.pitch(), pel = ( by*8 ) * pitch + bx*8;
     if( skipped_border( P, bx, by ) )
@@ -175,14 +175,14 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
             uint2 t[8];
             if( SATD )
             {
-                QpelRows<false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> r1( be.ref1, P, mv1x, mv1y, 0, -1, 0 );
+                QpelRows<false, PITCH, X264CU_FINAL_LD64, X264CU_FINAL_PTXPRED != 0> r1( be.ref1, P, mv1x, mv1y, 0, -1, 0 );
 #pragma unroll
                 for( int r = 0; r < 8; r++ ) t[r] = r1( r );
             }
             else
             {
                 const int i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
-                const RowSrc<X264CU_FINAL_LD64 != 0> q1( be.ref1, ( mv1x >> 2 ) + ( mv1y >> 2 ) * pitch + i1 * (int)P.plane_size );
+                const RowSrc<X264CU_FINAL_LD64> q1( be.ref1, ( mv1x >> 2 ) + ( mv1y >> 2 ) * pitch + i1 * (int)P.plane_size );
 #pragma unroll
                 for( int r = 0; r < 8; r++ ) t[r] = q1.row( r * ( pitch >> 2 ) );
             }
@@ -260,13 +260,13 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
 #endif
                     if( SATD )
                     {
-                        QpelRows<false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> r0( be.ref0, P, mv0x, mv0y, 0, -1, 0 );
+                        QpelRows<false, PITCH, X264CU_FINAL_LD64, X264CU_FINAL_PTXPRED != 0> r0( be.ref0, P, mv0x, mv0y, 0, -1, 0 );
                         cost = satd8x8_t( be.fenc, [&]( int r ) { const uint2 a = r0( r ), b = PRED1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
                     }
                     else
                     {
                         const int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 );
-                        const RowSrc<X264CU_FINAL_LD64 != 0> q0( be.ref0, ( mv0x >> 2 ) + ( mv0y >> 2 ) * pitch + i0 * (int)P.plane_size );
+                        const RowSrc<X264CU_FINAL_LD64> q0( be.ref0, ( mv0x >> 2 ) + ( mv0y >> 2 ) * pitch + i0 * (int)P.plane_size );
                         cost = sad8x8_t( be.fenc, [&]( int r ) { const uint2 a = q0.row( r * ( pitch >> 2 ) ), b = PRED1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
                     }
 #undef PRED1
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
     int bx, by;
     if( !warp_tile_block( P.tiles_f, P.ntiles_f, P, bx, by ) ) return;
     const int blk = by * P.mbw + bx;
-    ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64 != 0, X264CU_FINAL_PTXPRED != 0> be; be.P = &P;
+    ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64, X264CU_FINAL_PTXPRED != 0> be; be.P = &P;
     const int pel = ( by*8 ) * be.pitch() + bx*8;
 #pragma unroll 1
     for( int z = blockIdx.y * F_JOBS; z < min( njobs, ( blockIdx.y + 1 ) * F_JOBS ); z++ )

@@ -15,9 +15,9 @@
 #define S_TILE_H X264CU_S_TILE_H
 #define F_TILE_W X264CU_F_TILE_W
 #define F_TILE_H X264CU_F_TILE_H
-// row loads as two aligned 64-bit words (1) or three 32-bit words (0)
+// row loads as three 32-bit words (0), two aligned 64-bit words (1), or one 64-bit + one 32-bit word (2): RowSrc
 #ifndef X264CU_SEARCH_LD64
-#define X264CU_SEARCH_LD64 1
+#define X264CU_SEARCH_LD64 2
 #endif
 #ifndef X264CU_FINAL_LD64
 #define X264CU_FINAL_LD64 0
@@ -29,13 +29,14 @@
 #ifndef X264CU_FINAL_PTXPRED
 #define X264CU_FINAL_PTXPRED 0
 #endif
-// __launch_bounds__ minimum CTAs per SM: 3 leaves ptxas at ~115 registers (4 resident CTAs of 128 threads)
+// __launch_bounds__ minimum CTAs per SM: the search kernel at 5 gets 96 registers without spills (5 resident CTAs of 128
+// threads: 2112 CTAs of a 1080p pass are 2.85 instead of 3.57 waves), the decision kernel at 6 gets 80
 // dedicated half-pel diamond for even centres in the thread-per-block search (1) or the generic qpel fetch only (0)
 #ifndef X264CU_HPEL_EVEN
 #define X264CU_HPEL_EVEN 1
 #endif
 #ifndef X264CU_MINB_SEARCH
-#define X264CU_MINB_SEARCH 3
+#define X264CU_MINB_SEARCH 5
 #endif
 #ifndef X264CU_MINB_FINAL
 #define X264CU_MINB_FINAL 6
@@ -200,40 +201,60 @@ __device__ __forceinline__ bool in_range( const MeGeo &m, int mx, int my )
 // (4 L1 wavefronts per warp instead of 6) at the price of three selects.  B200 measurements (profiles/r01): the search
 // kernels gain from LD64, the decision kernels -- bound by L2->L1 fill traffic, which the wider window increases --
 // lose 28 %, so it is a per-kernel choice.  The pointer is aligned ONCE per candidate; rows are immediates off it.
-template<bool LD64>
+// LDM (load mode): 0 = three aligned 32-bit words; 1 = two aligned 64-bit words (16-byte window); 2 = one aligned 64-bit word + one
+// 32-bit word: the same 12-byte window as mode 0 in two L1 requests instead of three -- the 64-bit load takes words (0,1) when
+// the first word index is even and words (1,2) when it is odd, the 32-bit load takes the remaining one, three selects put
+// them back in order.
+template<int LDM>
 struct RowSrc
 {
-    const u32 *q;
+    const u32 *q;       // mode 2: the 64-bit pointer
+    const u32 *q3;      // mode 2 only: the 32-bit pointer
     u32 sh;
     int k;
     __device__ __forceinline__ RowSrc( const uint8_t *origin, int off )
     {
-        if( LD64 ) { q = (const u32 *)origin + ( ( off >> 3 ) << 1 ); k = off & 4; }
-        else       { q = (const u32 *)origin + ( off >> 2 ); k = 0; }
+        if( LDM == 1 )      { q = (const u32 *)origin + ( ( off >> 3 ) << 1 ); k = off & 4; }
+        else if( LDM == 2 ) { const int w = off >> 2; k = w & 1; q = (const u32 *)origin + w + k; q3 = (const u32 *)origin + w + ( k ? 0 : 2 ); }
+        else                { q = (const u32 *)origin + ( off >> 2 ); k = 0; }
         sh = ( off & 3 ) * 8;
         // pin the row-0 pointer, the shift and the word select in registers: under register pressure the compiler
         // otherwise rematerialises the whole offset computation (plane table lookup, multiply, 64-bit add) for every row
         asm volatile( "" : "+l"( q ), "+r"( sh ), "+r"( k ) );
+        if( LDM == 2 ) asm volatile( "" : "+l"( q3 ) );
     }
     __device__ __forceinline__ uint2 row( int w4 ) const      // w4: row offset in words (a multiple of 2)
     {
-        if( LD64 )
+        if( LDM == 1 )
         {
             const uint2 A = __ldg( (const uint2 *)( q + w4 ) ), B = __ldg( (const uint2 *)( q + w4 ) + 1 );
             const u32 a = k ? A.y : A.x, b = k ? B.x : A.y, c = k ? B.y : B.x;
             return make_uint2( __funnelshift_r( a, b, sh ), __funnelshift_r( b, c, sh ) );
         }
+        if( LDM == 2 )
+        {
+            const uint2 A = __ldg( (const uint2 *)( q + w4 ) ); const u32 c = __ldg( q3 + w4 );
+            const u32 w0 = k ? c : A.x, w1 = k ? A.x : A.y, w2 = k ? A.y : c;
+            return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+        }
         const u32 w0 = __ldg( q + w4 ), w1 = __ldg( q + w4 + 1 ), w2 = __ldg( q + w4 + 2 );
         return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
     }
-    // 9+ pixels of a row as three words (bytes 0..11 of the window; only byte 8 of the third word is guaranteed)
+    // 9 pixels of a row as three words (bytes 0..11 of the window; only byte 8 of the third word is guaranteed)
     __device__ __forceinline__ void row12( int w4, u32 &t0, u32 &t1, u32 &t2 ) const
     {
-        if( LD64 )
+        if( LDM == 1 )
         {
             const uint2 A = __ldg( (const uint2 *)( q + w4 ) ), B = __ldg( (const uint2 *)( q + w4 ) + 1 );
             const u32 a = k ? A.y : A.x, b = k ? B.x : A.y, c = k ? B.y : B.x, d = k ? B.y : B.y;
             t0 = __funnelshift_r( a, b, sh ); t1 = __funnelshift_r( b, c, sh ); t2 = __funnelshift_r( c, d, sh );
+            return;
+        }
+        if( LDM == 2 )
+        {
+            const uint2 A = __ldg( (const uint2 *)( q + w4 ) ); const u32 c = __ldg( q3 + w4 );
+            const u32 w0 = k ? c : A.x, w1 = k ? A.x : A.y, w2 = k ? A.y : c;
+            t0 = __funnelshift_r( w0, w1, sh ); t1 = __funnelshift_r( w1, w2, sh ); t2 = w2 >> sh;
             return;
         }
         const u32 w0 = __ldg( q + w4 ), w1 = __ldg( q + w4 + 1 ), w2 = __ldg( q + w4 + 2 ), w3 = __ldg( q + w4 + 3 );
@@ -246,13 +267,21 @@ struct RowSrc
     // from `v` comes back (the caller discards it).
     __device__ __forceinline__ uint2 row_if( int p, int w4, uint2 v ) const
     {
-        if( LD64 )
+        if( LDM == 1 )
         {
             u32 a0 = v.x, a1 = v.y, b0 = v.x, b1 = v.y;
             asm( "{ .reg .pred p;\n setp.ne.s32 p, %4, 0;\n @p ld.global.nc.v2.u32 {%0,%1}, [%5];\n @p ld.global.nc.v2.u32 {%2,%3}, [%5+8];\n}"
                  : "+r"( a0 ), "+r"( a1 ), "+r"( b0 ), "+r"( b1 ) : "r"( p ), "l"( q + w4 ) );
             const u32 a = k ? a1 : a0, b = k ? b0 : a1, c = k ? b1 : b0;
             return make_uint2( __funnelshift_r( a, b, sh ), __funnelshift_r( b, c, sh ) );
+        }
+        if( LDM == 2 )
+        {
+            u32 a0 = v.x, a1 = v.y, c = v.x;
+            asm( "{ .reg .pred p;\n setp.ne.s32 p, %3, 0;\n @p ld.global.nc.v2.u32 {%0,%1}, [%4];\n @p ld.global.nc.u32 %2, [%5];\n}"
+                 : "+r"( a0 ), "+r"( a1 ), "+r"( c ) : "r"( p ), "l"( q + w4 ), "l"( q3 + w4 ) );
+            const u32 w0 = k ? c : a0, w1 = k ? a0 : a1, w2 = k ? a1 : c;
+            return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
         }
         u32 w0 = v.x, w1 = v.y, w2 = v.x;
         asm( "{ .reg .pred p;\n setp.ne.s32 p, %3, 0;\n @p ld.global.nc.u32 %0, [%4];\n @p ld.global.nc.u32 %1, [%4+4];\n @p ld.global.nc.u32 %2, [%4+8];\n}"
@@ -515,7 +544,7 @@ __device__ __forceinline__ void ld12w( const u32 *q, u32 sh, u32 &a0, u32 &a1, u
 }
 
 // get_ref (mc.c:221-249) as a row generator: plane/offset selection hoisted out of the row loop
-template<bool WEIGHTED, int PITCH, bool LD64, bool PTXPRED>
+template<bool WEIGHTED, int PITCH, int LD64, bool PTXPRED>
 struct QpelRows
 {
     RowSrc<LD64> s1, s2;     // the two source planes at row 0
@@ -566,7 +595,7 @@ struct QpelRows
     }
 };
 
-template<bool SATD, bool WEIGHTED, int PITCH, bool LD64, bool PTXPRED>
+template<bool SATD, bool WEIGHTED, int PITCH, int LD64, bool PTXPRED>
 struct ThreadBE
 {
     static constexpr bool PAR4 = false, HPEL_EVEN = true;

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(S_TILE_W*S_TILE_H, X264CU_MINB_SEARCH) search_
     if( !warp_tile_block( P.tiles_s, P.ntiles_s, P, bx, by ) ) return;
     const int blk = by * P.mbw + bx;
     if( skipped_border( P, bx, by ) ) { ( (int *)J.mv_out )[blk] = 0; J.cost_out[blk] = 0; return; }
-    ThreadBE<SATD, WEIGHTED, PITCH, X264CU_SEARCH_LD64 != 0, X264CU_SEARCH_PTXPRED != 0> be; be.P = &P;
+    ThreadBE<SATD, WEIGHTED, PITCH, X264CU_SEARCH_LD64, X264CU_SEARCH_PTXPRED != 0> be; be.P = &P;
     const int pel = ( by*8 ) * be.pitch() + bx*8;
     const uint8_t *src = J.fenc + pel;
 #pragma unroll
