@@ -2,10 +2,15 @@
 // packing and sums, i.e. the tail of slicetype_mb_cost (slicetype.c:616-652,703-712,758-790,946-989).
 #include "la_block.cuh"
 
-// ---- mode decision + sums: the tail of slicetype_mb_cost for one block ----------------------------
+// ---- mode decision: the tail of slicetype_mb_cost for one block --------------------------------------
+// What one block adds to the sums of its evaluation (slicetype.c:762-788); the caller accumulates.
+struct BlockSums { int cost, cost_aq, row_aq, intra; };
+
+// icost / invq: the block's intra cost and AQ factor, fetched by the caller ahead of the bidir candidates
 template<class BE>
-__device__ __forceinline__ void final_block( const BE &be, const FinalJob &J, const LaParams &P, int bx, int by, int blk )
+__device__ __forceinline__ BlockSums final_block( const BE &be, const FinalJob &J, const LaParams &P, int bx, int by, int blk, int icost, int invq )
 {
+    BlockSums S = { 0, 0, 0, 0 };
     const bool border = bx == 0 || by == 0 || bx == P.mbw-1 || by == P.mbh-1;
     const bool tiny = P.mbw <= 2 || P.mbh <= 2;
     int bcost = X264CU_COST_MAX, list_used = 0;
@@ -58,27 +63,23 @@ __device__ __forceinline__ void final_block( const BE &be, const FinalJob &J, co
         }
         else if( mc0 < bcost ) { bcost = mc0; list_used = 1; }
     }
-    if( !be.leader() ) return;
+    if( !be.leader() ) return S;
     bcost += 4;                                         // lowres_penalty (slicetype.c:758)
     const bool score = !border || tiny;
     if( !J.b_bidir )
     {   // slicetype.c:762-773
-        int icost = J.intra[blk];
         int b_intra = icost < bcost;
         if( b_intra ) { bcost = icost; list_used = 0; }
-        if( score && b_intra ) atomicAdd( &J.stats[2], 1 );
+        if( score && b_intra ) S.intra = 1;
     }
     if( !J.b_intra_only )
     {   // slicetype.c:776-788
-        int bcost_aq = P.aq ? ( bcost * J.inv_qscale[blk] + 128 ) >> 8 : bcost;
-        atomicAdd( &J.row_satds[by], bcost_aq );
-        if( score )
-        {
-            atomicAdd( &J.stats[0], bcost );
-            atomicAdd( &J.stats[1], bcost_aq );
-        }
+        int bcost_aq = P.aq ? ( bcost * invq + 128 ) >> 8 : bcost;
+        S.row_aq = bcost_aq;
+        if( score ) { S.cost = bcost; S.cost_aq = bcost_aq; }
     }
     J.lowres_costs[blk] = (uint16_t)( min( bcost, 0x3FFF ) + ( list_used << 14 ) );     // slicetype.c:790
+    return S;
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *__restrict__ jobs, LaParams P )
@@ -96,7 +97,14 @@ __global__ void __launch_bounds__(CTA_THREADS) final_kernel_g( const FinalJob *_
     const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
     be.fenc = *(const uint2 *)( J.fenc + pel );
     be.ref0 = J.ref0 + pel; be.ref1 = J.ref1 + pel; be.ref_w = be.ref0;
-    final_block( be, J, P, bx, by, blk );
+    const BlockSums S = final_block( be, J, P, bx, by, blk, J.b_bidir ? 0 : (int)J.intra[blk], P.aq && !J.b_intra_only ? (int)J.inv_qscale[blk] : 256 );
+    if( be.g.r != 0 ) return;
+    if( S.intra ) atomicAdd( &J.stats[2], 1 );
+    if( !J.b_intra_only )
+    {
+        atomicAdd( &J.row_satds[by], S.row_aq );
+        if( S.cost | S.cost_aq ) { atomicAdd( &J.stats[0], S.cost ); atomicAdd( &J.stats[1], S.cost_aq ); }
+    }
 }
 
 // ---- thread-per-block decision kernel over CHUNKS of evaluations ---------------------------------------------------
@@ -312,8 +320,15 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
 template<bool SATD, int PITCH>
 __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_kernel_t( const FinalJob *__restrict__ jobs, int njobs, LaParams P )
 {
-    int bx, by;
-    if( !warp_tile_block( P.tiles_f, P.ntiles_f, P, bx, by ) ) return;
+    // every lane of a warp that owns a tile stays until the sums are accumulated: the 32 blocks' contributions are added up
+    // with warp reductions and leave as one atomic per sum and block row (integer adds: any order gives the same result) --
+    // per-thread atomics were 3.3 M same-address L2 operations per 1080p launch (154 evaluations x 8160 blocks x 3)
+    const int wt = blockIdx.x * ( blockDim.x >> 5 ) + ( threadIdx.x >> 5 ), lane = threadIdx.x & 31;
+    if( wt >= P.ntiles_f ) return;
+    const uint32_t td = __ldg( P.tiles_f + wt );
+    const int lw = td >> 24;
+    const int bx = (int)( td & 0xfff ) + ( lane & ( ( 1 << lw ) - 1 ) ), by = (int)( ( td >> 12 ) & 0xfff ) + ( lane >> lw );
+    const bool inside = bx < P.mbw && by < P.mbh;
     const int blk = by * P.mbw + bx;
     ThreadBE<SATD, false, PITCH, X264CU_FINAL_LD64, X264CU_FINAL_PTXPRED != 0> be; be.P = &P;
     const int pel = ( by*8 ) * be.pitch() + bx*8;
@@ -321,15 +336,40 @@ __global__ void __launch_bounds__(F_TILE_W*F_TILE_H, X264CU_MINB_FINAL) final_ke
     for( int z = blockIdx.y * F_JOBS; z < min( njobs, ( blockIdx.y + 1 ) * F_JOBS ); z++ )
     {
         const FinalJob J = jobs[z];
-        if( skipped_border( P, bx, by ) ) { if( !J.b_intra_only ) J.lowres_costs[blk] = 0; continue; }
-        const uint8_t *src = J.fenc + pel;
+        BlockSums S = { 0, 0, 0, 0 };
+        if( inside )
+        {
+            if( skipped_border( P, bx, by ) ) { if( !J.b_intra_only ) J.lowres_costs[blk] = 0; }
+            else
+            {
+                // the two scalars the decision needs last are requested first: their latency hides behind the candidates
+                const int icost = J.b_bidir ? 0 : (int)__ldg( J.intra + blk );
+                const int invq = P.aq && !J.b_intra_only ? (int)__ldg( J.inv_qscale + blk ) : 256;
+                const uint8_t *src = J.fenc + pel;
+                if( !J.b_intra_only )
+                {
+#pragma unroll
+                    for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * be.pitch() ) );
+                }
+                be.ref0 = J.ref0 + pel; be.ref1 = J.ref1 + pel; be.ref_w = be.ref0;
+                S = final_block( be, J, P, bx, by, blk, icost, invq );
+            }
+        }
+        if( !J.b_bidir )
+        {
+            const int n = __reduce_add_sync( 0xffffffffu, S.intra );
+            if( lane == 0 && n ) atomicAdd( &J.stats[2], n );
+        }
         if( !J.b_intra_only )
         {
-#pragma unroll
-            for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * be.pitch() ) );
+            const int c = __reduce_add_sync( 0xffffffffu, S.cost ), ca = __reduce_add_sync( 0xffffffffu, S.cost_aq );
+            if( lane == 0 && ( c | ca ) ) { atomicAdd( &J.stats[0], c ); atomicAdd( &J.stats[1], ca ); }
+            for( int j = 0; j < ( 32 >> lw ); j++ )
+            {   // one block row of the warp tile at a time (two for the 16-wide tiles)
+                const int r = __reduce_add_sync( 0xffffffffu, ( lane >> lw ) == j ? S.row_aq : 0 );
+                if( lane == ( j << lw ) && r ) atomicAdd( &J.row_satds[by], r );
+            }
         }
-        be.ref0 = J.ref0 + pel; be.ref1 = J.ref1 + pel; be.ref_w = be.ref0;
-        final_block( be, J, P, bx, by, blk );
     }
 }
 
