@@ -20,14 +20,14 @@
 #define X264CU_SEARCH_LD64 2
 #endif
 #ifndef X264CU_FINAL_LD64
-#define X264CU_FINAL_LD64 0
+#define X264CU_FINAL_LD64 2
 #endif
 // second-plane fetch of get_ref as PTX-predicated loads (1) or a C++ branch (0)
 #ifndef X264CU_SEARCH_PTXPRED
 #define X264CU_SEARCH_PTXPRED 1
 #endif
 #ifndef X264CU_FINAL_PTXPRED
-#define X264CU_FINAL_PTXPRED 0
+#define X264CU_FINAL_PTXPRED 1
 #endif
 // __launch_bounds__ minimum CTAs per SM: the search kernel at 5 gets 96 registers without spills (5 resident CTAs of 128
 // threads: 2112 CTAs of a 1080p pass are 2.85 instead of 3.57 waves), the decision kernel at 6 gets 80
@@ -287,6 +287,16 @@ struct RowSrc
         asm( "{ .reg .pred p;\n setp.ne.s32 p, %3, 0;\n @p ld.global.nc.u32 %0, [%4];\n @p ld.global.nc.u32 %1, [%4+4];\n @p ld.global.nc.u32 %2, [%4+8];\n}"
              : "+r"( w0 ), "+r"( w1 ), "+r"( w2 ) : "r"( p ), "l"( q + w4 ) );
         return make_uint2( __funnelshift_r( w0, w1, sh ), __funnelshift_r( w1, w2, sh ) );
+    }
+    // row12 under a per-thread predicate (see row_if)
+    __device__ __forceinline__ void row12_if( int p, int w4, u32 &t0, u32 &t1, u32 &t2 ) const
+    {
+        static_assert( LDM == 2, "row12_if: mode 2 only" );
+        u32 a0 = 0, a1 = 0, c = 0;
+        asm( "{ .reg .pred p;\n setp.ne.s32 p, %3, 0;\n @p ld.global.nc.v2.u32 {%0,%1}, [%4];\n @p ld.global.nc.u32 %2, [%5];\n}"
+             : "+r"( a0 ), "+r"( a1 ), "+r"( c ) : "r"( p ), "l"( q + w4 ), "l"( q3 + w4 ) );
+        const u32 w0 = k ? c : a0, w1 = k ? a0 : a1, w2 = k ? a1 : c;
+        t0 = __funnelshift_r( w0, w1, sh ); t1 = __funnelshift_r( w1, w2, sh ); t2 = w2 >> sh;
     }
 };
 
@@ -670,6 +680,62 @@ struct ThreadBE
             {
                 u32 t0, t1, t2;
                 src.row12( r*s4, t0, t1, t2 );
+                acc[2] = __vsadu4( fenc[r].x, t0 ) + __vsadu4( fenc[r].y, t1 ) + acc[2];
+                acc[3] = __vsadu4( fenc[r].x, __funnelshift_r( t0, t1, 8 ) ) + __vsadu4( fenc[r].y, __funnelshift_r( t1, t2, 8 ) ) + acc[3];
+            }
+        }
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            const int x = omx + ( k == 2 ? -2 : k == 3 ? 2 : 0 ), y = omy + ( k == 0 ? -2 : k == 1 ? 2 : 0 );
+            const int c = (int)acc[k] + mvcost( tab, m, x, y );
+            if( c < bcost ) { bcost = c; best = k; }
+        }
+    }
+    // The same diamond around ANY centre.  The two vertical candidates (omx, omy -+ 2) have the same quarter-pel phase, so
+    // get_ref reads the same one or two planes at the same columns, one row apart: 9 rows of each plane serve both.  The
+    // two horizontal candidates (omx -+ 2, omy) likewise read the same planes one pixel apart: 9 pixels per row serve both
+    // (the byte average commutes with the byte shift, so the planes are averaged once, on three words).  34 plane-row
+    // fetches instead of 64, in ONE code path for every lane -- a warp whose blocks disagree on the parity of their
+    // centres no longer runs hpel4_even AND four generic get_ref candidates.
+    __device__ __forceinline__ void hpel4_pairs( int omx, int omy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        static_assert( LD64 == 2 && PTXPRED, "hpel4_pairs is written for the 64+32-bit predicated row loader" );
+        const int s4 = pitch() >> 2, psz = (int)P->plane_size;
+        u32 acc[4] = {0, 0, 0, 0};
+        {   // up (omx, omy-2): rows 0..7, down (omx, omy+2): rows 1..8
+            const int y = omy - 2, qi = ( ( y & 3 ) << 2 ) + ( omx & 3 ), base = ( y >> 2 ) * pitch() + ( omx >> 2 );
+            const int avg = ( qi & 5 ) != 0;
+            const RowSrc<2> a( ref0, base + ( ( y & 3 ) == 3 ? pitch() : 0 ) + c_hpel_ref0[qi] * psz ),
+                            b( ref0, base + ( ( omx & 3 ) == 3 ) + c_hpel_ref1[qi] * psz );
+#pragma unroll
+            for( int r = 0; r < 9; r++ )
+            {
+                uint2 v = a.row( r*s4 );
+                const uint2 w = b.row_if( avg, r*s4, v );
+                v.x = avg ? avg4( v.x, w.x ) : v.x; v.y = avg ? avg4( v.y, w.y ) : v.y;
+                if( WEIGHTED && m.wdenom >= 0 ) { v.x = weight4( v.x, m.wscale, m.wdenom, m.woffset ); v.y = weight4( v.y, m.wscale, m.wdenom, m.woffset ); }
+                if( r < 8 ) acc[0] = __vsadu4( fenc[r].x, v.x ) + __vsadu4( fenc[r].y, v.y ) + acc[0];
+                if( r > 0 ) acc[1] = __vsadu4( fenc[r-1].x, v.x ) + __vsadu4( fenc[r-1].y, v.y ) + acc[1];
+            }
+        }
+        {   // left (omx-2, omy): bytes 0..7, right (omx+2, omy): bytes 1..8 of the same rows
+            const int x = omx - 2, qi = ( ( omy & 3 ) << 2 ) + ( x & 3 ), base = ( omy >> 2 ) * pitch() + ( x >> 2 );
+            const int avg = ( qi & 5 ) != 0;
+            const RowSrc<2> a( ref0, base + ( ( omy & 3 ) == 3 ? pitch() : 0 ) + c_hpel_ref0[qi] * psz ),
+                            b( ref0, base + ( ( x & 3 ) == 3 ) + c_hpel_ref1[qi] * psz );
+#pragma unroll
+            for( int r = 0; r < 8; r++ )
+            {
+                u32 t0, t1, t2, u0, u1, u2;
+                a.row12( r*s4, t0, t1, t2 );
+                b.row12_if( avg, r*s4, u0, u1, u2 );
+                t0 = avg ? avg4( t0, u0 ) : t0; t1 = avg ? avg4( t1, u1 ) : t1; t2 = avg ? avg4( t2, u2 ) : t2;
+                if( WEIGHTED && m.wdenom >= 0 )
+                {
+                    t0 = weight4( t0, m.wscale, m.wdenom, m.woffset ); t1 = weight4( t1, m.wscale, m.wdenom, m.woffset );
+                    t2 = weight4( t2, m.wscale, m.wdenom, m.woffset );
+                }
                 acc[2] = __vsadu4( fenc[r].x, t0 ) + __vsadu4( fenc[r].y, t1 ) + acc[2];
                 acc[3] = __vsadu4( fenc[r].x, __funnelshift_r( t0, t1, 8 ) ) + __vsadu4( fenc[r].y, __funnelshift_r( t1, t2, 8 ) ) + acc[3];
             }

@@ -6,6 +6,10 @@
 #include "la_block.cuh"
 
 #define FPEL(v) (((v)+2)>>2)
+// half-pel diamond around an odd centre with pairwise shared fetches (1, la_block.cuh hpel4_pairs) or as four get_ref candidates (0)
+#ifndef X264CU_HPEL_PAIRS
+#define X264CU_HPEL_PAIRS 1
+#endif
 
 // refine_subpel (me.c:865-992), p_halfpel_thresh == NULL, b_refine_qpel == 0, no chroma
 template<class BE>
@@ -31,9 +35,17 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
 #if X264CU_HPEL_EVEN
             if constexpr( BE::HPEL_EVEN )
             {
+#if X264CU_HPEL_PAIRS
+                // both forms give the same result for an even, unweighted centre, so the vote only decides what the warp runs:
+                // pass 1 (zero predictor) has even centres only and takes the cheaper single-plane form as a whole
+                const bool even = !( ( omx | omy ) & 1 ) && m.wdenom < 0;
+                if( __all_sync( __activemask(), even ) ) be.hpel4_even( omx, omy, tab, m, bcost, best );
+                else be.hpel4_pairs( omx, omy, tab, m, bcost, best );
+#else
                 if( !( ( omx | omy ) & 1 ) && m.wdenom < 0 ) be.hpel4_even( omx, omy, tab, m, bcost, best );
                 else be.qsad_best( 4, [&]( int k, int &x, int &y ) { x = omx + ( k == 2 ? -2 : k == 3 ? 2 : 0 ); y = omy + ( k == 0 ? -2 : k == 1 ? 2 : 0 ); },
                                    tab, m, bcost, best );
+#endif
             }
             else
 #endif
