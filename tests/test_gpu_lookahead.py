@@ -197,8 +197,12 @@ def test_batch_equals_sequential():
         gpu.close()
 
 
-def test_weighted_p_search():
-    """explicit weighted prediction of list 0 (weights supplied by the host, slicetype.c:859-864)."""
+@pytest.mark.parametrize("lanes", [0, 1])
+def test_weighted_p_search(monkeypatch, lanes):
+    """explicit weighted prediction of list 0 (weights supplied by the host, slicetype.c:859-864); lanes = 1 forces the
+    thread-per-block kernels with the compile-time pitch (weighted half-pel diamond with pairwise shared fetches)."""
+    if lanes:
+        monkeypatch.setenv("X264CU_LANES", str(lanes))
     x264cu = _cu()
     import ctypes as C
     W, H = 352, 288
