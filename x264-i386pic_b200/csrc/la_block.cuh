@@ -47,6 +47,10 @@
 
 static __constant__ uint8_t c_hpel_ref0[16] = {0,1,1,1,0,1,1,1,2,3,3,3,0,1,1,1};   // tables.c:183
 static __constant__ uint8_t c_hpel_ref1[16] = {0,0,1,0,2,2,3,2,2,2,3,2,2,2,3,2};   // tables.c:184
+// the same two tables as immediates (2 bits per entry): the index differs from lane to lane in the thread-per-block kernels,
+// where an indexed constant load is replayed once per distinct index
+__device__ __forceinline__ int hpel_ref0( int qidx ) { return (int)( ( 0x54fe5454u >> ( 2*qidx ) ) & 3u ); }
+__device__ __forceinline__ int hpel_ref1( int qidx ) { return (int)( ( 0xbababa10u >> ( 2*qidx ) ) & 3u ); }
 
 __device__ __forceinline__ int weight_px( int v, int scale, int denom, int offset )
 {   // mc.c:117-118
@@ -305,6 +309,8 @@ static __constant__ int8_t c_hex2[8][2] = {{-1,-2}, {-2,0}, {-1,2}, {1,2}, {2,0}
 __device__ __forceinline__ int hex2x( int i ) { return (int)( ( 0x01343101u >> ( 4*i ) ) & 7u ) - 2; }
 __device__ __forceinline__ int hex2y( int i ) { return (int)( ( 0x20024420u >> ( 4*i ) ) & 7u ) - 2; }
 static __constant__ int8_t c_sq1[9][2] = {{0,0}, {0,-1}, {0,1}, {-1,0}, {1,0}, {-1,-1}, {-1,1}, {1,-1}, {1,1}}; // me.c:56
+__device__ __forceinline__ int sq1x( int i ) { return (int)( ( 0x28215u >> ( 2*i ) ) & 3u ) - 1; }      // the same as immediates
+__device__ __forceinline__ int sq1y( int i ) { return (int)( ( 0x22161u >> ( 2*i ) ) & 3u ) - 1; }
 
 // ---- 8 lanes per block -------------------------------------------------------------------------------
 struct GroupBE
@@ -564,12 +570,12 @@ struct QpelRows
     __device__ __forceinline__ static int off1( const LaParams &P, int mvx, int mvy )
     {
         const int pitch = PITCH ? PITCH : P.stride;
-        return ( mvy >> 2 ) * pitch + ( mvx >> 2 ) + ( ( mvy & 3 ) == 3 ? pitch : 0 ) + c_hpel_ref0[( ( mvy & 3 ) << 2 ) + ( mvx & 3 )] * (int)P.plane_size;
+        return ( mvy >> 2 ) * pitch + ( mvx >> 2 ) + ( ( mvy & 3 ) == 3 ? pitch : 0 ) + hpel_ref0( ( ( mvy & 3 ) << 2 ) + ( mvx & 3 ) ) * (int)P.plane_size;
     }
     __device__ __forceinline__ static int off2( const LaParams &P, int mvx, int mvy )
     {
         const int pitch = PITCH ? PITCH : P.stride;
-        return ( mvy >> 2 ) * pitch + ( mvx >> 2 ) + ( ( mvx & 3 ) == 3 ) + c_hpel_ref1[( ( mvy & 3 ) << 2 ) + ( mvx & 3 )] * (int)P.plane_size;
+        return ( mvy >> 2 ) * pitch + ( mvx >> 2 ) + ( ( mvx & 3 ) == 3 ) + hpel_ref1( ( ( mvy & 3 ) << 2 ) + ( mvx & 3 ) ) * (int)P.plane_size;
     }
     // ref: 8-byte aligned block origin in the F plane; plane_size and the pitch are multiples of 8
     __device__ __forceinline__ QpelRows( const uint8_t *ref, const LaParams &P, int mvx, int mvy, int ws, int wd, int wo )
@@ -706,8 +712,8 @@ struct ThreadBE
         {   // up (omx, omy-2): rows 0..7, down (omx, omy+2): rows 1..8
             const int y = omy - 2, qi = ( ( y & 3 ) << 2 ) + ( omx & 3 ), base = ( y >> 2 ) * pitch() + ( omx >> 2 );
             const int avg = ( qi & 5 ) != 0;
-            const RowSrc<2> a( ref0, base + ( ( y & 3 ) == 3 ? pitch() : 0 ) + c_hpel_ref0[qi] * psz ),
-                            b( ref0, base + ( ( omx & 3 ) == 3 ) + c_hpel_ref1[qi] * psz );
+            const RowSrc<2> a( ref0, base + ( ( y & 3 ) == 3 ? pitch() : 0 ) + hpel_ref0( qi ) * psz ),
+                            b( ref0, base + ( ( omx & 3 ) == 3 ) + hpel_ref1( qi ) * psz );
 #pragma unroll
             for( int r = 0; r < 9; r++ )
             {
@@ -722,8 +728,8 @@ struct ThreadBE
         {   // left (omx-2, omy): bytes 0..7, right (omx+2, omy): bytes 1..8 of the same rows
             const int x = omx - 2, qi = ( ( omy & 3 ) << 2 ) + ( x & 3 ), base = ( omy >> 2 ) * pitch() + ( x >> 2 );
             const int avg = ( qi & 5 ) != 0;
-            const RowSrc<2> a( ref0, base + ( ( omy & 3 ) == 3 ? pitch() : 0 ) + c_hpel_ref0[qi] * psz ),
-                            b( ref0, base + ( ( x & 3 ) == 3 ) + c_hpel_ref1[qi] * psz );
+            const RowSrc<2> a( ref0, base + ( ( omy & 3 ) == 3 ? pitch() : 0 ) + hpel_ref0( qi ) * psz ),
+                            b( ref0, base + ( ( x & 3 ) == 3 ) + hpel_ref1( qi ) * psz );
 #pragma unroll
             for( int r = 0; r < 8; r++ )
             {

@@ -228,7 +228,7 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
             const int ox = bmx, oy = bmy;
             int bs = -1;
             be.square8( ox, oy, tab, m, bcost, bs );
-            bmx = ox + c_sq1[bs+1][0]; bmy = oy + c_sq1[bs+1][1];
+            bmx = ox + sq1x( bs+1 ); bmy = oy + sq1y( bs+1 );
         }
     }
 
