@@ -48,8 +48,13 @@ def raw(rep):
     launches = rows[2:]
     for r in launches:
         name = r[name_col] if name_col is not None else rep
-        if name in JSON_OUT:
+        if name in JSON_OUT and JSON_OUT[name]["report"] != rep.split("/")[-1]:
             continue
+        if name in JSON_OUT:                # further launches of the same kernel in one report (e.g. search pass 1, pass 2)
+            k = 1
+            while "%s #launch %d" % (name, k) in JSON_OUT:
+                k += 1
+            name = "%s #launch %d" % (name, k)
 
         def num(m, scale=1.0):
             try:
