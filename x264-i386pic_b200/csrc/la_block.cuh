@@ -139,11 +139,13 @@ __device__ __forceinline__ uint2 qpel_row( const uint8_t *ref, const LaParams &P
 __device__ __forceinline__ u32 biavg4( u32 a, u32 b, int w )
 {
     if( w == 32 ) return avg4( a, b );
-    const u32 w2 = 64 - w;
-    u32 ae = a & 0x00ff00ffu, ao = ( a >> 8 ) & 0x00ff00ffu, be = b & 0x00ff00ffu, bo = ( b >> 8 ) & 0x00ff00ffu;
-    u32 re = ( ( ae * w + be * w2 + 0x00200020u ) >> 6 ) & 0x00ff00ffu;
-    u32 ro = ( ( ao * w + bo * w2 + 0x00200020u ) << 2 ) & 0xff00ff00u;
-    return re | ro;
+    // everything scaled by 4, so that each result byte lands on a byte boundary (bits 8..15 of its 16-bit field; the field's
+    // maximum is 255 * 256 + 128 < 2^16): one PRMT then gathers the four bytes instead of two shifts, two masks and an OR
+    const u32 w4 = 4u * (u32)w, v4 = 256u - w4;
+    const u32 ae = __byte_perm( a, 0, 0x4240 ), ao = __byte_perm( a, 0, 0x4341 ), be = __byte_perm( b, 0, 0x4240 ), bo = __byte_perm( b, 0, 0x4341 );
+    const u32 re = ae * w4 + be * v4 + 0x00800080u;      // pixels 0, 2
+    const u32 ro = ao * w4 + bo * v4 + 0x00800080u;      // pixels 1, 3
+    return __byte_perm( re, ro, 0x7351 );
 }
 
 // ------------------------------------------------------------------------------------------------
