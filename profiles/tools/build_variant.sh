@@ -6,7 +6,7 @@ cd "$(dirname "$0")/../../x264-i386pic_b200"
 mkdir -p build/var
 FILES=$(echo $2 | tr ',' ' ')
 for f in $FILES; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --split-compile=0 $3 -c csrc/$f.cu -o build/var/${f}_$1.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $3 -c csrc/$f.cu -o build/var/${f}_$1.o
 done
 OBJS=""
 for o in lookahead search final aq_weights mbtree primitives primitives_mc capi stream; do

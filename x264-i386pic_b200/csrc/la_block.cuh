@@ -30,7 +30,7 @@
 #define X264CU_FINAL_PTXPRED 1
 #endif
 // __launch_bounds__ minimum CTAs per SM: the search kernel at 5 gets 96 registers without spills (5 resident CTAs of 128
-// threads: 2112 CTAs of a 1080p pass are 2.85 instead of 3.57 waves), the decision kernel at 6 gets 80
+// threads: 2112 CTAs of a 1080p pass are 2.85 instead of 3.57 waves), the decision kernel at 4 gets 128 (see X264CU_BIDIR_AHEAD)
 // dedicated half-pel diamond for even centres in the thread-per-block search (1) or the generic qpel fetch only (0)
 #ifndef X264CU_HPEL_EVEN
 #define X264CU_HPEL_EVEN 1
@@ -39,9 +39,19 @@
 #define X264CU_MINB_SEARCH 5
 #endif
 #ifndef X264CU_MINB_FINAL
-#define X264CU_MINB_FINAL 6
+#define X264CU_MINB_FINAL 4
 #endif
 
+#ifndef X264CU_ROWIF_ZERO
+#define X264CU_ROWIF_ZERO 0
+#endif
+// Decision kernel: how much of a bidir candidate is requested before its transform starts -- 0: row by row (r01, r02a);
+// 3: both motion-compensated predictions (8 rows x 2 references x up to 2 planes = up to 64 loads in flight per thread);
+// 4: also the two zero-MV windows.  The kernel is bound by the latency of its L2 -> L1 stream (65 % long-scoreboard stalls);
+// with row-by-row fetches a warp had 2 - 8 loads in flight.  Needs registers: 4 CTAs per SM at 128 (profiles/r02/tuning.md).
+#ifndef X264CU_BIDIR_AHEAD
+#define X264CU_BIDIR_AHEAD 4
+#endif
 #define GROUPS_PER_CTA 32
 #define CTA_THREADS (GROUPS_PER_CTA*8)
 
@@ -283,7 +293,11 @@ struct RowSrc
         }
         if( LDM == 2 )
         {
+#if X264CU_ROWIF_ZERO
+            u32 a0 = 0, a1 = 0, c = 0;          // nothing that depends on the first plane's data: the loads can leave at once
+#else
             u32 a0 = v.x, a1 = v.y, c = v.x;
+#endif
             asm( "{ .reg .pred p;\n setp.ne.s32 p, %3, 0;\n @p ld.global.nc.v2.u32 {%0,%1}, [%4];\n @p ld.global.nc.u32 %2, [%5];\n}"
                  : "+r"( a0 ), "+r"( a1 ), "+r"( c ) : "r"( p ), "l"( q + w4 ), "l"( q3 + w4 ) );
             const u32 w0 = k ? c : a0, w1 = k ? a0 : a1, w2 = k ? a1 : c;
@@ -850,17 +864,49 @@ struct ThreadBE
             const int i0 = ( ( mv0x & 2 ) >> 1 ) + ( mv0y & 2 ), i1 = ( ( mv1x & 2 ) >> 1 ) + ( mv1y & 2 );
             const int o0 = ( mv0x >> 2 ) + ( mv0y >> 2 ) * pitch() + i0*psz, o1 = ( mv1x >> 2 ) + ( mv1y >> 2 ) * pitch() + i1*psz;
             const RowSrc<LD64> q0( ref0, o0 ), q1( ref1, o1 );
+#if X264CU_BIDIR_AHEAD >= 3
+            uint2 A[8], Bv[8];
+#pragma unroll
+            for( int r = 0; r < 8; r++ ) { A[r] = q0.row( r*s4 ); Bv[r] = q1.row( r*s4 ); }
+            return sad8x8_t( fenc, [&]( int r ) { return make_uint2( biavg4( A[r].x, Bv[r].x, w ), biavg4( A[r].y, Bv[r].y, w ) ); } );
+#endif
             return sad8x8_t( fenc, [&]( int r ) { uint2 a = q0.row( r*s4 ), b = q1.row( r*s4 );
                                                   return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
         }
         QpelRows<false, PITCH, LD64, PTXPRED> r0( ref0, *P, mv0x, mv0y, 0, -1, 0 ), r1( ref1, *P, mv1x, mv1y, 0, -1, 0 );
+#if X264CU_BIDIR_AHEAD
+        // tuning: the whole list-0 prediction (8 rows, up to 32 loads) is requested before the transform starts, so that a warp
+        // has more than one row of each plane in flight (the kernel is bound by the latency of its L2 -> L1 stream)
+        uint2 A[8];
+#pragma unroll
+        for( int r = 0; r < 8; r++ ) A[r] = r0( r );
+#if X264CU_BIDIR_AHEAD == 2
+#pragma unroll
+        for( int r = 0; r < 8; r++ ) asm volatile( "" : "+r"( A[r].x ), "+r"( A[r].y ) );
+#endif
+#if X264CU_BIDIR_AHEAD >= 3
+        uint2 Bv[8];
+#pragma unroll
+        for( int r = 0; r < 8; r++ ) Bv[r] = r1( r );
+        return satd8x8_t( fenc, [&]( int r ) { const uint2 a = A[r], b = Bv[r]; return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+#endif
+        return satd8x8_t( fenc, [&]( int r ) { const uint2 a = A[r], b = r1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+#else
         return satd8x8_t( fenc, [&]( int r ) { uint2 a = r0( r ), b = r1( r ); return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); } );
+#endif
     }
     __device__ __forceinline__ int bidir_zero( int w ) const
     {
         const u32 *q0 = (const u32 *)ref0, *q1 = (const u32 *)ref1; const int s4 = pitch() >> 2;
+#if X264CU_BIDIR_AHEAD >= 4
+        uint2 A[8], Bv[8];
+#pragma unroll
+        for( int r = 0; r < 8; r++ ) { A[r] = __ldg( (const uint2 *)( q0 + r*s4 ) ); Bv[r] = __ldg( (const uint2 *)( q1 + r*s4 ) ); }
+        auto rows = [&]( int r ) { return make_uint2( biavg4( A[r].x, Bv[r].x, w ), biavg4( A[r].y, Bv[r].y, w ) ); };
+#else
         auto rows = [&]( int r ) { uint2 a = __ldg( (const uint2 *)( q0 + r*s4 ) ), b = __ldg( (const uint2 *)( q1 + r*s4 ) );
                                    return make_uint2( biavg4( a.x, b.x, w ), biavg4( a.y, b.y, w ) ); };
+#endif
         return SATD ? satd8x8_t( fenc, rows ) : sad8x8_t( fenc, rows );
     }
 };
