@@ -29,14 +29,16 @@
 #ifndef X264CU_FINAL_PTXPRED
 #define X264CU_FINAL_PTXPRED 1
 #endif
-// __launch_bounds__ minimum CTAs per SM: the search kernel at 5 gets 96 registers without spills (5 resident CTAs of 128
-// threads: 2112 CTAs of a 1080p pass are 2.85 instead of 3.57 waves), the decision kernel at 4 gets 128 (see X264CU_BIDIR_AHEAD)
+// __launch_bounds__ minimum CTAs per SM.  Search kernel: 32x8-block CTAs of 256 threads, 2 per SM (126 registers, 16 warps); with
+// 32x4-block CTAs 3 / 4 / 5 / 6 per SM (118 / 116 / 96 / 80 registers) all run one context within 3 % of each other, but under the
+// benchmarked load (4 contexts whose search and decision launches overlap) the 256-thread CTAs give 2 % more frames/s.
+// Decision kernel: 4 CTAs of 128 threads at 128 registers (see X264CU_BIDIR_AHEAD).
 // dedicated half-pel diamond for even centres in the thread-per-block search (1) or the generic qpel fetch only (0)
 #ifndef X264CU_HPEL_EVEN
 #define X264CU_HPEL_EVEN 1
 #endif
 #ifndef X264CU_MINB_SEARCH
-#define X264CU_MINB_SEARCH 5
+#define X264CU_MINB_SEARCH 2
 #endif
 #ifndef X264CU_MINB_FINAL
 #define X264CU_MINB_FINAL 4

@@ -6,7 +6,7 @@
 // table (capi.cu build_warp_tiles).  A CTA is TILE_W * TILE_H threads; a warp covers TILE_W x (32 / TILE_W) blocks.
 #ifndef X264CU_S_TILE_W
 #define X264CU_S_TILE_W 32
-#define X264CU_S_TILE_H 4
+#define X264CU_S_TILE_H 8
 #endif
 // the two compile-time plane pitches of the search / decision kernels (capi.cu picks the smaller one that fits)
 #ifndef X264CU_PITCH_A
