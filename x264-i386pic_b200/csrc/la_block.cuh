@@ -429,22 +429,26 @@ struct WarpBE
     const LaParams *P;
     int *err;                // error flag of the launch (bounded spins)
 
-    // an MV word of the row below: spin (L1-bypassing loads) until its producer has replaced the "not ready" pattern
-    __device__ __forceinline__ int wait_mv( const int *p ) const
+    // The three MV words of the row below (below, below-left, below-right; `need` bit i: word i exists): spin with L1-bypassing
+    // loads until their producers have replaced the "not ready" pattern.  Three lanes poll at once: one L2 round trip on the serial critical path instead of three (a word that its producer has already stored --
+    // the common case, the row below runs two blocks ahead -- comes back on the first try).
+    __device__ __forceinline__ void wait_mv3( const int *below, int need, int &v0, int &v1, int &v2 ) const
     {
-        int v;
+        const int lane = threadIdx.x & 31;
+        const int *p = below + ( lane == 1 ? -1 : lane == 2 ? 1 : 0 );
+        const bool mine = lane < 3 && ( ( need >> lane ) & 1 );
+        int v = 0;
         unsigned ns = X264CU_SPIN_NS0;
         for( int spins = 1; ; spins++ )
         {
-            asm volatile( "ld.volatile.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
-            if( v != 0x7F7F7F7F ) break;
-            if( ( spins & 1023 ) == 0 && ( *(volatile int *)err || spins > ( 1 << 22 ) ) ) { *(volatile int *)err = 1; v = 0; break; }
-            // exponential back-off: rows near the top of the frame wait for milliseconds before their first block, and a
-            // warp that polls every few cycles takes issue slots from the launches of other encode streams
+            if( mine ) asm volatile( "ld.volatile.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+            const bool pending = mine && v == 0x7F7F7F7F;
+            if( !__any_sync( 0xffffffffu, pending ) ) break;
+            if( ( spins & 1023 ) == 0 && ( *(volatile int *)err || spins > ( 1 << 22 ) ) ) { *(volatile int *)err = 1; if( pending ) v = 0; break; }
             __nanosleep( ns );
             ns = min( ns * 2, (unsigned)X264CU_SPIN_NS1 );
         }
-        return __shfl_sync( 0xffffffffu, v, 0 );      // one decision per warp, also on the time-out path
+        v0 = __shfl_sync( 0xffffffffu, v, 0 ); v1 = __shfl_sync( 0xffffffffu, v, 1 ); v2 = __shfl_sync( 0xffffffffu, v, 2 );
     }
     // sum over the 8 lanes of this lane's subgroup: xor-shuffles (REDUX with four different 8-lane masks per warp
     // measured 60 % slower, profiles/r01/tuning.md)

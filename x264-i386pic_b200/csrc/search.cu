@@ -271,9 +271,11 @@ __device__ __forceinline__ int search_block( const BE &be, const SearchJob &J, c
             if( bx < P.mbw-1 ) MVC_SET( right_mv )
             if( by < P.mbh-1 )
             {
-                MVC_SET( be.wait_mv( f + P.mbw ) )
-                if( bx > 0 ) MVC_SET( be.wait_mv( f + P.mbw-1 ) )
-                if( bx < P.mbw-1 ) MVC_SET( be.wait_mv( f + P.mbw+1 ) )
+                int v0, v1, v2;
+                be.wait_mv3( f + P.mbw, 1 | ( bx > 0 ? 2 : 0 ) | ( bx < P.mbw-1 ? 4 : 0 ), v0, v1, v2 );
+                MVC_SET( v0 )
+                if( bx > 0 ) MVC_SET( v1 )
+                if( bx < P.mbw-1 ) MVC_SET( v2 )
             }
         }
         else
