@@ -333,7 +333,7 @@ __device__ __forceinline__ int sq1y( int i ) { return (int)( ( 0x22161u >> ( 2*i
 // ---- 8 lanes per block -------------------------------------------------------------------------------
 struct GroupBE
 {
-    static constexpr bool PAR4 = false, HPEL_EVEN = false;
+    static constexpr bool PAR4 = false, HPEL_EVEN = false, SATD5 = false;
     Grp g;
     uint2 fenc;              // this lane's row of the block
     const uint8_t *ref0;     // this lane's row of reference 0's F plane at mv 0
@@ -421,7 +421,7 @@ struct GroupBE
 template<bool SATD>
 struct WarpBE
 {
-    static constexpr bool PAR4 = true, HPEL_EVEN = false;
+    static constexpr bool PAR4 = true, HPEL_EVEN = false, SATD5 = false;
     Grp g;                   // mask: the whole warp; r: pixel row
     int sub;                 // candidate slot of this lane
     uint2 fenc;
@@ -532,6 +532,146 @@ struct WarpBE
     { return satd8( fenc, qpel_row( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) ); }
 };
 
+// ---- 32 lanes per block: 8 candidates x 4 lanes x 2 pixel rows ------------------------------------------
+// The second latency-oriented mapping of the exact raster-serial mode (tuning build, -DX264CU_SERIAL_SLOTS=8).  A block search is a chain of candidate rounds, each
+// a dependent sequence of address arithmetic, loads, the metric, a shuffle reduction and the warp-wide minimum (~500 cycles);
+// with four slots the full hexagon, the square refine and the predictor set take two rounds each and the SATD re-measurement
+// of the winner is a round of its own.  Eight slots (lane >> 2 = slot, lane & 3 = row pair) make each of them ONE round --
+// the re-measurement shares its round with the four quarter-pel neighbours -- and the per-slot reductions are two shuffle
+// levels instead of three; every lane carries two rows, which adds instructions but not chain length.
+template<bool SATD>
+struct WarpBE8
+{
+    static constexpr bool PAR4 = true, HPEL_EVEN = false, SATD5 = true;
+    static constexpr int SLOTS = 8;
+    int sub, q;              // candidate slot of this lane; row pair: this lane holds rows 2q and 2q+1
+    uint2 fenc0, fenc1;
+    const uint8_t *ref0, *ref1, *ref_w;      // this lane's FIRST row at mv 0
+    const LaParams *P;
+    int *err;
+
+    __device__ __forceinline__ void wait_mv3( const int *below, int need, int &v0, int &v1, int &v2 ) const
+    {
+        const int lane = threadIdx.x & 31;
+        const int *p = below + ( lane == 1 ? -1 : lane == 2 ? 1 : 0 );
+        const bool mine = lane < 3 && ( ( need >> lane ) & 1 );
+        int v = 0;
+        unsigned ns = X264CU_SPIN_NS0;
+        for( int spins = 1; ; spins++ )
+        {
+            if( mine ) asm volatile( "ld.volatile.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+            const bool pending = mine && v == 0x7F7F7F7F;
+            if( !__any_sync( 0xffffffffu, pending ) ) break;
+            if( ( spins & 1023 ) == 0 && ( *(volatile int *)err || spins > ( 1 << 22 ) ) ) { *(volatile int *)err = 1; if( pending ) v = 0; break; }
+            __nanosleep( ns );
+            ns = min( ns * 2, (unsigned)X264CU_SPIN_NS1 );
+        }
+        v0 = __shfl_sync( 0xffffffffu, v, 0 ); v1 = __shfl_sync( 0xffffffffu, v, 1 ); v2 = __shfl_sync( 0xffffffffu, v, 2 );
+    }
+    __device__ __forceinline__ bool leader() const { return ( threadIdx.x & 31 ) == 0; }
+    __device__ __forceinline__ bool satd() const { return SATD; }
+    // sum over the 4 lanes of this lane's slot
+    __device__ __forceinline__ int rsum4( int v ) const
+    {
+        v += __shfl_xor_sync( 0xffffffffu, v, 1 );
+        return v + __shfl_xor_sync( 0xffffffffu, v, 2 );
+    }
+    __device__ __forceinline__ int sad2( uint2 a0, uint2 a1 ) const { return rsum4( (int)( sad8( fenc0, a0 ) + sad8( fenc1, a1 ) ) ); }
+    // x264_pixel_satd_8x8 (pixel.c:290-330): lanes q = 0,1 hold the upper 8x4 half, q = 2,3 the lower one.  Per column word the
+    // first vertical butterfly (row 2q +- row 2q+1) is in registers; the second one, between the two lanes of a half, is folded
+    // into the absolute sum: |u+v| + |u-v| == 2*max(|u|,|v|) per 16-bit field, so a lane only needs its partner's absolute
+    // values -- and only for the two column words it scores (even q: words 0,1; odd q: words 2,3).
+    __device__ __forceinline__ int satd2( uint2 a0, uint2 a1 ) const
+    {
+        u32 d[4], h0[4], h1[4];
+        diff_row8( fenc0, a0, d ); HADAMARD4( h0[0], h0[1], h0[2], h0[3], d[0], d[1], d[2], d[3] );
+        diff_row8( fenc1, a1, d ); HADAMARD4( h1[0], h1[1], h1[2], h1[3], d[0], d[1], d[2], d[3] );
+        u32 as[4], ad[4];
+#pragma unroll
+        for( int i = 0; i < 4; i++ ) { as[i] = abs2( h0[i] + h1[i] ); ad[i] = abs2( h0[i] - h1[i] ); }
+        const bool odd = q & 1;
+        // send the two words the partner scores, receive the partner's values for the two words this lane scores
+        const u32 ps0 = __shfl_xor_sync( 0xffffffffu, odd ? as[0] : as[2], 1 ), ps1 = __shfl_xor_sync( 0xffffffffu, odd ? as[1] : as[3], 1 );
+        const u32 pd0 = __shfl_xor_sync( 0xffffffffu, odd ? ad[0] : ad[2], 1 ), pd1 = __shfl_xor_sync( 0xffffffffu, odd ? ad[1] : ad[3], 1 );
+        const u32 ms0 = odd ? as[2] : as[0], ms1 = odd ? as[3] : as[1], md0 = odd ? ad[2] : ad[0], md1 = odd ? ad[3] : ad[1];
+        const u32 sum = __vmaxu2( ms0, ps0 ) + __vmaxu2( ms1, ps1 ) + __vmaxu2( md0, pd0 ) + __vmaxu2( md1, pd1 );
+        return rsum4( (int)( ( sum & 0xffff ) + ( sum >> 16 ) ) );
+    }
+    __device__ __forceinline__ int cmp2( uint2 a0, uint2 a1 ) const { return SATD ? satd2( a0, a1 ) : sad2( a0, a1 ); }
+    __device__ __forceinline__ int zero_cmp() const { return cmp2( load8u( ref0 ), load8u( ref0 + P->stride ) ); }
+    __device__ __forceinline__ int fpel_cost( int x, int y ) const
+    {
+        const uint8_t *p = ref_w + (int64_t)y * P->stride + x;
+        return sad2( load8u( p ), load8u( p + P->stride ) );
+    }
+    __device__ __forceinline__ int qsad_cost( const MeGeo &m, int x, int y ) const
+    {
+        return sad2( qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ), qpel_row( ref0 + P->stride, *P, x, y, m.wscale, m.wdenom, m.woffset ) );
+    }
+    __device__ __forceinline__ int qsatd_cost( const MeGeo &m, int x, int y ) const
+    {
+        return satd2( qpel_row( ref0, *P, x, y, m.wscale, m.wdenom, m.woffset ), qpel_row( ref0 + P->stride, *P, x, y, m.wscale, m.wdenom, m.woffset ) );
+    }
+    // slot s scores candidate k0 + s; `c` is this slot's full cost (identical in its 4 lanes).  The minimum of (cost << 3 | slot)
+    // is the reference's "strict <, earlier candidate wins ties" rule.
+    __device__ __forceinline__ void take_min8( int c, bool valid, int k0, int &bcost, int &best ) const
+    {
+        u32 key = valid ? ( (u32)c << 3 ) | (u32)sub : 0xffffffffu;
+        key = __reduce_min_sync( 0xffffffffu, key );
+        if( key != 0xffffffffu && (int)( key >> 3 ) < bcost ) { bcost = (int)( key >> 3 ); best = k0 + (int)( key & 7 ); }
+    }
+    template<class XY> __device__ __forceinline__ void fpel_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        for( int k0 = 0; k0 < n; k0 += SLOTS )
+        {
+            int x, y;
+            xy( min( k0 + sub, n-1 ), x, y );
+            const int c = fpel_cost( x, y ) + mvcost( tab, m, x*4, y*4 );
+            take_min8( c, k0 + sub < n, k0, bcost, best );
+        }
+    }
+    template<class XY> __device__ __forceinline__ void qsad_best( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        for( int k0 = 0; k0 < n; k0 += SLOTS )
+        {
+            int x, y;
+            xy( min( k0 + sub, n-1 ), x, y );
+            const int c = qsad_cost( m, x, y ) + mvcost( tab, m, x, y );
+            take_min8( c, k0 + sub < n, k0, bcost, best );
+        }
+    }
+    template<class XY> __device__ __forceinline__ void qsad_best0( int n, XY xy, const CostTab &tab, const MeGeo &m, int &bcost, int &best, int &cost0 ) const
+    {
+        for( int k0 = 0; k0 < n; k0 += SLOTS )
+        {
+            int x, y;
+            xy( min( k0 + sub, n-1 ), x, y );
+            const int c = qsad_cost( m, x, y ) + mvcost( tab, m, x, y );
+            if( k0 == 0 ) cost0 = __shfl_sync( 0xffffffffu, c, 0 );
+            take_min8( c, k0 + sub < n, k0, bcost, best );
+        }
+    }
+    // The SATD re-measurement of the winner (me.c:925-929, slot 0) and, when `diamond`, its four quarter-pel neighbours
+    // (me.c:947-963, slots 1..4) in one round: bcost becomes the centre's SATD cost unless a neighbour is strictly cheaper;
+    // best = -1: the centre stays, else the neighbour index 0..3 (up, down, left, right).
+    __device__ __forceinline__ void qsatd_best5( int omx, int omy, bool diamond, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    {
+        const int k = min( sub, 4 ) - 1;
+        const int x = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), y = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
+        const int c = qsatd_cost( m, x, y ) + mvcost( tab, m, x, y );
+        u32 key = ( sub == 0 || ( diamond && sub <= 4 ) ) ? ( (u32)c << 3 ) | (u32)sub : 0xffffffffu;
+        key = __reduce_min_sync( 0xffffffffu, key );
+        bcost = (int)( key >> 3 ); best = (int)( key & 7 ) - 1;
+    }
+    __device__ __forceinline__ void hex6( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    { fpel_best( 6, [&]( int k, int &x, int &y ) { x = ox + hex2x( k+1 ); y = oy + hex2y( k+1 ); }, tab, m, bcost, best ); }
+    __device__ __forceinline__ void square8( int ox, int oy, const CostTab &tab, const MeGeo &m, int &bcost, int &best ) const
+    { fpel_best( 8, [&]( int k, int &x, int &y ) { x = ox + sq1x( k+1 ); y = oy + sq1y( k+1 ); }, tab, m, bcost, best ); }
+    __device__ __forceinline__ int fpel1( int mx, int my ) const { return fpel_cost( mx, my ); }
+    __device__ __forceinline__ int qsad1( const MeGeo &m, int mx, int my ) const { return qsad_cost( m, mx, my ); }
+    __device__ __forceinline__ int qsatd( const MeGeo &m, int mx, int my ) const { return qsatd_cost( m, mx, my ); }
+};
+
 // ---- 1 thread per block ---------------------------------------------------------------------------
 // PITCH is the device plane pitch as a compile-time constant (0: read it from LaParams).  With a constant pitch the
 // eight row loads of a candidate are one base address plus immediates; with a run-time pitch every row costs two
@@ -636,7 +776,7 @@ struct QpelRows
 template<bool SATD, bool WEIGHTED, int PITCH, int LD64, bool PTXPRED>
 struct ThreadBE
 {
-    static constexpr bool PAR4 = false, HPEL_EVEN = true;
+    static constexpr bool PAR4 = false, HPEL_EVEN = true, SATD5 = false;
     uint2 fenc[8];
     const uint8_t *ref0, *ref1, *ref_w;      // block origins (8-byte aligned)
     const LaParams *P;

@@ -56,7 +56,18 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
             bmy = omy + ( best == 0 ? -2 : best == 1 ? 2 : 0 );
         }
     }
-    if constexpr( BE::PAR4 )
+    if constexpr( BE::PAR4 && BE::SATD5 )
+    {   // eight slots: the re-measurement and the quarter-pel diamond are one round
+        const bool diamond = qpel_iters && !( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx );
+        if( be.satd() )
+        {
+            const int omx = bmx, omy = bmy;
+            int best = -1;
+            be.qsatd_best5( omx, omy, diamond, tab, m, bcost, best );
+            if( best >= 0 ) { bmx = omx + ( best == 2 ? -1 : best == 3 ? 1 : 0 ); bmy = omy + ( best == 0 ? -1 : best == 1 ? 1 : 0 ); }
+        }
+    }
+    else if constexpr( BE::PAR4 )
     {
         if( be.satd() )   // mbcmp != fpelcmp: re-measure the winner with SATD (me.c:925-929)
             bcost = be.qsatd( m, bmx, bmy ) + mvcost( tab, m, bmx, bmy );
@@ -403,6 +414,12 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_wave( const SearchJ
 #ifndef SERIAL_WARPS
 #define SERIAL_WARPS 2
 #endif
+// candidate slots per round of the exact-mode kernel: 4 (WarpBE, default) or 8 (WarpBE8, tuning build).  Measured on B200
+// (profiles/r02/tuning.md): eight slots shorten one stream's serial chain by 4 % (1.213 -> 1.166 ms per step) but cost 4 - 6 % of
+// the throughput with 4 - 8 streams per GPU (two rows per lane, eight slots scored even when a round has three candidates).
+#ifndef X264CU_SERIAL_SLOTS
+#define X264CU_SERIAL_SLOTS 4
+#endif
 template<bool SATD>
 __global__ void __launch_bounds__(SERIAL_WARPS*32) search_kernel_serial( const SearchJob *__restrict__ jobs, LaParams P, int first_job, int njobs,
                                                                           int *__restrict__ err )
@@ -413,15 +430,25 @@ __global__ void __launch_bounds__(SERIAL_WARPS*32) search_kernel_serial( const S
     const int ji = first_job + worker / P.mbh, by = P.mbh - 1 - worker % P.mbh;      // bottom rows first
     SearchJob J = jobs[ji];
     resolve_device_weight( J );
+#if X264CU_SERIAL_SLOTS == 8
+    WarpBE8<SATD> be; be.q = lane & 3; be.sub = lane >> 2; be.P = &P; be.ref1 = NULL; be.err = err;
+    const int row0 = 2 * be.q;
+#else
     WarpBE<SATD> be; be.g.r = lane & 7; be.g.mask = 0xffffffffu; be.sub = lane >> 3; be.P = &P; be.ref1 = NULL; be.err = err;
+    const int row0 = be.g.r;
+#endif
     int right_mv = 0;
     for( int i = 0; i < P.mbw; i++ )
     {
         const int bx = P.mbw - 1 - i, blk = by * P.mbw + bx;
         if( !skipped_border( P, bx, by ) )
         {
-            const int64_t pel = (int64_t)( by*8 + be.g.r ) * P.stride + bx*8;
+            const int64_t pel = (int64_t)( by*8 + row0 ) * P.stride + bx*8;
+#if X264CU_SERIAL_SLOTS == 8
+            be.fenc0 = *(const uint2 *)( J.fenc + pel ); be.fenc1 = *(const uint2 *)( J.fenc + pel + P.stride );
+#else
             be.fenc = *(const uint2 *)( J.fenc + pel );
+#endif
             be.ref0 = J.ref + pel; be.ref_w = J.ref_w + pel;
             right_mv = search_block( be, J, P, tab, bx, by, blk, right_mv );
             // warm L1 for the next block of this row: 32 rows x 32 columns of the four phase planes around its
