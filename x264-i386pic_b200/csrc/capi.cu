@@ -944,7 +944,7 @@ static int run_searches( x264cu_ctx *c, const std::vector<SearchTask> &tasks )
             Span s( c, K_SEARCH, 1 );
             bool anyw = false;
             for( const SearchTask &t : tasks ) anyw = anyw || t.w.enabled;
-            launch_search( d, (int)sj.size(), anyw, P, c->st );
+            launch_search( d, (int)sj.size(), anyw, pass == 0, P, c->st );
         }
     }
     return 0;

@@ -81,7 +81,7 @@ void launch_lowres( const uint8_t *luma, int stride, int width, int height, uint
 void launch_weight_plane( const uint8_t *src, uint8_t *dst, int64_t bytes, int scale, int denom, int offset, cudaStream_t st );
 void launch_intra( const uint8_t *planeF, const uint16_t *inv_qscale, uint16_t *intra, int32_t *row_satds,
                    int32_t *stats, const LaParams &P, cudaStream_t st );
-void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st );
+void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, bool first_pass, const LaParams &P, cudaStream_t st );
 // d_chunks: (first job, count) per CTA row of the thread-per-block kernel; every chunk is homogeneous (all bidir with the
 // same fenc / ref1 / list-1 field, or all non-bidir), see capi.cu group_finals
 void launch_final( const FinalJob *d_jobs, int njobs, const int2 *d_chunks, int nchunks, const LaParams &P, cudaStream_t st );

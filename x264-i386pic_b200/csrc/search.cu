@@ -7,6 +7,10 @@
 
 #define FPEL(v) (((v)+2)>>2)
 // half-pel diamond around an odd centre with pairwise shared fetches (1, la_block.cuh hpel4_pairs) or as four get_ref candidates (0)
+// a dedicated instantiation of the thread-per-block search for pass 0 (1) or one kernel for every pass (0)
+#ifndef X264CU_FIRST_PASS
+#define X264CU_FIRST_PASS 1
+#endif
 #ifndef X264CU_HPEL_PAIRS
 #define X264CU_HPEL_PAIRS 1
 #endif
@@ -263,7 +267,9 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
 }
 
 // one block of one search pass (slicetype.c:654-702)
-template<class BE>
+// FIRST: the pass is known at compile time to have no predictor field (pass 0 of the dependency-free schedule): the predictor
+// is zero and the candidate list empty for every block, so the candidate loop, the probes and the odd-centre half-pel path fold away
+template<class BE, bool FIRST = false>
 __device__ __forceinline__ int search_block( const BE &be, const SearchJob &J, const LaParams &P, const CostTab &tab,
                                              int bx, int by, int blk, int right_mv = 0 )
 {
@@ -272,7 +278,7 @@ __device__ __forceinline__ int search_block( const BE &be, const SearchJob &J, c
     me_limits( m, P, bx, by );
     // MV predictor from the previous pass's field (slicetype.c:658-680): right, below, below-left, below-right
     int mvc[4][2] = {{0,0},{0,0},{0,0},{0,0}}, i_mvc = 0;
-    if( J.mv_in )
+    if( !FIRST && J.mv_in )
     {
         const int *f = (const int *)J.mv_in + blk;
 #define MVC_SET( v ) { int v_ = (v); mvc[i_mvc][0] = (int16_t)( v_ & 0xffff ); mvc[i_mvc][1] = v_ >> 16; i_mvc++; }
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(CTA_THREADS) search_kernel_g( const SearchJob 
     search_block( be, J, P, tab, bx, by, blk );
 }
 
-template<bool SATD, bool WEIGHTED, int PITCH>
+template<bool SATD, bool WEIGHTED, int PITCH, bool FIRST = false>
 __global__ void __launch_bounds__(S_TILE_W*S_TILE_H, X264CU_MINB_SEARCH) search_kernel_t( const SearchJob *__restrict__ jobs, LaParams P )
 {
     const CostTab tab = stage_cost_tab( P );
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(S_TILE_W*S_TILE_H, X264CU_MINB_SEARCH) search_
 #pragma unroll
     for( int r = 0; r < 8; r++ ) be.fenc[r] = __ldg( (const uint2 *)( src + r * be.pitch() ) );
     be.ref0 = J.ref + pel; be.ref1 = NULL; be.ref_w = J.ref_w + pel;
-    search_block( be, J, P, tab, bx, by, blk );
+    search_block<decltype( be ), FIRST>( be, J, P, tab, bx, by, blk );
 }
 
 // Exact raster-serial mode: the reference evaluates blocks in reverse raster order and
@@ -530,13 +536,16 @@ void launch_search_waves( const SearchJob *d_jobs, int njobs, const LaParams &P,
 }
 
 template<int PITCH>
-static void launch_search_t( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
+static void launch_search_t( const SearchJob *d_jobs, int njobs, bool any_weighted, bool first_pass, const LaParams &P, cudaStream_t st )
 {
     const int warps_per_cta = S_TILE_W * S_TILE_H / 32;
     dim3 grid( ( P.ntiles_s + warps_per_cta - 1 ) / warps_per_cta, njobs );
     if( P.b_satd )
     {
         if( any_weighted ) search_kernel_t<true, true, PITCH><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
+#if X264CU_FIRST_PASS
+        else if( first_pass && PITCH ) search_kernel_t<true, false, PITCH, true><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
+#endif
         else               search_kernel_t<true, false, PITCH><<<grid, S_TILE_W*S_TILE_H, 0, st>>>( d_jobs, P );
     }
     else
@@ -546,14 +555,15 @@ static void launch_search_t( const SearchJob *d_jobs, int njobs, bool any_weight
     }
 }
 
-void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, const LaParams &P, cudaStream_t st )
+// first_pass: every job of the launch has mv_in == NULL (pass 0 of the dependency-free schedule)
+void launch_search( const SearchJob *d_jobs, int njobs, bool any_weighted, bool first_pass, const LaParams &P, cudaStream_t st )
 {
     if( use_thread_mapping( P, njobs ) )
     {   // the context picks the pitch from {1024, 2048} whenever the padded width fits (capi.cu), anything wider runs the
         // run-time-pitch instantiation
-        if( P.stride == X264CU_PITCH_A )      launch_search_t<X264CU_PITCH_A>( d_jobs, njobs, any_weighted, P, st );
-        else if( P.stride == X264CU_PITCH_B ) launch_search_t<X264CU_PITCH_B>( d_jobs, njobs, any_weighted, P, st );
-        else                        launch_search_t<0>( d_jobs, njobs, any_weighted, P, st );
+        if( P.stride == X264CU_PITCH_A )      launch_search_t<X264CU_PITCH_A>( d_jobs, njobs, any_weighted, first_pass, P, st );
+        else if( P.stride == X264CU_PITCH_B ) launch_search_t<X264CU_PITCH_B>( d_jobs, njobs, any_weighted, first_pass, P, st );
+        else                        launch_search_t<0>( d_jobs, njobs, any_weighted, first_pass, P, st );
     }
     else
     {
