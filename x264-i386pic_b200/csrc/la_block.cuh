@@ -1002,6 +1002,23 @@ struct ThreadBE
     {
         return satd8x8_t( fenc, QpelRows<WEIGHTED, PITCH, LD64, PTXPRED>( ref0, *P, mx, my, m.wscale, m.wdenom, m.woffset ) );
     }
+    // SATD stage around a centre with even components (unweighted): the centre is one plane's rows K; a quarter-pel neighbour
+    // (mx, my) is the rounding average of K with ONE other window -- whichever of get_ref's two sources is not the centre's.
+    __device__ __forceinline__ void centre_rows( int omx, int omy, uint2 ( &K )[8] ) const
+    {
+        const int s4 = pitch() >> 2;
+        const RowSrc<LD64> c( ref0, QpelRows<false, PITCH, LD64, PTXPRED>::off1( *P, omx, omy ) );
+#pragma unroll
+        for( int r = 0; r < 8; r++ ) K[r] = c.row( r*s4 );
+    }
+    __device__ __forceinline__ int qsatd_even( const uint2 ( &K )[8], int omx, int omy, int mx, int my ) const
+    {
+        typedef QpelRows<false, PITCH, LD64, PTXPRED> Q;
+        const int s4 = pitch() >> 2, oc = Q::off1( *P, omx, omy ), o1 = Q::off1( *P, mx, my ), o2 = Q::off2( *P, mx, my );
+        // the centre itself (mx == omx, my == omy): o1 == oc and the "other" window is the centre again; avg4( x, x ) == x
+        const RowSrc<LD64> n( ref0, ( mx == omx && my == omy ) ? oc : o1 == oc ? o2 : o1 );
+        return satd8x8_t( fenc, [&]( int r ) { const uint2 w = n.row( r*s4 ); return make_uint2( avg4( K[r].x, w.x ), avg4( K[r].y, w.y ) ); } );
+    }
     __device__ __forceinline__ int bidir( int mv0x, int mv0y, int mv1x, int mv1y, int w ) const
     {
         if( !SATD )

@@ -8,6 +8,10 @@
 #define FPEL(v) (((v)+2)>>2)
 // half-pel diamond around an odd centre with pairwise shared fetches (1, la_block.cuh hpel4_pairs) or as four get_ref candidates (0)
 // a dedicated instantiation of the thread-per-block search for pass 0 (1) or one kernel for every pass (0)
+// pass 0: the SATD stage keeps the centre's rows and fetches one window per quarter-pel neighbour (1) or runs the generic get_ref (0)
+#ifndef X264CU_EVEN_SATD
+#define X264CU_EVEN_SATD 1
+#endif
 #ifndef X264CU_FIRST_PASS
 #define X264CU_FIRST_PASS 1
 #endif
@@ -16,7 +20,8 @@
 #endif
 
 // refine_subpel (me.c:865-992), p_halfpel_thresh == NULL, b_refine_qpel == 0, no chroma
-template<class BE>
+// EVEN: every centre is known to have even components (pass 0: the start is full-pel and the half-pel diamond moves by 2)
+template<class BE, bool EVEN = false>
 __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, const LaParams &P, const CostTab &tab,
                                                int &bmx, int &bmy, int &bcost, int hpel_iters, int qpel_iters )
 {
@@ -90,6 +95,26 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
         // instructions and the kernel is instruction-cache sensitive (ncu: 16 % no-instruction stalls)
         const int omx = bmx, omy = bmy;
         const bool diamond = qpel_iters && !( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx );
+#if X264CU_EVEN_SATD
+        if constexpr( EVEN && BE::HPEL_EVEN )
+        {   // an even centre is ONE plane's rows, and each of its four quarter-pel neighbours is the average of exactly those rows
+            // with one other window (mc.c:221-249 over the four even phases): the centre is fetched once and kept
+            if( be.satd() )
+            {
+                uint2 K[8];
+                be.centre_rows( omx, omy, K );
+#pragma unroll 1
+                for( int k = -1; k < ( diamond ? 4 : 0 ); k++ )
+                {
+                    const int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
+                    const int cost = be.qsatd_even( K, omx, omy, mx, my ) + mvcost( tab, m, mx, my );
+                    if( k < 0 ) bcost = cost;
+                    else if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
+                }
+            }
+        }
+        else
+#endif
 #pragma unroll 1
         for( int k = be.satd() ? -1 : 0; k < ( diamond ? 4 : 0 ); k++ )
         {
@@ -102,7 +127,7 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
 }
 
 // x264_me_search_ref (me.c:182-420,774-797) for one block; result mv (qpel) and cost
-template<class BE>
+template<class BE, bool FIRST = false>
 __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const LaParams &P, const CostTab &tab,
                                            const int (*mvc)[2], int i_mvc, int &out_mx, int &out_my, int &out_cost )
 {
@@ -261,7 +286,7 @@ __device__ __forceinline__ void me_search( const BE &be, const MeGeo &m, const L
         if( bpred_cost < bcost ) { mx = bpred_mx; my = bpred_my; }
         else                     { mx = bmx*4;    my = bmy*4; }
         cost = min( bpred_cost, bcost );
-        refine_subpel( be, m, P, tab, mx, my, cost, 1, 1 );      // subpel_iterations[4] = {0,2,1,1}
+        refine_subpel<BE, FIRST>( be, m, P, tab, mx, my, cost, 1, 1 );      // subpel_iterations[4] = {0,2,1,1}
     }
     out_mx = mx; out_my = my; out_cost = cost;
 }
@@ -322,7 +347,7 @@ __device__ __forceinline__ int search_block( const BE &be, const SearchJob &J, c
     }
     if( !skip )
     {
-        me_search( be, m, P, tab, mvc, i_mvc, mx, my, cost );
+        me_search<BE, FIRST>( be, m, P, tab, mvc, i_mvc, mx, my, cost );
         cost -= tab[0];                                // slicetype.c:695
         if( mx | my ) cost += 5;                       // 5 * lambda (:696-697)
     }
