@@ -95,34 +95,47 @@ __device__ __forceinline__ void refine_subpel( const BE &be, const MeGeo &m, con
         // instructions and the kernel is instruction-cache sensitive (ncu: 16 % no-instruction stalls)
         const int omx = bmx, omy = bmy;
         const bool diamond = qpel_iters && !( bmy <= m.sminy || bmy >= m.smaxy || bmx <= m.sminx || bmx >= m.smaxx );
+        auto generic = [&]()
+        {
+#pragma unroll 1
+            for( int k = be.satd() ? -1 : 0; k < ( diamond ? 4 : 0 ); k++ )
+            {
+                const int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
+                const int cost = be.qsatd( m, mx, my ) + mvcost( tab, m, mx, my );
+                if( k < 0 ) bcost = cost;
+                else if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
+            }
+        };
 #if X264CU_EVEN_SATD
-        if constexpr( EVEN && BE::HPEL_EVEN )
+        if constexpr( BE::HPEL_EVEN )
         {   // an even centre is ONE plane's rows, and each of its four quarter-pel neighbours is the average of exactly those rows
             // with one other window (mc.c:221-249 over the four even phases): the centre is fetched once and kept
-            if( be.satd() )
+            bool all_even = EVEN;
+#if X264CU_EVEN_SATD == 2
+            // later passes: a warp whose centres all happen to be even (and unweighted) takes the same path
+            if constexpr( !EVEN ) all_even = be.satd() && __all_sync( __activemask(), !( ( omx | omy ) & 1 ) && m.wdenom < 0 );
+#endif
+            if( all_even )
             {
-                uint2 K[8];
-                be.centre_rows( omx, omy, K );
-#pragma unroll 1
-                for( int k = -1; k < ( diamond ? 4 : 0 ); k++ )
+                if( be.satd() )
                 {
-                    const int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
-                    const int cost = be.qsatd_even( K, omx, omy, mx, my ) + mvcost( tab, m, mx, my );
-                    if( k < 0 ) bcost = cost;
-                    else if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
+                    uint2 K[8];
+                    be.centre_rows( omx, omy, K );
+#pragma unroll 1
+                    for( int k = -1; k < ( diamond ? 4 : 0 ); k++ )
+                    {
+                        const int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
+                        const int cost = be.qsatd_even( K, omx, omy, mx, my ) + mvcost( tab, m, mx, my );
+                        if( k < 0 ) bcost = cost;
+                        else if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
+                    }
                 }
             }
+            else generic();
         }
         else
 #endif
-#pragma unroll 1
-        for( int k = be.satd() ? -1 : 0; k < ( diamond ? 4 : 0 ); k++ )
-        {
-            const int mx = omx + ( k == 2 ? -1 : k == 3 ? 1 : 0 ), my = omy + ( k == 0 ? -1 : k == 1 ? 1 : 0 );
-            const int cost = be.qsatd( m, mx, my ) + mvcost( tab, m, mx, my );
-            if( k < 0 ) bcost = cost;
-            else if( cost < bcost ) { bcost = cost; bmx = mx; bmy = my; }
-        }
+        generic();
     }
 }
 
